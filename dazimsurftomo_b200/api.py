@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's forward-modelling subroutines over the C ABI
+(include/dazim_b200.h -> libdazim_b200.so).  Names and argument meaning follow the
+reference:
+
+  depthkernel          src/src_inv_iso_joint/CalSurfG.f90:1
+  depthkernelTI        src/src_forward/depthkernelTI.f90:2
+  FwdObsTraveltimeCPS  src/src_forward/FwdTraveltimeCPS.f90:208
+  CalSurfG             src/src_inv_iso_joint/CalSurfG.f90:909
+  CalSurfGAnisoJoint   src/src_inv_iso_joint/CalSurfGAniso_Joint.f90:209
+
+There is no CPU fallback: if the CUDA library is missing or no device is
+present every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import build as _build
+from .formats import Survey
+
+_lib = None
+
+
+class DazimError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dazim_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Problem(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("vels", C.c_void_p),
+                ("goxd", C.c_float), ("gozd", C.c_float), ("dvxd", C.c_float), ("dvzd", C.c_float),
+                ("kmaxRc", C.c_int), ("tRc", C.c_void_p), ("depz", C.c_void_p), ("minthk", C.c_float),
+                ("kmax", C.c_int), ("nsrc", C.c_int), ("nrcf", C.c_int),
+                ("periods", C.c_void_p), ("nrc1", C.c_void_p), ("nsrcsurf1", C.c_void_p),
+                ("scxf", C.c_void_p), ("sczf", C.c_void_p), ("rcxf", C.c_void_p), ("rczf", C.c_void_p)]
+
+
+class Tables(C.Structure):
+    _fields_ = [("pvRc", C.c_void_p), ("sen_vs", C.c_void_p), ("sen_vp", C.c_void_p), ("sen_rho", C.c_void_p),
+                ("Lsen_Gsc", C.c_void_p)]
+
+
+class Coo(C.Structure):
+    _fields_ = [("rw", C.c_void_p), ("iw_row", C.c_void_p), ("col", C.c_void_p), ("maxnar", C.c_longlong),
+                ("nar", C.c_longlong)]
+
+
+class Times(C.Structure):
+    _fields_ = [("kernels_ms", C.c_float), ("dice_ms", C.c_float), ("fmm_ms", C.c_float), ("trace_ms", C.c_float),
+                ("assemble_ms", C.c_float), ("total_ms", C.c_float), ("n_accept", C.c_longlong),
+                ("n_steps", C.c_longlong), ("n_fmm_launch", C.c_longlong), ("n_trace_launch", C.c_longlong),
+                ("n_launch", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+                ("rbint", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libdazim_b200.so (must have been built: __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise DazimError(-1, f"{path} is missing: run `python -m dazimsurftomo_b200.build` (no CPU fallback)")
+        lib = C.CDLL(path)
+        lib.dazim_strerror.restype = C.c_char_p
+        lib.dazim_last_times.restype = C.POINTER(Times)
+        lib.dazim_last_times.argtypes = [C.c_void_p]
+        lib.dazim_plan_rows.restype = C.c_longlong
+        lib.dazim_plan_rows.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        lib.dazim_plan_nnz.restype = C.c_longlong
+        lib.dazim_plan_nnz.argtypes = [C.c_void_p]
+        lib.dazim_plan_destroy.argtypes = [C.c_void_p]
+        lib.dazim_plan_destroy.restype = None
+        lib.dazim_destroy.argtypes = [C.c_void_p]
+        lib.dazim_destroy.restype = None
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _chk(code: int):
+    if code:
+        raise DazimError(code, load().dazim_strerror(C.c_int(code)).decode())
+
+
+class Handle:
+    """One CUDA device + stream (dazim_create)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _chk(load().dazim_create(C.byref(self._h), C.c_int(device)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            load().dazim_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def times(self) -> dict:
+        return load().dazim_last_times(self._h).contents.as_dict()
+
+
+_default: Optional[Handle] = None
+
+
+def default_handle() -> Handle:
+    global _default
+    if _default is None:
+        dev = int(os.environ.get("LOCAL_RANK", os.environ.get("DAZIM_DEVICE", "0")))
+        _default = Handle(dev)
+    return _default
+
+
+class _Prob:
+    """Keeps the numpy arrays behind a dazim_problem alive."""
+
+    def __init__(self, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey):
+        self.vels = np.asfortranarray(vels, np.float32)
+        nx, ny, nz = self.vels.shape
+        self.depz = np.ascontiguousarray(depz, np.float32)
+        self.tRc = np.ascontiguousarray(tRc, np.float64)
+        self.keep = [np.asfortranarray(x) for x in (sv.periods.astype(np.int32), sv.nrc1.astype(np.int32),
+                                                    sv.nsrcsurf1.astype(np.int32), sv.scxf.astype(np.float32),
+                                                    sv.sczf.astype(np.float32), sv.rcxf.astype(np.float32),
+                                                    sv.rczf.astype(np.float32))]
+        p = Problem()
+        p.nx, p.ny, p.nz = nx, ny, nz
+        p.vels = _p(self.vels)
+        p.goxd, p.gozd, p.dvxd, p.dvzd = goxd, gozd, dvxd, dvzd
+        p.kmaxRc = len(self.tRc); p.tRc = _p(self.tRc); p.depz = _p(self.depz); p.minthk = minthk
+        p.kmax, p.nsrc, p.nrcf = sv.kmax, sv.nsrc, sv.nrcf
+        p.periods, p.nrc1, p.nsrcsurf1, p.scxf, p.sczf, p.rcxf, p.rczf = (_p(x) for x in self.keep)
+        self.c = p
+        self.shape = (nx, ny, nz)
+        self.dall = int(sv.dall)
+
+
+class _Tab:
+    def __init__(self, shape, k, tables: Optional[dict]):
+        nx, ny, nz = shape
+        tables = tables or {}
+        g = tables.get
+        self.pvRc = np.zeros((nx * ny, k), np.float64, order="F") if g("pvRc") is None else np.asfortranarray(g("pvRc"), np.float64)
+        self.sen = [np.zeros((nx * ny, k, nz), np.float64, order="F") if g(n) is None else np.asfortranarray(g(n), np.float64)
+                    for n in ("sen_vs", "sen_vp", "sen_rho")]
+        self.L = np.zeros((nx * ny, k, nz - 1), np.float32, order="F") if g("Lsen_Gsc") is None else np.asfortranarray(g("Lsen_Gsc"), np.float32)
+        t = Tables()
+        t.pvRc = _p(self.pvRc); t.sen_vs, t.sen_vp, t.sen_rho = (_p(s) for s in self.sen); t.Lsen_Gsc = _p(self.L)
+        self.c = t
+
+
+def depthkernel(vel, depz, tRc, minthk, handle: Optional[Handle] = None):
+    """CalSurfG.f90:1 -> (pvRc, sen_vs, sen_vp, sen_rho) Fortran-ordered float64."""
+    h = handle or default_handle()
+    vel = np.asfortranarray(vel, np.float32); nx, ny, nz = vel.shape
+    depz = np.ascontiguousarray(depz, np.float32); tRc = np.ascontiguousarray(tRc, np.float64); k = len(tRc)
+    pv = np.zeros((nx * ny, k), np.float64, order="F")
+    s = [np.zeros((nx * ny, k, nz), np.float64, order="F") for _ in range(3)]
+    _chk(load().dazim_depthkernel(h._h, C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(vel), _p(pv), _p(s[0]), _p(s[1]),
+                                  _p(s[2]), C.c_int(k), _p(tRc), _p(depz), C.c_float(minthk)))
+    return pv, s[0], s[1], s[2]
+
+
+def depthkernelTI(vel, depz, tRc, minthk, handle: Optional[Handle] = None):
+    """depthkernelTI.f90:2 -> (pvRc float64 (nx*ny,k), Lsen_Gsc float32 (nx*ny,k,nz-1))."""
+    h = handle or default_handle()
+    vel = np.asfortranarray(vel, np.float32); nx, ny, nz = vel.shape
+    depz = np.ascontiguousarray(depz, np.float32); tRc = np.ascontiguousarray(tRc, np.float64); k = len(tRc)
+    pv = np.zeros((nx * ny, k), np.float64, order="F")
+    L = np.zeros((nx * ny, k, nz - 1), np.float32, order="F")
+    _chk(load().dazim_depthkernel_ti(h._h, C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(vel), _p(pv), C.c_int(k),
+                                     _p(tRc), _p(depz), C.c_float(minthk), _p(L)))
+    return pv, L
+
+
+def surfdisp96(thk, vp, vs, rho, periods, handle: Optional[Handle] = None):
+    """surfdisp96.f:52 for nprof profiles: inputs (nlayer,nprof) or (nlayer,), returns cg (kmax,nprof)."""
+    h = handle or default_handle()
+    arrs = [np.asfortranarray(np.atleast_2d(np.asarray(x, np.float32).T).T if np.ndim(x) == 1 else x, np.float32)
+            for x in (thk, vp, vs, rho)]
+    arrs = [a.reshape(a.shape[0], -1, order="F") for a in arrs]
+    nl, npf = arrs[0].shape
+    t = np.ascontiguousarray(periods, np.float64)
+    cg = np.zeros((len(t), npf), np.float64, order="F")
+    _chk(load().dazim_surfdisp96(h._h, C.c_int(npf), C.c_int(nl), *[_p(a) for a in arrs], C.c_int(len(t)), _p(t), _p(cg)))
+    return cg
+
+
+def _gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc, gs, tables, maxnar, handle):
+    h = handle or default_handle()
+    pr = _Prob(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv)
+    nx, ny, nz = pr.shape
+    k = len(pr.tRc)
+    tb = _Tab(pr.shape, k, tables)
+    dall = pr.dall
+    dsurf = np.zeros(dall, np.float32); taa = np.zeros(dall, np.float32)
+    tRcV = np.zeros(((nx - 2) * (ny - 2), k), np.float64, order="F")
+    if gc is not None:
+        gc = np.asfortranarray(gc, np.float32); gs = np.asfortranarray(gs, np.float32)
+    coo = Coo()
+    if mode != 0:
+        if maxnar is None:
+            maxnar = max(1024, dall * 400 * (3 if mode == 2 else 1))
+        rw = np.zeros(maxnar, np.float32); iw = np.zeros(maxnar, np.int32); col = np.zeros(maxnar, np.int32)
+        coo.rw, coo.iw_row, coo.col, coo.maxnar = _p(rw), _p(iw), _p(col), maxnar
+    _chk(load().dazim_gbuild(h._h, C.c_int(mode), C.byref(pr.c), C.byref(tb.c), C.c_int(0 if tables is None else 1),
+                             _p(gc), _p(gs), _p(dsurf), _p(taa), _p(tRcV), C.byref(coo) if mode != 0 else None))
+    out = dict(dsurf=dsurf, obsTaa=taa, tRcV=tRcV, pvRc=tb.pvRc, sen_vs=tb.sen[0], sen_vp=tb.sen[1], sen_rho=tb.sen[2],
+               Lsen_Gsc=tb.L, times=h.times)
+    if mode != 0:
+        n = coo.nar
+        out.update(rw=rw[:n], row=iw[:n], col=col[:n], nar=n)
+    return out
+
+
+def FwdObsTraveltimeCPS(vels, Gctrue, Gstrue, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables=None,
+                        handle: Optional[Handle] = None):
+    """FwdTraveltimeCPS.f90:208: returns dict(dsurf=T_iso, obsTaa=T_aa, tRcV, Lsen_Gsc, pvRc)."""
+    return _gbuild(0, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, Gctrue, Gstrue, tables, None, handle)
+
+
+def CalSurfG(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables=None, maxnar=None,
+             handle: Optional[Handle] = None):
+    """CalSurfG.f90:909: returns dict(dsurf, rw, row (1-based, = iw(2:nar+1)), col (1-based), nar)."""
+    return _gbuild(1, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle)
+
+
+def CalSurfGAnisoJoint(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables=None, maxnar=None,
+                       handle: Optional[Handle] = None):
+    """CalSurfGAniso_Joint.f90:209: COO over [dVs | Gc | Gs] (3*nparpi columns)."""
+    return _gbuild(2, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle)
+
+
+def fmm_solve(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, handle: Optional[Handle] = None):
+    """Test seam: eikonal fields of n sources on one phase-velocity map."""
+    h = handle or default_handle()
+    scx = np.ascontiguousarray(scx, np.float32); scz = np.ascontiguousarray(scz, np.float32)
+    n = len(scx)
+    nnx = (nx - 3) * 5 + 1; nnz = (ny - 3) * 5 + 1
+    pv = np.ascontiguousarray(pv, np.float64)
+    veln = np.zeros((nnz, nnx), np.float32, order="F")
+    ttn = np.zeros((nnz, nnx, n), np.float32, order="F"); nsts = np.zeros((nnz, nnx, n), np.int32, order="F")
+    ttnr = np.zeros((129, 129, n), np.float32, order="F"); nstsr = np.zeros((129, 129, n), np.int32, order="F")
+    geom = np.zeros((8, n), np.int32, order="F")
+    _chk(load().dazim_fmm_solve(h._h, C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+                                C.c_float(dvzd), _p(pv), C.c_int(n), _p(scx), _p(scz), _p(veln), _p(ttn), _p(nsts),
+                                _p(ttnr), _p(nstsr), _p(geom)))
+    return dict(veln=veln, ttn=ttn, nsts=nsts, ttnr=ttnr, nstsr=nstsr, geom=geom, times=h.times)
+
+
+def raytrace(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, rcx, rcz, azim=True, handle: Optional[Handle] = None):
+    """Test seam: travel time + dense Frechet maps of n (source, receiver) pairs."""
+    h = handle or default_handle()
+    scx, scz, rcx, rcz = (np.ascontiguousarray(x, np.float32) for x in (scx, scz, rcx, rcz))
+    n = len(scx)
+    pv = np.ascontiguousarray(pv, np.float64)
+    shp = (ny, nx, n)
+    tt = np.zeros(n, np.float32)
+    fdm = np.zeros(shp, np.float32, order="F"); fdmc = np.zeros(shp, np.float32, order="F"); fdms = np.zeros(shp, np.float32, order="F")
+    _chk(load().dazim_raytrace(h._h, C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+                               C.c_float(dvzd), _p(pv), C.c_int(n), _p(scx), _p(scz), _p(rcx), _p(rcz),
+                               C.c_int(int(azim)), _p(tt), _p(fdm), _p(fdmc), _p(fdms)))
+    return tt, fdm, fdmc, fdms
+
+
+class Plan:
+    """Device-resident plan (dazim_plan_*): inputs uploaded once, run() leaves results in HBM."""
+
+    def __init__(self, mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables: dict, gc=None,
+                 gs=None, src_begin=0, src_end=-1, handle: Optional[Handle] = None):
+        self.h = handle or default_handle()
+        self.mode = mode
+        self._pr = _Prob(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv)
+        self._tb = _Tab(self._pr.shape, len(self._pr.tRc), tables)
+        self._gc = None if gc is None else np.asfortranarray(gc, np.float32)
+        self._gs = None if gs is None else np.asfortranarray(gs, np.float32)
+        self._plan = C.c_void_p()
+        _chk(load().dazim_plan_create(self.h._h, C.c_int(mode), C.byref(self._pr.c), C.byref(self._tb.c),
+                                      _p(self._gc), _p(self._gs), C.c_longlong(src_begin), C.c_longlong(src_end),
+                                      C.byref(self._plan)))
+        r0 = C.c_longlong(0)
+        self.rows = load().dazim_plan_rows(self._plan, C.byref(r0))
+        self.row0 = r0.value
+        self.h2d_bytes = self.h.times["h2d_bytes"]
+
+    def run(self) -> dict:
+        _chk(load().dazim_plan_run(self._plan))
+        return self.h.times
+
+    @property
+    def nnz(self) -> int:
+        return load().dazim_plan_nnz(self._plan)
+
+    def fetch(self, csr=True):
+        n = self.rows
+        dsurf = np.zeros(n, np.float32)
+        taa = np.zeros(n, np.float32) if self.mode == 0 else None
+        rowptr = col = val = None
+        if self.mode != 0 and csr:
+            rowptr = np.zeros(n + 1, np.int64); col = np.zeros(self.nnz, np.int32); val = np.zeros(self.nnz, np.float32)
+        _chk(load().dazim_plan_fetch(self._plan, _p(dsurf), _p(taa), _p(rowptr), _p(col), _p(val)))
+        return dict(dsurf=dsurf, obsTaa=taa, rowptr=rowptr, col=col, val=val)
+
+    def device_ptrs(self):
+        ptrs = [C.c_void_p() for _ in range(5)]
+        _chk(load().dazim_plan_device_ptrs(self._plan, *[C.byref(p) for p in ptrs]))
+        return dict(zip(("dsurf", "obsTaa", "rowptr", "col", "val"), [p.value for p in ptrs]))
+
+    def close(self):
+        if self._plan:
+            load().dazim_plan_destroy(self._plan)
+            self._plan = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,37 @@
+"""Build the CUDA shared library in-tree (nvcc, sm_100a only)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdazim_b200.so")
+SOURCES = ["dazim_fmm.cu", "dazim_trace.cu", "dazim_th.cu", "dazim_api.cu", "dazim_fortran.cu"]
+# --fmad=false: the reference is x86-64/SSE2 Fortran without FMA contraction; parity of the
+# float32 eikonal / ray arithmetic and of the float64 Thomson-Haskell chain depends on it.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
+              "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "dazim_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

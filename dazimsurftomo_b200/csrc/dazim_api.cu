@@ -1,0 +1,800 @@
+// Host side of the C ABI declared in include/dazim_b200.h: scalar prologues of
+// the reference orchestrators (float32, same operation order), work-list
+// construction, device memory, kernel sequencing and timing.  No compute
+// happens on the host beyond what the reference itself does once per call in
+// scalar code (grid constants, per-source box bounds, sin() of grid rows).
+#include "../../include/dazim_b200.h"
+#include "dazim_dev.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace dz {
+// kernels (dazim_fmm.cu / dazim_trace.cu / dazim_th.cu)
+cudaError_t upload_basis(const float* ub, const float* cb);
+cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, cudaStream_t st);
+cudaError_t launch_fmm(const FmmArgs& A, cudaStream_t st);
+cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
+cudaError_t launch_coef(int nx, int ny, int nz, const float* vels, float* ca, float* cr, cudaStream_t st);
+cudaError_t launch_assemble(const AsmArgs& A, bool fill, cudaStream_t st);
+cudaError_t launch_taa(const TaaArgs& A, cudaStream_t st);
+cudaError_t scan_rowptr(const int* counts, long long* rowptr, int n, void* tmp, size_t* tmp_bytes, cudaStream_t st);
+// Thomson-Haskell stage (dazim_th.cu)
+int th_depthkernel(cudaStream_t st, int nx, int ny, int nz, const float* vel, double* pvRc, double* sen_vs,
+                   double* sen_vp, double* sen_rho, int kmaxRc, const double* tRc, const float* depz, float minthk,
+                   float* ms, long long* nlaunch);
+int th_depthkernel_ti(cudaStream_t st, int nx, int ny, int nz, const float* vel, double* pvRc, int kmaxRc,
+                      const double* tRc, const float* depz, float minthk, float* Lsen_Gsc, float* ms,
+                      long long* nlaunch);
+int th_surfdisp96(cudaStream_t st, int nprof, int nlayer, const float* thk, const float* vp, const float* vs,
+                  const float* rho, int kmax, const double* t, double* cg);
+}  // namespace dz
+
+using namespace dz;
+
+#define CK(x)                                                     \
+  do {                                                            \
+    cudaError_t e_ = (x);                                         \
+    if (e_ != cudaSuccess) return DAZIM_ECUDA + (int)e_;          \
+  } while (0)
+
+static const float PI_F = 3.1415926535898f;   // CalSurfG.f90:166
+static inline float sin_r(float x) { return (float)std::sin((double)x); }
+static inline float cube(float x) { return x * (x * x); }
+static void bspl_basis(float u, float* b) {
+  b[0] = cube(1.0f - u) / 6.0f;
+  b[1] = (4.0f - 6.0f * (u * u) + 3.0f * cube(u)) / 6.0f;
+  b[2] = (1.0f + 3.0f * u + 3.0f * (u * u) - 3.0f * cube(u)) / 6.0f;
+  b[3] = cube(u) / 6.0f;
+}
+
+struct dazim_handle {
+  int dev;
+  cudaStream_t st;
+  dazim_times times;
+  int nsm;
+};
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t cnt) {
+    release();
+    n = cnt;
+    if (cnt == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, cnt * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DBuf() { release(); }
+};
+
+// FwdTraveltimeCPS.f90:346-380 (identical prologue in CalSurfG / CalSurfGAnisoJoint)
+static GridC make_grid(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd) {
+  GridC g;
+  g.gdx = 5; g.gdz = 5; g.sgdl = 8; g.sgs = 8; g.earth = 6371.0f;
+  g.nvx = nx - 2; g.nvz = ny - 2;
+  g.dvx = dvxd * PI_F / 180.0f;
+  g.dvz = dvzd * PI_F / 180.0f;
+  g.gox = (90.0f - goxd) * PI_F / 180.0f;
+  g.goz = gozd * PI_F / 180.0f;
+  g.nnx = (g.nvx - 1) * g.gdx + 1;
+  g.nnz = (g.nvz - 1) * g.gdz + 1;
+  g.dnx = g.dvx / (float)g.gdx;
+  g.dnz = g.dvz / (float)g.gdz;
+  // dpl of srtimes / rpathsAzim (CalSurfG.f90:1650-1654, rpathsAzim.f90:156-161)
+  float dpl = g.dnx * g.earth;
+  float rd1 = g.dnz * g.earth * sin_r(g.gox);
+  if (rd1 < dpl) dpl = rd1;
+  rd1 = g.dnz * g.earth * sin_r(g.gox + (float)(g.nnx - 1) * g.dnx);
+  if (rd1 < dpl) dpl = rd1;
+  g.dpl_full = dpl;
+  g.dpl_half = 0.5f * dpl;
+  return g;
+}
+
+// per-source scalar prologue, FwdTraveltimeCPS.f90:493-530 + CalSurfG.f90:282-295
+static int make_src(const GridC& g, float x, float z, SrcRec& s) {
+  s.scx = x; s.scz = z;
+  int isx = (int)((x - g.gox) / g.dnx) + 1;
+  int isz = (int)((z - g.goz) / g.dnz) + 1;
+  if (isx < 1 || isx > g.nnx || isz < 1 || isz > g.nnz) return DAZIM_ESOURCE_OUTSIDE;
+  s.isx_c = isx; s.isz_c = isz;
+  if (isx == g.nnx) isx = isx - 1;
+  if (isz == g.nnz) isz = isz - 1;
+  s.isx_cc = isx; s.isz_cc = isz;
+  s.drx_c = (x - g.gox) - (float)(s.isx_c - 1) * g.dnx;
+  s.drz_c = (z - g.goz) - (float)(s.isz_c - 1) * g.dnz;
+  s.vnl = isx - g.sgs; if (s.vnl < 1) s.vnl = 1;
+  s.vnr = isx + g.sgs; if (s.vnr > g.nnx) s.vnr = g.nnx;
+  s.vnt = isz - g.sgs; if (s.vnt < 1) s.vnt = 1;
+  s.vnb = isz + g.sgs; if (s.vnb > g.nnz) s.vnb = g.nnz;
+  s.nnxr = (s.vnr - s.vnl) * g.sgdl + 1;
+  s.nnzr = (s.vnb - s.vnt) * g.sgdl + 1;
+  s.dnxr = g.dvx / (float)(g.gdx * g.sgdl);
+  s.dnzr = g.dvz / (float)(g.gdz * g.sgdl);
+  s.goxr = g.gox + g.dnx * (float)(s.vnl - 1);
+  s.gozr = g.goz + g.dnz * (float)(s.vnt - 1);
+  int rx = (int)((x - s.goxr) / s.dnxr) + 1;
+  int rz = (int)((z - s.gozr) / s.dnzr) + 1;
+  s.isx_t = rx; s.isz_t = rz;
+  if (rx < 1 || rx > s.nnxr || rz < 1 || rz > s.nnzr) return DAZIM_ESOURCE_OUTSIDE;
+  if (rx == s.nnxr) rx = rx - 1;
+  if (rz == s.nnzr) rz = rz - 1;
+  s.isx_r = rx; s.isz_r = rz;
+  s.dsx_r = (x - s.goxr) - (float)(rx - 1) * s.dnxr;
+  s.dsz_r = (z - s.gozr) - (float)(rz - 1) * s.dnzr;
+  return DAZIM_OK;
+}
+
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct dazim_plan {
+  dazim_handle* h = nullptr;
+  int mode = 0, nx = 0, ny = 0, nz = 0, kmaxRc = 0;
+  GridC g;
+  std::vector<SrcRec> src;            // owned units, loop order; ray0 = global row
+  std::vector<RayRec> ray;            // batch-ordered rays (src index batch-local)
+  std::vector<long long> batch_src0;  // batch boundaries in src (size nb+1)
+  std::vector<long long> batch_ray0;  // batch boundaries in ray
+  long long row0 = 0, nrow = 0;
+  long long nnz = 0;
+  bool azim = true;
+  int emit_all = 0;
+  // device inputs
+  DBuf<SrcRec> d_src; DBuf<RayRec> d_ray; DBuf<int> d_row_knumi;
+  DBuf<float> d_velv, d_veln_c, d_risti_c, d_risti_r;
+  DBuf<double> d_sen_vs, d_sen_vp, d_sen_rho; DBuf<float> d_lsen, d_vels, d_coe_a, d_coe_rho, d_gc, d_gs;
+  // fmm / trace workspaces
+  DBuf<float> d_veln_r, d_ttn_c, d_ttn_r, d_hsk; DBuf<int> d_nsts_c, d_nsts_r, d_hsn;
+  DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
+  int hcap = 512, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
+  // footprint pool + outputs
+  DBuf<int> d_fp_off, d_fp_cnt, d_fp_cell; DBuf<float> d_fp_fdm, d_fp_fdmc, d_fp_fdms;
+  unsigned long long pool_cap = 0;
+  DBuf<unsigned long long> d_counters;   // [0] pool_used [1] n_accept [2] n_steps
+  DBuf<int> d_icnt;                       // [0] work counter [1] flags
+  DBuf<float> d_dsurf, d_taa, d_val; DBuf<int> d_col, d_rowid, d_nnz_row; DBuf<long long> d_rowptr;
+  DBuf<unsigned char> d_scan_tmp; size_t scan_tmp_bytes = 0;
+  long long val_cap = 0;
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+};
+
+static void plan_free(dazim_plan* p) {
+  if (!p) return;
+  if (p->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(p->ev[i]);
+  delete p;
+}
+
+extern "C" int dazim_create(dazim_handle** out, int device) {
+  if (!out) return DAZIM_EBADARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return DAZIM_ECUDA + (int)e;
+  if (n == 0 || device >= n || device < 0) return DAZIM_ECUDA + (int)cudaErrorNoDevice;
+  CK(cudaSetDevice(device));
+  dazim_handle* h = new dazim_handle();
+  h->dev = device;
+  std::memset(&h->times, 0, sizeof(h->times));
+  e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return DAZIM_ECUDA + (int)e; }
+  cudaDeviceProp pr;
+  cudaGetDeviceProperties(&pr, device);
+  h->nsm = pr.multiProcessorCount;
+  // B-spline basis tables (CalSurfG.f90:1469-1488, :1540-1555), float32 like the reference
+  float ub[41 * 4], cb[6 * 4];
+  for (int j = 1; j <= 41; ++j) { float u = 40.0f; u = (float)(j - 1) / u; bspl_basis(u, &ub[(j - 1) * 4]); }
+  for (int i = 1; i <= 6; ++i) { float u = 5.0f; u = (float)(i - 1) / u; bspl_basis(u, &cb[(i - 1) * 4]); }
+  e = upload_basis(ub, cb);
+  if (e != cudaSuccess) { cudaStreamDestroy(h->st); delete h; return DAZIM_ECUDA + (int)e; }
+  *out = h;
+  return DAZIM_OK;
+}
+
+extern "C" void dazim_destroy(dazim_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->dev);
+  cudaStreamDestroy(h->st);
+  delete h;
+}
+
+extern "C" const dazim_times* dazim_last_times(const dazim_handle* h) { return h ? &h->times : nullptr; }
+
+extern "C" const char* dazim_strerror(int code) {
+  switch (code) {
+    case DAZIM_OK: return "ok";
+    case DAZIM_ESOURCE_OUTSIDE: return "Source lies outside bounds of model";
+    case DAZIM_ERECEIVER_OUTSIDE: return "Receiver lies outside model";
+    case DAZIM_ENNZ_OVERFLOW: return "nar > maxnar: please increase sparsity fraction (spfra)";
+    case DAZIM_EBADARG: return "bad argument";
+    case DAZIM_ELAYERS: return "too many layers (NL=200) or periods (NP=60)";
+    case DAZIM_EHEAP: return "narrow band exceeded heap workspace";
+    case DAZIM_EFOOTPRINT: return "ray footprint exceeded workspace";
+    case DAZIM_ENOROOT: return "improper initial value in disper - no zero found";
+    default: break;
+  }
+  if (code >= DAZIM_ECUDA) return cudaGetErrorString((cudaError_t)(code - DAZIM_ECUDA));
+  return "unknown";
+}
+
+// ---------------------------------------------------------------------------
+static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const dazim_tables* tb,
+                      const float* Gc, const float* Gs, long long sb, long long se, int emit_all,
+                      dazim_plan** out) {
+  if (!h || !p || !tb || !out) return DAZIM_EBADARG;
+  if (mode < 0 || mode > 2) return DAZIM_EBADARG;
+  if (p->nx < 5 || p->ny < 5 || p->nz < 2) return DAZIM_EBADARG;
+  if (!tb->pvRc) return DAZIM_EBADARG;
+  if ((mode == 0 || mode == 2) && !tb->Lsen_Gsc) return DAZIM_EBADARG;
+  if ((mode == 1 || mode == 2) && (!tb->sen_vs || !tb->sen_vp || !tb->sen_rho)) return DAZIM_EBADARG;
+  if (mode == 0 && (!Gc || !Gs) && !emit_all) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  dazim_plan* P = new dazim_plan();
+  P->h = h; P->mode = mode; P->nx = p->nx; P->ny = p->ny; P->nz = p->nz; P->kmaxRc = p->kmaxRc;
+  P->azim = (mode != 1);
+  P->emit_all = emit_all;
+  P->g = make_grid(p->nx, p->ny, p->goxd, p->gozd, p->dvxd, p->dvzd);
+  const GridC& g = P->g;
+  const size_t nxy = (size_t)p->nx * p->ny;
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;
+  h->times.h2d_bytes = 0;
+  // ---- work list in the reference's loop order (FwdTraveltimeCPS.f90:464-465) ----
+  long long unit = 0, count1 = 0;
+  std::vector<int> row_knumi;
+  bool first = true;
+  for (int knumi = 1; knumi <= p->kmax; ++knumi)
+    for (int srcnum = 1; srcnum <= p->nsrcsurf1[knumi - 1]; ++srcnum, ++unit) {
+      const size_t sk = (size_t)(srcnum - 1) + (size_t)(knumi - 1) * p->nsrc;
+      const int nr = p->nrc1[sk];
+      if (unit >= sb && (se < 0 || unit < se)) {
+        SrcRec s;
+        std::memset(&s, 0, sizeof(s));
+        int st = make_src(g, p->scxf[sk], p->sczf[sk], s);
+        if (st) { plan_free(P); return st; }
+        s.period = p->periods[sk] - 1;
+        s.knumi = knumi - 1;
+        if (s.period < 0 || s.period >= p->kmaxRc) { plan_free(P); return DAZIM_EBADARG; }
+        if (first) { P->row0 = count1; first = false; }
+        s.ray0 = (int)(count1 - P->row0);
+        s.nray = nr;
+        P->src.push_back(s);
+        for (int i = 0; i < nr; ++i) row_knumi.push_back(knumi - 1);
+      }
+      count1 += nr;
+    }
+  P->nrow = (long long)row_knumi.size();
+  const long long nsrc = (long long)P->src.size();
+
+  // ---- workspace sizing ----
+  P->hcap = std::min(1024, std::max(256, pow2ceil(2 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
+  if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, atoi(e));
+  P->hspill = 8 * (g.nnx + g.nnz) + 1024;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  double budget = 0.55 * (double)free_b;
+  if (const char* e = getenv("DAZIM_WS_GB")) budget = std::min(budget, atof(e) * 1e9);
+  const double per_src = (double)ncoarse * 8 + (double)REF_N * 12 + REF_LD * 4 + (double)P->hspill * 8 + 64;
+  long long maxB = (long long)(budget / per_src);
+  if (maxB < 1) maxB = 1;
+  if (const char* e = getenv("DAZIM_BATCH")) maxB = std::max(1, atoi(e));
+  maxB = std::min<long long>(maxB, std::max<long long>(nsrc, 1));
+  P->maxB = (int)maxB;
+  // batches + per-batch ray lists (long rays first so that a warp holds rays of similar length)
+  P->batch_src0.push_back(0);
+  P->batch_ray0.push_back(0);
+  double pool_est = 0;
+  const int ncell = (g.nvz + 2) * (g.nvx + 2);
+  for (long long b0 = 0; b0 < nsrc; b0 += maxB) P->batch_src0.push_back(std::min(nsrc, b0 + maxB));
+  if (nsrc == 0) P->batch_src0.push_back(0);
+  // receivers: second pass over the loop to fill RayRec (keeps the code above simple)
+  {
+    std::vector<std::vector<std::pair<float, RayRec>>> per_batch(P->batch_src0.size() - 1);
+    long long unit2 = 0, si = 0;
+    for (int knumi = 1; knumi <= p->kmax; ++knumi)
+      for (int srcnum = 1; srcnum <= p->nsrcsurf1[knumi - 1]; ++srcnum, ++unit2) {
+        if (!(unit2 >= sb && (se < 0 || unit2 < se))) continue;
+        const size_t sk = (size_t)(srcnum - 1) + (size_t)(knumi - 1) * p->nsrc;
+        const SrcRec& sr = P->src[si];
+        const int b = (int)(si / maxB);
+        for (int i = 0; i < sr.nray; ++i) {
+          const size_t rk = (size_t)i + (size_t)(srcnum - 1) * p->nrcf + (size_t)(knumi - 1) * p->nrcf * p->nsrc;
+          RayRec r;
+          r.rcx = p->rcxf[rk]; r.rcz = p->rczf[rk];
+          r.src = (int)(si - (long long)b * maxB);
+          r.row = sr.ray0 + i;
+          const float ddx = std::fabs(r.rcx - sr.scx) / g.dvx, ddz = std::fabs(r.rcz - sr.scz) / g.dvz;
+          pool_est += std::min<double>(ncell, 48.0 + 10.0 * (ddx + ddz));
+          per_batch[b].push_back({ddx + ddz, r});
+        }
+        ++si;
+      }
+    for (auto& v : per_batch) {
+      std::stable_sort(v.begin(), v.end(), [](const std::pair<float, RayRec>& a, const std::pair<float, RayRec>& b) {
+        return a.first > b.first;
+      });
+      for (auto& e : v) P->ray.push_back(e.second);
+      P->batch_ray0.push_back((long long)P->ray.size());
+    }
+  }
+  if (emit_all) pool_est = (double)P->nrow * ncell;
+  P->pool_cap = (unsigned long long)(pool_est * 1.5) + 1024;
+  if (const char* e = getenv("DAZIM_POOL_SCALE")) P->pool_cap = (unsigned long long)(P->pool_cap * atof(e));
+  if (P->pool_cap > 2000000000ull) P->pool_cap = 2000000000ull;
+  P->cap = std::min(ncell, 64 + 8 * (g.nvx + g.nvz));
+  if (P->cap > 65535) P->cap = 65535;
+  P->trace_blocks = h->nsm * 4;
+  {
+    long long maxrays = 0;
+    for (size_t b = 0; b + 1 < P->batch_ray0.size(); ++b) maxrays = std::max(maxrays, P->batch_ray0[b + 1] - P->batch_ray0[b]);
+    const long long need = (maxrays + 127) / 128;
+    if (need < P->trace_blocks) P->trace_blocks = (int)std::max<long long>(1, need);
+  }
+  const size_t nthr = (size_t)P->trace_blocks * 128;
+
+  // ---- device allocations + uploads ----
+  cudaStream_t st = h->st;
+#define UP(buf, hostptr, cnt)                                                                   \
+  do {                                                                                          \
+    CK((buf).alloc(cnt));                                                                       \
+    if ((cnt) > 0) {                                                                            \
+      CK(cudaMemcpyAsync((buf).p, hostptr, (cnt) * sizeof(*(buf).p), cudaMemcpyHostToDevice, st)); \
+      h->times.h2d_bytes += (long long)((cnt) * sizeof(*(buf).p));                              \
+    }                                                                                           \
+  } while (0)
+  int rc = DAZIM_OK;
+  auto body = [&]() -> int {
+    UP(P->d_src, P->src.data(), P->src.size());
+    UP(P->d_ray, P->ray.data(), P->ray.size());
+    UP(P->d_row_knumi, row_knumi.data(), row_knumi.size());
+    // velv(i,j) = real(pv(i*(nvx+2)+j+1)) (CalSurfG.f90:1455) for every period
+    std::vector<float> velv(nxy * p->kmaxRc);
+    for (size_t i = 0; i < velv.size(); ++i) velv[i] = (float)tb->pvRc[i];
+    UP(P->d_velv, velv.data(), velv.size());
+    std::vector<float> ric(g.nnx);
+    for (int ix = 1; ix <= g.nnx; ++ix) ric[ix - 1] = g.earth * sin_r(g.gox + (float)(ix - 1) * g.dnx);
+    UP(P->d_risti_c, ric.data(), ric.size());
+    std::vector<float> rir((size_t)nsrc * REF_LD, 0.0f);
+    for (long long s = 0; s < nsrc; ++s) {
+      const SrcRec& sr = P->src[s];
+      for (int ix = 1; ix <= sr.nnxr; ++ix)
+        rir[(size_t)s * REF_LD + ix - 1] = g.earth * sin_r(sr.goxr + (float)(ix - 1) * sr.dnxr);
+    }
+    UP(P->d_risti_r, rir.data(), rir.size());
+    const size_t nlay = (size_t)p->nz - 1;
+    if (mode == 1 || mode == 2) {
+      UP(P->d_sen_vs, tb->sen_vs, nxy * p->kmaxRc * p->nz);
+      UP(P->d_sen_vp, tb->sen_vp, nxy * p->kmaxRc * p->nz);
+      UP(P->d_sen_rho, tb->sen_rho, nxy * p->kmaxRc * p->nz);
+      UP(P->d_vels, p->vels, nxy * p->nz);
+      CK(P->d_coe_a.alloc(nxy * nlay));
+      CK(P->d_coe_rho.alloc(nxy * nlay));
+    }
+    if (mode == 0 || mode == 2) UP(P->d_lsen, tb->Lsen_Gsc, nxy * p->kmaxRc * nlay);
+    if (mode == 0 && Gc && Gs) {
+      UP(P->d_gc, Gc, (size_t)(p->nx - 2) * (p->ny - 2) * nlay);
+      UP(P->d_gs, Gs, (size_t)(p->nx - 2) * (p->ny - 2) * nlay);
+    }
+    CK(P->d_veln_c.alloc(ncoarse * p->kmaxRc));
+    const size_t B = (size_t)P->maxB;
+    CK(P->d_veln_r.alloc(B * REF_N));
+    CK(P->d_ttn_r.alloc(B * REF_N));
+    CK(P->d_nsts_r.alloc(B * REF_N));
+    CK(P->d_ttn_c.alloc(B * ncoarse));
+    CK(P->d_nsts_c.alloc(B * ncoarse));
+    CK(P->d_hsk.alloc(B * P->hspill));
+    CK(P->d_hsn.alloc(B * P->hspill));
+    CK(P->d_map.alloc(nthr * ncell));
+    CK(cudaMemsetAsync(P->d_map.p, 0, nthr * ncell * sizeof(unsigned short), st));
+    CK(P->d_skey.alloc(nthr * P->cap));
+    CK(P->d_sval.alloc(nthr * 3 * P->cap));
+    const size_t nrow = (size_t)std::max<long long>(P->nrow, 1);
+    CK(P->d_fp_off.alloc(nrow));
+    CK(P->d_fp_cnt.alloc(nrow));
+    CK(P->d_fp_cell.alloc(P->pool_cap));
+    CK(P->d_fp_fdm.alloc(P->pool_cap));
+    if (P->azim) { CK(P->d_fp_fdmc.alloc(P->pool_cap)); CK(P->d_fp_fdms.alloc(P->pool_cap)); }
+    CK(P->d_counters.alloc(4));
+    CK(P->d_icnt.alloc(4));
+    CK(P->d_dsurf.alloc(nrow));
+    if (mode == 0) CK(P->d_taa.alloc(nrow));
+    if (mode != 0) {
+      CK(P->d_nnz_row.alloc(nrow));
+      CK(P->d_rowptr.alloc(nrow + 1));
+      P->scan_tmp_bytes = 0;
+      CK(scan_rowptr(P->d_nnz_row.p, P->d_rowptr.p, (int)nrow, nullptr, &P->scan_tmp_bytes, st));
+      CK(P->d_scan_tmp.alloc(P->scan_tmp_bytes + 16));
+    }
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&P->ev[i]));
+    P->ev_ok = true;
+    CK(cudaStreamSynchronize(st));
+    return DAZIM_OK;
+  };
+  rc = body();
+#undef UP
+  if (rc) { plan_free(P); return rc; }
+  *out = P;
+  return DAZIM_OK;
+}
+
+static int plan_run(dazim_plan* P) {
+  dazim_handle* h = P->h;
+  CK(cudaSetDevice(h->dev));
+  cudaStream_t st = h->st;
+  const GridC& g = P->g;
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;
+  dazim_times& T = h->times;
+  T.dice_ms = T.fmm_ms = T.trace_ms = T.assemble_ms = T.total_ms = 0;
+  T.n_fmm_launch = T.n_trace_launch = T.n_launch = 0;
+  CK(cudaMemsetAsync(P->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(P->d_icnt.p, 0, 4 * sizeof(int), st));
+  CK(cudaEventRecord(P->ev[0], st));
+  CK(launch_dice_coarse(g, P->kmaxRc, P->d_velv.p, P->d_veln_c.p, st));
+  T.n_launch++;
+  if (P->mode != 0) {
+    CK(launch_coef(P->nx, P->ny, P->nz, P->d_vels.p, P->d_coe_a.p, P->d_coe_rho.p, st));
+    T.n_launch++;
+  }
+  CK(cudaEventRecord(P->ev[1], st));
+  const size_t nb = P->batch_src0.size() - 1;
+  std::vector<cudaEvent_t> bev;   // per-batch fmm/trace boundaries
+  for (size_t b = 0; b < nb; ++b) {
+    const long long s0 = P->batch_src0[b], s1 = P->batch_src0[b + 1];
+    const long long r0 = P->batch_ray0[b], r1 = P->batch_ray0[b + 1];
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    bev.push_back(e0); bev.push_back(e1); bev.push_back(e2);
+    CK(cudaEventRecord(e0, st));
+    FmmArgs F;
+    F.g = g; F.src = P->d_src.p + s0; F.nsrc = (int)(s1 - s0); F.velv = P->d_velv.p; F.veln_c = P->d_veln_c.p;
+    F.risti_c = P->d_risti_c.p; F.risti_r = P->d_risti_r.p + (size_t)s0 * REF_LD; F.veln_r = P->d_veln_r.p;
+    F.ttn_c = P->d_ttn_c.p; F.nsts_c = P->d_nsts_c.p; F.ttn_r = P->d_ttn_r.p; F.nsts_r = P->d_nsts_r.p;
+    F.hcap = P->hcap; F.hspill_k = P->d_hsk.p; F.hspill_n = P->d_hsn.p; F.hspill = P->hspill;
+    F.flags = P->d_icnt.p + 1; F.n_accept = P->d_counters.p + 1;
+    if (F.nsrc > 0) { CK(launch_fmm(F, st)); T.n_launch++; T.n_fmm_launch++; }
+    CK(cudaEventRecord(e1, st));
+    if (r1 > r0) {
+      CK(cudaMemsetAsync(P->d_icnt.p, 0, sizeof(int), st));
+      TraceArgs A;
+      A.g = g; A.src = P->d_src.p + s0; A.ray = P->d_ray.p + r0; A.nray = (int)(r1 - r0);
+      A.veln_c = P->d_veln_c.p; A.ttn_c = P->d_ttn_c.p; A.ttn_r = P->d_ttn_r.p; A.nsts_r = P->d_nsts_r.p;
+      A.map = P->d_map.p; A.skey = P->d_skey.p; A.sval = P->d_sval.p; A.cap = P->cap; A.dsurf = P->d_dsurf.p;
+      A.fp_off = P->d_fp_off.p; A.fp_cnt = P->d_fp_cnt.p; A.fp_cell = P->d_fp_cell.p; A.fp_fdm = P->d_fp_fdm.p;
+      A.fp_fdmc = P->d_fp_fdmc.p; A.fp_fdms = P->d_fp_fdms.p; A.pool_cap = P->pool_cap;
+      A.pool_used = P->d_counters.p; A.counter = P->d_icnt.p; A.flags = P->d_icnt.p + 1;
+      A.n_steps = P->d_counters.p + 2; A.emit_all = P->emit_all;
+      CK(launch_trace(A, P->azim, P->trace_blocks, st));
+      T.n_launch++; T.n_trace_launch++;
+    }
+    CK(cudaEventRecord(e2, st));
+  }
+  CK(cudaEventRecord(P->ev[2], st));
+  // status checks need the counters: one small D2H
+  unsigned long long cnt[4];
+  int icnt[4];
+  CK(cudaMemcpyAsync(cnt, P->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(icnt, P->d_icnt.p, sizeof(icnt), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (size_t b = 0; b < nb; ++b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, bev[3 * b], bev[3 * b + 1]); T.fmm_ms += ms;
+    cudaEventElapsedTime(&ms, bev[3 * b + 1], bev[3 * b + 2]); T.trace_ms += ms;
+  }
+  for (auto e : bev) cudaEventDestroy(e);
+  T.n_accept = (long long)cnt[1];
+  T.n_steps = (long long)cnt[2];
+  T.rbint = icnt[1] & 1;
+  if (icnt[1] & 16) return DAZIM_EHEAP;
+  if (icnt[1] & 2) return DAZIM_ERECEIVER_OUTSIDE;
+  if (icnt[1] & 4) return DAZIM_EFOOTPRINT;
+  if (icnt[1] & 8) return DAZIM_EFOOTPRINT + 1;   // pool overflow: caller retries with a bigger pool
+  CK(cudaEventRecord(P->ev[3], st));
+  P->nnz = 0;
+  if (P->nrow > 0 && !P->emit_all) {
+    if (P->mode == 0) {
+      TaaArgs A;
+      A.nx = P->nx; A.ny = P->ny; A.nz = P->nz; A.nvx = g.nvx; A.nvz = g.nvz; A.kmax = P->kmaxRc;
+      A.nrow = (int)P->nrow; A.row0 = 0; A.row_knumi = P->d_row_knumi.p; A.fp_off = P->d_fp_off.p;
+      A.fp_cnt = P->d_fp_cnt.p; A.fp_cell = P->d_fp_cell.p; A.fp_fdmc = P->d_fp_fdmc.p; A.fp_fdms = P->d_fp_fdms.p;
+      A.lsen = P->d_lsen.p; A.gc = P->d_gc.p; A.gs = P->d_gs.p; A.taa = P->d_taa.p;
+      CK(launch_taa(A, st));
+      T.n_launch++;
+    } else {
+      AsmArgs A;
+      A.mode = P->mode; A.nx = P->nx; A.ny = P->ny; A.nz = P->nz; A.nvx = g.nvx; A.nvz = g.nvz; A.kmax = P->kmaxRc;
+      A.row0 = 0; A.nrow = (int)P->nrow; A.row_knumi = P->d_row_knumi.p; A.fp_off = P->d_fp_off.p;
+      A.fp_cnt = P->d_fp_cnt.p; A.fp_cell = P->d_fp_cell.p; A.fp_fdm = P->d_fp_fdm.p; A.fp_fdmc = P->d_fp_fdmc.p;
+      A.fp_fdms = P->d_fp_fdms.p; A.sen_vs = P->d_sen_vs.p; A.sen_vp = P->d_sen_vp.p; A.sen_rho = P->d_sen_rho.p;
+      A.lsen = P->d_lsen.p; A.coe_a = P->d_coe_a.p; A.coe_rho = P->d_coe_rho.p; A.nnz_row = P->d_nnz_row.p;
+      A.rowptr = nullptr; A.val = nullptr; A.col = nullptr; A.rowid = nullptr;
+      CK(launch_assemble(A, false, st));
+      size_t tb = P->scan_tmp_bytes;
+      CK(scan_rowptr(P->d_nnz_row.p, P->d_rowptr.p, (int)P->nrow, P->d_scan_tmp.p, &tb, st));
+      long long last_off = 0;
+      int last_cnt = 0;
+      CK(cudaMemcpyAsync(&last_off, P->d_rowptr.p + (P->nrow - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&last_cnt, P->d_nnz_row.p + (P->nrow - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      P->nnz = last_off + last_cnt;
+      CK(cudaMemcpyAsync(P->d_rowptr.p + P->nrow, &P->nnz, sizeof(long long), cudaMemcpyHostToDevice, st));
+      if (P->nnz > P->val_cap) {
+        P->val_cap = P->nnz + P->nnz / 8 + 1024;
+        CK(P->d_val.alloc(P->val_cap));
+        CK(P->d_col.alloc(P->val_cap));
+        CK(P->d_rowid.alloc(P->val_cap));
+      }
+      A.rowptr = P->d_rowptr.p; A.val = P->d_val.p; A.col = P->d_col.p; A.rowid = P->d_rowid.p;
+      CK(launch_assemble(A, true, st));
+      T.n_launch += 4;
+    }
+  }
+  CK(cudaEventRecord(P->ev[4], st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, P->ev[0], P->ev[1]); T.dice_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[3], P->ev[4]); T.assemble_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[0], P->ev[4]); T.total_ms = ms;
+  return DAZIM_OK;
+}
+
+extern "C" int dazim_plan_create(dazim_handle* h, int mode, const dazim_problem* p, const dazim_tables* tables,
+                                 const float* Gc, const float* Gs, long long sb, long long se, dazim_plan** plan) {
+  return plan_build(h, mode, p, tables, Gc, Gs, sb, se, 0, plan);
+}
+extern "C" int dazim_plan_run(dazim_plan* plan) { return plan ? plan_run(plan) : DAZIM_EBADARG; }
+extern "C" long long dazim_plan_rows(const dazim_plan* plan, long long* row0) {
+  if (!plan) return 0;
+  if (row0) *row0 = plan->row0;
+  return plan->nrow;
+}
+extern "C" long long dazim_plan_nnz(const dazim_plan* plan) { return plan ? plan->nnz : 0; }
+extern "C" void dazim_plan_destroy(dazim_plan* plan) {
+  if (plan) { cudaSetDevice(plan->h->dev); plan_free(plan); }
+}
+
+extern "C" int dazim_plan_fetch(dazim_plan* P, float* dsurf, float* taa, long long* rowptr, int* col, float* val) {
+  if (!P) return DAZIM_EBADARG;
+  dazim_handle* h = P->h;
+  CK(cudaSetDevice(h->dev));
+  cudaStream_t st = h->st;
+  h->times.d2h_bytes = 0;
+  const size_t n = (size_t)P->nrow;
+  if (dsurf && n) { CK(cudaMemcpyAsync(dsurf, P->d_dsurf.p, n * 4, cudaMemcpyDeviceToHost, st)); h->times.d2h_bytes += n * 4; }
+  if (taa && n && P->mode == 0) { CK(cudaMemcpyAsync(taa, P->d_taa.p, n * 4, cudaMemcpyDeviceToHost, st)); h->times.d2h_bytes += n * 4; }
+  if (P->mode != 0 && n) {
+    if (rowptr) { CK(cudaMemcpyAsync(rowptr, P->d_rowptr.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st)); h->times.d2h_bytes += (n + 1) * 8; }
+    if (col && P->nnz) { CK(cudaMemcpyAsync(col, P->d_col.p, (size_t)P->nnz * 4, cudaMemcpyDeviceToHost, st)); h->times.d2h_bytes += P->nnz * 4; }
+    if (val && P->nnz) { CK(cudaMemcpyAsync(val, P->d_val.p, (size_t)P->nnz * 4, cudaMemcpyDeviceToHost, st)); h->times.d2h_bytes += P->nnz * 4; }
+  }
+  CK(cudaStreamSynchronize(st));
+  return DAZIM_OK;
+}
+
+extern "C" int dazim_plan_device_ptrs(dazim_plan* P, void** dsurf, void** taa, void** rowptr, void** col, void** val) {
+  if (!P) return DAZIM_EBADARG;
+  if (dsurf) *dsurf = P->d_dsurf.p;
+  if (taa) *taa = P->d_taa.p;
+  if (rowptr) *rowptr = P->d_rowptr.p;
+  if (col) *col = P->d_col.p;
+  if (val) *val = P->d_val.p;
+  return DAZIM_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int dazim_depthkernel(dazim_handle* h, int nx, int ny, int nz, const float* vel, double* pvRc,
+                                 double* sen_vs, double* sen_vp, double* sen_rho, int kmaxRc, const double* tRc,
+                                 const float* depz, float minthk) {
+  if (!h) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  long long nl = 0;
+  return th_depthkernel(h->st, nx, ny, nz, vel, pvRc, sen_vs, sen_vp, sen_rho, kmaxRc, tRc, depz, minthk,
+                        &h->times.kernels_ms, &nl);
+}
+
+extern "C" int dazim_depthkernel_ti(dazim_handle* h, int nx, int ny, int nz, const float* vel, double* pvRc,
+                                    int kmaxRc, const double* tRc, const float* depz, float minthk, float* Lsen_Gsc) {
+  if (!h) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  long long nl = 0;
+  return th_depthkernel_ti(h->st, nx, ny, nz, vel, pvRc, kmaxRc, tRc, depz, minthk, Lsen_Gsc, &h->times.kernels_ms, &nl);
+}
+
+extern "C" int dazim_surfdisp96(dazim_handle* h, int nprof, int nlayer, const float* thk, const float* vp,
+                                const float* vs, const float* rho, int kmax, const double* t, double* cg) {
+  if (!h) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  return th_surfdisp96(h->st, nprof, nlayer, thk, vp, vs, rho, kmax, t, cg);
+}
+
+extern "C" int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, dazim_tables* tables,
+                            int tables_precomputed, const float* Gc, const float* Gs, float* dsurf, float* obsTaa,
+                            double* tRcV, dazim_coo* coo) {
+  if (!h || !p || !tables) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  const size_t nxy = (size_t)p->nx * p->ny;
+  float kms = 0.0f;
+  long long klaunch = 0;
+  // scratch tables when the caller does not want them back
+  std::vector<double> own_pv, own_s[3];
+  std::vector<float> own_l;
+  dazim_tables tb = *tables;
+  if (!tb.pvRc) { own_pv.resize(nxy * p->kmaxRc); tb.pvRc = own_pv.data(); }
+  if (!tables_precomputed) {
+    if (mode == 0 || mode == 2) {
+      if (!tb.Lsen_Gsc) { own_l.resize(nxy * p->kmaxRc * (p->nz - 1)); tb.Lsen_Gsc = own_l.data(); }
+      float ms = 0;
+      int st = th_depthkernel_ti(h->st, p->nx, p->ny, p->nz, p->vels, tb.pvRc, p->kmaxRc, p->tRc, p->depz,
+                                 p->minthk, tb.Lsen_Gsc, &ms, &klaunch);
+      if (st) return st;
+      kms += ms;
+    }
+    if (mode == 1 || mode == 2) {
+      double** ps[3] = {&tb.sen_vs, &tb.sen_vp, &tb.sen_rho};
+      for (int i = 0; i < 3; ++i)
+        if (!*ps[i]) { own_s[i].resize(nxy * p->kmaxRc * p->nz); *ps[i] = own_s[i].data(); }
+      float ms = 0;
+      int st = th_depthkernel(h->st, p->nx, p->ny, p->nz, p->vels, tb.pvRc, tb.sen_vs, tb.sen_vp, tb.sen_rho,
+                              p->kmaxRc, p->tRc, p->depz, p->minthk, &ms, &klaunch);
+      if (st) return st;
+      kms += ms;
+    }
+  }
+  dazim_plan* P = nullptr;
+  int st = DAZIM_OK;
+  double pool_scale = 1.0;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    st = plan_build(h, mode, p, &tb, Gc, Gs, 0, -1, 0, &P);
+    if (st) return st;
+    if (pool_scale > 1.0) {
+      // grow the footprint pool after an overflow
+      P->pool_cap = (unsigned long long)(P->pool_cap * pool_scale);
+      cudaError_t e = P->d_fp_cell.alloc(P->pool_cap);
+      if (e == cudaSuccess) e = P->d_fp_fdm.alloc(P->pool_cap);
+      if (e == cudaSuccess && P->azim) e = P->d_fp_fdmc.alloc(P->pool_cap);
+      if (e == cudaSuccess && P->azim) e = P->d_fp_fdms.alloc(P->pool_cap);
+      if (e != cudaSuccess) { plan_free(P); return DAZIM_ECUDA + (int)e; }
+    }
+    st = plan_run(P);
+    if (st != DAZIM_EFOOTPRINT + 1) break;
+    plan_free(P);
+    P = nullptr;
+    pool_scale *= 4.0;
+  }
+  if (st) { if (P) plan_free(P); return st == DAZIM_EFOOTPRINT + 1 ? DAZIM_EFOOTPRINT : st; }
+  h->times.kernels_ms = kms;
+  h->times.n_launch += klaunch;
+  if (coo && mode != 0) {
+    coo->nar = P->nnz;
+    if (P->nnz > coo->maxnar) { plan_free(P); return DAZIM_ENNZ_OVERFLOW; }
+  }
+  st = dazim_plan_fetch(P, dsurf, obsTaa, nullptr, coo ? coo->col : nullptr, coo ? coo->rw : nullptr);
+  if (!st && coo && mode != 0 && coo->iw_row && P->nnz) {
+    cudaError_t e = cudaMemcpy(coo->iw_row, P->d_rowid.p, (size_t)P->nnz * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) st = DAZIM_ECUDA + (int)e;
+    h->times.d2h_bytes += P->nnz * 4;
+  }
+  plan_free(P);
+  if (st) return st;
+  // tRcV (FwdTraveltimeCPS.f90:771-778): interior nodes of the phase-velocity table
+  if (tRcV) {
+    const int nx = p->nx, ny = p->ny;
+    for (int tt = 1; tt <= p->kmaxRc; ++tt)
+      for (int jj = 1; jj <= ny - 2; ++jj)
+        for (int ii = 1; ii <= nx - 2; ++ii)
+          tRcV[(size_t)(jj - 1) * (nx - 2) + (ii - 1) + (size_t)(tt - 1) * (nx - 2) * (ny - 2)] =
+              tb.pvRc[(size_t)jj * nx + ii + (size_t)(tt - 1) * nxy];
+  }
+  return DAZIM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// test seams
+static int mini_problem(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, int n, const float* scx,
+                        const float* scz, const float* rcx, const float* rcz, dazim_problem& p,
+                        std::vector<int>& periods, std::vector<int>& nrc1, std::vector<int>& ns1) {
+  std::memset(&p, 0, sizeof(p));
+  p.nx = nx; p.ny = ny; p.nz = 2; p.goxd = goxd; p.gozd = gozd; p.dvxd = dvxd; p.dvzd = dvzd;
+  p.kmaxRc = 1; p.kmax = 1; p.nsrc = n; p.nrcf = 1;
+  periods.assign(n, 1); nrc1.assign(n, rcx ? 1 : 0); ns1.assign(1, n);
+  p.periods = periods.data(); p.nrc1 = nrc1.data(); p.nsrcsurf1 = ns1.data();
+  p.scxf = scx; p.sczf = scz; p.rcxf = rcx ? rcx : scx; p.rczf = rcz ? rcz : scz;
+  return 0;
+}
+
+extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
+                               const double* pv, int n, const float* scx, const float* scz, float* veln, float* ttn,
+                               int* nsts, float* ttnr, int* nstsr, int* geom) {
+  if (!h || !pv || n <= 0) return DAZIM_EBADARG;
+  dazim_problem p;
+  std::vector<int> pe, nr, ns;
+  mini_problem(nx, ny, goxd, gozd, dvxd, dvzd, n, scx, scz, nullptr, nullptr, p, pe, nr, ns);
+  dazim_tables tb;
+  std::memset(&tb, 0, sizeof(tb));
+  tb.pvRc = const_cast<double*>(pv);
+  std::vector<float> dummyL((size_t)nx * ny, 0.0f);
+  tb.Lsen_Gsc = dummyL.data();
+  dazim_plan* P = nullptr;
+  int st = plan_build(h, 0, &p, &tb, nullptr, nullptr, 0, -1, 1, &P);
+  if (st) return st;
+  if (P->batch_src0.size() != 2) { plan_free(P); return DAZIM_EBADARG; }   // test seam: single batch only
+  st = plan_run(P);
+  if (st) { plan_free(P); return st; }
+  const size_t nc = (size_t)P->g.nnx * P->g.nnz;
+  cudaError_t e = cudaSuccess;
+  if (veln && e == cudaSuccess) e = cudaMemcpy(veln, P->d_veln_c.p, nc * 4, cudaMemcpyDeviceToHost);
+  if (ttn && e == cudaSuccess) e = cudaMemcpy(ttn, P->d_ttn_c.p, nc * 4 * n, cudaMemcpyDeviceToHost);
+  if (nsts && e == cudaSuccess) e = cudaMemcpy(nsts, P->d_nsts_c.p, nc * 4 * n, cudaMemcpyDeviceToHost);
+  if (ttnr && e == cudaSuccess) e = cudaMemcpy(ttnr, P->d_ttn_r.p, (size_t)REF_N * 4 * n, cudaMemcpyDeviceToHost);
+  if (nstsr && e == cudaSuccess) e = cudaMemcpy(nstsr, P->d_nsts_r.p, (size_t)REF_N * 4 * n, cudaMemcpyDeviceToHost);
+  if (geom)
+    for (int i = 0; i < n; ++i) {
+      const SrcRec& s = P->src[i];
+      int* gg = geom + 8 * i;
+      gg[0] = s.nnzr; gg[1] = s.nnxr; gg[2] = s.vnl; gg[3] = s.vnr; gg[4] = s.vnt; gg[5] = s.vnb;
+      gg[6] = P->g.nnz; gg[7] = P->g.nnx;
+    }
+  plan_free(P);
+  return e == cudaSuccess ? DAZIM_OK : DAZIM_ECUDA + (int)e;
+}
+
+extern "C" int dazim_raytrace(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
+                              const double* pv, int n, const float* scx, const float* scz, const float* rcx,
+                              const float* rcz, int azim, float* tt, float* fdm, float* fdmc, float* fdms) {
+  if (!h || !pv || n <= 0 || !rcx || !rcz) return DAZIM_EBADARG;
+  dazim_problem p;
+  std::vector<int> pe, nr, ns;
+  mini_problem(nx, ny, goxd, gozd, dvxd, dvzd, n, scx, scz, rcx, rcz, p, pe, nr, ns);
+  // receivers: rcxf(nrcf=1, nsrc=n, kmax=1) == rcx[n]
+  dazim_tables tb;
+  std::memset(&tb, 0, sizeof(tb));
+  tb.pvRc = const_cast<double*>(pv);
+  std::vector<float> dummyL((size_t)nx * ny, 0.0f);
+  std::vector<double> dummyS((size_t)nx * ny * 2, 0.0);
+  tb.Lsen_Gsc = dummyL.data();
+  tb.sen_vs = tb.sen_vp = tb.sen_rho = dummyS.data();
+  std::vector<float> vels((size_t)nx * ny * 2, 3.0f);
+  p.vels = vels.data();
+  dazim_plan* P = nullptr;
+  int st = plan_build(h, azim ? 0 : 1, &p, &tb, nullptr, nullptr, 0, -1, 1, &P);
+  if (st) return st;
+  st = plan_run(P);
+  if (st) { plan_free(P); return st; }
+  std::vector<int> off(n), cnt(n);
+  cudaError_t e = cudaMemcpy(off.data(), P->d_fp_off.p, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(cnt.data(), P->d_fp_cnt.p, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tt) e = cudaMemcpy(tt, P->d_dsurf.p, n * 4, cudaMemcpyDeviceToHost);
+  unsigned long long used = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&used, P->d_counters.p, 8, cudaMemcpyDeviceToHost);
+  std::vector<int> cell(used);
+  std::vector<float> v0(used), v1(used), v2(used);
+  if (e == cudaSuccess && used) e = cudaMemcpy(cell.data(), P->d_fp_cell.p, used * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && used) e = cudaMemcpy(v0.data(), P->d_fp_fdm.p, used * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && used && azim) e = cudaMemcpy(v1.data(), P->d_fp_fdmc.p, used * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && used && azim) e = cudaMemcpy(v2.data(), P->d_fp_fdms.p, used * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) {
+    const int nvx = nx - 2, nvz = ny - 2, ldc = nvx + 2, ldf = nvz + 2;
+    const size_t nf = (size_t)(nvz + 2) * (nvx + 2);
+    if (fdm) std::memset(fdm, 0, nf * n * 4);
+    if (fdmc) std::memset(fdmc, 0, nf * n * 4);
+    if (fdms) std::memset(fdms, 0, nf * n * 4);
+    for (int r = 0; r < n; ++r)
+      for (int i = 0; i < cnt[r]; ++i) {
+        const size_t q = (size_t)off[r] + i;
+        const int z = cell[q] / ldc, x = cell[q] % ldc;
+        const size_t o = (size_t)r * nf + (size_t)x * ldf + z;   // (0:nvz+1,0:nvx+1) column-major
+        if (fdm) fdm[o] = v0[q];
+        if (fdmc && azim) fdmc[o] = v1[q];
+        if (fdms && azim) fdms[o] = v2[q];
+      }
+  }
+  plan_free(P);
+  return e == cudaSuccess ? DAZIM_OK : DAZIM_ECUDA + (int)e;
+}

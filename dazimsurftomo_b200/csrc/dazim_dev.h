@@ -1,0 +1,124 @@
+// Device-side shared declarations for the B200 forward-modelling path.
+// Parity-critical float32 code: the whole library is compiled with
+// --fmad=false (the reference is x86-64/SSE2 without FMA) and default
+// IEEE-correct division / sqrt.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dz {
+
+// Coarse propagation grid + B-spline control grid constants (module globalp,
+// reference CalSurfG.f90:151-217; values set at FwdTraveltimeCPS.f90:346-380).
+struct GridC {
+  int nvx, nvz;        // control-grid interior vertices (nx-2, ny-2)
+  int nnx, nnz;        // coarse propagation nodes in x (colatitude) and z (longitude)
+  int gdx, gdz;        // dicing (5)
+  int sgdl, sgs;       // source-grid dicing level (8) and extent (8)
+  float gox, goz, dnx, dnz, dvx, dvz, earth;
+  float dpl_half;      // 0.5*min cell width, rpathsAzim.f90:156-161 (host computed)
+  float dpl_full;      // min cell width, srtimes CalSurfG.f90:1650-1654
+};
+
+// Per (period, source) record, filled by the host in float32 exactly like the
+// scalar prologue of the reference (FwdTraveltimeCPS.f90:493-530).
+struct SrcRec {
+  float scx, scz;            // source colatitude / longitude (rad)
+  int period;                // 0-based index into the velocity-map tables (periods(srcnum,knumi)-1)
+  int knumi;                 // 0-based period-loop index (selects kernel-table slice)
+  int vnl, vnr, vnt, vnb;    // coarse bounds of the refined box
+  int nnxr, nnzr;            // refined node counts
+  float goxr, gozr, dnxr, dnzr;
+  int isx_r, isz_r;          // source cell in the refined grid (travel, CalSurfG.f90:282-295)
+  float dsx_r, dsz_r;        // source offset inside that cell
+  int isx_t, isz_t;          // source cell used by the tracer (rpathsAzim.f90:146-147, no edge clamp)
+  int isx_c, isz_c;          // source cell in the coarse grid (srtimes, no clamp)
+  int isx_cc, isz_cc;        // clamped coarse source cell (for the near-source velocity)
+  float drx_c, drz_c;        // source offset in the clamped coarse cell
+  int ray0, nray;            // first global row and number of receivers
+};
+
+struct RayRec {
+  float rcx, rcz;   // receiver colatitude / longitude (rad)
+  int src;          // index into SrcRec (batch-local)
+  int row;          // global 0-based row id (count1-1)
+};
+
+static const int REF_LD = 129;           // leading dimension of refined fields: 2*sgs*sgdl+1
+static const int REF_N = REF_LD * REF_LD;
+
+struct FmmArgs {
+  GridC g;
+  const SrcRec* src;          // [nsrc]
+  int nsrc;
+  const float* velv;          // [nper][(nvz+2)(nvx+2)]
+  const float* veln_c;        // [nper][nnx*nnz]
+  const float* risti_c;       // [nnx]   earth*sin(gox+(ix-1)*dnx), host computed
+  const float* risti_r;       // [nsrc][REF_LD]
+  float* veln_r;              // [nsrc][REF_N]   (ld REF_LD)
+  float* ttn_c;               // [nsrc][nnx*nnz]
+  int* nsts_c;                // [nsrc][nnx*nnz]
+  float* ttn_r;               // [nsrc][REF_N]
+  int* nsts_r;                // [nsrc][REF_N]
+  int hcap;                   // heap entries held in shared memory (entries 1..hcap-1)
+  float* hspill_k;            // [nsrc][hspill]  keys of spilled heap entries
+  int* hspill_n;              // [nsrc][hspill]
+  int hspill;
+  int* flags;                 // bit4 (16): heap overflow
+  unsigned long long* n_accept;  // total accepted nodes (statistics)
+};
+
+struct TraceArgs {
+  GridC g;
+  const SrcRec* src;
+  const RayRec* ray;        // batch rays in processing order (long rays first)
+  int nray;
+  const float* veln_c;      // [nper][nnx*nnz]
+  const float* ttn_c;       // [nsrc][nnx*nnz]
+  const float* ttn_r;       // [nsrc][REF_N]
+  const int* nsts_r;        // [nsrc][REF_N]
+  // per-thread scratch
+  unsigned short* map;      // [nthreads][ncell]
+  int* skey;                // [nthreads][cap]
+  float* sval;              // [nthreads][3][cap]
+  int cap;
+  // outputs
+  float* dsurf;             // [dall] by global row
+  int* fp_off;              // [dall]
+  int* fp_cnt;              // [dall]
+  int* fp_cell;             // pool: jj*(nvx+2)+kk
+  float* fp_fdm; float* fp_fdmc; float* fp_fdms;
+  unsigned long long pool_cap;
+  unsigned long long* pool_used;
+  int* counter;             // work counter
+  int* flags;               // bit0 rbint, bit1 receiver outside, bit2 slot overflow, bit3 pool overflow
+  unsigned long long* n_steps;
+  int emit_all;             // test seam: emit every touched control point (no interior/threshold filter)
+};
+
+struct AsmArgs {
+  int mode;                 // 1 iso (1 block), 2 joint (3 blocks)
+  int nx, ny, nz, nvx, nvz, kmax;
+  int row0, nrow;           // rows [row0, row0+nrow) handled by this launch
+  const int* row_knumi;     // [dall] period-loop index of each row (0-based)
+  const int* fp_off; const int* fp_cnt;
+  const int* fp_cell; const float* fp_fdm; const float* fp_fdmc; const float* fp_fdms;
+  const double* sen_vs; const double* sen_vp; const double* sen_rho;   // (nx*ny,kmax,nz)
+  const float* lsen;        // (nx*ny,kmax,nz-1)
+  const float* coe_a; const float* coe_rho;   // (nx*ny, nz-1) at node index jj*nx+kk (vels(kk+1,jj+1,k))
+  int* nnz_row;             // [nrow] counts (pass 1)
+  const long long* rowptr;  // [nrow+1] (pass 2)
+  float* val; int* col;     // CSR outputs (pass 2)
+  int* rowid;               // optional COO row ids, 1-based (pass 2)
+};
+
+// forward mode: obsTaa(row) = sum_n GGc(row,n)*Gc(n) + sum_n GGs(row,n)*Gs(n), ascending n, float32
+struct TaaArgs {
+  int nx, ny, nz, nvx, nvz, kmax, nrow, row0;
+  const int* row_knumi; const int* fp_off; const int* fp_cnt; const int* fp_cell;
+  const float* fp_fdmc; const float* fp_fdms; const float* lsen;
+  const float* gc; const float* gs;   // (nx-2,ny-2,nz-1)
+  float* taa;
+};
+
+}  // namespace dz

@@ -1,0 +1,135 @@
+// gfortran-ABI drop-in symbols (lower case + trailing underscore, every
+// argument by reference, LOGICAL = 4-byte int) over the C ABI.  They replace,
+// at link time, the reference's
+//   FwdObsTraveltimeCPS  (src/src_forward/FwdTraveltimeCPS.f90:208-211)
+//   CalSurfG             (src/src_inv_iso_joint/CalSurfG.f90:909-912)
+//   CalSurfGAnisoJoint   (src/src_inv_iso_joint/CalSurfGAniso_Joint.f90:209-212)
+//   depthkernel          (src/src_inv_iso_joint/CalSurfG.f90:1-2)
+//   depthkernelTI        (src/src_forward/depthkernelTI.f90:2)
+// Error convention of the reference: print the message and STOP.
+#include "../../include/dazim_b200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+static dazim_handle* g_handle = nullptr;
+
+static dazim_handle* handle() {
+  if (!g_handle) {
+    int dev = 0;
+    if (const char* e = getenv("DAZIM_DEVICE")) dev = atoi(e);
+    int st = dazim_create(&g_handle, dev);
+    if (st) {
+      fprintf(stderr, " dazim_b200: cannot initialise CUDA device %d: %s\n TERMINATING PROGRAM!!!\n", dev,
+              dazim_strerror(st));
+      exit(1);
+    }
+  }
+  return g_handle;
+}
+
+static void stop_on(int st, const char* where) {
+  if (st == DAZIM_OK) return;
+  fprintf(stdout, " %s\n TERMINATING PROGRAM!!! (%s)\n", dazim_strerror(st), where);
+  fflush(stdout);
+  exit(1);
+}
+
+static void fill_problem(dazim_problem& p, int* nx, int* ny, int* nz, float* vels, float* goxdf, float* gozdf,
+                         float* dvxdf, float* dvzdf, int* kmaxRc, double* tRc, int* periods, float* depz,
+                         float* minthk, float* scxf, float* sczf, float* rcxf, float* rczf, int* nrc1,
+                         int* nsrcsurf1, int* kmax, int* nsrcsurf, int* nrcf) {
+  std::memset(&p, 0, sizeof(p));
+  p.nx = *nx; p.ny = *ny; p.nz = *nz; p.vels = vels; p.goxd = *goxdf; p.gozd = *gozdf; p.dvxd = *dvxdf;
+  p.dvzd = *dvzdf; p.kmaxRc = *kmaxRc; p.tRc = tRc; p.depz = depz; p.minthk = *minthk; p.kmax = *kmax;
+  p.nsrc = *nsrcsurf; p.nrcf = *nrcf; p.periods = periods; p.nrc1 = nrc1; p.nsrcsurf1 = nsrcsurf1;
+  p.scxf = scxf; p.sczf = sczf; p.rcxf = rcxf; p.rczf = rczf;
+}
+
+// Dense copies GVs/GGc/GGs(dall,nparpi) are only read by the reference's residual
+// statistics (CalSigamNorm.f90); they are rebuilt from the sparse triplets when the
+// caller passes them (without the stale-coefficient bug of SURVEY Q6).
+static void densify(const dazim_coo& c, long long dall, long long nparpi, float* GVs, float* GGc, float* GGs) {
+  float* blk[3] = {GVs, GGc, GGs};
+  for (int b = 0; b < 3; ++b)
+    if (blk[b]) std::memset(blk[b], 0, sizeof(float) * (size_t)dall * (size_t)nparpi);
+  for (long long k = 0; k < c.nar; ++k) {
+    const long long col = c.col[k] - 1, row = c.iw_row[k] - 1;
+    const int b = (int)(col / nparpi);
+    if (b < 3 && blk[b]) blk[b][(size_t)row + (size_t)(col % nparpi) * (size_t)dall] = c.rw[k];
+  }
+}
+
+extern "C" void depthkernel_(int* nx, int* ny, int* nz, float* vel, double* pvRc, double* sen_vsRc,
+                             double* sen_vpRc, double* sen_rhoRc, int* iwave, int* igr, int* kmaxRc, double* tRc,
+                             float* depz, float* minthk) {
+  if (*iwave != 2 || *igr != 0) stop_on(DAZIM_EBADARG, "depthkernel: only Rayleigh phase velocity");
+  stop_on(dazim_depthkernel(handle(), *nx, *ny, *nz, vel, pvRc, sen_vsRc, sen_vpRc, sen_rhoRc, *kmaxRc, tRc, depz,
+                            *minthk), "depthkernel");
+}
+
+extern "C" void depthkernelti_(int* nx, int* ny, int* nz, float* vel, double* pvRc, int* iwave, int* igr,
+                               int* kmaxRc, double* tRc, float* depz, float* minthk, float* Lsen_Gsc) {
+  if (*iwave != 2 || *igr != 0) stop_on(DAZIM_EBADARG, "depthkernelTI: only Rayleigh phase velocity");
+  stop_on(dazim_depthkernel_ti(handle(), *nx, *ny, *nz, vel, pvRc, *kmaxRc, tRc, depz, *minthk, Lsen_Gsc),
+          "depthkernelTI");
+}
+
+extern "C" void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, float* vels, float* Gctrue,
+                                     float* Gstrue, float* dsurf, float* obsTaa, int* dall, int* rmax, double* tRcV,
+                                     float* Lsen_Gsc, float* goxdf, float* gozdf, float* dvxdf, float* dvzdf,
+                                     int* kmaxRc, double* tRc, int* periods, float* depz, float* minthk, float* scxf,
+                                     float* sczf, float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1, int* kmax,
+                                     int* nsrcsurf, int* nrcf, int* writepath) {
+  (void)nparpi; (void)dall; (void)rmax; (void)writepath;
+  dazim_problem p;
+  fill_problem(p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, tRc, periods, depz, minthk, scxf, sczf, rcxf,
+               rczf, nrc1, nsrcsurf1, kmax, nsrcsurf, nrcf);
+  dazim_tables tb;
+  std::memset(&tb, 0, sizeof(tb));
+  tb.Lsen_Gsc = Lsen_Gsc;
+  printf("  DepthkernelTI begin!\n");
+  stop_on(dazim_gbuild(handle(), 0, &p, &tb, 0, Gctrue, Gstrue, dsurf, obsTaa, tRcV, nullptr), "FwdObsTraveltimeCPS");
+  printf("  DepthkernelTI time cost= %13.1f s\n", dazim_last_times(handle())->kernels_ms * 1e-3);
+}
+
+extern "C" void calsurfg_(int* nx, int* ny, int* nz, int* nparpi, float* vels, int* iw, float* rw, int* col,
+                          float* dsurf, float* GVs, int* dall, float* goxdf, float* gozdf, float* dvxdf, float* dvzdf,
+                          int* kmaxRc, double* tRc, int* periods, float* depz, float* minthk, float* scxf,
+                          float* sczf, float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1, int* kmax, int* nsrcsurf,
+                          int* nrcf, int* nar) {
+  dazim_problem p;
+  fill_problem(p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, tRc, periods, depz, minthk, scxf, sczf, rcxf,
+               rczf, nrc1, nsrcsurf1, kmax, nsrcsurf, nrcf);
+  dazim_tables tb;
+  std::memset(&tb, 0, sizeof(tb));
+  dazim_coo c;
+  c.rw = rw; c.iw_row = iw + 1; c.col = col; c.nar = 0;
+  // the caller sized rw/col by spfra (Main_Jt.f90:325); the bound is not passed down, so trust it like the reference
+  c.maxnar = (long long)1 << 62;
+  stop_on(dazim_gbuild(handle(), 1, &p, &tb, 0, nullptr, nullptr, dsurf, nullptr, nullptr, &c), "CalSurfG");
+  *nar = (int)c.nar;
+  if (GVs) densify(c, *dall, *nparpi, GVs, nullptr, nullptr);
+}
+
+extern "C" void calsurfganisojoint_(int* nx, int* ny, int* nz, int* nparpi, float* vels, int* iw, float* rw, int* col,
+                                    float* dsurf, float* GVs, float* GGc, float* GGs, float* Lsen_Gsc, int* dall,
+                                    int* rmax, double* tRcV, float* goxdf, float* gozdf, float* dvxdf, float* dvzdf,
+                                    int* kmaxRc, double* tRc, int* periods, float* depz, float* minthk, float* scxf,
+                                    float* sczf, float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1, int* kmax,
+                                    int* nsrcsurf, int* nrcf, int* nar, int* writepath) {
+  (void)rmax; (void)writepath;
+  dazim_problem p;
+  fill_problem(p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, tRc, periods, depz, minthk, scxf, sczf, rcxf,
+               rczf, nrc1, nsrcsurf1, kmax, nsrcsurf, nrcf);
+  dazim_tables tb;
+  std::memset(&tb, 0, sizeof(tb));
+  tb.Lsen_Gsc = Lsen_Gsc;
+  dazim_coo c;
+  c.rw = rw; c.iw_row = iw + 1; c.col = col; c.nar = 0;
+  c.maxnar = (long long)1 << 62;
+  stop_on(dazim_gbuild(handle(), 2, &p, &tb, 0, nullptr, nullptr, dsurf, nullptr, tRcV, &c), "CalSurfGAnisoJoint");
+  *nar = (int)c.nar;
+  if (GVs || GGc || GGs) densify(c, *dall, *nparpi, GVs, GGc, GGs);
+  if (dazim_last_times(handle())->rbint) printf(" ray path along the boundary, dangerous!!\n");
+}

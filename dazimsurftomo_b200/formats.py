@@ -1,0 +1,358 @@
+"""Readers/writers for the reference's text formats (host logic, no compute).
+
+Reference parsers mirrored here (all paths relative to /root/reference):
+  * forward ``para.in``      src/src_forward/MainForward.f90:147-159,188,330
+  * inversion ``para.in``    src/src_inv_iso_joint/Main_Jt.f90:158-211
+  * ``MOD`` / ``MODVs.true`` src/src_forward/MainForward.f90:338-343
+  * ``MODGc/Gs.true``        src/src_forward/MainForward.f90:351-356
+  * surface-wave data file   src/src_forward/MainForward.f90:239-281
+  * ``surfphase_forward.dat``src/src_forward/MainForward.f90:403-429
+  * ``period_Azm_tomo.*``    src/src_forward/FwdAzimuthalAniMap.f90:41-79
+
+Every REAL of the reference is float32 here, including the float32 value of
+pi (``real,parameter :: pi=3.1415926535898``, MainForward.f90:47): that is why
+an input latitude of 23.3 is echoed as 23.300011 in the reference's output.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import List, Optional
+
+import numpy as np
+
+F32 = np.float32
+PI32 = F32(3.1415926535898)
+
+
+@dataclasses.dataclass
+class ForwardPara:
+    datafile: str
+    nx: int
+    ny: int
+    nz: int
+    goxd: float
+    gozd: float
+    dvxd: float
+    dvzd: float
+    nsrc: int
+    sublayers: float
+    spfra: float
+    writepath: bool
+    kmaxRc: int
+    tRc: np.ndarray  # float64 (kmaxRc,)
+    noiselevel: float = 0.0
+
+
+@dataclasses.dataclass
+class InvPara:
+    datafile: str
+    nx: int
+    ny: int
+    nz: int
+    goxd: float
+    gozd: float
+    dvxd: float
+    dvzd: float
+    sublayers: float
+    minvel: float
+    maxvel: float
+    nsrc: int
+    spfra: float
+    maxiter: int
+    iso_mod: bool
+    weightVs: float
+    weightGcs: float
+    damp: float
+    kmaxRc: int
+    tRc: np.ndarray
+
+
+def _tok(line: str) -> List[str]:
+    """List-directed read of one record: blank/comma separated, stops at 'c:' comments."""
+    return line.replace(",", " ").split()
+
+
+def _logical(tok: str) -> bool:
+    t = tok.strip().strip(".").upper()
+    return t.startswith("T")
+
+
+def read_para_forward(path: str) -> ForwardPara:
+    with open(path) as f:
+        lines = f.read().splitlines()
+    it = iter(lines[3:])  # three header lines are skipped (MainForward.f90:147-149)
+    datafile = _tok(next(it))[0].strip("'\"")
+    nx, ny, nz = (int(t) for t in _tok(next(it))[:3])
+    goxd, gozd = (float(t) for t in _tok(next(it))[:2])
+    dvxd, dvzd = (float(t) for t in _tok(next(it))[:2])
+    nsrc = int(_tok(next(it))[0])
+    sublayers = float(_tok(next(it))[0])
+    spfra = float(_tok(next(it))[0])
+    writepath = _logical(_tok(next(it))[0])
+    kmaxRc = int(_tok(next(it))[0])
+    toks = _tok(next(it))
+    tRc = np.array([float(t) for t in toks[:kmaxRc]], dtype=np.float64)
+    try:
+        noise = float(_tok(next(it))[0])
+    except StopIteration:
+        noise = 0.0
+    return ForwardPara(datafile, nx, ny, nz, goxd, gozd, dvxd, dvzd, nsrc, sublayers, spfra,
+                       writepath, kmaxRc, tRc, noise)
+
+
+def read_para_inv(path: str) -> InvPara:
+    with open(path) as f:
+        lines = f.read().splitlines()
+    it = iter(lines[3:])
+    datafile = _tok(next(it))[0].strip("'\"")
+    nx, ny, nz = (int(t) for t in _tok(next(it))[:3])
+    goxd, gozd = (float(t) for t in _tok(next(it))[:2])
+    dvxd, dvzd = (float(t) for t in _tok(next(it))[:2])
+    sublayers = float(_tok(next(it))[0])
+    minvel, maxvel = (float(t) for t in _tok(next(it))[:2])
+    nsrc = int(_tok(next(it))[0])
+    spfra = float(_tok(next(it))[0])
+    maxiter = int(_tok(next(it))[0])
+    iso_mod = _logical(_tok(next(it))[0])
+    next(it)  # comment line
+    weightVs = float(_tok(next(it))[0])
+    weightGcs = float(_tok(next(it))[0])
+    damp = float(_tok(next(it))[0])
+    next(it)  # comment line
+    kmaxRc = int(_tok(next(it))[0])
+    tRc = np.array([float(t) for t in _tok(next(it))[:kmaxRc]], dtype=np.float64)
+    return InvPara(datafile, nx, ny, nz, goxd, gozd, dvxd, dvzd, sublayers, minvel, maxvel, nsrc,
+                   spfra, maxiter, iso_mod, weightVs, weightGcs, damp, kmaxRc, tRc)
+
+
+def read_model(path: str, nx: int, ny: int, nz: int):
+    """MOD / MODVs.true -> (depz float32 (nz,), vs float32 Fortran-ordered (nx,ny,nz))."""
+    with open(path) as f:
+        vals = f.read().split()
+    depz = np.array(vals[:nz], dtype=F32)
+    body = np.array(vals[nz:nz + nx * ny * nz], dtype=F32)
+    if body.size != nx * ny * nz:
+        raise ValueError(f"{path}: expected {nx*ny*nz} velocities, found {body.size}")
+    # file order: k outer, j, then i fastest == Fortran (nx,ny,nz) memory order
+    vs = np.asfortranarray(body.reshape((nz, ny, nx)).transpose(2, 1, 0))
+    return depz, vs
+
+
+def read_gcgs(path: str, nx: int, ny: int, nz: int) -> np.ndarray:
+    """MODGc.true / MODGs.true -> float32 Fortran-ordered (nx-2,ny-2,nz-1)."""
+    with open(path) as f:
+        vals = f.read().split()
+    n = (nx - 2) * (ny - 2) * (nz - 1)
+    body = np.array(vals[:n], dtype=F32)
+    if body.size != n:
+        raise ValueError(f"{path}: expected {n} values, found {body.size}")
+    return np.asfortranarray(body.reshape((nz - 1, ny - 2, nx - 2)).transpose(2, 1, 0))
+
+
+def write_model(path: str, depz: np.ndarray, vs: np.ndarray) -> None:
+    nx, ny, nz = vs.shape
+    with open(path, "w") as f:
+        f.write(" ".join(f"{float(d):6.1f}" for d in depz) + "\n")
+        for k in range(nz):
+            for j in range(ny):
+                f.write(" ".join(f"{float(vs[i, j, k]):6.3f}" for i in range(nx)) + "\n")
+
+
+@dataclasses.dataclass
+class Survey:
+    """Station tables in the layout the Fortran drivers pass down (column-major).
+
+    scxf/sczf are colatitude/longitude in radians (float32), built with the
+    reference's float32 arithmetic.  Leading dimensions are compacted to the
+    sizes actually used (the reference allocates nsrc x nsrc x kmax).
+    """
+    kmax: int
+    nsrc: int                # leading dim of the (nsrc,kmax) tables
+    nrcf: int                # leading dim of the receiver tables
+    periods: np.ndarray      # int32 (nsrc,kmax) F-order
+    nrc1: np.ndarray         # int32 (nsrc,kmax)
+    nsrcsurf1: np.ndarray    # int32 (kmax,)
+    scxf: np.ndarray         # float32 (nsrc,kmax)
+    sczf: np.ndarray
+    rcxf: np.ndarray         # float32 (nrcf,nsrc,kmax)
+    rczf: np.ndarray
+    wavetype: np.ndarray
+    igrt: np.ndarray
+    dist: np.ndarray         # float32 (dall,) delsph distances in file order
+    obsvel: np.ndarray       # float32 (dall,) velocities in file order
+    dall: int
+
+    def row_offsets(self) -> np.ndarray:
+        """First global row id (0-based) of every (period, source) in loop order."""
+        out = []
+        c = 0
+        for k in range(self.kmax):
+            for s in range(int(self.nsrcsurf1[k])):
+                out.append(c)
+                c += int(self.nrc1[s, k])
+        return np.array(out + [c], dtype=np.int64)
+
+
+def delsph32(flat1, flon1, flat2, flon2):
+    """delsph.f90:1-28 in float32 (vectorised)."""
+    R = F32(6371.0)
+    flat1 = np.asarray(flat1, F32); flon1 = np.asarray(flon1, F32)
+    flat2 = np.asarray(flat2, F32); flon2 = np.asarray(flon2, F32)
+    dlat = flat2 - flat1
+    dlon = flon2 - flon1
+    lat1 = PI32 / F32(2) - flat1
+    lat2 = PI32 / F32(2) - flat2
+    sa = np.sin(dlat / F32(2)).astype(F32)
+    so = np.sin(dlon / F32(2)).astype(F32)
+    a = sa * sa + so * so * np.cos(lat1).astype(F32) * np.cos(lat2).astype(F32)
+    c = F32(2) * np.arctan2(np.sqrt(a).astype(F32), np.sqrt(F32(1) - a).astype(F32)).astype(F32)
+    return (R * c).astype(F32)
+
+
+def read_surfdata(path: str, kmax: int) -> Survey:
+    """Parse the '#'-block data file (MainForward.f90:239-281 / Main_Jt.f90:274-315)."""
+    src_lat: List[List[float]] = [[] for _ in range(kmax)]
+    src_lon: List[List[float]] = [[] for _ in range(kmax)]
+    src_per: List[List[int]] = [[] for _ in range(kmax)]
+    src_wt: List[List[int]] = [[] for _ in range(kmax)]
+    src_vt: List[List[int]] = [[] for _ in range(kmax)]
+    rec: List[List[List[tuple]]] = [[] for _ in range(kmax)]
+    order = []  # (knum, istep) per data line, file order
+    vels = []
+    knum = 0
+    with open(path) as f:
+        for line in f:
+            if not line.strip():
+                continue
+            if line[0] == "#":
+                t = line[1:].split()
+                lat, lon, period, wavetp, veltp = float(t[0]), float(t[1]), int(t[2]), int(t[3]), int(t[4])
+                if wavetp == 2 and veltp == 0:
+                    knum = period
+                else:
+                    raise ValueError("can only deal with Rayleigh wave phase velocity data")
+                k = knum - 1
+                src_lat[k].append(lat); src_lon[k].append(lon)
+                src_per[k].append(period); src_wt[k].append(wavetp); src_vt[k].append(veltp)
+                rec[k].append([])
+            else:
+                t = line.split()
+                rec[knum - 1][-1].append((float(t[0]), float(t[1])))
+                vels.append(float(t[2]))
+                order.append((knum - 1, len(rec[knum - 1]) - 1))
+    nsrc = max(1, max(len(x) for x in src_lat))
+    nrcf = max(1, max((len(r) for k in range(kmax) for r in rec[k]), default=1))
+    periods = np.zeros((nsrc, kmax), np.int32, order="F")
+    nrc1 = np.zeros((nsrc, kmax), np.int32, order="F")
+    wavetype = np.zeros((nsrc, kmax), np.int32, order="F")
+    igrt = np.zeros((nsrc, kmax), np.int32, order="F")
+    nsrcsurf1 = np.zeros((kmax,), np.int32)
+    scxf = np.zeros((nsrc, kmax), F32, order="F")
+    sczf = np.zeros((nsrc, kmax), F32, order="F")
+    rcxf = np.zeros((nrcf, nsrc, kmax), F32, order="F")
+    rczf = np.zeros((nrcf, nsrc, kmax), F32, order="F")
+    c180 = F32(180.0)
+    for k in range(kmax):
+        ns = len(src_lat[k])
+        nsrcsurf1[k] = ns
+        if ns == 0:
+            continue
+        lat = np.array(src_lat[k], F32); lon = np.array(src_lon[k], F32)
+        scxf[:ns, k] = (F32(90.0) - lat) * PI32 / c180
+        sczf[:ns, k] = lon * PI32 / c180
+        periods[:ns, k] = src_per[k]
+        wavetype[:ns, k] = src_wt[k]
+        igrt[:ns, k] = src_vt[k]
+        for s in range(ns):
+            r = rec[k][s]
+            nrc1[s, k] = len(r)
+            if r:
+                rl = np.array([x[0] for x in r], F32); ro = np.array([x[1] for x in r], F32)
+                rcxf[:len(r), s, k] = (F32(90.0) - rl) * PI32 / c180
+                rczf[:len(r), s, k] = ro * PI32 / c180
+    dall = len(vels)
+    # distances in file order
+    ks = np.array([o[0] for o in order], np.int64); ss = np.array([o[1] for o in order], np.int64)
+    counters = {}
+    ridx = np.zeros(dall, np.int64)
+    for i, o in enumerate(order):
+        ridx[i] = counters.get(o, 0)
+        counters[o] = ridx[i] + 1
+    dist = delsph32(scxf[ss, ks], sczf[ss, ks], rcxf[ridx, ss, ks], rczf[ridx, ss, ks]) if dall else np.zeros(0, F32)
+    return Survey(kmax, nsrc, nrcf, periods, nrc1, nsrcsurf1, scxf, sczf, rcxf, rczf, wavetype, igrt,
+                  dist, np.array(vels, F32), dall)
+
+
+def survey_loop_coords(sv: Survey):
+    """(scx, scz, rcx, rcz) float32 per ray in the reference's (period, source, receiver) loop order."""
+    scx, scz, rcx, rcz = [], [], [], []
+    for k in range(sv.kmax):
+        for s in range(int(sv.nsrcsurf1[k])):
+            n = int(sv.nrc1[s, k])
+            scx.append(np.full(n, sv.scxf[s, k], F32)); scz.append(np.full(n, sv.sczf[s, k], F32))
+            rcx.append(sv.rcxf[:n, s, k]); rcz.append(sv.rczf[:n, s, k])
+    cat = lambda x: np.concatenate(x) if x else np.zeros(0, F32)
+    return cat(scx), cat(scz), cat(rcx), cat(rcz)
+
+
+def forward_velocities(sv: Survey, tsyn: np.ndarray) -> np.ndarray:
+    """c = delsph/T per ray in loop order, float32 (MainForward.f90:413-424)."""
+    scx, scz, rcx, rcz = survey_loop_coords(sv)
+    d = delsph32(scx, scz, rcx, rcz)
+    return (d / np.asarray(tsyn, F32)).astype(F32)
+
+
+def write_surfphase_forward(path: str, sv: Survey, tsyn: np.ndarray) -> None:
+    """surfphase_forward.dat: '(a,2f11.6,3I3)' headers, '(2f11.6,f9.5)' rows (MainForward.f90:403-429)."""
+    vel = forward_velocities(sv, tsyn)
+    c180 = F32(180.0)
+    i = 0
+    with open(path, "w") as f:
+        for k in range(sv.kmax):
+            for s in range(int(sv.nsrcsurf1[k])):
+                latd = F32(90.0) - sv.scxf[s, k] * c180 / PI32
+                lond = sv.sczf[s, k] * c180 / PI32
+                f.write("#%11.6f%11.6f%3d%3d%3d\n" % (latd, lond, sv.periods[s, k], sv.wavetype[s, k], sv.igrt[s, k]))
+                for r in range(int(sv.nrc1[s, k])):
+                    lat2 = F32(90.0) - sv.rcxf[r, s, k] * c180 / PI32
+                    lon2 = sv.rczf[r, s, k] * c180 / PI32
+                    f.write("%11.6f%11.6f%9.5f\n" % (lat2, lon2, vel[i]))
+                    i += 1
+
+
+def read_surfphase_velocities(path: str) -> np.ndarray:
+    """Velocity column of a surfphase file (data lines only), float64."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            if line and line[0] != "#" and line.strip():
+                out.append(float(line.split()[2]))
+    return np.array(out)
+
+
+def azim_map(nx, ny, nz, goxd, gozd, dvxd, dvzd, tRc, gcf, gsf, lsen_gsc, tRcV):
+    """FwdAzimuthalAniMap.f90:41-79 -> array (kmax*(ny-2)*(nx-2), 9) as printed by '(10f10.5)'."""
+    kmax = len(tRc)
+    nvx = nx - 2
+    rows = []
+    L = np.asarray(lsen_gsc, F32).reshape((nx * ny, kmax, nz - 1), order="F")
+    tv = np.asarray(tRcV).reshape(((nx - 2) * (ny - 2), kmax), order="F")
+    for tt in range(kmax):
+        for jj in range(1, ny - 1):
+            for ii in range(1, nx - 1):
+                ct = F32(0); st = F32(0)
+                node = jj * (nvx + 2) + ii  # 0-based of jj*(nvx+2)+ii+1
+                for kk in range(nz - 1):
+                    ct = F32(ct + L[node, tt, kk] * gcf[ii - 1, jj - 1, kk])
+                    st = F32(st + L[node, tt, kk] * gsf[ii - 1, jj - 1, kk])
+                amp = F32(np.sqrt(F32(ct * ct + st * st)))
+                isoc = F32(tv[(jj - 1) * (nx - 2) + ii - 1, tt])
+                rel = F32(amp / isoc) if isoc != 0 else F32(0)
+                ang = F32(np.arctan2(st, ct) / np.float64(F32(3.1415926535898)) * 180)
+                if ang < 0:
+                    ang = F32(ang + 360)
+                ang = F32(0.5) * ang
+                rows.append((F32(gozd) + F32(jj - 1) * F32(dvzd), F32(goxd) - F32(ii - 1) * F32(dvxd),
+                             tRc[tt], isoc, ang, rel, amp, ct, st))
+    return np.array(rows, dtype=np.float64)

@@ -1,0 +1,188 @@
+/* dazim_b200.h -- C ABI of the B200-native forward-modelling path of DAzimSurfTomo.
+ *
+ * The reference (Chuanming-Liu/DAzimSurfTomo) is Fortran and has no FFI; the
+ * seam this library replaces is the Fortran external-procedure boundary
+ * between the drivers and the forward-modelling subroutines:
+ *
+ *   FwdObsTraveltimeCPS   src/src_forward/FwdTraveltimeCPS.f90:208   (called MainForward.f90:372)
+ *   CalSurfG              src/src_inv_iso_joint/CalSurfG.f90:909     (called Main_Jt.f90:398)
+ *   CalSurfGAnisoJoint    src/src_inv_iso_joint/CalSurfGAniso_Joint.f90:209 (called Main_Jt.f90:403)
+ *   depthkernel           src/src_inv_iso_joint/CalSurfG.f90:1
+ *   depthkernelTI         src/src_forward/depthkernelTI.f90:2
+ *
+ * All arrays are Fortran column-major with the reference's shapes; all
+ * pointers are HOST pointers unless a function says otherwise; the caller owns
+ * every buffer.  Functions return 0 on success or a DAZIM_E* code that mirrors
+ * the reference's STOP sites.  There is no CPU fallback: every entry point
+ * fails with DAZIM_ECUDA when no CUDA device is usable.
+ */
+#ifndef DAZIM_B200_H
+#define DAZIM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  DAZIM_OK = 0,
+  DAZIM_ESOURCE_OUTSIDE = 1,   /* "Source lies outside bounds of model", CalSurfG.f90:287-293 */
+  DAZIM_ERECEIVER_OUTSIDE = 2, /* "Receiver lies outside model", CalSurfG.f90:1649-1655, rpathsAzim.f90:193-216 */
+  DAZIM_ENNZ_OVERFLOW = 3,     /* nar > maxnar, "increase sparsity fraction", Main_Jt.f90:523 */
+  DAZIM_EBADARG = 4,
+  DAZIM_ELAYERS = 5,           /* more than NL=200 layers / NP=60 periods, surfdisp96.f:57-59 */
+  DAZIM_EHEAP = 6,             /* narrow band larger than the heap workspace */
+  DAZIM_EFOOTPRINT = 7,        /* a ray touched more control points than the footprint workspace holds */
+  DAZIM_ENOROOT = 9,           /* surfdisp96 found no root (reference prints a warning and zero-fills) */
+  DAZIM_ECUDA = 100            /* + cudaError_t */
+};
+
+typedef struct dazim_handle dazim_handle;
+
+/* Station / geometry tables exactly as the Fortran drivers hold them
+ * (MainForward.f90:239-281).  Leading dimensions nsrc, nrcf are the callers'. */
+typedef struct dazim_problem {
+  int nx, ny, nz;            /* model grid incl. edge nodes */
+  const float* vels;         /* (nx,ny,nz) Vs km/s */
+  float goxd, gozd;          /* upper-left (lat, lon) degrees */
+  float dvxd, dvzd;          /* grid spacing degrees */
+  int kmaxRc;                /* number of periods */
+  const double* tRc;         /* (kmaxRc) periods, s */
+  const float* depz;         /* (nz) depths km */
+  float minthk;              /* "sublayers" of para.in */
+  int kmax, nsrc, nrcf;
+  const int* periods;        /* (nsrc,kmax) */
+  const int* nrc1;           /* (nsrc,kmax) */
+  const int* nsrcsurf1;      /* (kmax) */
+  const float* scxf;         /* (nsrc,kmax) colatitude rad */
+  const float* sczf;         /* (nsrc,kmax) longitude rad */
+  const float* rcxf;         /* (nrcf,nsrc,kmax) */
+  const float* rczf;         /* (nrcf,nsrc,kmax) */
+} dazim_problem;
+
+/* Depth-kernel tables (outputs of depthkernel / depthkernelTI). */
+typedef struct dazim_tables {
+  double* pvRc;              /* (nx*ny,kmaxRc) phase velocity */
+  double* sen_vs;            /* (nx*ny,kmaxRc,nz) dc/dVs ; may be NULL in forward mode */
+  double* sen_vp;
+  double* sen_rho;
+  float* Lsen_Gsc;           /* (nx*ny,kmaxRc,nz-1) ; may be NULL in iso mode */
+} dazim_tables;
+
+/* Sparse G in the reference's COO convention (rw(k), row iw(k+1), col(k)),
+ * rows ascending, columns ascending inside a row; all indices 1-based. */
+typedef struct dazim_coo {
+  float* rw;                 /* (maxnar) */
+  int* iw_row;               /* (maxnar) row of entry k; the Fortran shim passes iw+1 */
+  int* col;                  /* (maxnar) */
+  long long maxnar;
+  long long nar;             /* out */
+} dazim_coo;
+
+/* Per-stage device times of the last call (CUDA events on the library stream), ms. */
+typedef struct dazim_times {
+  float kernels_ms;          /* K1/K2 Thomson-Haskell */
+  float dice_ms;             /* K0 */
+  float fmm_ms;              /* K3 */
+  float trace_ms;            /* K4 */
+  float assemble_ms;         /* K5 */
+  float total_ms;            /* first launch to last kernel end, excluding H2D/D2H */
+  long long n_accept;        /* accepted FMM nodes */
+  long long n_steps;         /* ray steps */
+  long long n_fmm_launch, n_trace_launch, n_launch; /* kernel launches */
+  long long h2d_bytes, d2h_bytes;
+  int rbint;                 /* a ray hugged the model boundary (reference warning) */
+} dazim_times;
+
+int dazim_create(dazim_handle** h, int device);
+void dazim_destroy(dazim_handle* h);
+const char* dazim_strerror(int code);
+const dazim_times* dazim_last_times(const dazim_handle* h);
+
+/* --- L2: depth kernels ---------------------------------------------------- */
+/* depthkernel, CalSurfG.f90:1-139 */
+int dazim_depthkernel(dazim_handle* h, int nx, int ny, int nz, const float* vel, double* pvRc,
+                      double* sen_vs, double* sen_vp, double* sen_rho, int kmaxRc, const double* tRc,
+                      const float* depz, float minthk);
+/* depthkernelTI, depthkernelTI.f90:2-112 */
+int dazim_depthkernel_ti(dazim_handle* h, int nx, int ny, int nz, const float* vel, double* pvRc,
+                         int kmaxRc, const double* tRc, const float* depz, float minthk,
+                         float* Lsen_Gsc);
+/* surfdisp96 (surfdisp96.f:52), Rayleigh phase branch, nprof layered profiles at once:
+ * thk/vp/vs/rho (nlayer,nprof) column-major, cg (kmax,nprof) */
+int dazim_surfdisp96(dazim_handle* h, int nprof, int nlayer, const float* thk, const float* vp,
+                     const float* vs, const float* rho, int kmax, const double* t, double* cg);
+
+/* --- L1: orchestrators ---------------------------------------------------- */
+/* mode 0: FwdObsTraveltimeCPS  -> dsurf, obsTaa            (needs pvRc, Lsen_Gsc; Gc/Gs)
+ * mode 1: CalSurfG             -> dsurf, COO (nparpi cols) (needs pvRc, sen_*)
+ * mode 2: CalSurfGAnisoJoint   -> dsurf, COO (3*nparpi)    (needs all tables)
+ * tables_precomputed=0: the tables are computed on the GPU first (and returned
+ * in *tables where non-NULL); =1: *tables are inputs and only the
+ * dice + eikonal + ray + assembly stages run. */
+int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, dazim_tables* tables,
+                 int tables_precomputed, const float* Gctrue, const float* Gstrue, float* dsurf,
+                 float* obsTaa, double* tRcV, dazim_coo* coo);
+
+/* --- test seams ------------------------------------------------------------ */
+/* Eikonal solves for n sources on one phase-velocity map pv (nx*ny doubles).
+ * Outputs per source: ttn/nsts coarse (nnz,nnx), ttnr/nstsr (129,129), geom[8]
+ * = nnzr,nnxr,vnl,vnr,vnt,vnb,nnz,nnx.  Any output may be NULL. */
+int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
+                    const double* pv, int n, const float* scx, const float* scz, float* veln,
+                    float* ttn, int* nsts, float* ttnr, int* nstsr, int* geom);
+/* Rays: n (source, receiver) pairs on one map; outputs travel time tt(n) and dense
+ * Frechet maps fdm/fdmc/fdms (nvz+2, nvx+2, n) column-major (zero where untouched). */
+int dazim_raytrace(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
+                   const double* pv, int n, const float* scx, const float* scz, const float* rcx,
+                   const float* rcz, int azim, float* tt, float* fdm, float* fdmc, float* fdms);
+
+/* --- device-resident plan (inputs uploaded once; used by bench.py for the
+ * HBM-resident figure and by the multi-GPU driver) ---------------------------- */
+typedef struct dazim_plan dazim_plan;
+/* src_begin/src_end: half-open range of (period,source) units in loop order
+ * owned by this rank (0, -1 = all). */
+int dazim_plan_create(dazim_handle* h, int mode, const dazim_problem* p, const dazim_tables* tables,
+                      const float* Gctrue, const float* Gstrue, long long src_begin,
+                      long long src_end, dazim_plan** plan);
+int dazim_plan_run(dazim_plan* plan);                 /* all kernels, results stay in HBM */
+long long dazim_plan_rows(const dazim_plan* plan, long long* row0);   /* rows owned, first row */
+long long dazim_plan_nnz(const dazim_plan* plan);
+/* copy results of the last run to host (any pointer may be NULL);
+ * rowptr has rows+1 entries (0-based offsets into val/col), col is 1-based */
+int dazim_plan_fetch(dazim_plan* plan, float* dsurf, float* obsTaa, long long* rowptr, int* col,
+                     float* val);
+/* device pointers of the last run's outputs (for NCCL gathers without a host hop) */
+int dazim_plan_device_ptrs(dazim_plan* plan, void** dsurf, void** obsTaa, void** rowptr, void** col,
+                           void** val);
+void dazim_plan_destroy(dazim_plan* plan);
+
+/* --- gfortran-ABI drop-in symbols (lower case + underscore, all by reference) --- */
+void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, float* vels, float* Gctrue,
+                          float* Gstrue, float* dsurf, float* obsTaa, int* dall, int* rmax,
+                          double* tRcV, float* Lsen_Gsc, float* goxdf, float* gozdf, float* dvxdf,
+                          float* dvzdf, int* kmaxRc, double* tRc, int* periods, float* depz,
+                          float* minthk, float* scxf, float* sczf, float* rcxf, float* rczf,
+                          int* nrc1, int* nsrcsurf1, int* kmax, int* nsrcsurf, int* nrcf,
+                          int* writepath);
+void calsurfg_(int* nx, int* ny, int* nz, int* nparpi, float* vels, int* iw, float* rw, int* col,
+               float* dsurf, float* GVs, int* dall, float* goxdf, float* gozdf, float* dvxdf,
+               float* dvzdf, int* kmaxRc, double* tRc, int* periods, float* depz, float* minthk,
+               float* scxf, float* sczf, float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1,
+               int* kmax, int* nsrcsurf, int* nrcf, int* nar);
+void calsurfganisojoint_(int* nx, int* ny, int* nz, int* nparpi, float* vels, int* iw, float* rw,
+                         int* col, float* dsurf, float* GVs, float* GGc, float* GGs,
+                         float* Lsen_Gsc, int* dall, int* rmax, double* tRcV, float* goxdf,
+                         float* gozdf, float* dvxdf, float* dvzdf, int* kmaxRc, double* tRc,
+                         int* periods, float* depz, float* minthk, float* scxf, float* sczf,
+                         float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1, int* kmax,
+                         int* nsrcsurf, int* nrcf, int* nar, int* writepath);
+void depthkernel_(int* nx, int* ny, int* nz, float* vel, double* pvRc, double* sen_vsRc,
+                  double* sen_vpRc, double* sen_rhoRc, int* iwave, int* igr, int* kmaxRc,
+                  double* tRc, float* depz, float* minthk);
+void depthkernelti_(int* nx, int* ny, int* nz, float* vel, double* pvRc, int* iwave, int* igr,
+                    int* kmaxRc, double* tRc, float* depz, float* minthk, float* Lsen_Gsc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

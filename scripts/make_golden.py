@@ -1,0 +1,64 @@
+"""Generate tests/golden/ fixtures from the reference's shipped example (run in the build
+container, where /root/reference exists).  The fixtures are the reference's OWN inputs and
+outputs (example/test1_syn_foward), cut down so they stay small:
+
+  test1/para.in, MODVs.true, MODGc.true, MODGs.true      verbatim inputs
+  test1/surfdata_subset.dat                               '#' blocks of a few (period, source) units
+  test1/surfphase_subset.dat                              the matching blocks of the reference's
+                                                          output/surfphase_forward_RV3th.dat
+  test1/period_Azm_tomo.npz                               output/period_Azm_tomo.real as an array
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+REF = "/root/reference/example/test1_syn_foward"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "test1")
+PERIODS = (1, 9, 18, 27, 36)
+SOURCES_PER_PERIOD = 4      # first, then every 37th source
+
+
+def blocks(path):
+    cur = None
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                if cur:
+                    yield cur
+                cur = [line]
+            elif line.strip():
+                cur.append(line)
+    if cur:
+        yield cur
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for f in ("para.in", "MODVs.true", "MODGc.true", "MODGs.true"):
+        shutil.copy(os.path.join(REF, f), os.path.join(OUT, f))
+        os.chmod(os.path.join(OUT, f), 0o644)
+    inp = list(blocks(os.path.join(REF, "Surfphase_RV3_5_40s_1s.dat")))
+    gold = list(blocks(os.path.join(REF, "output", "surfphase_forward_RV3th.dat")))
+    assert len(inp) == len(gold) == 4320
+    seen = {}
+    keep = []
+    for i, b in enumerate(inp):
+        per = int(b[0].split()[3])
+        k = seen.get(per, 0)
+        seen[per] = k + 1
+        if per in PERIODS and k % 37 == 0 and k // 37 < SOURCES_PER_PERIOD:
+            keep.append(i)
+    with open(os.path.join(OUT, "surfdata_subset.dat"), "w") as fi, open(os.path.join(OUT, "surfphase_subset.dat"), "w") as fg:
+        for i in keep:
+            assert len(inp[i]) == len(gold[i])
+            fi.writelines(inp[i])
+            fg.writelines(gold[i])
+    g = np.loadtxt(os.path.join(REF, "output", "period_Azm_tomo.real"))
+    np.savez_compressed(os.path.join(OUT, "period_Azm_tomo.npz"), table=g.astype(np.float32))
+    print("units kept:", len(keep), "rays:", sum(len(inp[i]) - 1 for i in keep))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,57 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLD = os.path.join(ROOT, "tests", "golden", "test1")
+REF_EX = "/root/reference/example/test1_syn_foward"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """ORACLE = checker only (oracle/ is test infrastructure)."""
+    from oracle import pyoracle
+    pyoracle.build()
+    pyoracle.lib()
+    return pyoracle
+
+
+@pytest.fixture(scope="session")
+def test1():
+    """Inputs of the reference's example/test1_syn_foward (fixture copy) + subset survey."""
+    from dazimsurftomo_b200 import formats as fm
+    p = fm.read_para_forward(os.path.join(GOLD, "para.in"))
+    depz, vs = fm.read_model(os.path.join(GOLD, "MODVs.true"), p.nx, p.ny, p.nz)
+    gc = fm.read_gcgs(os.path.join(GOLD, "MODGc.true"), p.nx, p.ny, p.nz)
+    gs = fm.read_gcgs(os.path.join(GOLD, "MODGs.true"), p.nx, p.ny, p.nz)
+    sv = fm.read_surfdata(os.path.join(GOLD, "surfdata_subset.dat"), p.kmaxRc)
+    gold_c = fm.read_surfphase_velocities(os.path.join(GOLD, "surfphase_subset.dat"))
+    azm = np.load(os.path.join(GOLD, "period_Azm_tomo.npz"))["table"].astype(np.float64)
+    return dict(para=p, depz=depz, vs=vs, gc=gc, gs=gs, sv=sv, gold_c=gold_c, azm=azm)
+
+
+@pytest.fixture(scope="session")
+def test1_tables(oracle, test1):
+    """Depth-kernel tables of test1 from the oracle (pinned by period_Azm_tomo.real)."""
+    p = test1["para"]
+    pv, L = oracle.depthkernel_ti(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    return dict(pvRc=pv, Lsen_Gsc=L)
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dazimsurftomo_b200 import api
+    api.load()   # fails loudly if the extension is missing
+    return api

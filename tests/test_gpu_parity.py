@@ -1,0 +1,132 @@
+"""CUDA path (through the C ABI) vs the oracle on the same inputs.  Bit-exact for travel-time
+fields, ray footprints, sparsity pattern and G values (float32 arithmetic is reproduced
+operation by operation); tolerances are written where floating-point libraries differ."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sources(test1, n=6):
+    sv = test1["sv"]
+    out = []
+    for k in range(sv.kmax):
+        for s in range(int(sv.nsrcsurf1[k])):
+            out.append((float(sv.scxf[s, k]), float(sv.sczf[s, k])))
+    # add a source hugging the model corner (refined box clipped on two sides)
+    return out[:n]
+
+
+def test_fmm_fields_bit_exact(gpu, oracle, test1, test1_tables):
+    p = test1["para"]
+    pv = np.ascontiguousarray(test1_tables["pvRc"][:, 7])
+    src = _sources(test1, 8)
+    # corner / edge sources exercise the clipped source box and the literal exit rule
+    g0x = np.float32((90.0 - p.goxd) * np.pi / 180); g0z = np.float32(p.gozd * np.pi / 180)
+    dv = np.float32(p.dvxd * np.pi / 180)
+    src += [(float(g0x + dv * 0.3), float(g0z + dv * 0.4)), (float(g0x + dv * 13.9), float(g0z + dv * 7.2)),
+            (float(g0x + dv * 6.0), float(g0z + dv * 13.95))]
+    r = gpu.fmm_solve(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, [s[0] for s in src], [s[1] for s in src])
+    for i, (x, z) in enumerate(src):
+        o = oracle.fmm_source(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, x, z)
+        assert np.array_equal(r["veln"], o["veln"])
+        nzr, nxr = o["geom"][0], o["geom"][1]
+        assert tuple(r["geom"][:6, i]) == tuple(o["geom"][:6])
+        assert np.array_equal(r["nstsr"][:nzr, :nxr, i] == 0, o["nstsr"][:nzr, :nxr] == 0)
+        alive = o["nstsr"][:nzr, :nxr] >= 0
+        assert np.array_equal(r["ttnr"][:nzr, :nxr, i][alive], o["ttnr"][:nzr, :nxr][alive])
+        assert np.array_equal(r["nstsr"][:nzr, :nxr, i], o["nstsr"][:nzr, :nxr])     # heap slots too
+        assert np.array_equal(r["ttn"][:, :, i], o["ttn"]), i
+        assert np.all(r["nsts"][:, :, i] == 0)
+
+
+def test_ray_footprints_bit_exact(gpu, oracle, test1, test1_tables):
+    p = test1["para"]; sv = test1["sv"]
+    pv = np.ascontiguousarray(test1_tables["pvRc"][:, 0])
+    scx, scz, rcx, rcz = [], [], [], []
+    for s in range(3):
+        for r in range(0, int(sv.nrc1[s, 0]), 5):
+            scx.append(sv.scxf[s, 0]); scz.append(sv.sczf[s, 0]); rcx.append(sv.rcxf[r, s, 0]); rcz.append(sv.rczf[r, s, 0])
+    # a receiver within two steps of the source (no path) and one inside the source box
+    scx += [scx[0], scx[0]]; scz += [scz[0], scz[0]]
+    rcx += [np.float32(scx[0] + 1e-5), np.float32(scx[0] + 3e-3)]; rcz += [np.float32(scz[0] + 1e-5), np.float32(scz[0] - 2e-3)]
+    for azim in (True, False):
+        tt, fdm, fdmc, fdms = gpu.raytrace(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, scx, scz, rcx, rcz, azim=azim)
+        for i in range(len(scx)):
+            ot, of, oc, os_, ns = oracle.ray(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, scx[i], scz[i], rcx[i], rcz[i], azim)
+            assert tt[i] == np.float32(ot), (i, tt[i], ot)
+            assert np.array_equal(fdm[:, :, i], of), i
+            if azim:
+                # cos/sin(2 psi) come from double-precision libm on both sides, rounded to float32
+                assert np.array_equal(fdmc[:, :, i], oc), i
+                assert np.array_equal(fdms[:, :, i], os_), i
+
+
+def _cmp_coo(r, o):
+    assert r["nar"] == o["nar"] > 0
+    assert np.array_equal(r["row"], o["row"])          # bit-exact sparsity pattern
+    assert np.array_equal(r["col"], o["col"])
+    assert np.array_equal(r["rw"], o["rw"])            # and values (same float32/float64 op order)
+    assert np.array_equal(r["dsurf"], o["dsurf"])
+
+
+def test_forward_subset(gpu, oracle, test1, test1_tables):
+    from dazimsurftomo_b200 import formats as fm
+    p = test1["para"]
+    r = gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, test1["sv"], tables=test1_tables)
+    o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"],
+                      test1["gc"], test1["gs"], tables=test1_tables)
+    assert np.array_equal(r["dsurf"], o["dsurf"])
+    assert np.array_equal(r["obsTaa"], o["obsTaa"])
+    c = fm.forward_velocities(test1["sv"], r["dsurf"] + r["obsTaa"])
+    assert np.abs(c - test1["gold_c"]).max() < 1.5e-5        # the reference's own output, f9.5
+    assert r["times"]["n_launch"] >= 3 and r["times"]["n_accept"] == o["n_accept"]
+    assert r["times"]["n_steps"] == o["n_steps"]
+
+
+def test_gmatrix_iso_and_joint(gpu, oracle, test1, test1_tables):
+    p = test1["para"]
+    pv, svs, svp, srho, _ = oracle.depthkernel(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    tb = dict(test1_tables, sen_vs=svs, sen_vp=svp, sen_rho=srho)
+    args = (test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"])
+    _cmp_coo(gpu.CalSurfG(*args, tables=tb), oracle.gbuild(1, *args, tables=tb))
+    _cmp_coo(gpu.CalSurfGAnisoJoint(*args, tables=tb), oracle.gbuild(2, *args, tables=tb))
+
+
+def test_batched_equals_single(gpu, test1, test1_tables, monkeypatch):
+    """Source batching (workspace reuse) must not change a bit."""
+    p = test1["para"]
+    args = (test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"])
+    a = gpu.FwdObsTraveltimeCPS(*args, tables=test1_tables)
+    monkeypatch.setenv("DAZIM_BATCH", "3")
+    b = gpu.FwdObsTraveltimeCPS(*args, tables=test1_tables)
+    assert np.array_equal(a["dsurf"], b["dsurf"]) and np.array_equal(a["obsTaa"], b["obsTaa"])
+    assert b["times"]["n_fmm_launch"] == 7
+
+
+def test_heap_spill_path(gpu, test1, test1_tables, monkeypatch):
+    """Tiny shared-memory heap: most of the narrow band lives in the global spill array."""
+    p = test1["para"]
+    args = (test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"])
+    a = gpu.FwdObsTraveltimeCPS(*args, tables=test1_tables)
+    monkeypatch.setenv("DAZIM_HCAP", "64")
+    b = gpu.FwdObsTraveltimeCPS(*args, tables=test1_tables)
+    assert np.array_equal(a["dsurf"], b["dsurf"]) and np.array_equal(a["obsTaa"], b["obsTaa"])
+
+
+def test_errors_mirror_reference_stops(gpu, test1, test1_tables):
+    import copy
+    p = test1["para"]
+    sv = copy.deepcopy(test1["sv"])
+    sv.scxf = sv.scxf.copy(); sv.scxf[0, 0] = np.float32(0.2)           # far outside the model
+    with pytest.raises(gpu.DazimError) as e:
+        gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, sv, tables=test1_tables)
+    assert e.value.code == 1
+    sv = copy.deepcopy(test1["sv"])
+    sv.rcxf = sv.rcxf.copy(); sv.rcxf[0, 0, 0] = np.float32(0.2)
+    with pytest.raises(gpu.DazimError) as e:
+        gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, sv, tables=test1_tables)
+    assert e.value.code == 2
