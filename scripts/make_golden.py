@@ -16,8 +16,8 @@ import numpy as np
 
 REF = "/root/reference/example/test1_syn_foward"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "test1")
-PERIODS = (1, 9, 18, 27, 36)
-SOURCES_PER_PERIOD = 4      # first, then every 37th source
+PERIODS = (1, 2, 3, 4)          # T = 5..8 s: the span on which the shipped outputs are mutually consistent
+SOURCES_PER_PERIOD = 5      # first, then every 29th source
 
 
 def blocks(path):
@@ -48,7 +48,7 @@ def main():
         per = int(b[0].split()[3])
         k = seen.get(per, 0)
         seen[per] = k + 1
-        if per in PERIODS and k % 37 == 0 and k // 37 < SOURCES_PER_PERIOD:
+        if per in PERIODS and k % 29 == 0 and k // 29 < SOURCES_PER_PERIOD:
             keep.append(i)
     with open(os.path.join(OUT, "surfdata_subset.dat"), "w") as fi, open(os.path.join(OUT, "surfphase_subset.dat"), "w") as fg:
         for i in keep:
