@@ -197,9 +197,12 @@ def depthkernelTI(vel, depz, tRc, minthk, handle: Optional[Handle] = None):
 def surfdisp96(thk, vp, vs, rho, periods, handle: Optional[Handle] = None):
     """surfdisp96.f:52 for nprof profiles: inputs (nlayer,nprof) or (nlayer,), returns cg (kmax,nprof)."""
     h = handle or default_handle()
-    arrs = [np.asfortranarray(np.atleast_2d(np.asarray(x, np.float32).T).T if np.ndim(x) == 1 else x, np.float32)
-            for x in (thk, vp, vs, rho)]
-    arrs = [a.reshape(a.shape[0], -1, order="F") for a in arrs]
+    arrs = []
+    for x in (thk, vp, vs, rho):
+        x = np.asarray(x, np.float32)
+        if x.ndim == 1:
+            x = x[:, None]
+        arrs.append(np.asfortranarray(x))
     nl, npf = arrs[0].shape
     t = np.ascontiguousarray(periods, np.float64)
     cg = np.zeros((len(t), npf), np.float64, order="F")

@@ -130,3 +130,74 @@ def test_errors_mirror_reference_stops(gpu, test1, test1_tables):
         gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
                                 p.dvxd, p.dvzd, sv, tables=test1_tables)
     assert e.value.code == 2
+
+
+# ---------------------------------------------------------------------------------------------
+# Thomson-Haskell stage (K1 root search, K2 eigenfunction partials)
+def test_surfdisp96_kat_and_random_profiles(gpu, oracle):
+    rng = np.random.default_rng(3)
+    T = np.arange(5, 41, dtype=float)
+    profs = []
+    vs = [3.2, 3.4, 3.8, 4.2]; dep = [0, 10, 35, 60]
+    vp, rho = zip(*[oracle.brocher(v) for v in vs])
+    profs.append(oracle.refine_layer_mdl(2.0, dep, vp, vs, rho))
+    for _ in range(63):
+        v = np.sort(rng.uniform(2.6, 4.6, 4)).astype(np.float32)
+        if rng.random() < 0.3:
+            v[1], v[2] = v[2], v[1]          # low-velocity zone
+        vp, rho = zip(*[oracle.brocher(float(x)) for x in v])
+        profs.append(oracle.refine_layer_mdl(2.0, dep, vp, v, rho))
+    nl = profs[0]["rmax"]
+    arr = {k: np.asfortranarray(np.stack([p[k] for p in profs], 1).astype(np.float32)) for k in ("rthk", "rvp", "rvs", "rrho")}
+    cg = gpu.surfdisp96(arr["rthk"], arr["rvp"], arr["rvs"], arr["rrho"], T)
+    ref = np.stack([oracle.surfdisp96(p["rthk"], p["rvp"], p["rvs"], p["rrho"], T)[0] for p in profs], 1)
+    assert cg.shape == ref.shape == (36, 64)
+    kat = [3.04704, 3.06911, 3.09024, 3.11063, 3.13054, 3.15021, 3.16979, 3.18940]
+    assert np.abs(cg[:8, 0] - kat).max() < 5.1e-6
+    # float32-rounded roots: identical except where CUDA/glibc exp,sin,cos differ in the last ulp
+    # exactly at a rounding boundary (tolerance north_star: 1e-5 relative)
+    assert np.abs(cg - ref).max() <= 1e-5 * ref.max()
+    assert (cg != ref).mean() < 0.01
+
+
+def test_depthkernel_ti_vs_oracle(gpu, oracle, test1):
+    p = test1["para"]
+    pv, L = gpu.depthkernelTI(test1["vs"], test1["depz"], p.tRc, p.sublayers)
+    opv, oL = oracle.depthkernel_ti(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    assert np.array_equal(pv, opv), int((pv != opv).sum())       # 289 x 36 float32-rounded roots
+    scale = np.abs(oL).max()
+    assert np.abs(L - oL).max() <= 1e-5 * scale                     # tolerance of north_star
+    rel = np.abs(L - oL) / np.maximum(np.abs(oL), 1e-3 * scale)
+    assert rel.max() < 1e-4 and np.median(rel) < 1e-6
+    # and against the reference's own period_Azm_tomo.real (col 4)
+    g = test1["azm"]
+    mine = [pv[jj * p.nx + ii, tt] for tt in range(p.kmaxRc) for jj in range(1, p.ny - 1) for ii in range(1, p.nx - 1)]
+    assert np.abs(np.array(mine) - g[:, 3]).max() < 6e-6
+
+
+def test_depthkernel_fd_vs_oracle(gpu, oracle, test1):
+    p = test1["para"]
+    vs = np.asfortranarray(test1["vs"][3:9, 4:8, :])          # 24 nodes x 25 variants x 36 periods
+    pv, s1, s2, s3 = gpu.depthkernel(vs, test1["depz"], p.tRc, p.sublayers)
+    opv, o1, o2, o3, _ = oracle.depthkernel(vs, test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    assert np.array_equal(pv, opv)
+    for a, b in ((s1, o1), (s2, o2), (s3, o3)):
+        # (cg2-cg1)/(0.01*par): a single float32-ulp flip of a root moves an entry by ~2.4e-7/0.03;
+        # count them instead of hiding them
+        bad = np.abs(a - b) > 1e-5 * np.abs(b).max()
+        assert bad.mean() < 0.005, bad.mean()
+
+
+def test_forward_end_to_end_gpu_tables(gpu, oracle, test1):
+    """Whole hot path on the GPU (K1,K2,K0,K3,K4,K5), checked against the reference's own output."""
+    from dazimsurftomo_b200 import formats as fm
+    p = test1["para"]
+    r = gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, test1["sv"])
+    c = fm.forward_velocities(test1["sv"], r["dsurf"] + r["obsTaa"])
+    assert np.abs(c - test1["gold_c"]).max() < 1.5e-5
+    assert r["times"]["kernels_ms"] > 0
+    o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"],
+                      test1["gc"], test1["gs"], nthreads=4)
+    assert np.array_equal(r["dsurf"], o["dsurf"])
+    assert np.abs(r["obsTaa"] - o["obsTaa"]).max() <= 1e-5 * np.abs(o["obsTaa"]).max()
