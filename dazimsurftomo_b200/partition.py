@@ -1,0 +1,134 @@
+"""(period x source) partition of the forward-modelling path across ranks and the one
+exchange step before the solver.
+
+Units are the (period, source) pairs in the reference's loop order
+(FwdTraveltimeCPS.f90:464-465).  Every rank owns a contiguous range of units, hence a
+contiguous range of global row ids (`count1`, CalSurfGAniso_Joint.f90:693): no data-path
+collective is needed while G is being built.  Only "where the inversion step needs the full
+system" are the row blocks exchanged: an all-gather of per-rank sizes, then an all-gather of
+equal-size padded blocks (NCCL has no gather-v), trimmed on arrival.  Works on any
+torch.distributed backend (NCCL with CUDA tensors on the B200 box, gloo with CPU tensors in
+the CPU tests).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .formats import Survey
+
+
+def split_units(sv: Survey, world: int, align_periods: bool = False) -> List[int]:
+    """Unit boundaries [b_0=0, ..., b_world=nunit], contiguous, balanced by ray count.
+
+    align_periods=True snaps every boundary to a period boundary (BASELINE config 4:
+    "period-sharded")."""
+    offs = sv.row_offsets()
+    nunit = len(offs) - 1
+    pstart = np.concatenate([[0], np.cumsum(sv.nsrcsurf1.astype(np.int64))])
+    bounds = [0]
+    for r in range(1, world):
+        target = offs[-1] * r / world
+        b = int(np.searchsorted(offs, target))
+        if align_periods:
+            b = int(pstart[np.argmin(np.abs(offs[pstart] - target))])
+        b = min(max(b, bounds[-1]), nunit)
+        bounds.append(b)
+    bounds.append(nunit)
+    return bounds
+
+
+def sub_survey(sv: Survey, ub: int, ue: int):
+    """Survey restricted to units [ub, ue) (same loop order) and the global id of its first row."""
+    offs = sv.row_offsets()
+    out = copy.copy(sv)
+    kmax = sv.kmax
+    ns1 = np.zeros(kmax, np.int32)
+    sel = []   # (k, s) kept
+    u = 0
+    for k in range(kmax):
+        for s in range(int(sv.nsrcsurf1[k])):
+            if ub <= u < ue:
+                sel.append((k, s))
+                ns1[k] += 1
+            u += 1
+    nsrc = max(1, int(ns1.max()) if len(sel) else 1)
+    z2 = lambda a: np.zeros((nsrc, kmax), a.dtype, order="F")
+    periods, nrc1, scxf, sczf = z2(sv.periods), z2(sv.nrc1), z2(sv.scxf), z2(sv.sczf)
+    wavetype, igrt = z2(sv.wavetype), z2(sv.igrt)
+    rcxf = np.zeros((sv.nrcf, nsrc, kmax), sv.rcxf.dtype, order="F")
+    rczf = np.zeros((sv.nrcf, nsrc, kmax), sv.rczf.dtype, order="F")
+    pos = np.zeros(kmax, np.int64)
+    for k, s in sel:
+        j = int(pos[k]); pos[k] += 1
+        periods[j, k] = sv.periods[s, k]; nrc1[j, k] = sv.nrc1[s, k]
+        scxf[j, k] = sv.scxf[s, k]; sczf[j, k] = sv.sczf[s, k]
+        wavetype[j, k] = sv.wavetype[s, k]; igrt[j, k] = sv.igrt[s, k]
+        rcxf[:, j, k] = sv.rcxf[:, s, k]; rczf[:, j, k] = sv.rczf[:, s, k]
+    out.nsrc = nsrc
+    out.periods, out.nrc1, out.nsrcsurf1, out.scxf, out.sczf = periods, nrc1, ns1, scxf, sczf
+    out.wavetype, out.igrt, out.rcxf, out.rczf = wavetype, igrt, rcxf, rczf
+    row0, row1 = int(offs[min(ub, len(offs) - 1)]), int(offs[min(ue, len(offs) - 1)])
+    out.dall = row1 - row0
+    # dist/obsvel are in FILE order == loop order for period-sorted files
+    out.dist = sv.dist[row0:row1] if len(sv.dist) == sv.dall else sv.dist
+    out.obsvel = sv.obsvel[row0:row1] if len(sv.obsvel) == sv.dall else sv.obsvel
+    return out, row0
+
+
+def _all_gather_v(t, dist, group=None):
+    """All-gather of 1-D tensors of different length (same dtype/device): sizes first, then padded blocks."""
+    import torch
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(max(sizes), 1)
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    blocks = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(blocks, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(blocks, sizes)]), sizes
+
+
+def gather_rows(block: Dict[str, "object"], row0: int, group=None) -> Dict[str, "object"]:
+    """Exchange step: every rank contributes its CSR row block
+    {dsurf (rows,), nnz_row (rows,), col (nnz,), val (nnz,)} (torch tensors on one device) whose first
+    global row is row0; every rank receives the full system in the reference's COO convention
+    (rw, row 1-based = iw(2:nar+1), col 1-based) in global row order.  Ranks hold contiguous,
+    ascending row ranges, so concatenation in rank order IS global row order (bit-identical
+    for any world size)."""
+    import torch
+    import torch.distributed as dist
+    dsurf, _ = _all_gather_v(block["dsurf"], dist, group)
+    nnz_row, rsizes = _all_gather_v(block["nnz_row"].to(torch.int64), dist, group)
+    col, _ = _all_gather_v(block["col"], dist, group)
+    val, _ = _all_gather_v(block["val"], dist, group)
+    r0 = torch.tensor([row0], dtype=torch.int64, device=dsurf.device)
+    r0s = [torch.zeros_like(r0) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(r0s, r0, group=group)
+    exp = 0
+    for r, n in zip(r0s, rsizes):
+        if int(r.item()) != exp:
+            raise RuntimeError("row blocks are not contiguous in rank order")
+        exp += n
+    rows = torch.repeat_interleave(torch.arange(1, nnz_row.numel() + 1, device=nnz_row.device, dtype=torch.int64), nnz_row)
+    return dict(dsurf=dsurf, rw=val, col=col, row=rows.to(torch.int32), nar=int(val.numel()), nnz_row=nnz_row)
+
+
+def misfit_sums(obst, dsurf, group=None):
+    """mean / std / rms inputs of Main_Jt.f90:432-434 as three float64 partial sums reduced over ranks:
+    returns (n, sum(r), sum(r^2)) of r = obst - dsurf over all ranks."""
+    import torch
+    import torch.distributed as dist
+    r = (obst.to(torch.float64) - dsurf.to(torch.float64))
+    s = torch.stack([torch.tensor(float(r.numel()), dtype=torch.float64, device=r.device), r.sum(), (r * r).sum()])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        # fixed rank order: gather then sum on every rank identically (deterministic for any backend)
+        parts = [torch.zeros_like(s) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, s, group=group)
+        s = torch.stack(parts).sum(0)
+    return s

@@ -1,0 +1,114 @@
+"""N>1 host logic on CPU (gloo, world_size 2 and 3): the (period x source) partition covers
+every unit once with contiguous global rows, and the exchange step (all-gather-v of CSR row
+blocks + dsurf) rebuilds exactly the single-rank system.  The per-rank compute is the ORACLE
+here (tests may use it); on the GPU box the same partition/gather code runs over NCCL with
+the CUDA path (tests/test_gpu_parity.py::test_partition_matches_single)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, ROOT
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _load():
+    from dazimsurftomo_b200 import formats as fm
+    p = fm.read_para_forward(os.path.join(GOLD, "para.in"))
+    depz, vs = fm.read_model(os.path.join(GOLD, "MODVs.true"), p.nx, p.ny, p.nz)
+    sv = fm.read_surfdata(os.path.join(GOLD, "surfdata_subset.dat"), p.kmaxRc)
+    return p, depz, vs, sv
+
+
+def _tables(p, depz, vs):
+    from oracle import pyoracle as po
+    pv, L = po.depthkernel_ti(vs, depz, p.tRc, p.sublayers, nthreads=2)
+    nx, ny, nz = vs.shape
+    rng = np.random.default_rng(5)
+    # isotropic FD kernels are expensive on CPU; a smooth synthetic table exercises the same assembly code
+    sen = [np.asfortranarray(0.02 * rng.standard_normal((nx * ny, len(p.tRc), nz))) for _ in range(3)]
+    return dict(pvRc=pv, Lsen_Gsc=L, sen_vs=sen[0], sen_vp=sen[1], sen_rho=sen[2])
+
+
+def _worker(rank, world, port, align, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from dazimsurftomo_b200 import partition as pt
+    from oracle import pyoracle as po
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p, depz, vs, sv = _load()
+    tb = _tables(p, depz, vs)
+    b = pt.split_units(sv, world, align_periods=align)
+    sub, row0 = pt.sub_survey(sv, b[rank], b[rank + 1])
+    o = po.gbuild(2, vs, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sub, tables=tb)
+    nnz_row = np.bincount(o["row"] - 1, minlength=sub.dall).astype(np.int64)
+    blk = dict(dsurf=torch.from_numpy(o["dsurf"]), nnz_row=torch.from_numpy(nnz_row),
+               col=torch.from_numpy(o["col"].copy()), val=torch.from_numpy(o["rw"].copy()))
+    full = pt.gather_rows(blk, row0)
+    obst = torch.from_numpy(sub.dist / np.maximum(sub.obsvel, 1e-3))
+    ms = pt.misfit_sums(obst, blk["dsurf"])
+    if rank == 0:
+        q.put(dict(bounds=b, dsurf=full["dsurf"].numpy(), rw=full["rw"].numpy(), col=full["col"].numpy(),
+                   row=full["row"].numpy(), nar=full["nar"], misfit=ms.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,align", [(2, False), (3, True)])
+def test_partition_and_gather_match_single_rank(oracle, world, align):
+    import torch.multiprocessing as mp
+    from dazimsurftomo_b200 import partition as pt
+    p, depz, vs, sv = _load()
+    tb = _tables(p, depz, vs)
+    ref = oracle.gbuild(2, vs, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, tables=tb)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, align, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = q.get(timeout=600)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    b = got["bounds"]
+    assert b[0] == 0 and b[-1] == int(sv.nsrcsurf1.sum()) and all(b[i] <= b[i + 1] for i in range(world))
+    if align:
+        pstart = set(np.concatenate([[0], np.cumsum(sv.nsrcsurf1)]).tolist())
+        assert all(x in pstart for x in b)
+    # bit-identical to the single-rank result for any world size
+    assert got["nar"] == ref["nar"]
+    assert np.array_equal(got["dsurf"], ref["dsurf"])
+    assert np.array_equal(got["row"], ref["row"])
+    assert np.array_equal(got["col"], ref["col"])
+    assert np.array_equal(got["rw"], ref["rw"])
+    obst = sv.dist / np.maximum(sv.obsvel, 1e-3)
+    r = obst.astype(np.float64) - ref["dsurf"].astype(np.float64)
+    assert got["misfit"][0] == len(r)
+    assert abs(got["misfit"][1] - r.sum()) <= 1e-9 * max(1.0, abs(r.sum()))
+    assert abs(got["misfit"][2] - (r * r).sum()) <= 1e-9 * (r * r).sum()
+
+
+def test_sub_survey_row_ranges():
+    from dazimsurftomo_b200 import partition as pt
+    p, depz, vs, sv = _load()
+    offs = sv.row_offsets()
+    for world in (1, 2, 4, 8):
+        b = pt.split_units(sv, world)
+        tot = 0
+        for r in range(world):
+            sub, row0 = pt.sub_survey(sv, b[r], b[r + 1])
+            assert row0 == offs[b[r]] == tot
+            tot += sub.dall
+            assert int(sub.nrc1.sum()) == sub.dall
+        assert tot == sv.dall
+    # empty range
+    sub, row0 = pt.sub_survey(sv, 3, 3)
+    assert sub.dall == 0 and int(sub.nsrcsurf1.sum()) == 0
