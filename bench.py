@@ -94,14 +94,8 @@ def workload(args):
 
 def split_units(w, world):
     """Contiguous (period, source) ranges balanced by ray count (stage B)."""
-    offs = w.sv.row_offsets()
-    nunit = len(offs) - 1
-    bounds = [0]
-    for r in range(1, world):
-        target = offs[-1] * r / world
-        bounds.append(int(np.searchsorted(offs, target)))
-    bounds.append(nunit)
-    return bounds
+    from dazimsurftomo_b200 import partition
+    return partition.split_units(w.sv, world)
 
 
 def cpu_sample(w, nsrc, nthreads, mode=2):

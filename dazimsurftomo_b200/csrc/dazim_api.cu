@@ -16,8 +16,10 @@
 namespace dz {
 // kernels (dazim_fmm.cu / dazim_trace.cu / dazim_th.cu)
 cudaError_t upload_basis(const float* ub, const float* cb);
-cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, cudaStream_t st);
-cudaError_t launch_fmm(const FmmArgs& A, cudaStream_t st);
+cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, float* slow, cudaStream_t st);
+cudaError_t fmm_max_ctas(int hcap, int nsm, int* nctas);
+cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
+cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, float* ttn, int* nsts, cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
 cudaError_t launch_coef(int nx, int ny, int nz, const float* vels, float* ca, float* cr, cudaStream_t st);
 cudaError_t launch_assemble(const AsmArgs& A, bool fill, cudaStream_t st);
@@ -151,10 +153,12 @@ struct dazim_plan {
   int emit_all = 0;
   // device inputs
   DBuf<SrcRec> d_src; DBuf<RayRec> d_ray; DBuf<int> d_row_knumi;
-  DBuf<float> d_velv, d_veln_c, d_risti_c, d_risti_r;
+  DBuf<float> d_velv, d_veln_c, d_slow_c, d_risti_c, d_risti_r;
   DBuf<double> d_sen_vs, d_sen_vp, d_sen_rho; DBuf<float> d_lsen, d_vels, d_coe_a, d_coe_rho, d_gc, d_gs;
   // fmm / trace workspaces
-  DBuf<float> d_veln_r, d_ttn_c, d_ttn_r, d_hsk; DBuf<int> d_nsts_c, d_nsts_r, d_hsn;
+  DBuf<unsigned> d_E_c, d_E_r;            // per solve: encoded travel-time/status fields
+  DBuf<int> d_hpos_c, d_hpos_r, d_slot_of; DBuf<float> d_slow_r; DBuf<int2> d_hspill;   // per slot
+  int nctas = 0;
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
   int hcap = 512, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
@@ -275,18 +279,35 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   const long long nsrc = (long long)P->src.size();
 
   // ---- workspace sizing ----
-  P->hcap = std::min(1024, std::max(256, pow2ceil(2 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
-  if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, atoi(e));
-  P->hspill = 8 * (g.nnx + g.nnz) + 1024;
+  // heap capacity in shared memory: bounded by the largest narrow band (~3 x grid edge; measured max 2.7 x on
+  // S200), halved while that buys more solves in flight, never below hcap_min.
+  const long long npairs_all = (nsrc + 1) / 2;
+  int hneed = std::min(4096, std::max(256, pow2ceil(3 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
+  int hmin = std::min(hneed, 2048);
+  if (const char* e = getenv("DAZIM_HCAP_MIN")) hmin = std::max(64, std::min(hneed, atoi(e)));
+  P->hcap = hneed;
+  int nctas = 1;
+  CK(fmm_max_ctas(P->hcap, h->nsm, &nctas));
+  while (P->hcap > hmin && nctas < npairs_all) {
+    P->hcap /= 2;
+    CK(fmm_max_ctas(P->hcap, h->nsm, &nctas));
+  }
+  if (const char* e = getenv("DAZIM_HCAP")) { P->hcap = std::max(64, atoi(e)); CK(fmm_max_ctas(P->hcap, h->nsm, &nctas)); }
+  if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
+  P->hspill = std::max(0, 8 * (g.nnx + g.nnz) + 1024 - P->hcap) + 16;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  double budget = 0.55 * (double)free_b;
+  double budget = 0.60 * (double)free_b;
   if (const char* e = getenv("DAZIM_WS_GB")) budget = std::min(budget, atof(e) * 1e9);
-  const double per_src = (double)ncoarse * 8 + (double)REF_N * 12 + REF_LD * 4 + (double)P->hspill * 8 + 64;
-  long long maxB = (long long)(budget / per_src);
-  if (maxB < 1) maxB = 1;
+  const double per_src = (double)ncoarse * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
+  const double per_slot = (double)ncoarse * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
+  nctas = (int)std::min<long long>(nctas, std::max<long long>(npairs_all, 1));
+  long long maxB = (long long)((budget - 2.0 * nctas * per_slot) / per_src);
+  if (maxB < 2) maxB = 2;
   if (const char* e = getenv("DAZIM_BATCH")) maxB = std::max(1, atoi(e));
   maxB = std::min<long long>(maxB, std::max<long long>(nsrc, 1));
+  nctas = (int)std::min<long long>(nctas, (maxB + 1) / 2);
+  P->nctas = nctas;
   P->maxB = (int)maxB;
   // batches + per-batch ray lists (long rays first so that a warp holds rays of similar length)
   P->batch_src0.push_back(0);
@@ -384,14 +405,15 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
       UP(P->d_gs, Gs, (size_t)(p->nx - 2) * (p->ny - 2) * nlay);
     }
     CK(P->d_veln_c.alloc(ncoarse * p->kmaxRc));
-    const size_t B = (size_t)P->maxB;
-    CK(P->d_veln_r.alloc(B * REF_N));
-    CK(P->d_ttn_r.alloc(B * REF_N));
-    CK(P->d_nsts_r.alloc(B * REF_N));
-    CK(P->d_ttn_c.alloc(B * ncoarse));
-    CK(P->d_nsts_c.alloc(B * ncoarse));
-    CK(P->d_hsk.alloc(B * P->hspill));
-    CK(P->d_hsn.alloc(B * P->hspill));
+    CK(P->d_slow_c.alloc(ncoarse * p->kmaxRc));
+    const size_t B = (size_t)P->maxB, nslot = 2 * (size_t)P->nctas;
+    CK(P->d_E_r.alloc(B * REF_N));
+    CK(P->d_E_c.alloc(B * ncoarse));
+    CK(P->d_hpos_c.alloc(nslot * ncoarse));
+    CK(P->d_hpos_r.alloc(nslot * REF_N));
+    CK(P->d_slow_r.alloc(nslot * REF_N));
+    CK(P->d_hspill.alloc(nslot * P->hspill));
+    CK(P->d_slot_of.alloc(B));
     CK(P->d_map.alloc(nthr * ncell));
     CK(cudaMemsetAsync(P->d_map.p, 0, nthr * ncell * sizeof(unsigned short), st));
     CK(P->d_skey.alloc(nthr * P->cap));
@@ -437,7 +459,7 @@ static int plan_run(dazim_plan* P) {
   CK(cudaMemsetAsync(P->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
   CK(cudaMemsetAsync(P->d_icnt.p, 0, 4 * sizeof(int), st));
   CK(cudaEventRecord(P->ev[0], st));
-  CK(launch_dice_coarse(g, P->kmaxRc, P->d_velv.p, P->d_veln_c.p, st));
+  CK(launch_dice_coarse(g, P->kmaxRc, P->d_velv.p, P->d_veln_c.p, P->d_slow_c.p, st));
   T.n_launch++;
   if (P->mode != 0) {
     CK(launch_coef(P->nx, P->ny, P->nz, P->d_vels.p, P->d_coe_a.p, P->d_coe_rho.p, st));
@@ -454,18 +476,26 @@ static int plan_run(dazim_plan* P) {
     bev.push_back(e0); bev.push_back(e1); bev.push_back(e2);
     CK(cudaEventRecord(e0, st));
     FmmArgs F;
-    F.g = g; F.src = P->d_src.p + s0; F.nsrc = (int)(s1 - s0); F.velv = P->d_velv.p; F.veln_c = P->d_veln_c.p;
-    F.risti_c = P->d_risti_c.p; F.risti_r = P->d_risti_r.p + (size_t)s0 * REF_LD; F.veln_r = P->d_veln_r.p;
-    F.ttn_c = P->d_ttn_c.p; F.nsts_c = P->d_nsts_c.p; F.ttn_r = P->d_ttn_r.p; F.nsts_r = P->d_nsts_r.p;
-    F.hcap = P->hcap; F.hspill_k = P->d_hsk.p; F.hspill_n = P->d_hsn.p; F.hspill = P->hspill;
+    F.g = g; F.src = P->d_src.p + s0; F.nsrc = (int)(s1 - s0); F.velv = P->d_velv.p; F.slow_c = P->d_slow_c.p;
+    F.risti_c = P->d_risti_c.p; F.risti_r = P->d_risti_r.p + (size_t)s0 * REF_LD;
+    F.E_c = P->d_E_c.p; F.E_r = P->d_E_r.p; F.hpos_c = P->d_hpos_c.p; F.hpos_r = P->d_hpos_r.p;
+    F.slow_r = P->d_slow_r.p; F.hspill = P->d_hspill.p; F.hspill_n = P->hspill; F.hcap = P->hcap;
+    F.queue = P->d_icnt.p + 2; F.slot_of = P->d_slot_of.p;
     F.flags = P->d_icnt.p + 1; F.n_accept = P->d_counters.p + 1;
-    if (F.nsrc > 0) { CK(launch_fmm(F, st)); T.n_launch++; T.n_fmm_launch++; }
+    if (F.nsrc > 0) {
+      // far = 0xFFFFFFFF everywhere on the coarse grids of this batch; the refined boxes reset themselves
+      CK(cudaMemsetAsync(P->d_E_c.p, 0xFF, (size_t)F.nsrc * ncoarse * sizeof(unsigned), st));
+      CK(cudaMemsetAsync(P->d_icnt.p + 2, 0, sizeof(int), st));
+      CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + 1) / 2), st));
+      T.n_launch++; T.n_fmm_launch++;
+    }
     CK(cudaEventRecord(e1, st));
     if (r1 > r0) {
       CK(cudaMemsetAsync(P->d_icnt.p, 0, sizeof(int), st));
       TraceArgs A;
       A.g = g; A.src = P->d_src.p + s0; A.ray = P->d_ray.p + r0; A.nray = (int)(r1 - r0);
-      A.veln_c = P->d_veln_c.p; A.ttn_c = P->d_ttn_c.p; A.ttn_r = P->d_ttn_r.p; A.nsts_r = P->d_nsts_r.p;
+      A.veln_c = P->d_veln_c.p; A.ttn_c = reinterpret_cast<const float*>(P->d_E_c.p);
+      A.ttn_r = reinterpret_cast<const float*>(P->d_E_r.p);
       A.map = P->d_map.p; A.skey = P->d_skey.p; A.sval = P->d_sval.p; A.cap = P->cap; A.dsurf = P->d_dsurf.p;
       A.fp_off = P->d_fp_off.p; A.fp_cnt = P->d_fp_cnt.p; A.fp_cell = P->d_fp_cell.p; A.fp_fdm = P->d_fp_fdm.p;
       A.fp_fdmc = P->d_fp_fdmc.p; A.fp_fdms = P->d_fp_fdms.p; A.pool_cap = P->pool_cap;
@@ -730,10 +760,28 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
   const size_t nc = (size_t)P->g.nnx * P->g.nnz;
   cudaError_t e = cudaSuccess;
   if (veln && e == cudaSuccess) e = cudaMemcpy(veln, P->d_veln_c.p, nc * 4, cudaMemcpyDeviceToHost);
-  if (ttn && e == cudaSuccess) e = cudaMemcpy(ttn, P->d_ttn_c.p, nc * 4 * n, cudaMemcpyDeviceToHost);
-  if (nsts && e == cudaSuccess) e = cudaMemcpy(nsts, P->d_nsts_c.p, nc * 4 * n, cudaMemcpyDeviceToHost);
-  if (ttnr && e == cudaSuccess) e = cudaMemcpy(ttnr, P->d_ttn_r.p, (size_t)REF_N * 4 * n, cudaMemcpyDeviceToHost);
-  if (nstsr && e == cudaSuccess) e = cudaMemcpy(nstsr, P->d_nsts_r.p, (size_t)REF_N * 4 * n, cudaMemcpyDeviceToHost);
+  // decode K3's (E, hpos) encoding into the reference's (ttn, nsts) pair; hpos lives in the slot that solved s
+  {
+    std::vector<int> slot_of(n);
+    if (e == cudaSuccess) e = cudaMemcpy(slot_of.data(), P->d_slot_of.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    DBuf<float> d_t; DBuf<int> d_s;
+    if (e == cudaSuccess) e = d_t.alloc(std::max(nc, (size_t)REF_N));
+    if (e == cudaSuccess) e = d_s.alloc(std::max(nc, (size_t)REF_N));
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+      // the coarse hpos of a slot is only valid for the LAST solve it ran; the final coarse field is all alive anyway
+      e = launch_decode_status(P->d_E_c.p + (size_t)i * nc, nullptr, nc, d_t.p, d_s.p, h->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+      if (ttn && e == cudaSuccess) e = cudaMemcpy(ttn + (size_t)i * nc, d_t.p, nc * 4, cudaMemcpyDeviceToHost);
+      if (nsts && e == cudaSuccess) e = cudaMemcpy(nsts + (size_t)i * nc, d_s.p, nc * 4, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) break;
+      const bool own_slot = (2 * (size_t)P->nctas >= (size_t)n);   // one solve per slot: refined heap slots are intact
+      e = launch_decode_status(P->d_E_r.p + (size_t)i * REF_N,
+                               own_slot ? P->d_hpos_r.p + (size_t)slot_of[i] * REF_N : nullptr, REF_N, d_t.p, d_s.p, h->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+      if (ttnr && e == cudaSuccess) e = cudaMemcpy(ttnr + (size_t)i * REF_N, d_t.p, (size_t)REF_N * 4, cudaMemcpyDeviceToHost);
+      if (nstsr && e == cudaSuccess) e = cudaMemcpy(nstsr + (size_t)i * REF_N, d_s.p, (size_t)REF_N * 4, cudaMemcpyDeviceToHost);
+    }
+  }
   if (geom)
     for (int i = 0; i < n; ++i) {
       const SrcRec& s = P->src[i];

@@ -52,18 +52,22 @@ struct FmmArgs {
   const SrcRec* src;          // [nsrc]
   int nsrc;
   const float* velv;          // [nper][(nvz+2)(nvx+2)]
-  const float* veln_c;        // [nper][nnx*nnz]
+  const float* slow_c;        // [nper][nnx*nnz]  1/veln (fouds2's slown)
   const float* risti_c;       // [nnx]   earth*sin(gox+(ix-1)*dnx), host computed
   const float* risti_r;       // [nsrc][REF_LD]
-  float* veln_r;              // [nsrc][REF_N]   (ld REF_LD)
-  float* ttn_c;               // [nsrc][nnx*nnz]
-  int* nsts_c;                // [nsrc][nnx*nnz]
-  float* ttn_r;               // [nsrc][REF_N]
-  int* nsts_r;                // [nsrc][REF_N]
-  int hcap;                   // heap entries held in shared memory (entries 1..hcap-1)
-  float* hspill_k;            // [nsrc][hspill]  keys of spilled heap entries
-  int* hspill_n;              // [nsrc][hspill]
-  int hspill;
+  // per-solve fields (persist for the ray tracer).  One 32-bit word per node:
+  // alive = +t, close = t | sign bit, far = 0xFFFFFFFF (preset by the host)
+  unsigned* E_c;              // [nsrc][nnx*nnz]
+  unsigned* E_r;              // [nsrc][REF_N]   (ld REF_LD)
+  // per-slot workspaces (slot = resident half-warp = 2*blockIdx.x + half)
+  int* hpos_c;                // [nslot][nnx*nnz]  heap position of close nodes
+  int* hpos_r;                // [nslot][REF_N]
+  float* slow_r;              // [nslot][REF_N]    refined slowness
+  int2* hspill;               // [nslot][hspill_n] heap entries beyond the shared capacity
+  int hspill_n;
+  int hcap;                   // heap entries held in shared memory per solve (positions 1..hcap-1)
+  int* queue;                 // work counter (solve pairs)
+  int* slot_of;               // optional [nsrc]: slot that solved source s (test seam)
   int* flags;                 // bit4 (16): heap overflow
   unsigned long long* n_accept;  // total accepted nodes (statistics)
 };
@@ -74,9 +78,8 @@ struct TraceArgs {
   const RayRec* ray;        // batch rays in processing order (long rays first)
   int nray;
   const float* veln_c;      // [nper][nnx*nnz]
-  const float* ttn_c;       // [nsrc][nnx*nnz]
-  const float* ttn_r;       // [nsrc][REF_N]
-  const int* nsts_r;        // [nsrc][REF_N]
+  const float* ttn_c;       // [nsrc][nnx*nnz]  final coarse field (all alive => plain travel times)
+  const float* ttn_r;       // [nsrc][REF_N]    refined field in K3's encoding: alive iff sign bit clear
   // per-thread scratch
   unsigned short* map;      // [nthreads][ncell]
   int* skey;                // [nthreads][cap]

@@ -4,15 +4,26 @@
 // (module traveltime, CalSurfG.f90:234-893) step for step: the accepted value
 // of a node depends on the order in which the binary heap pops nodes
 // (SURVEY H1), so the heap discipline (addtree/downtree/updtree) is kept
-// exactly.  The parallelism is (a) across (period, source) solves -- one warp
-// per solve, up to 32 solves resident per SM, the whole batch in flight at
-// once -- and (b) inside one accept step: the four neighbour updates are
-// mutually independent (a node being updated is never "alive", and only alive
-// nodes are read), so the 32 lanes fetch the 4 x 8 stencil nodes in one
-// coalesced-by-line gather, 16 lanes solve the 4 x 4 quadrant quadratics, and
-// a shuffle-min collapses them.  The heap lives in shared memory as
-// (key, node) pairs so sift operations never touch global memory for keys;
-// levels beyond the shared capacity spill to a per-solve global array.
+// exactly.  The accept chain of one solve is inherently serial; the design
+// therefore minimises the LATENCY of one accept step and takes its throughput
+// from the (period x source) axis:
+//
+//  * one HALF-WARP (16 lanes) per solve, two solves per warp, persistent CTAs
+//    pulling solve pairs from a queue.  16 lanes is exactly the width of one
+//    accept step: 4 neighbours x 4 quadrant quadratics (fouds2), 4 x 4 stencil
+//    directions, 4 x 4 per-neighbour scalars.
+//  * the binary heap lives in shared memory as (key, node) pairs (one LDS.128
+//    fetches both children of a sift-down level); only positions beyond the
+//    shared capacity spill to a per-slot global array.
+//  * status and travel time share one 32-bit word per node ("E"): alive = +t,
+//    close (in the heap) = -t (sign bit), far = 0xFFFFFFFF.  A stencil gather is
+//    then 32 loads per accept instead of 64, and the final coarse field IS the
+//    travel-time array the ray tracer reads.
+//  * the stencil gather for the four neighbours is ISSUED BEFORE the heap pop,
+//    so its global-memory latency hides behind the shared-memory sift-down.
+//    Heap positions of the four neighbours are loaded at the same time and
+//    patched in registers while the pop / earlier sift-ups move entries, so no
+//    global read-after-write sits on the critical path.
 #include "dazim_dev.h"
 
 namespace dz {
@@ -29,8 +40,9 @@ cudaError_t upload_basis(const float* ub, const float* cb) {
 // ---------------------------------------------------------------------------
 // K0: coarse dicing, one thread per propagation node, one grid.y per period.
 // velv: [nper][(nvz+2)*(nvx+2)] float, velv(i,j) at i*(nvx+2)+j  (gridder, CalSurfG.f90:1450-1457)
-// veln: [nper][nnx*nnz] column-major (z fastest)
-__global__ void k_dice_coarse(GridC g, const float* __restrict__ velv, float* __restrict__ veln) {
+// veln: [nper][nnx*nnz] column-major (z fastest); slow = 1/veln (fouds2's slown, CalSurfG.f90:583)
+__global__ void k_dice_coarse(GridC g, const float* __restrict__ velv, float* __restrict__ veln,
+                              float* __restrict__ slow) {
   const int per = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.nnx * g.nnz) return;
@@ -52,83 +64,137 @@ __global__ void k_dice_coarse(GridC g, const float* __restrict__ velv, float* __
     sumi = sumi + c_cbasis[(l - 1) * 4 + (i1 - 1)] * sumj;
   }
   veln[(size_t)per * g.nnx * g.nnz + idx] = sumi;
+  slow[(size_t)per * g.nnx * g.nnz + idx] = 1.0f / sumi;
 }
 
 // ---------------------------------------------------------------------------
 // K3
 
+#define E_FAR 0xFFFFFFFFu     // never touched (nsts = -1)
+#define E_OUT 0xFFFFFFFEu     // outside the grid (register-only sentinel)
+#define E_SIGN 0x80000000u    // close: trial value with the sign bit set (nsts > 0)
 
+// Heap entries are (key bits, node id) with node id = (ix << 16) | iz, 0-based (grid edges <= 32767
+// like the reference's INTEGER*2 heap pointers, CalSurfG.f90:239).
 struct Heap {
-  float* sk; int* sn;          // shared part
-  float* gk; int* gn;          // spill part
+  int2* sm;            // shared part, positions 1..hcap-1 (entry 0 unused)
+  int2* gl;            // spill part, positions hcap.. (per slot)
   int hcap, hspill;
   int ntr;
-  __device__ __forceinline__ float key(int p) const { return p < hcap ? sk[p] : gk[p - hcap]; }
-  __device__ __forceinline__ int node(int p) const { return p < hcap ? sn[p] : gn[p - hcap]; }
-  __device__ __forceinline__ void set(int p, float k, int n) {
-    if (p < hcap) { sk[p] = k; sn[p] = n; } else { gk[p - hcap] = k; gn[p - hcap] = n; }
+  int ld;              // leading dimension of the grid being marched (node id -> offset)
+  __device__ __forceinline__ int off(int id) const { return (id >> 16) * ld + (id & 0xffff); }
+  __device__ __forceinline__ int2 get(int p) const { return p < hcap ? sm[p] : gl[p - hcap]; }
+  __device__ __forceinline__ void put(int p, int2 v) {
+    if (p < hcap) sm[p] = v; else gl[p - hcap] = v;
+  }
+  // both children of a sift-down level; p is even
+  __device__ __forceinline__ void get2(int p, int2& a, int2& b) const {
+    if (p + 1 < hcap) {
+      const int4 v = *reinterpret_cast<const int4*>(sm + p);
+      a = make_int2(v.x, v.y);
+      b = make_int2(v.z, v.w);
+    } else {
+      a = get(p);
+      b = get(p + 1);
+    }
   }
 };
 
-// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890)
-__device__ __forceinline__ void sift_up(Heap& h, int* __restrict__ nsts, int tpc, float k, int n) {
+// Register copies of the heap positions of the four neighbours of the node being accepted
+// (ids cid[q], -1 = none).  Every heap move records the node's new position in hpos[] (the
+// reference's nsts back pointer) and patches these copies, so the accept step never has to
+// read a position back from global memory.
+struct Track {
+  int cid[4];
+  int hp[4];
+};
+
+#define HEAP_MOVE(h, pos, ent)                                  \
+  do {                                                          \
+    (h).put((pos), (ent));                                      \
+    hpos[(h).off((ent).y)] = (pos);                             \
+    _Pragma("unroll") for (int q_ = 0; q_ < 4; ++q_)            \
+      if ((ent).y == tk.cid[q_]) tk.hp[q_] = (pos);             \
+  } while (0)
+
+// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).  Parent and
+// grandparent are fetched together so the shared-memory latency is paid once.
+__device__ __forceinline__ void sift_up(Heap& h, int* __restrict__ hpos, int tpc, float k, int n, Track& tk) {
   int tpp = tpc >> 1;
+  int2 par = make_int2(0, 0), gpar = make_int2(0, 0);
+  if (tpp > 0) par = h.get(tpp);
+  if ((tpp >> 1) > 0) gpar = h.get(tpp >> 1);
   while (tpp > 0) {
-    const float kp = h.key(tpp);
-    if (k < kp) {
-      const int np = h.node(tpp);
-      h.set(tpc, kp, np);
-      nsts[np] = tpc;
+    if (k < __int_as_float(par.x)) {
+      HEAP_MOVE(h, tpc, par);
       tpc = tpp;
       tpp = tpc >> 1;
+      par = gpar;
+      if ((tpp >> 1) > 0) gpar = h.get(tpp >> 1);
     } else {
       break;
     }
   }
-  h.set(tpc, k, n);
-  nsts[n] = tpc;
+  const int2 me = make_int2(__float_as_int(k), n);
+  HEAP_MOVE(h, tpc, me);
 }
 
-// downtree (CalSurfG.f90:786-855)
-__device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ nsts) {
+// downtree (CalSurfG.f90:786-855).  While one level is being decided, both pairs of
+// grandchildren are already being fetched (4 consecutive entries), which takes the
+// shared-memory latency off the level-to-level dependency chain.
+__device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, Track& tk) {
   if (h.ntr == 1) { h.ntr = 0; return; }
-  const float k = h.key(h.ntr);
-  const int n = h.node(h.ntr);
+  const int2 last = h.get(h.ntr);
+  const float k = __int_as_float(last.x);
   h.ntr -= 1;
   const int ntr = h.ntr;
   int tpp = 1, tpc = 2;
+  int2 c0 = make_int2(0, 0), c1 = make_int2(0, 0);
+  if (tpc < ntr) h.get2(tpc, c0, c1);
   while (tpc < ntr) {
-    float rd1 = h.key(tpc);
-    const float rd2 = h.key(tpc + 1);
-    if (rd1 > rd2) { tpc = tpc + 1; rd1 = rd2; }
+    const int g = 2 * tpc;                 // grandchildren live at g .. g+3
+    const bool pf = (g + 3 < h.hcap);
+    int4 ga = make_int4(0, 0, 0, 0), gb = ga;
+    if (pf) {
+      ga = *reinterpret_cast<const int4*>(h.sm + g);
+      gb = *reinterpret_cast<const int4*>(h.sm + g + 2);
+    }
+    float rd1 = __int_as_float(c0.x);
+    const float rd2 = __int_as_float(c1.x);
+    const bool right = rd1 > rd2;
+    if (right) { tpc = tpc + 1; rd1 = rd2; c0 = c1; }
     if (rd1 < k) {
-      const int nc = h.node(tpc);
-      h.set(tpp, rd1, nc);
-      nsts[nc] = tpp;
+      HEAP_MOVE(h, tpp, c0);
       tpp = tpc;
       tpc = 2 * tpp;
+      if (tpc < ntr) {
+        if (pf) {
+          const int4 pk = right ? gb : ga;
+          c0 = make_int2(pk.x, pk.y);
+          c1 = make_int2(pk.z, pk.w);
+        } else {
+          h.get2(tpc, c0, c1);
+        }
+      }
     } else {
       tpc = ntr + 1;
     }
   }
   if (tpc == ntr) {
-    const float rd1 = h.key(tpc);
-    if (rd1 < k) {
-      const int nc = h.node(tpc);
-      h.set(tpp, rd1, nc);
-      nsts[nc] = tpp;
+    const int2 cc = h.get(tpc);
+    if (__int_as_float(cc.x) < k) {
+      HEAP_MOVE(h, tpp, cc);
       tpp = tpc;
     }
   }
-  h.set(tpp, k, n);
-  nsts[n] = tpp;
+  HEAP_MOVE(h, tpp, last);
 }
 
 // One quadrant of fouds2 (CalSurfG.f90:634-723): returns trial time, valid flag through ok.
 __device__ __forceinline__ float quadrant(int sj, int sj2, float tj, float tj2, int sk, int sk2, float tk,
                                           float tk2, float slown, float ri, float risti, float dnx,
                                           float dnz, bool& ok) {
-  // sj/sk: status of first neighbours (-2 = outside grid); sj2/sk2: second neighbours
+  // sj/sk: status of first neighbours (0 alive, -2 = outside grid); sj2/sk2: second neighbours
   int swj = -1, swk = -1;
   if (sj2 == 0 && sj == 0 && tj > tj2) swj = 0;
   if (sk2 == 0 && sk == 0 && tk > tk2) swk = 0;
@@ -215,258 +281,329 @@ __device__ __forceinline__ float quadrant(int sj, int sj2, float tj, float tj2, 
   return (tref + tdsh) / tdiv;
 }
 
-// The narrow-band march (travel's DO WHILE, CalSurfG.f90:356-456) on one grid.
-// urg==1: refined grid with the early exit of :362-382.
-__device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const float dnx, const float dnz,
-                      const float earth, const float* __restrict__ veln, const float* __restrict__ risti_tab,
-                      float* __restrict__ ttn, int* __restrict__ nsts, const int urg, const bool ex_l,
-                      const bool ex_r, const bool ex_t, const bool ex_b, const int lane,
-                      unsigned long long& nacc, int& overflow) {
-  const int nb = lane >> 3;          // neighbour 0..3: (iz,ix-1),(iz,ix+1),(iz-1,ix),(iz+1,ix)
-  const int m = lane & 7;            // stencil slot around that neighbour
-  // stencil slot offsets: 0:(0,-1) 1:(0,-2) 2:(0,+1) 3:(0,+2) 4:(-1,0) 5:(-2,0) 6:(+1,0) 7:(+2,0)
-  const int mdx = (m < 4) ? ((m & 2) ? 1 : -1) * ((m & 1) ? 2 : 1) : 0;
-  const int mdz = (m >= 4) ? ((m & 2) ? 1 : -1) * ((m & 1) ? 2 : 1) : 0;
+__device__ __forceinline__ int e_status(unsigned e) { return e == E_OUT ? -2 : ((int)e >= 0 ? 0 : 1); }
+
+// The narrow-band march (travel's DO WHILE, CalSurfG.f90:356-456) on one grid,
+// executed by one half-warp: sl = lane within the half, hm = its shuffle mask.
+// URG==1: refined grid with the early exit of :362-382.
+template <int URG>
+__device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const float dnx,
+                      const float dnz, const float earth, const float* __restrict__ slow,
+                      const float* __restrict__ risti_tab, unsigned* __restrict__ E, int* __restrict__ hpos,
+                      const bool ex_l, const bool ex_r, const bool ex_t, const bool ex_b, const int sl,
+                      const unsigned hm, unsigned long long& nacc, int& overflow) {
+  const int nb = sl >> 2;            // neighbour 0..3: (iz,ix-1),(iz,ix+1),(iz-1,ix),(iz+1,ix)
+  const int d = sl & 3;              // stencil direction of this lane: x-1, x+1, z-1, z+1
   const int ndx = (nb == 0) ? -1 : (nb == 1 ? 1 : 0);
   const int ndz = (nb == 2) ? -1 : (nb == 3 ? 1 : 0);
+  const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0);
+  const int ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+  const int base = sl & 12;
+  Track tk;
   while (h.ntr > 0) {
-    const int pn = h.node(1);
-    const int ix = pn / ld + 1, iz = pn % ld + 1;
-    if (urg == 1) {
-      if ((ix == 1 && ex_l) || (ix == nnx && ex_r) || (iz == 1 && ex_t) || (iz == nnz && ex_b)) {
-        nsts[pn] = 0;
-        break;
-      }
+    const int2 root = h.sm[1];
+    const int ix = root.y >> 16, iz = root.y & 0xffff;     // 0-based
+    const int pn = ix * ld + iz;
+    // the popped node becomes alive with its trial value (= its heap key)
+    E[pn] = (unsigned)root.x & ~E_SIGN;
+    if (URG == 1) {
+      if ((ix == 0 && ex_l) || (ix == nnx - 1 && ex_r) || (iz == 0 && ex_t) || (iz == nnz - 1 && ex_b)) break;
     }
-    nsts[pn] = 0;
     ++nacc;
-    pop_root(h, nsts);
-    // ---- gather the 4 x 8 stencil ----
+    // ---- issue the gather: 4 neighbours x 4 directions x (first, second) stencil node ----
     const int cx = ix + ndx, cz = iz + ndz;            // neighbour handled by this lane group
-    const bool cin = (cx >= 1 && cx <= nnx && cz >= 1 && cz <= nnz);
-    const int sx = cx + mdx, sz = cz + mdz;
-    int st = -2;
-    float tt = 0.0f;
-    if (cin && sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz) {
-      const int o = (sx - 1) * ld + (sz - 1);
-      st = nsts[o];
-      tt = ttn[o];
+    const bool cin = (cx >= 0 && cx < nnx && cz >= 0 && cz < nnz);
+    const int co = cx * ld + cz;
+    unsigned e1 = E_OUT, e2 = E_OUT;
+    {
+      const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+      if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[s1x * ld + s1z];
+      if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[s2x * ld + s2z];
     }
-    int cst = -2;
-    float slown = 0.0f, risti = 0.0f;
+    unsigned cval = 0;                                 // d=0: E[c], 1: hpos[c], 2: slowness, 3: R sin(theta)
     if (cin) {
-      const int o = (cx - 1) * ld + (cz - 1);
-      cst = nsts[o];
-      slown = 1.0f / veln[o];
-      risti = risti_tab[cx - 1];
+      if (d == 0) cval = E[co];
+      else if (d == 1) cval = (unsigned)hpos[co];
+      else if (d == 2) cval = __float_as_uint(slow[co]);
+      else cval = __float_as_uint(risti_tab[cx]);
     }
-    // ---- 16 quadrant solves: lane q = nb*8 + (jside*2+kside) uses slots {2*jside, 2*jside+1, 4+2*kside, 5+2*kside}
-    const int base = lane & 24;
-    const int js = (lane >> 1) & 1, ks = lane & 1;
-    const int sj = __shfl_sync(0xffffffffu, st, base + 2 * js);
-    const int sj2 = __shfl_sync(0xffffffffu, st, base + 2 * js + 1);
-    const int sk = __shfl_sync(0xffffffffu, st, base + 4 + 2 * ks);
-    const int sk2 = __shfl_sync(0xffffffffu, st, base + 5 + 2 * ks);
-    const float tj = __shfl_sync(0xffffffffu, tt, base + 2 * js);
-    const float tj2 = __shfl_sync(0xffffffffu, tt, base + 2 * js + 1);
-    const float tk = __shfl_sync(0xffffffffu, tt, base + 4 + 2 * ks);
-    const float tk2 = __shfl_sync(0xffffffffu, tt, base + 5 + 2 * ks);
+    // ---- pop the root while the loads are in flight; track the neighbours' heap positions ----
+    tk.cid[0] = (ix > 0) ? (((ix - 1) << 16) | iz) : -1;
+    tk.cid[1] = (ix + 1 < nnx) ? (((ix + 1) << 16) | iz) : -1;
+    tk.cid[2] = (iz > 0) ? ((ix << 16) | (iz - 1)) : -1;
+    tk.cid[3] = (iz + 1 < nnz) ? ((ix << 16) | (iz + 1)) : -1;
+    tk.hp[0] = tk.hp[1] = tk.hp[2] = tk.hp[3] = -1;
+    pop_root(h, hpos, tk);
+    // ---- neighbour scalars ----
+    const unsigned cE = __shfl_sync(hm, cval, base + 0, 16);
+    const float slown = __uint_as_float(__shfl_sync(hm, cval, base + 2, 16));
+    const float risti = __uint_as_float(__shfl_sync(hm, cval, base + 3, 16));
+    const int cst = !cin ? -2 : (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
+    // ---- 16 quadrant solves: lane (nb, js, ks) pairs x-direction js with z-direction 2+ks ----
+    const int js = (sl >> 1) & 1, ks = sl & 1;
+    const unsigned ej1 = __shfl_sync(hm, e1, base + js, 16), ej2 = __shfl_sync(hm, e2, base + js, 16);
+    const unsigned ek1 = __shfl_sync(hm, e1, base + 2 + ks, 16), ek2 = __shfl_sync(hm, e2, base + 2 + ks, 16);
     bool ok = false;
-    float trav = quadrant(sj, sj2, tj, tj2, sk, sk2, tk, tk2, slown, earth, risti, dnx, dnz, ok);
-    if (!ok || (lane & 4)) trav = __int_as_float(0x7f800000);  // +inf: lanes 4..7 of each group idle
-    trav = fminf(trav, __shfl_xor_sync(0xffffffffu, trav, 1));
-    trav = fminf(trav, __shfl_xor_sync(0xffffffffu, trav, 2));
+    float trav = quadrant(e_status(ej1), e_status(ej2), __uint_as_float(ej1), __uint_as_float(ej2), e_status(ek1),
+                          e_status(ek2), __uint_as_float(ek1), __uint_as_float(ek2), slown, earth, risti, dnx, dnz, ok);
+    if (!ok) trav = __int_as_float(0x7f800000);
+    trav = fminf(trav, __shfl_xor_sync(hm, trav, 1, 16));
+    trav = fminf(trav, __shfl_xor_sync(hm, trav, 2, 16));
+    int qst[4];
+    float qt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      qst[q] = __shfl_sync(hm, cst, q * 4, 16);
+      qt[q] = __shfl_sync(hm, trav, q * 4, 16);
+      const int hl = (int)__shfl_sync(hm, cval, q * 4 + 1, 16);
+      if (tk.hp[q] < 0) tk.hp[q] = hl;
+    }
     // ---- apply in the reference order: x-1, x+1, z-1, z+1 ----
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int qst = __shfl_sync(0xffffffffu, cst, q * 8);
-      const float qt = __shfl_sync(0xffffffffu, trav, q * 8);
-      if (qst == -2 || qst == 0) continue;
+      if (qst[q] == -2 || qst[q] == 0) continue;
       const int qx = ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0));
       const int qz = iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0));
-      const int o = (qx - 1) * ld + (qz - 1);
-      ttn[o] = qt;
-      if (qst == -1) {
+      E[qx * ld + qz] = __float_as_uint(qt[q]) | E_SIGN;
+      int pos = tk.hp[q];
+      if (qst[q] == -1) {
         if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; return; }
         h.ntr += 1;
-        sift_up(h, nsts, h.ntr, qt, o);
-      } else {
-        // position may have moved while earlier neighbours sifted: re-read it
-        sift_up(h, nsts, nsts[o], qt, o);
+        pos = h.ntr;
       }
+      sift_up(h, hpos, pos, qt[q], tk.cid[q], tk);
     }
   }
+}
+
+// refined velocity node (bsplrefine, CalSurfG.f90:1559-1590); idm1/idm2 1-based refined indices
+__device__ __forceinline__ float refined_vel(const GridC& g, const SrcRec& sr, const float* __restrict__ vv,
+                                             int idm1, int idm2) {
+  const int ldv = g.nvx + 2;
+  const int nrxr = g.gdx * g.sgdl, nrzr = g.gdz * g.sgdl;
+  const int origx = (sr.vnl - 1) * g.sgdl + 1, origz = (sr.vnt - 1) * g.sgdl + 1;
+  const int st1 = idm1 + origz - 1, st2 = idm2 + origx - 1;
+  int i = (st1 - 1) / nrzr + 1, k = (st1 - 1) % nrzr + 1;
+  if (i > g.nvz - 1) { i = g.nvz - 1; k = nrzr + 1; }
+  int j = (st2 - 1) / nrxr + 1, l = (st2 - 1) % nrxr + 1;
+  if (j > g.nvx - 1) { j = g.nvx - 1; l = nrxr + 1; }
+  float sum[4];
+#pragma unroll
+  for (int i1 = 1; i1 <= 4; ++i1) {
+    float sacc = 0.0f;
+#pragma unroll
+    for (int j1 = 1; j1 <= 4; ++j1)
+      sacc = sacc + c_ubasis[(l - 1) * 4 + (j1 - 1)] * vv[(i - 2 + i1) * ldv + (j - 2 + j1)];
+    sum[i1 - 1] = c_ubasis[(k - 1) * 4 + (i1 - 1)] * sacc;
+  }
+  return sum[0] + sum[1] + sum[2] + sum[3];
 }
 
 __global__ void __launch_bounds__(32) k_fmm(FmmArgs A) {
-  extern __shared__ unsigned char smem_raw[];
-  const int s = blockIdx.x;
-  if (s >= A.nsrc) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
+  const int half = lane >> 4, sl = lane & 15;
+  const unsigned hm = 0xffffu << (half * 16);
   const GridC& g = A.g;
-  const SrcRec sr = A.src[s];
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;
+  const int slot = blockIdx.x * 2 + half;
   Heap h;
-  h.sk = reinterpret_cast<float*>(smem_raw);
-  h.sn = reinterpret_cast<int*>(smem_raw + sizeof(float) * A.hcap);
-  h.gk = A.hspill_k + (size_t)s * A.hspill;
-  h.gn = A.hspill_n + (size_t)s * A.hspill;
+  h.sm = reinterpret_cast<int2*>(smem_raw) + (size_t)half * A.hcap;
+  h.gl = A.hspill + (size_t)slot * A.hspill_n;
   h.hcap = A.hcap;
-  h.hspill = A.hspill;
-  h.ntr = 0;
+  h.hspill = A.hspill_n;
+  int* hpos_c = A.hpos_c + (size_t)slot * ncoarse;
+  int* hpos_r = A.hpos_r + (size_t)slot * REF_N;
+  float* slow_r = A.slow_r + (size_t)slot * REF_N;
   unsigned long long nacc = 0;
   int overflow = 0;
 
-  float* veln_r = A.veln_r + (size_t)s * REF_N;
-  float* ttn_r = A.ttn_r + (size_t)s * REF_N;
-  int* nsts_r = A.nsts_r + (size_t)s * REF_N;
-  const size_t ncoarse = (size_t)g.nnx * g.nnz;
-  float* ttn_c = A.ttn_c + (size_t)s * ncoarse;
-  int* nsts_c = A.nsts_c + (size_t)s * ncoarse;
-  const float* veln_c = A.veln_c + (size_t)sr.period * ncoarse;
-  const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
-  const int ldv = g.nvx + 2;
+  // first pair = own CTA index, later pairs from the queue (so a grid that covers all pairs is one pair per CTA)
+  for (int pair = blockIdx.x;;) {
+    __syncwarp();
+    if (pair < 0) {
+      if (lane == 0) pair = gridDim.x + atomicAdd(A.queue, 1);
+      pair = __shfl_sync(0xffffffffu, pair, 0);
+    }
+    if (pair * 2 >= A.nsrc) break;
+    const int s = pair * 2 + half;
+    const bool active = (s < A.nsrc) && !overflow;
+    if (active) {
+      const SrcRec sr = A.src[s];
+      if (A.slot_of && sl == 0) A.slot_of[s] = slot;
+      unsigned* E_r = A.E_r + (size_t)s * REF_N;
+      unsigned* E_c = A.E_c + (size_t)s * ncoarse;
+      const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
+      const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
+      h.ntr = 0;
 
-  // ---- refined velocity nodes (bsplrefine, CalSurfG.f90:1559-1590) + status reset ----
-  const int nrxr = g.gdx * g.sgdl, nrzr = g.gdz * g.sgdl;
-  const int origx = (sr.vnl - 1) * g.sgdl + 1, origz = (sr.vnt - 1) * g.sgdl + 1;
-  for (int e = lane; e < sr.nnxr * sr.nnzr; e += 32) {
-    const int idm1 = e % sr.nnzr + 1, idm2 = e / sr.nnzr + 1;
-    const int st1 = idm1 + origz - 1, st2 = idm2 + origx - 1;
-    int i = (st1 - 1) / nrzr + 1, k = (st1 - 1) % nrzr + 1;
-    if (i > g.nvz - 1) { i = g.nvz - 1; k = nrzr + 1; }
-    int j = (st2 - 1) / nrxr + 1, l = (st2 - 1) % nrxr + 1;
-    if (j > g.nvx - 1) { j = g.nvx - 1; l = nrxr + 1; }
-    float sum[4];
-#pragma unroll
-    for (int i1 = 1; i1 <= 4; ++i1) {
-      float sacc = 0.0f;
-#pragma unroll
-      for (int j1 = 1; j1 <= 4; ++j1)
-        sacc = sacc + c_ubasis[(l - 1) * 4 + (j1 - 1)] * vv[(i - 2 + i1) * ldv + (j - 2 + j1)];
-      sum[i1 - 1] = c_ubasis[(k - 1) * 4 + (i1 - 1)] * sacc;
-    }
-    const int o = (idm2 - 1) * REF_LD + (idm1 - 1);
-    veln_r[o] = sum[0] + sum[1] + sum[2] + sum[3];
-    nsts_r[o] = -1;
-  }
-  __syncwarp();
+      // ---- refined slowness nodes (bsplrefine) + status reset ----
+      for (int e = sl; e < sr.nnxr * sr.nnzr; e += 16) {
+        const int idm1 = e % sr.nnzr + 1, idm2 = e / sr.nnzr + 1;
+        const int o = (idm2 - 1) * REF_LD + (idm1 - 1);
+        slow_r[o] = 1.0f / refined_vel(g, sr, vv, idm1, idm2);
+        E_r[o] = E_FAR;
+      }
+      __syncwarp(hm);
 
-  // ---- source cell initialisation (travel, CalSurfG.f90:324-345) ----
-  {
-    const int isx = sr.isx_r, isz = sr.isz_r;
-    float vss[2][2];
+      // ---- source cell initialisation (travel, CalSurfG.f90:324-345) ----
+      {
+        const int isx = sr.isx_r, isz = sr.isz_r;
+        float vss[2][2];
 #pragma unroll
-    for (int i = 1; i <= 2; ++i)
+        for (int i = 1; i <= 2; ++i)
 #pragma unroll
-      for (int j = 1; j <= 2; ++j) vss[i - 1][j - 1] = veln_r[(isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1)];
-    const float dsx = sr.dsx_r, dsz = sr.dsz_r;
-    float vsrc = 0.0f;
+          for (int j = 1; j <= 2; ++j) vss[i - 1][j - 1] = refined_vel(g, sr, vv, isz - 1 + j, isx - 1 + i);
+        const float dsx = sr.dsx_r, dsz = sr.dsz_r;
+        float vsrc = 0.0f;
 #pragma unroll
-    for (int i = 1; i <= 2; ++i)
+        for (int i = 1; i <= 2; ++i)
 #pragma unroll
-      for (int j = 1; j <= 2; ++j) {
-        const float produ = (1.0f - fabsf(((float)(i - 1) * sr.dnxr - dsx) / sr.dnxr)) *
-                            (1.0f - fabsf(((float)(j - 1) * sr.dnzr - dsz) / sr.dnzr));
-        vsrc = vsrc + vss[i - 1][j - 1] * produ;
+          for (int j = 1; j <= 2; ++j) {
+            const float produ = (1.0f - fabsf(((float)(i - 1) * sr.dnxr - dsx) / sr.dnxr)) *
+                                (1.0f - fabsf(((float)(j - 1) * sr.dnzr - dsz) / sr.dnzr));
+            vsrc = vsrc + vss[i - 1][j - 1] * produ;
+          }
+        Track tk;
+        tk.cid[0] = tk.cid[1] = tk.cid[2] = tk.cid[3] = -1;
+        h.ld = REF_LD;
+#pragma unroll
+        for (int i = 1; i <= 2; ++i)
+#pragma unroll
+          for (int j = 1; j <= 2; ++j) {
+            const float ax = dsx - (float)(i - 1) * sr.dnxr;
+            const float az = dsz - (float)(j - 1) * sr.dnzr;
+            const float ds = sqrtf(ax * ax + az * az);
+            const float t0 = 2.0f * ds / (vss[i - 1][j - 1] + vsrc);
+            const int o = (isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1);
+            E_r[o] = __float_as_uint(t0) | E_SIGN;
+            h.ntr += 1;
+            sift_up(h, hpos_r, h.ntr, t0, ((isx - 1 + i - 1) << 16) | (isz - 1 + j - 1), tk);
+          }
       }
-#pragma unroll
-    for (int i = 1; i <= 2; ++i)
-#pragma unroll
-      for (int j = 1; j <= 2; ++j) {
-        const float ax = dsx - (float)(i - 1) * sr.dnxr;
-        const float az = dsz - (float)(j - 1) * sr.dnzr;
-        const float ds = sqrtf(ax * ax + az * az);
-        const float t0 = 2.0f * ds / (vss[i - 1][j - 1] + vsrc);
-        const int o = (isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1);
-        ttn_r[o] = t0;
-        h.ntr += 1;
-        sift_up(h, nsts_r, h.ntr, t0, o);
-      }
-  }
-  // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
-  march(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, veln_r, A.risti_r + (size_t)s * REF_LD, ttn_r,
-        nsts_r, 1, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1, sr.vnb != sr.nnzr, lane, nacc, overflow);
-  __syncwarp();
+      // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
+      h.ld = REF_LD;
+      march<1>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
+               A.risti_r + (size_t)s * REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
+               sr.vnb != sr.nnzr, sl, hm, nacc, overflow);
+      __syncwarp(hm);
 
-  // ---- hand-off to the coarse grid (FwdTraveltimeCPS.f90:576-632) ----
-  for (size_t e = lane; e < ncoarse; e += 32) nsts_c[e] = -1;
-  __syncwarp();
-  {
-    const int nkx = (sr.nnxr - 1) / g.sgdl + 1, nkz = (sr.nnzr - 1) / g.sgdl + 1;
-    for (int e = lane; e < nkx * nkz; e += 32) {
-      const int kz = e % nkz, kx = e / nkz;
-      const int k = 1 + kz * g.sgdl, l = 1 + kx * g.sgdl;
-      const int idm1 = sr.vnt + kz, idm2 = sr.vnl + kx;
-      const int orf = (l - 1) * REF_LD + (k - 1);
-      const int oc = (idm2 - 1) * g.nnz + (idm1 - 1);
-      const int v = nsts_r[orf];
-      nsts_c[oc] = v;
-      if (v >= 0) ttn_c[oc] = ttn_r[orf];
-    }
-  }
-  __syncwarp();
-  // alive nodes with a far neighbour become close (:615-632).  Restricted to the
-  // injected box: everything outside it is far.
-  for (int e = lane; e < (sr.vnr - sr.vnl + 1) * (sr.vnb - sr.vnt + 1); e += 32) {
-    const int nz_b = sr.vnb - sr.vnt + 1;
-    const int l = sr.vnt + e % nz_b, k = sr.vnl + e / nz_b;
-    const int o = (k - 1) * g.nnz + (l - 1);
-    if (nsts_c[o] == 0) {
-      bool mk = false;
-      if (l - 1 >= 1 && nsts_c[o - 1] == -1) mk = true;
-      if (l + 1 <= g.nnz && nsts_c[o + 1] == -1) mk = true;
-      if (k - 1 >= 1 && nsts_c[o - g.nnz] == -1) mk = true;
-      if (k + 1 <= g.nnx && nsts_c[o + g.nnz] == -1) mk = true;
-      if (mk) nsts_c[o] = 1;
-    }
-  }
-  __syncwarp();
-  // ---- heap build in scan order i=1..nnx, j=1..nnz (travel urg=2, CalSurfG.f90:311-317) ----
-  h.ntr = 0;
-  for (int k = sr.vnl; k <= sr.vnr && !overflow; ++k) {
-    for (int l0 = sr.vnt; l0 <= sr.vnb; l0 += 32) {
-      const int l = l0 + lane;
-      int v = -1;
-      float t = 0.0f;
-      const int o = (k - 1) * g.nnz + (l - 1);
-      if (l <= sr.vnb) { v = nsts_c[o]; t = ttn_c[o]; }
-      unsigned msk = __ballot_sync(0xffffffffu, v > 0);
-      while (msk) {
-        const int b = __ffs(msk) - 1;
-        msk &= msk - 1;
-        const float tb = __shfl_sync(0xffffffffu, t, b);
-        const int ob = (k - 1) * g.nnz + (l0 + b - 1);
-        if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; break; }
-        h.ntr += 1;
-        sift_up(h, nsts_c, h.ntr, tb, ob);
+      // ---- hand-off to the coarse grid (FwdTraveltimeCPS.f90:576-632); E_c was preset to FAR ----
+      {
+        const int nkx = (sr.nnxr - 1) / g.sgdl + 1, nkz = (sr.nnzr - 1) / g.sgdl + 1;
+        for (int e = sl; e < nkx * nkz; e += 16) {
+          const int kz = e % nkz, kx = e / nkz;
+          const int orf = (kx * g.sgdl) * REF_LD + (kz * g.sgdl);
+          const int oc = (sr.vnl + kx - 1) * g.nnz + (sr.vnt + kz - 1);
+          E_c[oc] = E_r[orf];
+        }
       }
+      __syncwarp(hm);
+      // alive nodes with a far neighbour become close (:615-632).  Restricted to the
+      // injected box: everything outside it is far.  Two passes (decide, then mark) keep
+      // the test on the *original* alive set exactly like a scan that only turns 0 into 1.
+      {
+        const int nz_b = sr.vnb - sr.vnt + 1, nb_tot = (sr.vnr - sr.vnl + 1) * nz_b;
+        for (int e0 = 0; e0 < nb_tot; e0 += 16) {
+          const int e = e0 + sl;
+          bool mk = false;
+          int o = 0;
+          if (e < nb_tot) {
+            const int l = sr.vnt + e % nz_b, k = sr.vnl + e / nz_b;
+            o = (k - 1) * g.nnz + (l - 1);
+            if ((int)E_c[o] >= 0) {
+              if (l - 1 >= 1 && E_c[o - 1] == E_FAR) mk = true;
+              if (l + 1 <= g.nnz && E_c[o + 1] == E_FAR) mk = true;
+              if (k - 1 >= 1 && E_c[o - g.nnz] == E_FAR) mk = true;
+              if (k + 1 <= g.nnx && E_c[o + g.nnz] == E_FAR) mk = true;
+            }
+          }
+          __syncwarp(hm);
+          if (mk) E_c[o] |= E_SIGN;
+        }
+      }
+      __syncwarp(hm);
+      // ---- heap build in scan order i=1..nnx, j=1..nnz (travel urg=2, CalSurfG.f90:311-317) ----
+      h.ntr = 0;
+      {
+        Track tk;
+        tk.cid[0] = tk.cid[1] = tk.cid[2] = tk.cid[3] = -1;
+        h.ld = g.nnz;
+        for (int k = sr.vnl; k <= sr.vnr && !overflow; ++k) {
+          for (int l0 = sr.vnt; l0 <= sr.vnb; l0 += 16) {
+            const int l = l0 + sl;
+            unsigned ev = E_FAR;
+            const int o = (k - 1) * g.nnz + (l - 1);
+            if (l <= sr.vnb) ev = E_c[o];
+            unsigned msk = __ballot_sync(hm, (int)ev < 0 && ev != E_FAR) >> (half * 16);
+            while (msk) {
+              const int b = __ffs(msk) - 1;
+              msk &= msk - 1;
+              const float tb = __uint_as_float(__shfl_sync(hm, ev, b, 16) & ~E_SIGN);
+              if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; break; }
+              h.ntr += 1;
+              sift_up(h, hpos_c, h.ntr, tb, ((k - 1) << 16) | (l0 + b - 1), tk);
+            }
+          }
+        }
+      }
+      __syncwarp(hm);
+      if (!overflow)
+        march<2>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
+                 false, false, false, false, sl, hm, nacc, overflow);
     }
+    pair = -1;
   }
-  __syncwarp();
-  if (!overflow)
-    march(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, veln_c, A.risti_c, ttn_c, nsts_c, 2, false, false, false,
-          false, lane, nacc, overflow);
-  if (lane == 0) {
+  if (sl == 0) {
     if (overflow) atomicOr(A.flags, 16);
-    atomicAdd(A.n_accept, nacc);
+    if (nacc) atomicAdd(A.n_accept, nacc);
   }
 }
 
-cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, cudaStream_t st) {
-  dim3 grid((g.nnx * g.nnz + 255) / 256, nper);
-  k_dice_coarse<<<grid, 256, 0, st>>>(g, velv, veln);
+// test seam: (E, hpos) -> the reference's (ttn, nsts) pair
+__global__ void k_decode_status(const unsigned* __restrict__ E, const int* __restrict__ hpos, size_t n,
+                                float* __restrict__ ttn, int* __restrict__ nsts) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned e = E[i];
+  int st;
+  float t;
+  if (e == E_FAR) { st = -1; t = 0.0f; }
+  else if ((int)e >= 0) { st = 0; t = __uint_as_float(e); }
+  else { st = hpos ? hpos[i] : 1; t = __uint_as_float(e & ~E_SIGN); }
+  if (ttn) ttn[i] = t;
+  if (nsts) nsts[i] = st;
+}
+
+cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, float* ttn, int* nsts, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_decode_status<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, hpos, n, ttn, nsts);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fmm(const FmmArgs& A, cudaStream_t st) {
-  const size_t smem = (size_t)A.hcap * 8;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_fmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  k_fmm<<<A.nsrc, 32, smem, st>>>(A);
+cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, float* slow, cudaStream_t st) {
+  dim3 grid((g.nnx * g.nnz + 255) / 256, nper);
+  k_dice_coarse<<<grid, 256, 0, st>>>(g, velv, veln, slow);
+  return cudaGetLastError();
+}
+
+// number of CTAs (= solve pairs in flight) the device can hold for a given shared heap capacity
+cudaError_t fmm_max_ctas(int hcap, int nsm, int* nctas) {
+  const size_t smem = (size_t)hcap * 16;
+  cudaError_t e = cudaFuncSetAttribute(k_fmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fmm, 32, smem);
+  if (e != cudaSuccess) return e;
+  *nctas = per_sm * nsm;
+  return cudaSuccess;
+}
+
+cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st) {
+  const size_t smem = (size_t)A.hcap * 16;
+  cudaError_t e = cudaFuncSetAttribute(k_fmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_fmm<<<nctas, 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 

@@ -201,3 +201,30 @@ def test_forward_end_to_end_gpu_tables(gpu, oracle, test1):
                       test1["gc"], test1["gs"], nthreads=4)
     assert np.array_equal(r["dsurf"], o["dsurf"])
     assert np.abs(r["obsTaa"] - o["obsTaa"]).max() <= 1e-5 * np.abs(o["obsTaa"]).max()
+
+
+def test_partition_matches_single(gpu, oracle, test1, test1_tables):
+    """(period x source) ranges run as separate plans (what each rank of a multi-GPU job does) and
+    concatenated in rank order give exactly the single-plan system: same rows, columns, values."""
+    from dazimsurftomo_b200 import partition as pt
+    p = test1["para"]; sv = test1["sv"]
+    pv, svs, svp, srho, _ = oracle.depthkernel(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    tb = dict(test1_tables, sen_vs=svs, sen_vp=svp, sen_rho=srho)
+    args = (test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv)
+    full = gpu.CalSurfGAnisoJoint(*args, tables=tb)
+    for world in (2, 3):
+        b = pt.split_units(sv, world)
+        ds, rows, cols, vals = [], [], [], []
+        for r in range(world):
+            plan = gpu.Plan(2, *args, tb, src_begin=b[r], src_end=b[r + 1])
+            plan.run()
+            out = plan.fetch()
+            assert plan.row0 == sv.row_offsets()[b[r]]
+            ds.append(out["dsurf"]); cols.append(out["col"]); vals.append(out["val"])
+            cnt = np.diff(out["rowptr"])
+            rows.append(np.repeat(np.arange(plan.row0 + 1, plan.row0 + plan.rows + 1), cnt))
+            plan.close()
+        assert np.array_equal(np.concatenate(ds), full["dsurf"])
+        assert np.array_equal(np.concatenate(rows), full["row"])
+        assert np.array_equal(np.concatenate(cols), full["col"])
+        assert np.array_equal(np.concatenate(vals), full["rw"])
