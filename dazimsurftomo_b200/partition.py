@@ -132,3 +132,52 @@ def misfit_sums(obst, dsurf, group=None):
         dist.all_gather(parts, s, group=group)
         s = torch.stack(parts).sum(0)
     return s
+
+
+# ---------------------------------------------------------------------------------------------
+# Stage A (Thomson-Haskell depth kernels): nodes are independent, so the model is cut into strips
+# of grid rows (the jj index of depthkernel's outer loop, CalSurfG.f90:39-43), each rank computes
+# its strip, and ONE exchange (all-gather of the strip tables) gives every rank the full
+# phase-velocity map it needs to dice any period (SURVEY 8e stage A).
+
+def node_strips(ny: int, world: int) -> List[int]:
+    """Row boundaries [0, ..., ny] of the per-rank strips (contiguous, near-equal)."""
+    return [int(round(ny * r / world)) for r in range(world + 1)]
+
+
+def strip_model(vels: np.ndarray, j0: int, j1: int) -> np.ndarray:
+    """vels(nx, j0:j1, nz) as its own Fortran-ordered model (a strip is a valid model for the depth kernels)."""
+    return np.asfortranarray(vels[:, j0:j1, :])
+
+
+def place_strip(full: np.ndarray, part: np.ndarray, nx: int, j0: int, j1: int) -> None:
+    """Write a strip table (nx*(j1-j0), k[, nz]) into the full table (nx*ny, k[, nz]): node = jj*nx + ii."""
+    full[j0 * nx:j1 * nx, ...] = part
+
+
+def gather_tables(local: Dict[str, np.ndarray], nx: int, ny: int, strips: List[int], rank: int, group=None,
+                  device=None) -> Dict[str, np.ndarray]:
+    """All-gather the depth-kernel tables computed on the strips.  `local` maps table name ->
+    array (nx*(j1-j0), k[, nz]) for this rank's strip; returns the full (nx*ny, k[, nz]) tables
+    (numpy, Fortran order).  Bit-identical for any world size: no arithmetic crosses ranks."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    for name in sorted(local):
+        part = local[name]
+        # move the node axis last so that a strip is a contiguous block: shape (k[, nz], nodes)
+        flat = torch.from_numpy(np.ascontiguousarray(np.moveaxis(part, 0, -1)).reshape(-1))
+        if device is not None:
+            flat = flat.to(device)
+        allv, sizes = _all_gather_v(flat, dist, group)
+        allv = allv.cpu().numpy()
+        tail = part.shape[1:]
+        full = np.zeros((nx * ny,) + tail, part.dtype, order="F")
+        o = 0
+        for r, n in enumerate(sizes):
+            j0, j1 = strips[r], strips[r + 1]
+            blk = allv[o:o + n].reshape(tail + (nx * (j1 - j0),))
+            place_strip(full, np.moveaxis(blk, -1, 0), nx, j0, j1)
+            o += n
+        out[name] = full
+    return out

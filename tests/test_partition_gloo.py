@@ -112,3 +112,42 @@ def test_sub_survey_row_ranges():
     # empty range
     sub, row0 = pt.sub_survey(sv, 3, 3)
     assert sub.dall == 0 and int(sub.nsrcsurf1.sum()) == 0
+
+
+def _worker_tables(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dazimsurftomo_b200 import partition as pt
+    from oracle import pyoracle as po
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p, depz, vs, sv = _load()
+    nx, ny, nz = vs.shape
+    strips = pt.node_strips(ny, world)
+    sub = pt.strip_model(vs, strips[rank], strips[rank + 1])
+    pv, L = po.depthkernel_ti(sub, depz, p.tRc, p.sublayers, nthreads=1)
+    full = pt.gather_tables(dict(pvRc=pv, Lsen_Gsc=L), nx, ny, strips, rank)
+    if rank == world - 1:
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stage_a_strips_gather(oracle):
+    """Depth-kernel tables computed on per-rank strips of grid rows and all-gathered equal the full-model tables."""
+    import torch.multiprocessing as mp
+    p, depz, vs, sv = _load()
+    pv, L = oracle.depthkernel_ti(vs, depz, p.tRc, p.sublayers, nthreads=4)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_tables, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = q.get(timeout=600)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    assert np.array_equal(got["pvRc"], pv)
+    assert np.array_equal(got["Lsen_Gsc"], L)
