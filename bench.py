@@ -191,14 +191,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from dazimsurftomo_b200 import partition
+    strips = partition.node_strips(w.ny, world)
+    dev = torch.device("cuda", local)
+
     def one_step(keep_plan=None):
-        """depth kernels -> plan upload -> kernels; returns (plan, stage times)."""
+        """depth kernels -> plan upload -> kernels; returns (plan, stage times).
+        N>1: stage A on this rank's strip of grid rows + one all-gather of the tables (NCCL), stage B on this
+        rank's contiguous (period, source) range -- no collective inside stage B."""
         t0 = time.perf_counter()
-        pv, svs, svp, srho = api.depthkernel(w.vs, w.depz, w.tRc, w.sublayers, handle=h)
+        vs_loc = w.vs if world == 1 else partition.strip_model(w.vs, strips[rank], strips[rank + 1])
+        pv, svs, svp, srho = api.depthkernel(vs_loc, w.depz, w.tRc, w.sublayers, handle=h)
         k1_ms = h.times["kernels_ms"]
-        pv2, L = api.depthkernelTI(w.vs, w.depz, w.tRc, w.sublayers, handle=h)
+        pv2, L = api.depthkernelTI(vs_loc, w.depz, w.tRc, w.sublayers, handle=h)
         k2_ms = h.times["kernels_ms"]
         tb = dict(pvRc=pv, sen_vs=svs, sen_vp=svp, sen_rho=srho, Lsen_Gsc=L)
+        if world > 1:
+            tb = partition.gather_tables(tb, w.nx, w.ny, strips, rank, device=dev)
         plan = api.Plan(2, w.vs, w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv, tb, src_begin=sb,
                         src_end=se, handle=h)
         tm = plan.run()
@@ -250,9 +259,20 @@ def main():
             h2d = tms["h2d_bytes"] + w.vs.nbytes * 2
             d2h = tms["d2h_bytes"] + sum(r[k].nbytes for k in ("pvRc", "sen_vs", "sen_vp", "sen_rho", "Lsen_Gsc"))
         else:
+            # N>1 end to end: host model -> strips -> table all-gather -> row blocks -> the one exchange step the
+            # inversion needs (all-gather-v of CSR row blocks + dsurf over NCCL) -> rank 0 reads the system back
             plan, tm = one_step()
-            out = plan.fetch()
-            h2d = plan.h2d_bytes; d2h = h.times["d2h_bytes"]
+            dtens = plan.device_tensors()
+            blk = dict(dsurf=dtens["dsurf"], nnz_row=dtens["rowptr"][1:] - dtens["rowptr"][:-1],
+                       col=dtens["col"], val=dtens["val"])
+            full = partition.gather_rows(blk, plan.row0)
+            h2d = plan.h2d_bytes + w.vs.nbytes
+            d2h = 0
+            if rank == 0:
+                host = {k: full[k].cpu() for k in ("dsurf", "rw", "col", "row")}
+                d2h = sum(v.numel() * v.element_size() for v in host.values())
+                assert host["dsurf"].numel() == w.n_rays
+            del full, blk, dtens
             plan.close()
         barrier()
         if i > 0:

@@ -330,6 +330,31 @@ class Plan:
         _chk(load().dazim_plan_device_ptrs(self._plan, *[C.byref(p) for p in ptrs]))
         return dict(zip(("dsurf", "obsTaa", "rowptr", "col", "val"), [p.value for p in ptrs]))
 
+    def device_tensors(self):
+        """Zero-copy torch views of the last run's outputs in HBM (for NCCL exchanges without a host hop).
+        plan.run() has synchronised the library stream, so the views are safe on torch's current stream."""
+        import torch
+        p = self.device_ptrs()
+        dev = "cuda:%d" % self.h.device
+
+        class _View:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        def view(name, n, ts, dt):
+            if not p[name] or n == 0:
+                return torch.zeros(0, dtype=dt, device=dev)
+            return torch.as_tensor(_View(p[name], n, ts), device=dev)
+
+        n, nnz = self.rows, self.nnz
+        out = dict(dsurf=view("dsurf", n, "<f4", torch.float32))
+        if self.mode == 0:
+            out["obsTaa"] = view("obsTaa", n, "<f4", torch.float32)
+        else:
+            out.update(rowptr=view("rowptr", n + 1, "<i8", torch.int64), col=view("col", nnz, "<i4", torch.int32),
+                       val=view("val", nnz, "<f4", torch.float32))
+        return out
+
     def close(self):
         if self._plan:
             load().dazim_plan_destroy(self._plan)

@@ -150,7 +150,7 @@ __device__ __forceinline__ void dunkin_step(double (&e)[5], double wvno2, double
 }
 
 // dltar4 (surfdisp96.f:767-865), solid layers (llw=1)
-__device__ double dltar4_dev(const DispArgs& A, int task, double wvno, double omga) {
+__device__ __noinline__ double dltar4_dev(const DispArgs& A, int task, double wvno, double omga) {
   const int mmax = A.nlayer;
   const size_t n = (size_t)A.ntask;
   double omega = omga;
