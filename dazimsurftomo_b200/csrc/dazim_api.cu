@@ -61,23 +61,44 @@ struct dazim_handle {
   int nsm;
 };
 
+// Device buffers come from the stream-ordered allocator (cudaMallocAsync on the library stream;
+// the default pool keeps freed blocks, dazim_create raises its release threshold), so the
+// multi-GB workspaces of consecutive calls are recycled instead of going back to the driver.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
 template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t st = nullptr;
   cudaError_t alloc(size_t cnt) {
     release();
     n = cnt;
+    st = g_alloc_stream;
     if (cnt == 0) return cudaSuccess;
-    return cudaMalloc((void**)&p, cnt * sizeof(T));
+    return cudaMallocAsync((void**)&p, cnt * sizeof(T), st);
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
     p = nullptr;
     n = 0;
   }
   ~DBuf() { release(); }
 };
+
+// memory the allocator could hand out right now: free device memory + what the pool holds but does not use
+static cudaError_t available_bytes(int dev, size_t* out) {
+  size_t free_b = 0, total_b = 0;
+  cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+  if (e != cudaSuccess) return e;
+  cudaMemPool_t pool;
+  unsigned long long reserved = 0, used = 0;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+    free_b += (size_t)(reserved - used);
+  *out = free_b;
+  return cudaSuccess;
+}
 
 // FwdTraveltimeCPS.f90:346-380 (identical prologue in CalSurfG / CalSurfGAnisoJoint)
 static GridC make_grid(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd) {
@@ -191,6 +212,13 @@ extern "C" int dazim_create(dazim_handle** out, int device) {
   std::memset(&h->times, 0, sizeof(h->times));
   e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return DAZIM_ECUDA + (int)e; }
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaDeviceProp pr;
   cudaGetDeviceProperties(&pr, device);
   h->nsm = pr.multiProcessorCount;
@@ -242,6 +270,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   if ((mode == 1 || mode == 2) && (!tb->sen_vs || !tb->sen_vp || !tb->sen_rho)) return DAZIM_EBADARG;
   if (mode == 0 && (!Gc || !Gs) && !emit_all) return DAZIM_EBADARG;
   CK(cudaSetDevice(h->dev));
+  g_alloc_stream = h->st;
   dazim_plan* P = new dazim_plan();
   P->h = h; P->mode = mode; P->nx = p->nx; P->ny = p->ny; P->nz = p->nz; P->kmaxRc = p->kmaxRc;
   P->azim = (mode != 1);
@@ -283,7 +312,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   // S200), halved while that buys more solves in flight, never below hcap_min.
   const long long npairs_all = (nsrc + 1) / 2;
   int hneed = std::min(4096, std::max(256, pow2ceil(3 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
-  int hmin = std::min(hneed, 2048);
+  int hmin = std::min(hneed, 512);
   if (const char* e = getenv("DAZIM_HCAP_MIN")) hmin = std::max(64, std::min(hneed, atoi(e)));
   P->hcap = hneed;
   int nctas = 1;
@@ -292,11 +321,11 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     P->hcap /= 2;
     CK(fmm_max_ctas(P->hcap, h->nsm, &nctas));
   }
-  if (const char* e = getenv("DAZIM_HCAP")) { P->hcap = std::max(64, atoi(e)); CK(fmm_max_ctas(P->hcap, h->nsm, &nctas)); }
+  if (const char* e = getenv("DAZIM_HCAP")) { P->hcap = std::max(64, pow2ceil(atoi(e))); CK(fmm_max_ctas(P->hcap, h->nsm, &nctas)); }
   if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
   P->hspill = std::max(0, 8 * (g.nnx + g.nnz) + 1024 - P->hcap) + 16;
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
+  size_t free_b = 0;
+  CK(available_bytes(h->dev, &free_b));
   double budget = 0.60 * (double)free_b;
   if (const char* e = getenv("DAZIM_WS_GB")) budget = std::min(budget, atof(e) * 1e9);
   const double per_src = (double)ncoarse * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
@@ -450,6 +479,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
 static int plan_run(dazim_plan* P) {
   dazim_handle* h = P->h;
   CK(cudaSetDevice(h->dev));
+  g_alloc_stream = h->st;
   cudaStream_t st = h->st;
   const GridC& g = P->g;
   const size_t ncoarse = (size_t)g.nnx * g.nnz;

@@ -74,120 +74,121 @@ __global__ void k_dice_coarse(GridC g, const float* __restrict__ velv, float* __
 #define E_OUT 0xFFFFFFFEu     // outside the grid (register-only sentinel)
 #define E_SIGN 0x80000000u    // close: trial value with the sign bit set (nsts > 0)
 
-// Heap entries are (key bits, node id) with node id = (ix << 16) | iz, 0-based (grid edges <= 32767
-// like the reference's INTEGER*2 heap pointers, CalSurfG.f90:239).
+// Heap entries are (key bits, node offset) pairs.  Positions 1..hcap-1 live in shared memory,
+// positions >= hcap in a per-slot global array ("spill").  hpos[node] is the reference's nsts
+// back pointer (heap position of a close node); every move of an entry updates it.
 struct Heap {
-  int2* sm;            // shared part, positions 1..hcap-1 (entry 0 unused)
-  int2* gl;            // spill part, positions hcap.. (per slot)
+  int2* sm;            // shared part (entry 0 unused)
+  int2* gl;            // spill part
   int hcap, hspill;
   int ntr;
-  int ld;              // leading dimension of the grid being marched (node id -> offset)
-  __device__ __forceinline__ int off(int id) const { return (id >> 16) * ld + (id & 0xffff); }
-  __device__ __forceinline__ int2 get(int p) const { return p < hcap ? sm[p] : gl[p - hcap]; }
-  __device__ __forceinline__ void put(int p, int2 v) {
-    if (p < hcap) sm[p] = v; else gl[p - hcap] = v;
-  }
-  // both children of a sift-down level; p is even
-  __device__ __forceinline__ void get2(int p, int2& a, int2& b) const {
-    if (p + 1 < hcap) {
-      const int4 v = *reinterpret_cast<const int4*>(sm + p);
-      a = make_int2(v.x, v.y);
-      b = make_int2(v.z, v.w);
-    } else {
-      a = get(p);
-      b = get(p + 1);
-    }
-  }
 };
+#define HKEY(e) __int_as_float((e).x)
 
-// Register copies of the heap positions of the four neighbours of the node being accepted
-// (ids cid[q], -1 = none).  Every heap move records the node's new position in hpos[] (the
-// reference's nsts back pointer) and patches these copies, so the accept step never has to
-// read a position back from global memory.
-struct Track {
-  int cid[4];
-  int hp[4];
-};
+__device__ __forceinline__ int2 hget(const Heap& h, int p) { return p < h.hcap ? h.sm[p] : h.gl[p - h.hcap]; }
+__device__ __forceinline__ void hput(Heap& h, int* __restrict__ hpos, int p, int2 e) {
+  if (p < h.hcap) h.sm[p] = e; else h.gl[p - h.hcap] = e;
+  hpos[e.y] = p;
+}
+__device__ __forceinline__ int2 shfl2(unsigned hm, int2 v, int src) {
+  return make_int2(__shfl_sync(hm, v.x, src, 16), __shfl_sync(hm, v.y, src, 16));
+}
 
-#define HEAP_MOVE(h, pos, ent)                                  \
-  do {                                                          \
-    (h).put((pos), (ent));                                      \
-    hpos[(h).off((ent).y)] = (pos);                             \
-    _Pragma("unroll") for (int q_ = 0; q_ < 4; ++q_)            \
-      if ((ent).y == tk.cid[q_]) tk.hp[q_] = (pos);             \
-  } while (0)
-
-// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).  Parent and
-// grandparent are fetched together so the shared-memory latency is paid once.
-__device__ __forceinline__ void sift_up(Heap& h, int* __restrict__ hpos, int tpc, float k, int n, Track& tk) {
+// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).  Plain version
+// (source-cell initialisation, coarse heap build, fall-back of the accept step).
+// Returns the final position; *moved is set when at least one parent was moved down.
+__device__ __forceinline__ int sift_up(Heap& h, int* __restrict__ hpos, int tpc, float k, int n, bool* moved) {
   int tpp = tpc >> 1;
-  int2 par = make_int2(0, 0), gpar = make_int2(0, 0);
-  if (tpp > 0) par = h.get(tpp);
-  if ((tpp >> 1) > 0) gpar = h.get(tpp >> 1);
   while (tpp > 0) {
-    if (k < __int_as_float(par.x)) {
-      HEAP_MOVE(h, tpc, par);
+    const int2 par = hget(h, tpp);
+    if (k < HKEY(par)) {
+      hput(h, hpos, tpc, par);
+      if (moved) *moved = true;
       tpc = tpp;
       tpp = tpc >> 1;
-      par = gpar;
-      if ((tpp >> 1) > 0) gpar = h.get(tpp >> 1);
     } else {
       break;
     }
   }
-  const int2 me = make_int2(__float_as_int(k), n);
-  HEAP_MOVE(h, tpc, me);
+  hput(h, hpos, tpc, make_int2(__float_as_int(k), n));
+  return tpc;
 }
 
-// downtree (CalSurfG.f90:786-855).  While one level is being decided, both pairs of
-// grandchildren are already being fetched (4 consecutive entries), which takes the
-// shared-memory latency off the level-to-level dependency chain.
-__device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, Track& tk) {
+// downtree (CalSurfG.f90:786-855).  `last` = heap[ntr] (fetched early by the caller).
+// Shared levels: while one level is being decided both pairs of grandchildren are already being
+// fetched.  Spill levels: the 14 entries of the next three levels under the hole are fetched by
+// 14 lanes in ONE round trip and resolved with shuffles.
+__device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, const int2 last, const int sl,
+                                         const unsigned hm) {
   if (h.ntr == 1) { h.ntr = 0; return; }
-  const int2 last = h.get(h.ntr);
-  const float k = __int_as_float(last.x);
+  const float k = HKEY(last);
   h.ntr -= 1;
   const int ntr = h.ntr;
   int tpp = 1, tpc = 2;
-  int2 c0 = make_int2(0, 0), c1 = make_int2(0, 0);
-  if (tpc < ntr) h.get2(tpc, c0, c1);
-  while (tpc < ntr) {
-    const int g = 2 * tpc;                 // grandchildren live at g .. g+3
-    const bool pf = (g + 3 < h.hcap);
-    int4 ga = make_int4(0, 0, 0, 0), gb = ga;
-    if (pf) {
-      ga = *reinterpret_cast<const int4*>(h.sm + g);
-      gb = *reinterpret_cast<const int4*>(h.sm + g + 2);
-    }
-    float rd1 = __int_as_float(c0.x);
-    const float rd2 = __int_as_float(c1.x);
-    const bool right = rd1 > rd2;
-    if (right) { tpc = tpc + 1; rd1 = rd2; c0 = c1; }
-    if (rd1 < k) {
-      HEAP_MOVE(h, tpp, c0);
+  bool placed = false;
+  const int lim = min(ntr, h.hcap - 1);      // tpc < lim  <=>  both children exist and live in shared memory
+  if (tpc < lim) {
+    int4 pr = *reinterpret_cast<const int4*>(h.sm + tpc);
+    for (;;) {
+      const int g = 2 * tpc;                 // grandchildren live at g .. g+3
+      const bool pf = (g + 3 < h.hcap);
+      int4 ga = make_int4(0, 0, 0, 0), gb = ga;
+      if (pf) {
+        ga = *reinterpret_cast<const int4*>(h.sm + g);
+        gb = *reinterpret_cast<const int4*>(h.sm + g + 2);
+      }
+      const bool right = __int_as_float(pr.x) > __int_as_float(pr.z);
+      const int2 c = right ? make_int2(pr.z, pr.w) : make_int2(pr.x, pr.y);
+      tpc += right ? 1 : 0;
+      if (!(HKEY(c) < k)) { placed = true; break; }
+      h.sm[tpp] = c;
+      hpos[c.y] = tpp;
       tpp = tpc;
       tpc = 2 * tpp;
-      if (tpc < ntr) {
-        if (pf) {
-          const int4 pk = right ? gb : ga;
-          c0 = make_int2(pk.x, pk.y);
-          c1 = make_int2(pk.z, pk.w);
-        } else {
-          h.get2(tpc, c0, c1);
-        }
+      if (!(tpc < lim)) break;
+      if (pf) pr = right ? gb : ga;
+      else pr = *reinterpret_cast<const int4*>(h.sm + tpc);
+    }
+  }
+  if (!placed && tpc <= ntr) {
+    if (tpc < h.hcap) {
+      // tpc == ntr: a single child, in shared memory
+      const int2 c = h.sm[tpc];
+      if (HKEY(c) < k) {
+        h.sm[tpp] = c;
+        hpos[c.y] = tpp;
+        tpp = tpc;
       }
     } else {
-      tpc = ntr + 1;
+      // children live in the spill part
+      const int j = (sl < 2) ? 1 : (sl < 6 ? 2 : 3);
+      const int i = sl - ((1 << j) - 2);
+      for (;;) {
+        const int p = (tpp << j) + i;
+        int2 ent = make_int2(0x7f800000, -1);
+        if (sl < 14 && p <= ntr) ent = h.gl[p - h.hcap];
+        int rel = 0, lvbase = 0;
+        bool done = false;
+#pragma unroll
+        for (int lv = 1; lv <= 3; ++lv) {
+          if (done || tpc > ntr) { done = true; continue; }
+          const int l0 = lvbase + 2 * rel;
+          const int2 c0 = shfl2(hm, ent, l0), c1 = shfl2(hm, ent, l0 + 1);
+          const bool right = (tpc < ntr) && (HKEY(c0) > HKEY(c1));
+          const int2 c = right ? c1 : c0;
+          tpc += right ? 1 : 0;
+          if (!(HKEY(c) < k)) { done = true; continue; }
+          hput(h, hpos, tpp, c);
+          tpp = tpc;
+          tpc = 2 * tpp;
+          rel = 2 * rel + (right ? 1 : 0);
+          lvbase = (2 << lv) - 2;
+        }
+        if (done || tpc > ntr) break;
+      }
     }
   }
-  if (tpc == ntr) {
-    const int2 cc = h.get(tpc);
-    if (__int_as_float(cc.x) < k) {
-      HEAP_MOVE(h, tpp, cc);
-      tpp = tpc;
-    }
-  }
-  HEAP_MOVE(h, tpp, last);
+  hput(h, hpos, tpp, last);
 }
 
 // One quadrant of fouds2 (CalSurfG.f90:634-723): returns trial time, valid flag through ok.
@@ -299,11 +300,16 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
   const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0);
   const int ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
   const int base = sl & 12;
-  Track tk;
+  const float inv_ld = 1.0f / (float)ld;
   while (h.ntr > 0) {
     const int2 root = h.sm[1];
-    const int ix = root.y >> 16, iz = root.y & 0xffff;     // 0-based
-    const int pn = ix * ld + iz;
+    const int pn = root.y;
+    // the element that will be sifted down from the root (may live in the spill part: fetch it now)
+    const int2 last = hget(h, h.ntr);
+    // (ix, iz) 0-based from the linear offset: float quotient, exact after one correction
+    int ix = (int)((float)pn * inv_ld);
+    int iz = pn - ix * ld;
+    if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
     // the popped node becomes alive with its trial value (= its heap key)
     E[pn] = (unsigned)root.x & ~E_SIGN;
     if (URG == 1) {
@@ -327,13 +333,8 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
       else if (d == 2) cval = __float_as_uint(slow[co]);
       else cval = __float_as_uint(risti_tab[cx]);
     }
-    // ---- pop the root while the loads are in flight; track the neighbours' heap positions ----
-    tk.cid[0] = (ix > 0) ? (((ix - 1) << 16) | iz) : -1;
-    tk.cid[1] = (ix + 1 < nnx) ? (((ix + 1) << 16) | iz) : -1;
-    tk.cid[2] = (iz > 0) ? ((ix << 16) | (iz - 1)) : -1;
-    tk.cid[3] = (iz + 1 < nnz) ? ((ix << 16) | (iz + 1)) : -1;
-    tk.hp[0] = tk.hp[1] = tk.hp[2] = tk.hp[3] = -1;
-    pop_root(h, hpos, tk);
+    // ---- pop the root while the loads are in flight ----
+    pop_root(h, hpos, last, sl, hm);
     // ---- neighbour scalars ----
     const unsigned cE = __shfl_sync(hm, cval, base + 0, 16);
     const float slown = __uint_as_float(__shfl_sync(hm, cval, base + 2, 16));
@@ -349,29 +350,110 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
     if (!ok) trav = __int_as_float(0x7f800000);
     trav = fminf(trav, __shfl_xor_sync(hm, trav, 1, 16));
     trav = fminf(trav, __shfl_xor_sync(hm, trav, 2, 16));
-    int qst[4];
+    // ---- per-neighbour uniform scalars + start positions of the four sift-ups ----
+    int qst[4], qo[4], spos[4];
     float qt[4];
+    int nins = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       qst[q] = __shfl_sync(hm, cst, q * 4, 16);
       qt[q] = __shfl_sync(hm, trav, q * 4, 16);
-      const int hl = (int)__shfl_sync(hm, cval, q * 4 + 1, 16);
-      if (tk.hp[q] < 0) tk.hp[q] = hl;
+      const int hl = (int)__shfl_sync(hm, cval, q * 4 + 1, 16);      // hpos[neighbour] as of before the pop
+      qo[q] = (ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0))) * ld + (iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0)));
+      spos[q] = 0;
+      if (qst[q] == -1) spos[q] = h.ntr + (++nins);
+      else if (qst[q] == 1) spos[q] = hl;
+    }
+    if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; return; }
+    if (h.ntr + nins < h.hcap) {
+      // ---- fast path: every heap position this step can touch lives in shared memory ----
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (qst[q] != 1) continue;
+        // a position read before the pop is still right iff that heap slot holds the neighbour
+        int vn = -1;
+        if (spos[q] >= 1 && spos[q] <= h.ntr) vn = h.sm[spos[q]].y;
+        if (vn != qo[q]) spos[q] = hpos[qo[q]];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (qst[q] == -2 || qst[q] == 0) continue;
+        E[qo[q]] = __float_as_uint(qt[q]) | E_SIGN;
+        if (qst[q] == -1) h.ntr += 1;
+        const float k = qt[q];
+        int tpc = spos[q];
+        bool moved = false;
+        for (int tpp = tpc >> 1; tpp > 0; tpp >>= 1) {
+          const int2 par = h.sm[tpp];
+          if (!(k < HKEY(par))) break;
+          h.sm[tpc] = par;
+          hpos[par.y] = tpc;
+          moved = true;
+          tpc = tpp;
+        }
+        h.sm[tpc] = make_int2(__float_as_int(k), qo[q]);
+        hpos[qo[q]] = tpc;
+        if (moved && q < 3) {
+#pragma unroll
+          for (int r = q + 1; r < 4; ++r)
+            if (qst[r] == 1) spos[r] = hpos[qo[r]];
+        }
+      }
+      continue;
+    }
+    // ---- deep path.  One round trip for every spilled entry the sift-ups can need: lane (q, j)
+    //      fetches the entry at spos[q] >> j (j = 0: the entry itself, to verify a close
+    //      neighbour's position) ----
+    int myp = 0;
+    {
+      const int sp = (nb == 0) ? spos[0] : (nb == 1 ? spos[1] : (nb == 2 ? spos[2] : spos[3]));
+      myp = sp >> d;
+    }
+    int2 cent = make_int2(0, -1);
+    if (myp >= h.hcap && myp <= h.ntr) cent = h.gl[myp - h.hcap];
+    bool chain_ok = true;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (qst[q] != 1) continue;
+      int2 v = make_int2(0, -1);
+      if (spos[q] >= 1 && spos[q] <= h.ntr) v = (spos[q] < h.hcap) ? h.sm[spos[q]] : shfl2(hm, cent, q * 4);
+      if (v.y != qo[q]) {                  // moved by the pop: take the fresh back pointer
+        spos[q] = hpos[qo[q]];
+        chain_ok = false;
+      }
     }
     // ---- apply in the reference order: x-1, x+1, z-1, z+1 ----
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (qst[q] == -2 || qst[q] == 0) continue;
-      const int qx = ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0));
-      const int qz = iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0));
-      E[qx * ld + qz] = __float_as_uint(qt[q]) | E_SIGN;
-      int pos = tk.hp[q];
-      if (qst[q] == -1) {
-        if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; return; }
-        h.ntr += 1;
-        pos = h.ntr;
+      E[qo[q]] = __float_as_uint(qt[q]) | E_SIGN;
+      if (qst[q] == -1) h.ntr += 1;
+      const float k = qt[q];
+      int tpc = spos[q];
+      bool moved = false;
+      for (int j = 1;; ++j) {
+        const int tpp = tpc >> 1;
+        if (tpp == 0) break;
+        int2 par;
+        if (tpp < h.hcap) par = h.sm[tpp];
+        else if (chain_ok && j <= 3) par = shfl2(hm, cent, q * 4 + j);
+        else par = h.gl[tpp - h.hcap];
+        if (!(k < HKEY(par))) break;
+        hput(h, hpos, tpc, par);
+        moved = true;
+        tpc = tpp;
       }
-      sift_up(h, hpos, pos, qt[q], tk.cid[q], tk);
+      hput(h, hpos, tpc, make_int2(__float_as_int(k), qo[q]));
+      if (q < 3) {
+        // later sift-ups: prefetched entries are stale if this one changed a spilled position they use
+        if (moved) chain_ok = false;
+        else if (tpc >= h.hcap && __ballot_sync(hm, myp == tpc && nb > q) != 0u) chain_ok = false;
+        if (moved) {
+#pragma unroll
+          for (int r = q + 1; r < 4; ++r)
+            if (qst[r] == 1) spos[r] = hpos[qo[r]];
+        }
+      }
     }
   }
 }
@@ -399,7 +481,7 @@ __device__ __forceinline__ float refined_vel(const GridC& g, const SrcRec& sr, c
   return sum[0] + sum[1] + sum[2] + sum[3];
 }
 
-__global__ void __launch_bounds__(32) k_fmm(FmmArgs A) {
+__global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
   const int half = lane >> 4, sl = lane & 15;
@@ -464,9 +546,6 @@ __global__ void __launch_bounds__(32) k_fmm(FmmArgs A) {
                                 (1.0f - fabsf(((float)(j - 1) * sr.dnzr - dsz) / sr.dnzr));
             vsrc = vsrc + vss[i - 1][j - 1] * produ;
           }
-        Track tk;
-        tk.cid[0] = tk.cid[1] = tk.cid[2] = tk.cid[3] = -1;
-        h.ld = REF_LD;
 #pragma unroll
         for (int i = 1; i <= 2; ++i)
 #pragma unroll
@@ -478,11 +557,10 @@ __global__ void __launch_bounds__(32) k_fmm(FmmArgs A) {
             const int o = (isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1);
             E_r[o] = __float_as_uint(t0) | E_SIGN;
             h.ntr += 1;
-            sift_up(h, hpos_r, h.ntr, t0, ((isx - 1 + i - 1) << 16) | (isz - 1 + j - 1), tk);
+            sift_up(h, hpos_r, h.ntr, t0, o, nullptr);
           }
       }
       // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
-      h.ld = REF_LD;
       march<1>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
                A.risti_r + (size_t)s * REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
                sr.vnb != sr.nnzr, sl, hm, nacc, overflow);
@@ -526,9 +604,6 @@ __global__ void __launch_bounds__(32) k_fmm(FmmArgs A) {
       // ---- heap build in scan order i=1..nnx, j=1..nnz (travel urg=2, CalSurfG.f90:311-317) ----
       h.ntr = 0;
       {
-        Track tk;
-        tk.cid[0] = tk.cid[1] = tk.cid[2] = tk.cid[3] = -1;
-        h.ld = g.nnz;
         for (int k = sr.vnl; k <= sr.vnr && !overflow; ++k) {
           for (int l0 = sr.vnt; l0 <= sr.vnb; l0 += 16) {
             const int l = l0 + sl;
@@ -542,7 +617,7 @@ __global__ void __launch_bounds__(32) k_fmm(FmmArgs A) {
               const float tb = __uint_as_float(__shfl_sync(hm, ev, b, 16) & ~E_SIGN);
               if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; break; }
               h.ntr += 1;
-              sift_up(h, hpos_c, h.ntr, tb, ((k - 1) << 16) | (l0 + b - 1), tk);
+              sift_up(h, hpos_c, h.ntr, tb, (k - 1) * g.nnz + (l0 + b - 1), nullptr);
             }
           }
         }

