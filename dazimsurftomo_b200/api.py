@@ -84,12 +84,41 @@ def load():
         lib.dazim_plan_destroy.restype = None
         lib.dazim_destroy.argtypes = [C.c_void_p]
         lib.dazim_destroy.restype = None
+        lib.dazim_host_free.argtypes = [C.c_void_p]
+        lib.dazim_host_free.restype = None
         _lib = lib
     return _lib
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _Pinned:
+    """Cache of page-locked host buffers (dazim_host_alloc) handed out as numpy arrays; the multi-GB COO
+    outputs are written into these so the device->host copy runs at PCIe speed and repeated calls
+    (outer iterations) do not re-fault fresh pages."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, tag: str, n: int, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n), 1) * dtype.itemsize
+        ptr, cap = self.bufs.get(tag, (None, 0))
+        if cap < nbytes:
+            if ptr:
+                load().dazim_host_free(C.c_void_p(ptr))
+            vp = C.c_void_p()
+            cap = nbytes + nbytes // 8
+            _chk(load().dazim_host_alloc(C.byref(vp), C.c_ulonglong(cap)))
+            ptr = vp.value
+            self.bufs[tag] = (ptr, cap)
+        arr = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(ptr)).view(dtype)
+        return arr[:n]
+
+
+_pinned = _Pinned()
 
 
 def _chk(code: int):
@@ -225,7 +254,9 @@ def _gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc, gs, t
     if mode != 0:
         if maxnar is None:
             maxnar = max(1024, dall * 400 * (3 if mode == 2 else 1))
-        rw = np.zeros(maxnar, np.float32); iw = np.zeros(maxnar, np.int32); col = np.zeros(maxnar, np.int32)
+        # outputs land in cached page-locked buffers: valid until the next call of the same routine
+        rw = _pinned.get("rw", maxnar, np.float32); iw = _pinned.get("iw", maxnar, np.int32)
+        col = _pinned.get("col", maxnar, np.int32)
         coo.rw, coo.iw_row, coo.col, coo.maxnar = _p(rw), _p(iw), _p(col), maxnar
     _chk(load().dazim_gbuild(h._h, C.c_int(mode), C.byref(pr.c), C.byref(tb.c), C.c_int(0 if tables is None else 1),
                              _p(gc), _p(gs), _p(dsurf), _p(taa), _p(tRcV), C.byref(coo) if mode != 0 else None))

@@ -17,7 +17,7 @@ namespace dz {
 // kernels (dazim_fmm.cu / dazim_trace.cu / dazim_th.cu)
 cudaError_t upload_basis(const float* ub, const float* cb);
 cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, float* slow, cudaStream_t st);
-cudaError_t fmm_max_ctas(int hcap, int nsm, int* nctas);
+cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
 cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, float* ttn, int* nsts, cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
@@ -181,7 +181,7 @@ struct dazim_plan {
   DBuf<int> d_hpos_c, d_hpos_r, d_slot_of; DBuf<float> d_slow_r; DBuf<int2> d_hspill;   // per slot
   int nctas = 0;
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
-  int hcap = 512, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
+  int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
   DBuf<int> d_fp_off, d_fp_cnt, d_fp_cell; DBuf<float> d_fp_fdm, d_fp_fdmc, d_fp_fdms;
   unsigned long long pool_cap = 0;
@@ -231,6 +231,13 @@ extern "C" int dazim_create(dazim_handle** out, int device) {
   *out = h;
   return DAZIM_OK;
 }
+
+extern "C" int dazim_host_alloc(void** p, unsigned long long bytes) {
+  if (!p) return DAZIM_EBADARG;
+  cudaError_t e = cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault);
+  return e == cudaSuccess ? DAZIM_OK : DAZIM_ECUDA + (int)e;
+}
+extern "C" void dazim_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" void dazim_destroy(dazim_handle* h) {
   if (!h) return;
@@ -309,20 +316,36 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
 
   // ---- workspace sizing ----
   // heap capacity in shared memory: bounded by the largest narrow band (~3 x grid edge; measured max 2.7 x on
-  // S200), halved while that buys more solves in flight, never below hcap_min.
-  const long long npairs_all = (nsrc + 1) / 2;
+  // S200).  Few solves (latency-bound): one solve per CTA with the whole heap in shared memory.  Many solves
+  // (issue-bound): two solves per CTA and the capacity halved while that buys more solves in flight (measured
+  // optimum 512 on S200: profiles/).
   int hneed = std::min(4096, std::max(256, pow2ceil(3 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
   int hmin = std::min(hneed, 512);
   if (const char* e = getenv("DAZIM_HCAP_MIN")) hmin = std::max(64, std::min(hneed, atoi(e)));
   P->hcap = hneed;
+  P->spc = 1;
   int nctas = 1;
-  CK(fmm_max_ctas(P->hcap, h->nsm, &nctas));
-  while (P->hcap > hmin && nctas < npairs_all) {
+  CK(fmm_max_ctas(P->hcap, 1, h->nsm, &nctas));
+  while (nctas < nsrc && P->hcap > 2048) {     // one solve per CTA still fits with a (rarely spilling) smaller heap?
     P->hcap /= 2;
-    CK(fmm_max_ctas(P->hcap, h->nsm, &nctas));
+    CK(fmm_max_ctas(P->hcap, 1, h->nsm, &nctas));
   }
-  if (const char* e = getenv("DAZIM_HCAP")) { P->hcap = std::max(64, pow2ceil(atoi(e))); CK(fmm_max_ctas(P->hcap, h->nsm, &nctas)); }
+  if (nctas < nsrc) {
+    P->hcap = hneed;
+    P->spc = 2;
+    CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
+    while (P->hcap > hmin && (long long)nctas * 2 < nsrc) {
+      P->hcap /= 2;
+      CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
+    }
+  }
+  if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
+  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC")) {
+    if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, pow2ceil(atoi(e)));
+    CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
+  }
   if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
+  const long long npairs_all = (nsrc + P->spc - 1) / P->spc;
   P->hspill = std::max(0, 8 * (g.nnx + g.nnz) + 1024 - P->hcap) + 16;
   size_t free_b = 0;
   CK(available_bytes(h->dev, &free_b));
@@ -331,11 +354,11 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   const double per_src = (double)ncoarse * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
   const double per_slot = (double)ncoarse * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
   nctas = (int)std::min<long long>(nctas, std::max<long long>(npairs_all, 1));
-  long long maxB = (long long)((budget - 2.0 * nctas * per_slot) / per_src);
+  long long maxB = (long long)((budget - 2.0 * nctas * per_slot) / per_src);   // 2 slots per CTA are always laid out
   if (maxB < 2) maxB = 2;
   if (const char* e = getenv("DAZIM_BATCH")) maxB = std::max(1, atoi(e));
   maxB = std::min<long long>(maxB, std::max<long long>(nsrc, 1));
-  nctas = (int)std::min<long long>(nctas, (maxB + 1) / 2);
+  nctas = (int)std::min<long long>(nctas, (maxB + P->spc - 1) / P->spc);
   P->nctas = nctas;
   P->maxB = (int)maxB;
   // batches + per-batch ray lists (long rays first so that a warp holds rays of similar length)
@@ -509,14 +532,14 @@ static int plan_run(dazim_plan* P) {
     F.g = g; F.src = P->d_src.p + s0; F.nsrc = (int)(s1 - s0); F.velv = P->d_velv.p; F.slow_c = P->d_slow_c.p;
     F.risti_c = P->d_risti_c.p; F.risti_r = P->d_risti_r.p + (size_t)s0 * REF_LD;
     F.E_c = P->d_E_c.p; F.E_r = P->d_E_r.p; F.hpos_c = P->d_hpos_c.p; F.hpos_r = P->d_hpos_r.p;
-    F.slow_r = P->d_slow_r.p; F.hspill = P->d_hspill.p; F.hspill_n = P->hspill; F.hcap = P->hcap;
+    F.slow_r = P->d_slow_r.p; F.hspill = P->d_hspill.p; F.hspill_n = P->hspill; F.hcap = P->hcap; F.spc = P->spc;
     F.queue = P->d_icnt.p + 2; F.slot_of = P->d_slot_of.p;
     F.flags = P->d_icnt.p + 1; F.n_accept = P->d_counters.p + 1;
     if (F.nsrc > 0) {
       // far = 0xFFFFFFFF everywhere on the coarse grids of this batch; the refined boxes reset themselves
       CK(cudaMemsetAsync(P->d_E_c.p, 0xFF, (size_t)F.nsrc * ncoarse * sizeof(unsigned), st));
       CK(cudaMemsetAsync(P->d_icnt.p + 2, 0, sizeof(int), st));
-      CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + 1) / 2), st));
+      CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + P->spc - 1) / P->spc), st));
       T.n_launch++; T.n_fmm_launch++;
     }
     CK(cudaEventRecord(e1, st));
@@ -804,7 +827,7 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
       if (ttn && e == cudaSuccess) e = cudaMemcpy(ttn + (size_t)i * nc, d_t.p, nc * 4, cudaMemcpyDeviceToHost);
       if (nsts && e == cudaSuccess) e = cudaMemcpy(nsts + (size_t)i * nc, d_s.p, nc * 4, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) break;
-      const bool own_slot = (2 * (size_t)P->nctas >= (size_t)n);   // one solve per slot: refined heap slots are intact
+      const bool own_slot = ((size_t)P->spc * (size_t)P->nctas >= (size_t)n);   // one solve per slot: refined heap slots are intact
       e = launch_decode_status(P->d_E_r.p + (size_t)i * REF_N,
                                own_slot ? P->d_hpos_r.p + (size_t)slot_of[i] * REF_N : nullptr, REF_N, d_t.p, d_s.p, h->st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);

@@ -66,6 +66,8 @@ struct FmmArgs {
   int2* hspill;               // [nslot][hspill_n] heap entries beyond the shared capacity
   int hspill_n;
   int hcap;                   // heap entries held in shared memory per solve (positions 1..hcap-1)
+  int spc;                    // solves per CTA: 2 (one per half-warp; throughput mode) or 1 (half 1 idle: no
+                              // cross-solve divergence; used when every solve can be resident anyway)
   int* queue;                 // work counter (solve pairs)
   int* slot_of;               // optional [nsrc]: slot that solved source s (test seam)
   int* flags;                 // bit4 (16): heap overflow

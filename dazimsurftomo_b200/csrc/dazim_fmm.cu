@@ -115,11 +115,14 @@ __device__ __forceinline__ int sift_up(Heap& h, int* __restrict__ hpos, int tpc,
 }
 
 // downtree (CalSurfG.f90:786-855).  `last` = heap[ntr] (fetched early by the caller).
-// Shared levels: while one level is being decided both pairs of grandchildren are already being
-// fetched.  Spill levels: the 14 entries of the next three levels under the hole are fetched by
+// Shared levels: one LDS.128 fetches both children; the loop is kept to the fewest instructions
+// (the accept chain is bound by dependent-issue latency, not by the shared-memory latency).
+// Spill levels: the 14 entries of the next three levels under the hole are fetched by
 // 14 lanes in ONE round trip and resolved with shuffles.
+template <unsigned CM>
 __device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, const int2 last, const int sl,
-                                         const unsigned hm) {
+                                         const unsigned hm_rt) {
+  const unsigned hm = CM ? CM : hm_rt;   // compile-time mask: no convergence check (MATCH.ANY) per shuffle
   if (h.ntr == 1) { h.ntr = 0; return; }
   const float k = HKEY(last);
   h.ntr -= 1;
@@ -127,28 +130,16 @@ __device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, const 
   int tpp = 1, tpc = 2;
   bool placed = false;
   const int lim = min(ntr, h.hcap - 1);      // tpc < lim  <=>  both children exist and live in shared memory
-  if (tpc < lim) {
-    int4 pr = *reinterpret_cast<const int4*>(h.sm + tpc);
-    for (;;) {
-      const int g = 2 * tpc;                 // grandchildren live at g .. g+3
-      const bool pf = (g + 3 < h.hcap);
-      int4 ga = make_int4(0, 0, 0, 0), gb = ga;
-      if (pf) {
-        ga = *reinterpret_cast<const int4*>(h.sm + g);
-        gb = *reinterpret_cast<const int4*>(h.sm + g + 2);
-      }
-      const bool right = __int_as_float(pr.x) > __int_as_float(pr.z);
-      const int2 c = right ? make_int2(pr.z, pr.w) : make_int2(pr.x, pr.y);
-      tpc += right ? 1 : 0;
-      if (!(HKEY(c) < k)) { placed = true; break; }
-      h.sm[tpp] = c;
-      hpos[c.y] = tpp;
-      tpp = tpc;
-      tpc = 2 * tpp;
-      if (!(tpc < lim)) break;
-      if (pf) pr = right ? gb : ga;
-      else pr = *reinterpret_cast<const int4*>(h.sm + tpc);
-    }
+  while (tpc < lim) {
+    const int4 pr = *reinterpret_cast<const int4*>(h.sm + tpc);
+    const bool right = __int_as_float(pr.x) > __int_as_float(pr.z);
+    const int2 c = right ? make_int2(pr.z, pr.w) : make_int2(pr.x, pr.y);
+    tpc += right ? 1 : 0;
+    if (!(HKEY(c) < k)) { placed = true; break; }
+    h.sm[tpp] = c;
+    hpos[c.y] = tpp;
+    tpp = tpc;
+    tpc = 2 * tpp;
   }
   if (!placed && tpc <= ntr) {
     if (tpc < h.hcap) {
@@ -287,12 +278,13 @@ __device__ __forceinline__ int e_status(unsigned e) { return e == E_OUT ? -2 : (
 // The narrow-band march (travel's DO WHILE, CalSurfG.f90:356-456) on one grid,
 // executed by one half-warp: sl = lane within the half, hm = its shuffle mask.
 // URG==1: refined grid with the early exit of :362-382.
-template <int URG>
+template <int URG, unsigned CM>
 __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const float dnx,
                       const float dnz, const float earth, const float* __restrict__ slow,
                       const float* __restrict__ risti_tab, unsigned* __restrict__ E, int* __restrict__ hpos,
                       const bool ex_l, const bool ex_r, const bool ex_t, const bool ex_b, const int sl,
-                      const unsigned hm, unsigned long long& nacc, int& overflow) {
+                      const unsigned hm_rt, unsigned long long& nacc, int& overflow) {
+  const unsigned hm = CM ? CM : hm_rt;
   const int nb = sl >> 2;            // neighbour 0..3: (iz,ix-1),(iz,ix+1),(iz-1,ix),(iz+1,ix)
   const int d = sl & 3;              // stencil direction of this lane: x-1, x+1, z-1, z+1
   const int ndx = (nb == 0) ? -1 : (nb == 1 ? 1 : 0);
@@ -334,7 +326,7 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
       else cval = __float_as_uint(risti_tab[cx]);
     }
     // ---- pop the root while the loads are in flight ----
-    pop_root(h, hpos, last, sl, hm);
+    pop_root<CM>(h, hpos, last, sl, hm);
     // ---- neighbour scalars ----
     const unsigned cE = __shfl_sync(hm, cval, base + 0, 16);
     const float slown = __uint_as_float(__shfl_sync(hm, cval, base + 2, 16));
@@ -481,11 +473,13 @@ __device__ __forceinline__ float refined_vel(const GridC& g, const SrcRec& sr, c
   return sum[0] + sum[1] + sum[2] + sum[3];
 }
 
+template <int SPC>
 __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
+  constexpr unsigned CM = (SPC == 1) ? 0xffffu : 0u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
   const int half = lane >> 4, sl = lane & 15;
-  const unsigned hm = 0xffffu << (half * 16);
+  const unsigned hm = CM ? CM : (0xffffu << (half * 16));
   const GridC& g = A.g;
   const size_t ncoarse = (size_t)g.nnx * g.nnz;
   const int slot = blockIdx.x * 2 + half;
@@ -507,9 +501,9 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
       if (lane == 0) pair = gridDim.x + atomicAdd(A.queue, 1);
       pair = __shfl_sync(0xffffffffu, pair, 0);
     }
-    if (pair * 2 >= A.nsrc) break;
-    const int s = pair * 2 + half;
-    const bool active = (s < A.nsrc) && !overflow;
+    if (pair * SPC >= A.nsrc) break;
+    const int s = pair * SPC + half;
+    const bool active = (half < SPC) && (s < A.nsrc) && !overflow;
     if (active) {
       const SrcRec sr = A.src[s];
       if (A.slot_of && sl == 0) A.slot_of[s] = slot;
@@ -561,7 +555,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
           }
       }
       // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
-      march<1>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
+      march<1, CM>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
                A.risti_r + (size_t)s * REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
                sr.vnb != sr.nnzr, sl, hm, nacc, overflow);
       __syncwarp(hm);
@@ -624,7 +618,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
       }
       __syncwarp(hm);
       if (!overflow)
-        march<2>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
+        march<2, CM>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
                  false, false, false, false, sl, hm, nacc, overflow);
     }
     pair = -1;
@@ -663,22 +657,23 @@ cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, floa
 }
 
 // number of CTAs (= solve pairs in flight) the device can hold for a given shared heap capacity
-cudaError_t fmm_max_ctas(int hcap, int nsm, int* nctas) {
-  const size_t smem = (size_t)hcap * 16;
-  cudaError_t e = cudaFuncSetAttribute(k_fmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas) {
+  const size_t smem = (size_t)hcap * 8 * spc;
+  cudaError_t e = cudaFuncSetAttribute(spc == 1 ? k_fmm<1> : k_fmm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fmm, 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spc == 1 ? k_fmm<1> : k_fmm<2>, 32, smem);
   if (e != cudaSuccess) return e;
   *nctas = per_sm * nsm;
   return cudaSuccess;
 }
 
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st) {
-  const size_t smem = (size_t)A.hcap * 16;
-  cudaError_t e = cudaFuncSetAttribute(k_fmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)A.hcap * 8 * A.spc;
+  cudaError_t e = cudaFuncSetAttribute(A.spc == 1 ? k_fmm<1> : k_fmm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_fmm<<<nctas, 32, smem, st>>>(A);
+  if (A.spc == 1) k_fmm<1><<<nctas, 32, smem, st>>>(A);
+  else k_fmm<2><<<nctas, 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 

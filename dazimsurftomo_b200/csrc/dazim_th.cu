@@ -19,6 +19,7 @@
 // Smith quotient) like gfortran expands them.
 #include "dazim_dev.h"
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace dz {
@@ -244,7 +245,8 @@ __device__ double nevill_dev(const DispArgs& A, int task, double t, double c1, d
 }
 
 // surfdisp96 main loop (:186-305) + getsol (:384-476), fundamental mode, phase velocity
-__global__ void __launch_bounds__(128) k_disp(DispArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_disp(DispArgs A) {
   const int task = blockIdx.x * blockDim.x + threadIdx.x;
   if (task >= A.ntask) return;
   const int mmax = A.nlayer;
@@ -317,6 +319,15 @@ __global__ void __launch_bounds__(128) k_disp(DispArgs A) {
     atomicOr(A.noroot, 1);
     for (; k < A.kmax; ++k) A.cg[(size_t)k * n + task] = 0.0;
   }
+}
+
+static void launch_disp(const DispArgs& D, unsigned nblk, cudaStream_t st) {
+  int minb = 6;   // measured on S200: 4 -> 967 ms, 5 -> 905, 6 -> 872, 8 -> 875 (profiles/README.md)
+  if (const char* e = getenv("DAZIM_KDISP_MINB")) minb = atoi(e);
+  if (minb >= 8) k_disp<8><<<nblk, 128, 0, st>>>(D);
+  else if (minb >= 6) k_disp<6><<<nblk, 128, 0, st>>>(D);
+  else if (minb == 5) k_disp<5><<<nblk, 128, 0, st>>>(D);
+  else k_disp<4><<<nblk, 128, 0, st>>>(D);
 }
 
 // ---- profile construction -------------------------------------------------
@@ -968,7 +979,7 @@ static int run_disp(cudaStream_t st, int nx, int ny, int nz, int nvar, const flo
   DispArgs D;
   D.ntask = (int)ntask; D.nlayer = nlayer; D.kmax = kmax; D.t = d_t; D.d = d.p; D.a = a.p; D.b = b.p; D.rho = rho.p;
   D.cg = d_cg; D.noroot = flag.p;
-  k_disp<<<(unsigned)((ntask + 127) / 128), 128, 0, st>>>(D);
+  launch_disp(D, (unsigned)((ntask + 127) / 128), st);
   TCK(cudaGetLastError());
   TCK(cudaMemcpyAsync(noroot_host, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   TCK(cudaStreamSynchronize(st));
@@ -1117,7 +1128,7 @@ int th_surfdisp96(cudaStream_t st, int nprof, int nlayer, const float* thk, cons
   DispArgs D;
   D.ntask = nprof; D.nlayer = nlayer; D.kmax = kmax; D.t = d_t.p; D.d = fl[0].p; D.a = fl[1].p; D.b = fl[2].p;
   D.rho = fl[3].p; D.cg = d_cg.p; D.noroot = flag.p;
-  k_disp<<<(nprof + 127) / 128, 128, 0, st>>>(D);
+  launch_disp(D, (unsigned)((nprof + 127) / 128), st);
   TCK(cudaGetLastError());
   // cg comes back as (kmax, nprof) column-major == [prof][k]; device layout is [k][prof]
   std::vector<double> tmp((size_t)nprof * kmax);

@@ -94,6 +94,10 @@ typedef struct dazim_times {
 } dazim_times;
 
 int dazim_create(dazim_handle** h, int device);
+/* page-locked host buffers for callers that want full-speed PCIe copies of the (multi-GB) COO
+ * outputs; plain malloc'ed / Fortran arrays work too, only slower */
+int dazim_host_alloc(void** p, unsigned long long bytes);
+void dazim_host_free(void* p);
 void dazim_destroy(dazim_handle* h);
 const char* dazim_strerror(int code);
 const dazim_times* dazim_last_times(const dazim_handle* h);
