@@ -175,7 +175,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="S200")
-    ap.add_argument("--cpu-sources", type=int, default=48)
+    ap.add_argument("--cpu-sources", type=int, default=640,
+                    help="sources of period 1 in the CPU sample (640 ~ 8-10 s of wall time on 16 cores for S200)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()

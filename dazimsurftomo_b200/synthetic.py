@@ -134,3 +134,41 @@ def proxy_tables(w: Workload, seed=7):
     sen = [np.asfortranarray(0.05 + 0.2 * rng.random((nxy, k, w.nz))) for _ in range(3)]
     L = np.asfortranarray((0.3 * rng.random((nxy, k, w.nz - 1)) + 0.05).astype(F32))
     return dict(pvRc=pv, sen_vs=sen[0], sen_vp=sen[1], sen_rho=sen[2], Lsen_Gsc=L)
+
+
+def yunnan_shaped(nsta=300, src_per_period=None, nrec=None, kmax=36, seed=4242) -> Workload:
+    """BASELINE config 5 shape: the grid, depth nodes, spacing, periods and sub-layering of
+    example/test4_Yunnan (para.in: 38 42 18; 29.0 98.0; 0.25 0.25; sublayers 4; 36 periods 5..40 s;
+    MOD line 1 depths) with a seeded synthetic model and station geometry (the real data file is not
+    redistributed).  Every station is a source at every period; receivers = the stations that
+    follow it in the station list (all pairs once), optionally capped at nrec."""
+    nx, ny, nz = 38, 42, 18
+    goxd, gozd, dv = 29.0, 98.0, 0.25
+    depz = np.array([0, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50, 55, 60, 70, 80, 90, 100, 120], F32)
+    _, vs, gc, gs = make_model(nx, ny, nz, cells=6, seed=seed)
+    # crustal/upper-mantle ramp on the real depth nodes (make_model's ramp is per index)
+    tRc = (5.0 + np.arange(kmax)).astype(np.float64)
+    rng = np.random.default_rng(seed)
+    lat_hi = goxd; lat_lo = goxd - (nx - 3) * dv
+    lon_lo = gozd; lon_hi = gozd + (ny - 3) * dv
+    lat = rng.uniform(lat_lo + 0.4, lat_hi - 0.4, nsta).astype(F32)
+    lon = rng.uniform(lon_lo + 0.4, lon_hi - 0.4, nsta).astype(F32)
+    colat = ((F32(90.0) - lat) * PI32 / F32(180.0)).astype(F32)
+    lonr = (lon * PI32 / F32(180.0)).astype(F32)
+    ns = nsta - 1 if src_per_period is None else min(nsta - 1, src_per_period)
+    nrcf = (nsta - 1) if nrec is None else nrec
+    periods = np.zeros((ns, kmax), np.int32, order="F"); nrc1 = np.zeros((ns, kmax), np.int32, order="F")
+    scxf = np.zeros((ns, kmax), F32, order="F"); sczf = np.zeros((ns, kmax), F32, order="F")
+    rcxf = np.zeros((nrcf, ns, kmax), F32, order="F"); rczf = np.zeros((nrcf, ns, kmax), F32, order="F")
+    for k in range(kmax):
+        for s in range(ns):
+            n = min(nsta - 1 - s, nrcf)
+            periods[s, k] = k + 1; nrc1[s, k] = n
+            scxf[s, k] = colat[s]; sczf[s, k] = lonr[s]
+            rcxf[:n, s, k] = colat[s + 1:s + 1 + n]; rczf[:n, s, k] = lonr[s + 1:s + 1 + n]
+    dall = int(nrc1.sum())
+    wave = np.full((ns, kmax), 2, np.int32, order="F"); igrt = np.zeros((ns, kmax), np.int32, order="F")
+    sv = Survey(kmax, ns, nrcf, periods, nrc1, np.full(kmax, ns, np.int32), scxf, sczf, rcxf, rczf, wave, igrt,
+                np.zeros(dall, F32), np.zeros(dall, F32), dall)
+    return Workload(f"YN-{nsta}sta" + ("" if src_per_period is None else f"-{src_per_period}src"), nx, ny, nz, goxd, gozd,
+                    dv, dv, 4.0, depz, tRc, vs, gc, gs, sv)

@@ -228,3 +228,73 @@ def test_partition_matches_single(gpu, oracle, test1, test1_tables):
         assert np.array_equal(np.concatenate(rows), full["row"])
         assert np.array_equal(np.concatenate(cols), full["col"])
         assert np.array_equal(np.concatenate(vals), full["rw"])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5 shape (test4_Yunnan grid: 38 x 42 x 18, 86 layers, non-square propagation grid)
+@pytest.fixture(scope="module")
+def yunnan():
+    from dazimsurftomo_b200 import synthetic
+    return synthetic.yunnan_shaped(nsta=24, src_per_period=3, nrec=8, kmax=6)
+
+
+def test_yunnan_shape_depth_kernels(gpu, oracle, yunnan):
+    """K1/K2 on 86-layer profiles: roots identical, TI kernels within the north-star tolerance."""
+    w = yunnan
+    sub = np.asfortranarray(w.vs[5:11, 7:11, :])                # 24 nodes
+    pv, L = gpu.depthkernelTI(sub, w.depz, w.tRc, w.sublayers)
+    opv, oL = oracle.depthkernel_ti(sub, w.depz, w.tRc, w.sublayers, nthreads=8)
+    assert (pv != opv).mean() < 0.01 and np.abs(pv - opv).max() <= 1e-5 * opv.max()
+    scale = np.abs(oL).max()
+    assert np.abs(L - oL).max() <= 2e-5 * scale
+    pv2, s1, s2, s3 = gpu.depthkernel(sub[:2, :2, :], w.depz, w.tRc[:3], w.sublayers)   # 4 nodes x 109 variants
+    opv2, o1, o2, o3, _ = oracle.depthkernel(sub[:2, :2, :], w.depz, w.tRc[:3], w.sublayers, nthreads=8)
+    assert (pv2 != opv2).mean() < 0.01
+    for a, b in ((s1, o1), (s2, o2), (s3, o3)):
+        bad = np.abs(a - b) > 1e-5 * np.abs(b).max()
+        assert bad.mean() < 0.01, bad.mean()
+
+
+def test_yunnan_shape_gmatrix(gpu, oracle, yunnan):
+    """Iso and joint G on the non-square 176 x 196 propagation grid, tables from the oracle so that the
+    eikonal / ray / assembly stages are compared bit for bit."""
+    w = yunnan
+    pv, L = oracle.depthkernel_ti(w.vs, w.depz, w.tRc, w.sublayers, nthreads=8)
+    rng = np.random.default_rng(11)
+    nxy = w.nx * w.ny
+    sen = [np.asfortranarray(0.05 + 0.2 * rng.random((nxy, len(w.tRc), w.nz))) for _ in range(3)]
+    tb = dict(pvRc=pv, Lsen_Gsc=L, sen_vs=sen[0], sen_vp=sen[1], sen_rho=sen[2])
+    args = (w.vs, w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv)
+    mx = int(w.sv.dall) * 3 * (w.nx - 2) * (w.ny - 2) * (w.nz - 1) // 8
+    _cmp_coo(gpu.CalSurfG(*args, tables=tb, maxnar=mx), oracle.gbuild(1, *args, tables=tb, maxnar=mx))
+    _cmp_coo(gpu.CalSurfGAnisoJoint(*args, tables=tb, maxnar=mx), oracle.gbuild(2, *args, tables=tb, maxnar=mx))
+    r = gpu.FwdObsTraveltimeCPS(w.vs, w.gc, w.gs, w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv, tables=tb)
+    o = oracle.gbuild(0, w.vs, w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv, w.gc, w.gs, tables=tb)
+    assert np.array_equal(r["dsurf"], o["dsurf"]) and np.array_equal(r["obsTaa"], o["obsTaa"])
+
+
+def test_empty_and_ragged_surveys(gpu, oracle, test1, test1_tables):
+    """Edge cases: a period without sources, a source without receivers, a single-ray survey."""
+    import copy
+    from dazimsurftomo_b200 import partition as pt
+    p = test1["para"]; sv0 = test1["sv"]
+    sv = copy.deepcopy(sv0)
+    ks = [k for k in range(sv.kmax) if sv.nsrcsurf1[k] > 0]
+    k0 = ks[0]
+    sv.nrc1 = sv.nrc1.copy(); sv.nsrcsurf1 = sv.nsrcsurf1.copy()
+    sv.nrc1[0, k0] = 0                      # a source with no receivers
+    if len(ks) > 1:
+        sv.nsrcsurf1[ks[1]] = 0             # a period with no sources
+    sv.dall = int(sum(sv.nrc1[s, k] for k in range(sv.kmax) for s in range(int(sv.nsrcsurf1[k]))))
+    args = (test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv)
+    r = gpu.FwdObsTraveltimeCPS(*args, tables=test1_tables)
+    o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv,
+                      test1["gc"], test1["gs"], tables=test1_tables)
+    assert len(r["dsurf"]) == sv.dall and np.array_equal(r["dsurf"], o["dsurf"]) and np.array_equal(r["obsTaa"], o["obsTaa"])
+    one, row0 = pt.sub_survey(sv0, 1, 2)
+    one.nrc1 = one.nrc1.copy(); one.nrc1[one.nrc1 > 0] = 1; one.dall = int(one.nrc1.sum())
+    r = gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, one, tables=test1_tables)
+    o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, one,
+                      test1["gc"], test1["gs"], tables=test1_tables)
+    assert one.dall == 1 and np.array_equal(r["dsurf"], o["dsurf"]) and np.array_equal(r["obsTaa"], o["obsTaa"])
