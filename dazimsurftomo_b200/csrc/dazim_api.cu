@@ -19,6 +19,8 @@ cudaError_t upload_basis(const float* ub, const float* cb);
 cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, float* slow, cudaStream_t st);
 cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
+cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas);
+cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st);
 cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, float* ttn, int* nsts, cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
 cudaError_t launch_coef(int nx, int ny, int nz, const float* vels, float* ca, float* cr, cudaStream_t st);
@@ -181,6 +183,7 @@ struct dazim_plan {
   DBuf<int> d_hpos_c, d_hpos_r, d_slot_of; DBuf<float> d_slow_r; DBuf<int2> d_hspill;   // per slot
   int nctas = 0;
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
+  int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
   DBuf<int> d_fp_off, d_fp_cnt, d_fp_cell; DBuf<float> d_fp_fdm, d_fp_fdmc, d_fp_fdms;
@@ -324,13 +327,15 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   if (const char* e = getenv("DAZIM_HCAP_MIN")) hmin = std::max(64, std::min(hneed, atoi(e)));
   P->hcap = hneed;
   P->spc = 1;
+  P->duo = 1;
   int nctas = 1;
-  CK(fmm_max_ctas(P->hcap, 1, h->nsm, &nctas));
-  while (nctas < nsrc && P->hcap > 2048) {     // one solve per CTA still fits with a (rarely spilling) smaller heap?
+  CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+  while (nctas < nsrc && P->hcap > 2048) {     // every solve resident with a (rarely spilling) smaller heap?
     P->hcap /= 2;
-    CK(fmm_max_ctas(P->hcap, 1, h->nsm, &nctas));
+    CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
   }
   if (nctas < nsrc) {
+    P->duo = 0;
     P->hcap = hneed;
     P->spc = 2;
     CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
@@ -339,10 +344,13 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
       CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
     }
   }
-  if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
-  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC")) {
+  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC") || getenv("DAZIM_DUO")) {
+    if (const char* e = getenv("DAZIM_DUO")) P->duo = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
+    if (P->duo) P->spc = 1;
     if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, pow2ceil(atoi(e)));
-    CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
+    if (P->duo) CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+    else CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
   }
   if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
   const long long npairs_all = (nsrc + P->spc - 1) / P->spc;
@@ -539,7 +547,8 @@ static int plan_run(dazim_plan* P) {
       // far = 0xFFFFFFFF everywhere on the coarse grids of this batch; the refined boxes reset themselves
       CK(cudaMemsetAsync(P->d_E_c.p, 0xFF, (size_t)F.nsrc * ncoarse * sizeof(unsigned), st));
       CK(cudaMemsetAsync(P->d_icnt.p + 2, 0, sizeof(int), st));
-      CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + P->spc - 1) / P->spc), st));
+      if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
+      else CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + P->spc - 1) / P->spc), st));
       T.n_launch++; T.n_fmm_launch++;
     }
     CK(cudaEventRecord(e1, st));

@@ -629,6 +629,360 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// K3, latency mode ("duo"): one CTA of TWO warps per solve.  Used when every solve of the launch
+// can be resident at once, i.e. when the run time is the length of one solve's serial accept chain.
+// Warp H owns the heap (pop, verification, sift-ups); warp Q owns the stencil work of the same
+// accept step (gather of the 4 neighbours' stencils, the 16 quadrant quadratics, the status
+// stores).  Q's ~350 instructions run while H sifts the root down, so the serial chain of one
+// accept shrinks to  pop + apply  instead of  pop + gather + quadrants + apply.  Two block
+// barriers per accept hand the node id to Q and the four trial times back to H.  The arithmetic
+// and the heap discipline are the same functions as in k_fmm: results are bit-identical.
+#define DUO_FULL 0xffffffffu
+
+template <int URG>
+__device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, const int ld,
+                            unsigned* __restrict__ E, int* __restrict__ hpos, const bool ex_l, const bool ex_r,
+                            const bool ex_t, const bool ex_b, const int sl, unsigned long long& nacc, int& overflow) {
+  const int nb = sl >> 2, d = sl & 3;
+  const float inv_ld = 1.0f / (float)ld;
+  for (;;) {
+    bool stop = (h.ntr == 0) || overflow;
+    int2 root = make_int2(0, 0), last = make_int2(0, 0);
+    if (!stop) {
+      root = h.sm[1];
+      last = hget(h, h.ntr);
+      E[root.y] = (unsigned)root.x & ~E_SIGN;       // the popped node becomes alive with its heap key
+      if (URG == 1) {
+        const int pn = root.y;
+        int ix = (int)((float)pn * inv_ld);
+        int iz = pn - ix * ld;
+        if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+        if ((ix == 0 && ex_l) || (ix == nnx - 1 && ex_r) || (iz == 0 && ex_t) || (iz == nnz - 1 && ex_b)) stop = true;
+      }
+    }
+    if (threadIdx.x == 0) comm[0] = stop ? -1 : root.y;
+    __syncthreads();                                  // A: node id (and every earlier E store) visible to Q
+    if (stop) break;
+    ++nacc;
+    pop_root<DUO_FULL>(h, hpos, last, sl, DUO_FULL);
+    __syncthreads();                                  // B: Q's results are in comm[16..31]
+    int qst[4], qo[4], spos[4];
+    float qt[4];
+    int nins = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int4 r = reinterpret_cast<const int4*>(comm + 16)[q];    // (status, hpos before the pop, trial time, offset)
+      qst[q] = r.x;
+      qt[q] = __int_as_float(r.z);
+      qo[q] = r.w;
+      spos[q] = 0;
+      if (qst[q] == -1) spos[q] = h.ntr + (++nins);
+      else if (qst[q] == 1) spos[q] = r.y;
+    }
+    if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; continue; }
+    if (h.ntr + nins < h.hcap) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (qst[q] != 1) continue;
+        int vn = -1;
+        if (spos[q] >= 1 && spos[q] <= h.ntr) vn = h.sm[spos[q]].y;
+        if (vn != qo[q]) spos[q] = hpos[qo[q]];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (qst[q] == -2 || qst[q] == 0) continue;
+        if (qst[q] == -1) h.ntr += 1;
+        const float k = qt[q];
+        int tpc = spos[q];
+        bool moved = false;
+        for (int tpp = tpc >> 1; tpp > 0; tpp >>= 1) {
+          const int2 par = h.sm[tpp];
+          if (!(k < HKEY(par))) break;
+          h.sm[tpc] = par;
+          hpos[par.y] = tpc;
+          moved = true;
+          tpc = tpp;
+        }
+        h.sm[tpc] = make_int2(__float_as_int(k), qo[q]);
+        hpos[qo[q]] = tpc;
+        if (moved && q < 3) {
+#pragma unroll
+          for (int r = q + 1; r < 4; ++r)
+            if (qst[r] == 1) spos[r] = hpos[qo[r]];
+        }
+      }
+      continue;
+    }
+    // deep path (rare in this mode): same scheme as k_fmm
+    int myp = 0;
+    {
+      const int sp = (nb == 0) ? spos[0] : (nb == 1 ? spos[1] : (nb == 2 ? spos[2] : spos[3]));
+      myp = sp >> d;
+    }
+    int2 cent = make_int2(0, -1);
+    if (myp >= h.hcap && myp <= h.ntr) cent = h.gl[myp - h.hcap];
+    bool chain_ok = true;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (qst[q] != 1) continue;
+      int2 v = make_int2(0, -1);
+      if (spos[q] >= 1 && spos[q] <= h.ntr) v = (spos[q] < h.hcap) ? h.sm[spos[q]] : shfl2(DUO_FULL, cent, q * 4);
+      if (v.y != qo[q]) {
+        spos[q] = hpos[qo[q]];
+        chain_ok = false;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (qst[q] == -2 || qst[q] == 0) continue;
+      if (qst[q] == -1) h.ntr += 1;
+      const float k = qt[q];
+      int tpc = spos[q];
+      bool moved = false;
+      for (int j = 1;; ++j) {
+        const int tpp = tpc >> 1;
+        if (tpp == 0) break;
+        int2 par;
+        if (tpp < h.hcap) par = h.sm[tpp];
+        else if (chain_ok && j <= 3) par = shfl2(DUO_FULL, cent, q * 4 + j);
+        else par = h.gl[tpp - h.hcap];
+        if (!(k < HKEY(par))) break;
+        hput(h, hpos, tpc, par);
+        moved = true;
+        tpc = tpp;
+      }
+      hput(h, hpos, tpc, make_int2(__float_as_int(k), qo[q]));
+      if (q < 3) {
+        if (moved) chain_ok = false;
+        else if (tpc >= h.hcap && __ballot_sync(DUO_FULL, myp == tpc && nb > q) != 0u) chain_ok = false;
+        if (moved) {
+#pragma unroll
+          for (int r = q + 1; r < 4; ++r)
+            if (qst[r] == 1) spos[r] = hpos[qo[r]];
+        }
+      }
+    }
+  }
+}
+
+__device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int ld, const float dnx, const float dnz,
+                            const float earth, const float* __restrict__ slow, const float* __restrict__ risti_tab,
+                            unsigned* __restrict__ E, const int* __restrict__ hpos, const int sl) {
+  const int nb = sl >> 2, d = sl & 3;
+  const int ndx = (nb == 0) ? -1 : (nb == 1 ? 1 : 0);
+  const int ndz = (nb == 2) ? -1 : (nb == 3 ? 1 : 0);
+  const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0);
+  const int ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+  const int base = sl & 12;
+  const float inv_ld = 1.0f / (float)ld;
+  for (;;) {
+    __syncthreads();                                  // A
+    const int pn = comm[0];
+    if (pn < 0) break;
+    int ix = (int)((float)pn * inv_ld);
+    int iz = pn - ix * ld;
+    if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+    const int cx = ix + ndx, cz = iz + ndz;
+    const bool cin = (cx >= 0 && cx < nnx && cz >= 0 && cz < nnz);
+    const int co = cx * ld + cz;
+    unsigned e1 = E_OUT, e2 = E_OUT;
+    {
+      const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+      if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[s1x * ld + s1z];
+      if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[s2x * ld + s2z];
+    }
+    unsigned cval = 0;                                 // d=0: E[c], 1: hpos[c], 2: slowness, 3: R sin(theta)
+    if (cin) {
+      if (d == 0) cval = E[co];
+      else if (d == 1) cval = (unsigned)hpos[co];
+      else if (d == 2) cval = __float_as_uint(slow[co]);
+      else cval = __float_as_uint(risti_tab[cx]);
+    }
+    const unsigned cE = __shfl_sync(DUO_FULL, cval, base + 0, 16);
+    const float slown = __uint_as_float(__shfl_sync(DUO_FULL, cval, base + 2, 16));
+    const float risti = __uint_as_float(__shfl_sync(DUO_FULL, cval, base + 3, 16));
+    const int cst = !cin ? -2 : (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
+    const int js = (sl >> 1) & 1, ks = sl & 1;
+    const unsigned ej1 = __shfl_sync(DUO_FULL, e1, base + js, 16), ej2 = __shfl_sync(DUO_FULL, e2, base + js, 16);
+    const unsigned ek1 = __shfl_sync(DUO_FULL, e1, base + 2 + ks, 16), ek2 = __shfl_sync(DUO_FULL, e2, base + 2 + ks, 16);
+    bool ok = false;
+    float trav = quadrant(e_status(ej1), e_status(ej2), __uint_as_float(ej1), __uint_as_float(ej2), e_status(ek1),
+                          e_status(ek2), __uint_as_float(ek1), __uint_as_float(ek2), slown, earth, risti, dnx, dnz, ok);
+    if (!ok) trav = __int_as_float(0x7f800000);
+    trav = fminf(trav, __shfl_xor_sync(DUO_FULL, trav, 1, 16));
+    trav = fminf(trav, __shfl_xor_sync(DUO_FULL, trav, 2, 16));
+    // hand the four (status, position-before-pop, trial time, offset) records to H; mark the
+    // neighbours close with their new trial time (nothing reads E between here and the next gather)
+    int out = cst;
+    if (d == 1) out = (int)cval;
+    else if (d == 2) out = __float_as_int(trav);
+    else if (d == 3) out = co;
+    if (threadIdx.x - 32 < 16) comm[16 + sl] = out;
+    if (d == 0 && (cst == -1 || cst == 1) && threadIdx.x - 32 < 16) E[co] = __float_as_uint(trav) | E_SIGN;
+    __syncthreads();                                  // B
+  }
+}
+
+__global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sl = lane & 15;
+  const GridC& g = A.g;
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;
+  const int slot = blockIdx.x * 2;
+  Heap h;
+  h.sm = reinterpret_cast<int2*>(smem_raw);
+  h.gl = A.hspill + (size_t)slot * A.hspill_n;
+  h.hcap = A.hcap;
+  h.hspill = A.hspill_n;
+  h.ntr = 0;
+  int* comm = reinterpret_cast<int*>(smem_raw + (size_t)A.hcap * 8);       // 32 ints
+  int* hpos_c = A.hpos_c + (size_t)slot * ncoarse;
+  int* hpos_r = A.hpos_r + (size_t)slot * REF_N;
+  float* slow_r = A.slow_r + (size_t)slot * REF_N;
+  unsigned long long nacc = 0;
+  int overflow = 0;
+  for (int s = blockIdx.x; s < A.nsrc;) {
+    const SrcRec sr = A.src[s];
+    if (A.slot_of && tid == 0) A.slot_of[s] = slot;
+    unsigned* E_r = A.E_r + (size_t)s * REF_N;
+    unsigned* E_c = A.E_c + (size_t)s * ncoarse;
+    const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
+    const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
+    // ---- refined slowness nodes (bsplrefine) + status reset: all 64 threads ----
+    for (int e = tid; e < sr.nnxr * sr.nnzr; e += 64) {
+      const int idm1 = e % sr.nnzr + 1, idm2 = e / sr.nnzr + 1;
+      const int o = (idm2 - 1) * REF_LD + (idm1 - 1);
+      slow_r[o] = 1.0f / refined_vel(g, sr, vv, idm1, idm2);
+      E_r[o] = E_FAR;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // ---- source cell initialisation (travel, CalSurfG.f90:324-345) ----
+      h.ntr = 0;
+      const int isx = sr.isx_r, isz = sr.isz_r;
+      float vss[2][2];
+#pragma unroll
+      for (int i = 1; i <= 2; ++i)
+#pragma unroll
+        for (int j = 1; j <= 2; ++j) vss[i - 1][j - 1] = refined_vel(g, sr, vv, isz - 1 + j, isx - 1 + i);
+      const float dsx = sr.dsx_r, dsz = sr.dsz_r;
+      float vsrc = 0.0f;
+#pragma unroll
+      for (int i = 1; i <= 2; ++i)
+#pragma unroll
+        for (int j = 1; j <= 2; ++j) {
+          const float produ = (1.0f - fabsf(((float)(i - 1) * sr.dnxr - dsx) / sr.dnxr)) *
+                              (1.0f - fabsf(((float)(j - 1) * sr.dnzr - dsz) / sr.dnzr));
+          vsrc = vsrc + vss[i - 1][j - 1] * produ;
+        }
+#pragma unroll
+      for (int i = 1; i <= 2; ++i)
+#pragma unroll
+        for (int j = 1; j <= 2; ++j) {
+          const float ax = dsx - (float)(i - 1) * sr.dnxr;
+          const float az = dsz - (float)(j - 1) * sr.dnzr;
+          const float ds = sqrtf(ax * ax + az * az);
+          const float t0 = 2.0f * ds / (vss[i - 1][j - 1] + vsrc);
+          const int o = (isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1);
+          E_r[o] = __float_as_uint(t0) | E_SIGN;
+          h.ntr += 1;
+          sift_up(h, hpos_r, h.ntr, t0, o, nullptr);
+        }
+      // ---- refined march; exit tests literal to CalSurfG.f90:366-377 ----
+      march_duo_H<1>(h, comm, sr.nnxr, sr.nnzr, REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
+                     sr.vnb != sr.nnzr, sl, nacc, overflow);
+    } else {
+      march_duo_Q(comm, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r, A.risti_r + (size_t)s * REF_LD, E_r,
+                  hpos_r, sl);
+    }
+    __syncthreads();
+    // ---- hand-off to the coarse grid (FwdTraveltimeCPS.f90:576-632); E_c was preset to FAR ----
+    {
+      const int nkx = (sr.nnxr - 1) / g.sgdl + 1, nkz = (sr.nnzr - 1) / g.sgdl + 1;
+      for (int e = tid; e < nkx * nkz; e += 64) {
+        const int kz = e % nkz, kx = e / nkz;
+        E_c[(sr.vnl + kx - 1) * g.nnz + (sr.vnt + kz - 1)] = E_r[(kx * g.sgdl) * REF_LD + (kz * g.sgdl)];
+      }
+    }
+    __syncthreads();
+    {
+      // alive nodes with a far neighbour become close (:615-632): decide on the original field, then mark
+      const int nz_b = sr.vnb - sr.vnt + 1, nb_tot = (sr.vnr - sr.vnl + 1) * nz_b;
+      for (int e0 = 0; e0 < nb_tot; e0 += 64) {
+        const int e = e0 + tid;
+        bool mk = false;
+        int o = 0;
+        if (e < nb_tot) {
+          const int l = sr.vnt + e % nz_b, k = sr.vnl + e / nz_b;
+          o = (k - 1) * g.nnz + (l - 1);
+          if ((int)E_c[o] >= 0) {
+            if (l - 1 >= 1 && E_c[o - 1] == E_FAR) mk = true;
+            if (l + 1 <= g.nnz && E_c[o + 1] == E_FAR) mk = true;
+            if (k - 1 >= 1 && E_c[o - g.nnz] == E_FAR) mk = true;
+            if (k + 1 <= g.nnx && E_c[o + g.nnz] == E_FAR) mk = true;
+          }
+        }
+        __syncthreads();
+        if (mk) E_c[o] |= E_SIGN;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // ---- heap build in scan order i=1..nnx, j=1..nnz (travel urg=2, CalSurfG.f90:311-317) ----
+      h.ntr = 0;
+      for (int k = sr.vnl; k <= sr.vnr && !overflow; ++k) {
+        for (int l0 = sr.vnt; l0 <= sr.vnb; l0 += 16) {
+          const int l = l0 + sl;
+          unsigned ev = E_FAR;
+          if (l <= sr.vnb) ev = E_c[(k - 1) * g.nnz + (l - 1)];
+          unsigned msk = __ballot_sync(DUO_FULL, (int)ev < 0 && ev != E_FAR) & 0xffffu;
+          while (msk) {
+            const int b = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const float tb = __uint_as_float(__shfl_sync(DUO_FULL, ev, b, 16) & ~E_SIGN);
+            if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; break; }
+            h.ntr += 1;
+            sift_up(h, hpos_c, h.ntr, tb, (k - 1) * g.nnz + (l0 + b - 1), nullptr);
+          }
+        }
+      }
+      march_duo_H<2>(h, comm, g.nnx, g.nnz, g.nnz, E_c, hpos_c, false, false, false, false, sl, nacc, overflow);
+    } else {
+      march_duo_Q(comm, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c, sl);
+    }
+    __syncthreads();
+    // next solve: first one = own CTA index, later ones from the queue
+    if (tid == 0) comm[1] = gridDim.x + atomicAdd(A.queue, 1);
+    __syncthreads();
+    s = comm[1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (overflow) atomicOr(A.flags, 16);
+    if (nacc) atomicAdd(A.n_accept, nacc);
+  }
+}
+
+cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas) {
+  const size_t smem = (size_t)hcap * 8 + 128;
+  cudaError_t e = cudaFuncSetAttribute(k_fmm_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fmm_duo, 64, smem);
+  if (e != cudaSuccess) return e;
+  *nctas = per_sm * nsm;
+  return cudaSuccess;
+}
+
+cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st) {
+  const size_t smem = (size_t)A.hcap * 8 + 128;
+  cudaError_t e = cudaFuncSetAttribute(k_fmm_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_fmm_duo<<<nctas, 64, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
 // test seam: (E, hpos) -> the reference's (ttn, nsts) pair
 __global__ void k_decode_status(const unsigned* __restrict__ E, const int* __restrict__ hpos, size_t n,
                                 float* __restrict__ ttn, int* __restrict__ nsts) {
