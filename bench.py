@@ -81,6 +81,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_PINNED = {}
+
+
 def _measured_traffic(workload_name, solves):
     """DRAM bytes per k_fmm launch from the committed ncu capture (profiles/k3_dram_traffic.json:
     bytes per solve measured with dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch."""
@@ -283,7 +286,17 @@ def main():
             h2d = plan.h2d_bytes + w.vs.nbytes
             d2h = 0
             if rank == 0:
-                host = {k: full[k].cpu() for k in ("dsurf", "rw", "col", "row")}
+                # rank 0 reads the full system back into cached page-locked buffers (what a caller would keep)
+                host = {}
+                for k in ("dsurf", "rw", "col", "row"):
+                    src = full[k]
+                    buf = _PINNED.get(k)
+                    if buf is None or buf.numel() < src.numel() or buf.dtype != src.dtype:
+                        buf = torch.empty(int(src.numel() * 1.1) + 16, dtype=src.dtype, pin_memory=True)
+                        _PINNED[k] = buf
+                    host[k] = buf[:src.numel()]
+                    host[k].copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
                 d2h = sum(v.numel() * v.element_size() for v in host.values())
                 assert host["dsurf"].numel() == w.n_rays
             del full, blk, dtens

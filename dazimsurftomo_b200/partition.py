@@ -79,13 +79,21 @@ def sub_survey(sv: Survey, ub: int, ue: int):
 
 
 def _all_gather_v(t, dist, group=None):
-    """All-gather of 1-D tensors of different length (same dtype/device): sizes first, then padded blocks."""
+    """All-gather of 1-D tensors of different length (same dtype/device) in rank order.
+    NCCL: one collective straight into exact-size slices of a single output buffer (uneven all-gather,
+    no padding, no concatenation copy).  gloo (CPU tests): sizes first, then padded equal blocks."""
     import torch
     world = dist.get_world_size(group)
     n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    allsz = torch.zeros(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(allsz, n, group=group)
+    sizes = [int(x) for x in allsz.tolist()]
+    if t.is_cuda:
+        out = torch.empty(sum(sizes), dtype=t.dtype, device=t.device)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        views = [out[int(offs[r]):int(offs[r + 1])] for r in range(world)]
+        dist.all_gather(views, t.contiguous(), group=group)
+        return out, sizes
     m = max(max(sizes), 1)
     pad = torch.zeros(m, dtype=t.dtype, device=t.device)
     pad[: t.numel()] = t
@@ -115,8 +123,8 @@ def gather_rows(block: Dict[str, "object"], row0: int, group=None) -> Dict[str, 
         if int(r.item()) != exp:
             raise RuntimeError("row blocks are not contiguous in rank order")
         exp += n
-    rows = torch.repeat_interleave(torch.arange(1, nnz_row.numel() + 1, device=nnz_row.device, dtype=torch.int64), nnz_row)
-    return dict(dsurf=dsurf, rw=val, col=col, row=rows.to(torch.int32), nar=int(val.numel()), nnz_row=nnz_row)
+    rows = torch.repeat_interleave(torch.arange(1, nnz_row.numel() + 1, device=nnz_row.device, dtype=torch.int32), nnz_row)
+    return dict(dsurf=dsurf, rw=val, col=col, row=rows, nar=int(val.numel()), nnz_row=nnz_row)
 
 
 def misfit_sums(obst, dsurf, group=None):
