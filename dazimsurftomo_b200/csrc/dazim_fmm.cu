@@ -283,7 +283,7 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
                       const float dnz, const float earth, const float* __restrict__ slow,
                       const float* __restrict__ risti_tab, unsigned* __restrict__ E, int* __restrict__ hpos,
                       const bool ex_l, const bool ex_r, const bool ex_t, const bool ex_b, const int sl,
-                      const unsigned hm_rt, unsigned long long& nacc, int& overflow) {
+                      const unsigned hm_rt, unsigned long long& nacc, int& overflow, const bool act0) {
   const unsigned hm = CM ? CM : hm_rt;
   const int nb = sl >> 2;            // neighbour 0..3: (iz,ix-1),(iz,ix+1),(iz-1,ix),(iz+1,ix)
   const int d = sl & 3;              // stencil direction of this lane: x-1, x+1, z-1, z+1
@@ -293,7 +293,14 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
   const int ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
   const int base = sl & 12;
   const float inv_ld = 1.0f / (float)ld;
-  while (h.ntr > 0) {
+  // CM == 0 (two solves per warp): the call is warp-collective and both halves re-converge at the
+  // vote below once per accept step, so the instruction stream they have in common is issued once.
+  bool done = !act0;
+  for (;;) {
+    const bool act = !done && h.ntr > 0;
+    if (CM == 0) { if (!__any_sync(0xffffffffu, act)) break; }
+    else if (!act) break;
+    if (!act) continue;
     const int2 root = h.sm[1];
     const int pn = root.y;
     // the element that will be sifted down from the root (may live in the spill part: fetch it now)
@@ -305,7 +312,10 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
     // the popped node becomes alive with its trial value (= its heap key)
     E[pn] = (unsigned)root.x & ~E_SIGN;
     if (URG == 1) {
-      if ((ix == 0 && ex_l) || (ix == nnx - 1 && ex_r) || (iz == 0 && ex_t) || (iz == nnz - 1 && ex_b)) break;
+      if ((ix == 0 && ex_l) || (ix == nnx - 1 && ex_r) || (iz == 0 && ex_t) || (iz == nnz - 1 && ex_b)) {
+        done = true;
+        continue;
+      }
     }
     ++nacc;
     // ---- issue the gather: 4 neighbours x 4 directions x (first, second) stencil node ----
@@ -356,7 +366,7 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
       if (qst[q] == -1) spos[q] = h.ntr + (++nins);
       else if (qst[q] == 1) spos[q] = hl;
     }
-    if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; return; }
+    if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; done = true; continue; }
     if (h.ntr + nins < h.hcap) {
       // ---- fast path: every heap position this step can touch lives in shared memory ----
 #pragma unroll
@@ -504,13 +514,14 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
     if (pair * SPC >= A.nsrc) break;
     const int s = pair * SPC + half;
     const bool active = (half < SPC) && (s < A.nsrc) && !overflow;
+    const int sc = min(s, A.nsrc - 1);                 // inactive half: valid addresses, no side effects
+    const SrcRec sr = A.src[sc];
+    unsigned* E_r = A.E_r + (size_t)sc * REF_N;
+    unsigned* E_c = A.E_c + (size_t)sc * ncoarse;
+    const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
+    const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
     if (active) {
-      const SrcRec sr = A.src[s];
       if (A.slot_of && sl == 0) A.slot_of[s] = slot;
-      unsigned* E_r = A.E_r + (size_t)s * REF_N;
-      unsigned* E_c = A.E_c + (size_t)s * ncoarse;
-      const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
-      const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
       h.ntr = 0;
 
       // ---- refined slowness nodes (bsplrefine) + status reset ----
@@ -554,10 +565,12 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
             sift_up(h, hpos_r, h.ntr, t0, o, nullptr);
           }
       }
-      // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
-      march<1, CM>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
-               A.risti_r + (size_t)s * REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
-               sr.vnb != sr.nnzr, sl, hm, nacc, overflow);
+    }
+    // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
+    march<1, CM>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
+                 A.risti_r + (size_t)sc * REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
+                 sr.vnb != sr.nnzr, sl, hm, nacc, overflow, active);
+    if (active) {
       __syncwarp(hm);
 
       // ---- hand-off to the coarse grid (FwdTraveltimeCPS.f90:576-632); E_c was preset to FAR ----
@@ -617,10 +630,9 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
         }
       }
       __syncwarp(hm);
-      if (!overflow)
-        march<2, CM>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
-                 false, false, false, false, sl, hm, nacc, overflow);
     }
+    march<2, CM>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
+                 false, false, false, false, sl, hm, nacc, overflow, active && !overflow);
     pair = -1;
   }
   if (sl == 0) {
