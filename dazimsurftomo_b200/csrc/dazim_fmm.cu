@@ -25,6 +25,7 @@
 //    patched in registers while the pop / earlier sift-ups move entries, so no
 //    global read-after-write sits on the critical path.
 #include "dazim_dev.h"
+#include <cstdio>
 
 namespace dz {
 
@@ -384,22 +385,20 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
         if (qst[q] == -1) h.ntr += 1;
         const float k = qt[q];
         int tpc = spos[q];
-        bool moved = false;
         for (int tpp = tpc >> 1; tpp > 0; tpp >>= 1) {
           const int2 par = h.sm[tpp];
           if (!(k < HKEY(par))) break;
           h.sm[tpc] = par;
           hpos[par.y] = tpc;
-          moved = true;
+          // a later neighbour that sits on this path moves down with its parent slot: keep its
+          // position in registers (a read-back of hpos would put a global round trip on the chain)
+#pragma unroll
+          for (int r = q + 1; r < 4; ++r)
+            if (par.y == qo[r]) spos[r] = tpc;
           tpc = tpp;
         }
         h.sm[tpc] = make_int2(__float_as_int(k), qo[q]);
         hpos[qo[q]] = tpc;
-        if (moved && q < 3) {
-#pragma unroll
-          for (int r = q + 1; r < 4; ++r)
-            if (qst[r] == 1) spos[r] = hpos[qo[r]];
-        }
       }
       continue;
     }
@@ -443,6 +442,9 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
         if (!(k < HKEY(par))) break;
         hput(h, hpos, tpc, par);
         moved = true;
+#pragma unroll
+        for (int r = q + 1; r < 4; ++r)
+          if (par.y == qo[r]) spos[r] = tpc;
         tpc = tpp;
       }
       hput(h, hpos, tpc, make_int2(__float_as_int(k), qo[q]));
@@ -450,11 +452,6 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
         // later sift-ups: prefetched entries are stale if this one changed a spilled position they use
         if (moved) chain_ok = false;
         else if (tpc >= h.hcap && __ballot_sync(hm, myp == tpc && nb > q) != 0u) chain_ok = false;
-        if (moved) {
-#pragma unroll
-          for (int r = q + 1; r < 4; ++r)
-            if (qst[r] == 1) spos[r] = hpos[qo[r]];
-        }
       }
     }
   }
@@ -651,6 +648,11 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
 // barriers per accept hand the node id to Q and the four trial times back to H.  The arithmetic
 // and the heap discipline are the same functions as in k_fmm: results are bit-identical.
 #define DUO_FULL 0xffffffffu
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifdef DAZIM_DUO_PROF
+// per-thread accumulator of barrier wait cycles (H: at B waiting for Q's results; Q: at A waiting for H)
+#define g_prof_wait prof_wait_local
+#endif
 
 template <int URG>
 __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, const int ld,
@@ -658,7 +660,14 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
                             const bool ex_t, const bool ex_b, const int sl, unsigned long long& nacc, int& overflow) {
   const int nb = sl >> 2, d = sl & 3;
   const float inv_ld = 1.0f / (float)ld;
+#ifdef DAZIM_DUO_PROF
+  long long prof_wait_local = 0, prof_pop = 0, prof_apply = 0, prof_napply = 0, prof_waitA = 0, prof_read = 0, prof_verify = 0, prof_vfail = 0, prof_nsift = 0;
+  const long long tmarch0 = clock64();
+#endif
   for (;;) {
+#ifdef DAZIM_DUO_PROF
+    if (prof_napply > 0) { prof_apply += clock64(); prof_napply = 0; }
+#endif
     bool stop = (h.ntr == 0) || overflow;
     int2 root = make_int2(0, 0), last = make_int2(0, 0);
     if (!stop) {
@@ -674,11 +683,35 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
       }
     }
     if (threadIdx.x == 0) comm[0] = stop ? -1 : root.y;
+#ifdef DAZIM_DUO_PROF
+    const long long ta0 = clock64();
+#endif
     __syncthreads();                                  // A: node id (and every earlier E store) visible to Q
+#ifdef DAZIM_DUO_PROF
+    prof_waitA += clock64() - ta0;
+    if (stop && URG == 2 && blockIdx.x == 0 && threadIdx.x == 0)
+      printf("[duo prof] H: march cycles %lld, pop %lld, apply(+loop top) %lld [read %lld verify %lld vfail %lld nsift %lld], barrier A %lld, barrier B %lld, accepts %llu\n",
+             clock64() - tmarch0, prof_pop, prof_apply, prof_read, prof_verify, prof_vfail, prof_nsift, prof_waitA, prof_wait_local, nacc);
+#endif
     if (stop) break;
     ++nacc;
+#ifdef DAZIM_DUO_PROF
+    const long long tp0 = clock64();
+#endif
     pop_root<DUO_FULL>(h, hpos, last, sl, DUO_FULL);
+    // the new heap root is (almost always) the next node to be accepted: let Q warm its stencil lines
+    if (threadIdx.x == 0) comm[2] = (h.ntr > 0) ? h.sm[1].y : -1;
+#ifdef DAZIM_DUO_PROF
+    const long long tb0 = clock64();
+    prof_pop += tb0 - tp0;
+#endif
     __syncthreads();                                  // B: Q's results are in comm[16..31]
+#ifdef DAZIM_DUO_PROF
+    const long long tb1 = clock64();
+    g_prof_wait += tb1 - tb0;
+    prof_apply -= tb1;
+    prof_napply += 1;
+#endif
     int qst[4], qo[4], spos[4];
     float qt[4];
     int nins = 0;
@@ -693,36 +726,50 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
       else if (qst[q] == 1) spos[q] = r.y;
     }
     if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; continue; }
+#ifdef DAZIM_DUO_PROF
+    const long long tv0 = clock64();
+    prof_read += tv0 - tb1;
+#endif
     if (h.ntr + nins < h.hcap) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (qst[q] != 1) continue;
         int vn = -1;
         if (spos[q] >= 1 && spos[q] <= h.ntr) vn = h.sm[spos[q]].y;
-        if (vn != qo[q]) spos[q] = hpos[qo[q]];
+        if (vn != qo[q]) {
+          spos[q] = hpos[qo[q]];
+#ifdef DAZIM_DUO_PROF
+          prof_vfail += 1;
+#endif
+        }
       }
+#ifdef DAZIM_DUO_PROF
+      const long long tv1 = clock64();
+      prof_verify += tv1 - tv0;
+#endif
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (qst[q] == -2 || qst[q] == 0) continue;
+#ifdef DAZIM_DUO_PROF
+        prof_nsift += 1;
+#endif
         if (qst[q] == -1) h.ntr += 1;
         const float k = qt[q];
         int tpc = spos[q];
-        bool moved = false;
         for (int tpp = tpc >> 1; tpp > 0; tpp >>= 1) {
           const int2 par = h.sm[tpp];
           if (!(k < HKEY(par))) break;
           h.sm[tpc] = par;
           hpos[par.y] = tpc;
-          moved = true;
+          // a later neighbour that sits on this path moves down with its parent slot: keep its
+          // position in registers (a read-back of hpos would put a global round trip on the chain)
+#pragma unroll
+          for (int r = q + 1; r < 4; ++r)
+            if (par.y == qo[r]) spos[r] = tpc;
           tpc = tpp;
         }
         h.sm[tpc] = make_int2(__float_as_int(k), qo[q]);
         hpos[qo[q]] = tpc;
-        if (moved && q < 3) {
-#pragma unroll
-          for (int r = q + 1; r < 4; ++r)
-            if (qst[r] == 1) spos[r] = hpos[qo[r]];
-        }
       }
       continue;
     }
@@ -762,17 +809,15 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
         if (!(k < HKEY(par))) break;
         hput(h, hpos, tpc, par);
         moved = true;
+#pragma unroll
+        for (int r = q + 1; r < 4; ++r)
+          if (par.y == qo[r]) spos[r] = tpc;
         tpc = tpp;
       }
       hput(h, hpos, tpc, make_int2(__float_as_int(k), qo[q]));
       if (q < 3) {
         if (moved) chain_ok = false;
         else if (tpc >= h.hcap && __ballot_sync(DUO_FULL, myp == tpc && nb > q) != 0u) chain_ok = false;
-        if (moved) {
-#pragma unroll
-          for (int r = q + 1; r < 4; ++r)
-            if (qst[r] == 1) spos[r] = hpos[qo[r]];
-        }
       }
     }
   }
@@ -788,9 +833,24 @@ __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int l
   const int ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
   const int base = sl & 12;
   const float inv_ld = 1.0f / (float)ld;
+#ifdef DAZIM_DUO_PROF
+  long long prof_wait_local = 0;
+  const long long tq0 = clock64();
+#endif
   for (;;) {
+#ifdef DAZIM_DUO_PROF
+    const long long ta0 = clock64();
+#endif
     __syncthreads();                                  // A
+#ifdef DAZIM_DUO_PROF
+    g_prof_wait += clock64() - ta0;
+#endif
     const int pn = comm[0];
+#ifdef DAZIM_DUO_PROF
+    if (pn < 0 && ld != REF_LD && blockIdx.x == 0 && threadIdx.x == 32)
+      printf("[duo prof] Q: march cycles %lld, waiting at A %lld (%.1f%%)\n", clock64() - tq0, prof_wait_local,
+             100.0 * prof_wait_local / (double)(clock64() - tq0));
+#endif
     if (pn < 0) break;
     int ix = (int)((float)pn * inv_ld);
     int iz = pn - ix * ld;
@@ -833,6 +893,23 @@ __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int l
     if (threadIdx.x - 32 < 16) comm[16 + sl] = out;
     if (d == 0 && (cst == -1 || cst == 1) && threadIdx.x - 32 < 16) E[co] = __float_as_uint(trav) | E_SIGN;
     __syncthreads();                                  // B
+    // while H applies the four sift-ups: pull the stencil lines of the predicted next node towards the SM
+    const int pp = comm[2];
+    if (pp >= 0) {
+      int px = (int)((float)pp * inv_ld);
+      int pz = pp - px * ld;
+      if (pz < 0) { px -= 1; pz += ld; } else if (pz >= ld) { px += 1; pz -= ld; }
+      const int qx = px + ndx, qz = pz + ndz;
+      if (qx >= 0 && qx < nnx && qz >= 0 && qz < nnz) {
+        const int qo = qx * ld + qz;
+        const int s1x = qx + ddx, s1z = qz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+        if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l1(E + s1x * ld + s1z);
+        if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l1(E + s2x * ld + s2z);
+        if (d == 0) prefetch_l1(E + qo);
+        else if (d == 1) prefetch_l1(hpos + qo);
+        else if (d == 2) prefetch_l1(slow + qo);
+      }
+    }
   }
 }
 
