@@ -184,90 +184,58 @@ __device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, const 
 }
 
 // One quadrant of fouds2 (CalSurfG.f90:634-723): returns trial time, valid flag through ok.
+// sj/sk: status of the first neighbours (0 alive, -2 = outside grid); sj2/sk2: second neighbours.
+// The reference selects one of nine stencils (first/second order in x and z, or one-sided) by
+// nested IFs.  The 16 lanes of an accept step fall into different cases, so the nest is evaluated
+// here WITHOUT branches: every case's operands are chosen with selects and one common expression
+// tree is evaluated.  Each case keeps the reference's operation order (x2 and the commutations
+// used are exact in IEEE arithmetic), so the result is bit-identical to the branchy form:
+//   A swj&swk  : u=2Rdx v=2Rsdz em=4tj-tj2-4tk+tk2  a=v2+u2   b=(2em)u2   c=u2(em2-s2v2) tref=4tj-tj2 /3
+//   B swj&k1   : u=Rsdz v=2Rdx  em=3tk-4tj+tj2      a=v2+9u2  b=(6em)u2   c=u2(em2-s2v2) tref=tk
+//   C swj only : u=2Rdx                             a=1 b=0   c=-(u2 s2)                tref=4tj-tj2 /3
+//   D j1&swk   : u=Rdx  v=2Rsdz em=3tj-4tk+tk2      a=v2+9u2  b=(6em)u2   c=u2(em2-v2s2) tref=tj
+//   E j1&k1    : u=Rdx  v=Rsdz  em=tk-tj            a=u2+v2   b=(-2u2)em  c=u2(em2-v2s2) tref=tj
+//   F j1 only  :                                    a=1 b=0   c=-(s2 R2)dx2             tref=tj
+//   G swk only : u=2Rsdz                            a=1 b=0   c=-(u2 s2)                tref=4tk-tk2 /3
+//   H k1 only  :                                    a=1 b=0   c=-(s2 Rs2)dz2            tref=tk
 __device__ __forceinline__ float quadrant(int sj, int sj2, float tj, float tj2, int sk, int sk2, float tk,
                                           float tk2, float slown, float ri, float risti, float dnx,
                                           float dnz, bool& ok) {
-  // sj/sk: status of first neighbours (0 alive, -2 = outside grid); sj2/sk2: second neighbours
-  int swj = -1, swk = -1;
-  if (sj2 == 0 && sj == 0 && tj > tj2) swj = 0;
-  if (sk2 == 0 && sk == 0 && tk > tk2) swk = 0;
-  float a = 1.0f, b = 0.0f, c = 0.0f, tref = 0.0f, tdiv = 1.0f, u, v, em;
-  bool sol = false;
-  if (swj == 0) {
-    sol = true;
-    if (swk == 0) {
-      u = 2.0f * ri * dnx;
-      v = 2.0f * risti * dnz;
-      em = 4.0f * tj - tj2 - 4.0f * tk;
-      em = em + tk2;
-      a = v * v + u * u;
-      b = 2.0f * em * (u * u);
-      c = (u * u) * (em * em - (slown * slown) * (v * v));
-      tref = 4.0f * tj - tj2;
-      tdiv = 3.0f;
-    } else if (sk == 0) {
-      u = risti * dnz;
-      v = 2.0f * ri * dnx;
-      em = 3.0f * tk - 4.0f * tj + tj2;
-      a = v * v + 9.0f * (u * u);
-      b = 6.0f * em * (u * u);
-      c = (u * u) * (em * em - (slown * slown) * (v * v));
-      tref = tk;
-      tdiv = 1.0f;
-    } else {
-      u = 2.0f * ri * dnx;
-      a = 1.0f;
-      b = 0.0f;
-      c = -(u * u) * (slown * slown);
-      tref = 4.0f * tj - tj2;
-      tdiv = 3.0f;
-    }
-  } else if (sj == 0) {
-    sol = true;
-    if (swk == 0) {
-      u = ri * dnx;
-      v = 2.0f * risti * dnz;
-      em = 3.0f * tj - 4.0f * tk + tk2;
-      a = v * v + 9.0f * (u * u);
-      b = 6.0f * em * (u * u);
-      c = (u * u) * (em * em - (v * v) * (slown * slown));
-      tref = tj;
-      tdiv = 1.0f;
-    } else if (sk == 0) {
-      u = ri * dnx;
-      v = risti * dnz;
-      em = tk - tj;
-      a = u * u + v * v;
-      b = -2.0f * (u * u) * em;
-      c = (u * u) * (em * em - (v * v) * (slown * slown));
-      tref = tj;
-      tdiv = 1.0f;
-    } else {
-      a = 1.0f;
-      b = 0.0f;
-      c = -(slown * slown) * (ri * ri) * (dnx * dnx);
-      tref = tj;
-      tdiv = 1.0f;
-    }
-  } else {
-    if (swk == 0) {
-      sol = true;
-      u = 2.0f * risti * dnz;
-      a = 1.0f;
-      b = 0.0f;
-      c = -(u * u) * (slown * slown);
-      tref = 4.0f * tk - tk2;
-      tdiv = 3.0f;
-    } else if (sk == 0) {
-      sol = true;
-      a = 1.0f;
-      b = 0.0f;
-      c = -(slown * slown) * (risti * risti) * (dnz * dnz);
-      tref = tk;
-      tdiv = 1.0f;
-    }
-  }
-  ok = sol && sj != -2 && sk != -2;
+  const bool j1 = (sj == 0), k1 = (sk == 0);
+  const bool swj = j1 && (sj2 == 0) && (tj > tj2);
+  const bool swk = k1 && (sk2 == 0) && (tk > tk2);
+  const bool cA = swj && swk, cB = swj && !swk && k1, cC = swj && !k1;
+  const bool cD = !swj && j1 && swk, cE = !swj && j1 && !swk && k1, cF = !swj && j1 && !k1;
+  const bool cG = !j1 && swk, cH = !j1 && !swk && k1;
+  ok = (cA || cB || cC || cD || cE || cF || cG || cH) && sj != -2 && sk != -2;
+  const float ux1 = ri * dnx, ux2 = 2.0f * ri * dnx;          // 2.0f*ri*dnx == 2*(ri*dnx) exactly
+  const float vz1 = risti * dnz, vz2 = 2.0f * risti * dnz;
+  const float s2 = slown * slown;
+  const float u = (cA || cC) ? ux2 : (cB ? vz1 : (cG ? vz2 : ux1));
+  const float v = (cA || cD) ? vz2 : (cB ? ux2 : vz1);
+  const float fj = 4.0f * tj - tj2, fk = 4.0f * tk - tk2;      // second-order one-sided values
+  float emA = fj - 4.0f * tk;
+  emA = emA + tk2;
+  const float emB = 3.0f * tk - 4.0f * tj + tj2;
+  const float emD = 3.0f * tj - 4.0f * tk + tk2;
+  const float emE = tk - tj;
+  const float em = cA ? emA : (cB ? emB : (cD ? emD : emE));
+  const float uu = u * u, vv = v * v;
+  const bool two = cA || cB || cD || cE;                       // both directions contribute
+  float a = 1.0f;
+  if (cA || cE) a = vv + uu;
+  if (cB || cD) a = vv + 9.0f * uu;
+  float b = 0.0f;
+  if (cA) b = 2.0f * em * uu;
+  if (cB || cD) b = 6.0f * em * uu;
+  if (cE) b = -2.0f * uu * em;
+  float c = uu * (em * em - s2 * vv);                          // A, B, D, E
+  if (cC || cG) c = -uu * s2;
+  if (cF) c = -s2 * (ri * ri) * (dnx * dnx);
+  if (cH) c = -s2 * (risti * risti) * (dnz * dnz);
+  (void)two;
+  const float tref = (cA || cC) ? fj : (cG ? fk : ((cB || cH) ? tk : tj));
+  const float tdiv = (cA || cC || cG) ? 3.0f : 1.0f;
   float rd1 = b * b - 4.0f * a * c;
   if (rd1 < 0.0f) rd1 = 0.0f;
   const float tdsh = (-b + sqrtf(rd1)) / (2.0f * a);
@@ -648,11 +616,16 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
 // barriers per accept hand the node id to Q and the four trial times back to H.  The arithmetic
 // and the heap discipline are the same functions as in k_fmm: results are bit-identical.
 #define DUO_FULL 0xffffffffu
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#ifdef DAZIM_DUO_PROF
-// per-thread accumulator of barrier wait cycles (H: at B waiting for Q's results; Q: at A waiting for H)
-#define g_prof_wait prof_wait_local
-#endif
+// Producer/consumer barriers between the two warps (PTX named barriers, 64 threads):
+//   DUO_X: H arrives after posting the node it is about to accept (+ the predicted next one), Q waits
+//   DUO_Y: Q arrives after posting the four trial times of that node, H waits before its sift-ups
+#define DUO_X 1
+#define DUO_Y 2
+__device__ __forceinline__ void duo_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void duo_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
 
 template <int URG>
 __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, const int ld,
@@ -661,15 +634,17 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
   const int nb = sl >> 2, d = sl & 3;
   const float inv_ld = 1.0f / (float)ld;
 #ifdef DAZIM_DUO_PROF
-  long long prof_wait_local = 0, prof_pop = 0, prof_apply = 0, prof_napply = 0, prof_waitA = 0, prof_read = 0, prof_verify = 0, prof_vfail = 0, prof_nsift = 0;
-  const long long tmarch0 = clock64();
+  long long p_top = 0, p_pop = 0, p_wait = 0, p_apply = 0;
+  int p_open = 0;
 #endif
   for (;;) {
 #ifdef DAZIM_DUO_PROF
-    if (prof_napply > 0) { prof_apply += clock64(); prof_napply = 0; }
+    const long long t0 = clock64();
+    if (p_open) { p_apply += t0; p_open = 0; }
 #endif
     bool stop = (h.ntr == 0) || overflow;
     int2 root = make_int2(0, 0), last = make_int2(0, 0);
+    int pred = -1, cand0 = -1, cand1 = -1, cand2 = -1;
     if (!stop) {
       root = h.sm[1];
       last = hget(h, h.ntr);
@@ -681,43 +656,55 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
         if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
         if ((ix == 0 && ex_l) || (ix == nnx - 1 && ex_r) || (iz == 0 && ex_t) || (iz == nnz - 1 && ex_b)) stop = true;
       }
+      // Which node will be the root after this pop?  (first level of downtree, decided now.)  Unless one of
+      // the four sift-ups puts a smaller key on top it is the next node to be accepted, and Q works on it
+      // speculatively while this warp pops and sifts.
+      const int n1 = h.ntr - 1;
+      if (n1 == 1) pred = last.y;
+      else if (n1 >= 2) {
+        int2 c = h.sm[2];
+        int wpos = 2;
+        if (n1 >= 3) {
+          const int2 c3 = h.sm[3];
+          if (HKEY(c) > HKEY(c3)) { c = c3; wpos = 3; }
+        }
+        pred = (HKEY(c) < HKEY(last)) ? c.y : last.y;
+        // candidates for the step after that (the loser of the two children and the winner's children):
+        // Q only pulls their stencil lines into the L2, one step ahead of the speculation that will need them
+        if (n1 >= 3) cand0 = h.sm[5 - wpos].y;
+        if (2 * wpos <= n1 && 2 * wpos < h.hcap) cand1 = h.sm[2 * wpos].y;
+        if (2 * wpos + 1 <= n1 && 2 * wpos + 1 < h.hcap) cand2 = h.sm[2 * wpos + 1].y;
+      }
     }
-    if (threadIdx.x == 0) comm[0] = stop ? -1 : root.y;
+    if (threadIdx.x == 0) {
+      comm[0] = stop ? -1 : root.y;
+      comm[2] = pred;
+      comm[3] = cand0;
+      comm[4] = cand1;
+      comm[5] = cand2;
+    }
+    duo_arrive(DUO_X);
 #ifdef DAZIM_DUO_PROF
-    const long long ta0 = clock64();
-#endif
-    __syncthreads();                                  // A: node id (and every earlier E store) visible to Q
-#ifdef DAZIM_DUO_PROF
-    prof_waitA += clock64() - ta0;
     if (stop && URG == 2 && blockIdx.x == 0 && threadIdx.x == 0)
-      printf("[duo prof] H: march cycles %lld, pop %lld, apply(+loop top) %lld [read %lld verify %lld vfail %lld nsift %lld], barrier A %lld, barrier B %lld, accepts %llu\n",
-             clock64() - tmarch0, prof_pop, prof_apply, prof_read, prof_verify, prof_vfail, prof_nsift, prof_waitA, prof_wait_local, nacc);
+      printf("[duo prof] H: per accept cycles: top %.0f pop %.0f waitY+read %.0f apply %.0f (accepts %llu)\n",
+             (double)p_top / nacc, (double)p_pop / nacc, (double)p_wait / nacc, (double)p_apply / nacc, nacc);
+    const long long t1 = clock64();
+    p_top += t1 - t0;
 #endif
     if (stop) break;
     ++nacc;
-#ifdef DAZIM_DUO_PROF
-    const long long tp0 = clock64();
-#endif
     pop_root<DUO_FULL>(h, hpos, last, sl, DUO_FULL);
-    // the new heap root is (almost always) the next node to be accepted: let Q warm its stencil lines
-    if (threadIdx.x == 0) comm[2] = (h.ntr > 0) ? h.sm[1].y : -1;
 #ifdef DAZIM_DUO_PROF
-    const long long tb0 = clock64();
-    prof_pop += tb0 - tp0;
+    const long long t2 = clock64();
+    p_pop += t2 - t1;
 #endif
-    __syncthreads();                                  // B: Q's results are in comm[16..31]
-#ifdef DAZIM_DUO_PROF
-    const long long tb1 = clock64();
-    g_prof_wait += tb1 - tb0;
-    prof_apply -= tb1;
-    prof_napply += 1;
-#endif
+    duo_sync(DUO_Y);                                   // Q's results for this node are in comm[16..31]
     int qst[4], qo[4], spos[4];
     float qt[4];
     int nins = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int4 r = reinterpret_cast<const int4*>(comm + 16)[q];    // (status, hpos before the pop, trial time, offset)
+      const int4 r = reinterpret_cast<const int4*>(comm + 16)[q];    // (status, hpos read earlier, trial time, offset)
       qst[q] = r.x;
       qt[q] = __int_as_float(r.z);
       qo[q] = r.w;
@@ -725,34 +712,25 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
       if (qst[q] == -1) spos[q] = h.ntr + (++nins);
       else if (qst[q] == 1) spos[q] = r.y;
     }
-    if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; continue; }
 #ifdef DAZIM_DUO_PROF
-    const long long tv0 = clock64();
-    prof_read += tv0 - tb1;
+    const long long t3 = clock64();
+    p_wait += t3 - t2;
+    p_apply -= t3;
+    p_open = 1;
 #endif
+    if (h.ntr + nins >= h.hcap + h.hspill) { overflow = 1; h.ntr = 0; continue; }
     if (h.ntr + nins < h.hcap) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (qst[q] != 1) continue;
+        // Q read this position while the heap was moving: it is right iff that slot holds the neighbour
         int vn = -1;
         if (spos[q] >= 1 && spos[q] <= h.ntr) vn = h.sm[spos[q]].y;
-        if (vn != qo[q]) {
-          spos[q] = hpos[qo[q]];
-#ifdef DAZIM_DUO_PROF
-          prof_vfail += 1;
-#endif
-        }
+        if (vn != qo[q]) spos[q] = hpos[qo[q]];
       }
-#ifdef DAZIM_DUO_PROF
-      const long long tv1 = clock64();
-      prof_verify += tv1 - tv0;
-#endif
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (qst[q] == -2 || qst[q] == 0) continue;
-#ifdef DAZIM_DUO_PROF
-        prof_nsift += 1;
-#endif
         if (qst[q] == -1) h.ntr += 1;
         const float k = qt[q];
         int tpc = spos[q];
@@ -761,8 +739,6 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
           if (!(k < HKEY(par))) break;
           h.sm[tpc] = par;
           hpos[par.y] = tpc;
-          // a later neighbour that sits on this path moves down with its parent slot: keep its
-          // position in registers (a read-back of hpos would put a global round trip on the chain)
 #pragma unroll
           for (int r = q + 1; r < 4; ++r)
             if (par.y == qo[r]) spos[r] = tpc;
@@ -823,92 +799,142 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
   }
 }
 
-__device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int ld, const float dnx, const float dnz,
-                            const float earth, const float* __restrict__ slow, const float* __restrict__ risti_tab,
-                            unsigned* __restrict__ E, const int* __restrict__ hpos, const int sl) {
+// stencil work of one accept step for node pn (warp Q).  patch >= 0: the node itself is still marked
+// close in E (speculative call): read it as alive with its trial value, which is what H will have
+// written by the time the result is used.
+struct QRes { int cst; unsigned cval; float trav; int co; };
+#ifdef DAZIM_DUO_PROF
+__device__ long long g_q_t[6];
+#define QT(i) do { if (blockIdx.x == 0 && threadIdx.x == 32) { const long long t_ = clock64(); g_q_t[i] += t_ - tq_; tq_ = t_; } } while (0)
+#else
+#define QT(i)
+#endif
+__device__ __forceinline__ QRes duo_stencil(const int pn, const int patch, const int nnx, const int nnz, const int ld,
+                                            const float inv_ld, const float dnx, const float dnz, const float earth,
+                                            const float* __restrict__ slow, const float* __restrict__ risti_tab,
+                                            const unsigned* E, const int* hpos, const int sl) {
   const int nb = sl >> 2, d = sl & 3;
   const int ndx = (nb == 0) ? -1 : (nb == 1 ? 1 : 0);
   const int ndz = (nb == 2) ? -1 : (nb == 3 ? 1 : 0);
   const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0);
   const int ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
   const int base = sl & 12;
+#ifdef DAZIM_DUO_PROF
+  long long tq_ = clock64();
+#endif
+  int ix = (int)((float)pn * inv_ld);
+  int iz = pn - ix * ld;
+  if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+  const int cx = ix + ndx, cz = iz + ndz;
+  const bool cin = (cx >= 0 && cx < nnx && cz >= 0 && cz < nnz);
+  const int co = cx * ld + cz;
+  unsigned e1 = E_OUT, e2 = E_OUT;
+  {
+    const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+    const int o1 = s1x * ld + s1z, o2 = s2x * ld + s2z;
+    if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[o1];
+    if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[o2];
+    if (o1 == patch && e1 != E_OUT) e1 &= ~E_SIGN;
+    if (o2 == patch && e2 != E_OUT) e2 &= ~E_SIGN;
+  }
+  unsigned cval = 0;                                 // d=0: E[c], 1: hpos[c], 2: slowness, 3: R sin(theta)
+  if (cin) {
+    if (d == 0) cval = E[co];
+    else if (d == 1) cval = (unsigned)hpos[co];
+    else if (d == 2) cval = __float_as_uint(slow[co]);
+    else cval = __float_as_uint(risti_tab[cx]);
+  }
+  QT(0);
+  const unsigned cE = __shfl_sync(DUO_FULL, cval, base + 0, 16);
+  QT(1);
+  const float slown = __uint_as_float(__shfl_sync(DUO_FULL, cval, base + 2, 16));
+  const float risti = __uint_as_float(__shfl_sync(DUO_FULL, cval, base + 3, 16));
+  QRes r;
+  r.cst = !cin ? -2 : (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
+  const int js = (sl >> 1) & 1, ks = sl & 1;
+  const unsigned ej1 = __shfl_sync(DUO_FULL, e1, base + js, 16), ej2 = __shfl_sync(DUO_FULL, e2, base + js, 16);
+  const unsigned ek1 = __shfl_sync(DUO_FULL, e1, base + 2 + ks, 16), ek2 = __shfl_sync(DUO_FULL, e2, base + 2 + ks, 16);
+  QT(2);
+  bool ok = false;
+  float trav = quadrant(e_status(ej1), e_status(ej2), __uint_as_float(ej1), __uint_as_float(ej2), e_status(ek1),
+                        e_status(ek2), __uint_as_float(ek1), __uint_as_float(ek2), slown, earth, risti, dnx, dnz, ok);
+  if (!ok) trav = __int_as_float(0x7f800000);
+  QT(3);
+  trav = fminf(trav, __shfl_xor_sync(DUO_FULL, trav, 1, 16));
+  trav = fminf(trav, __shfl_xor_sync(DUO_FULL, trav, 2, 16));
+  QT(4);
+  r.cval = cval;
+  r.trav = trav;
+  r.co = co;
+  return r;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void duo_prefetch(const int pn, const int nnx, const int nnz, const int ld, const float inv_ld,
+                                             const float* slow, const unsigned* E, const int* hpos, const int sl) {
+  if (pn < 0) return;
+  const int nb = sl >> 2, d = sl & 3;
+  int ix = (int)((float)pn * inv_ld);
+  int iz = pn - ix * ld;
+  if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+  const int cx = ix + ((nb == 0) ? -1 : (nb == 1 ? 1 : 0)), cz = iz + ((nb == 2) ? -1 : (nb == 3 ? 1 : 0));
+  if (cx < 0 || cx >= nnx || cz < 0 || cz >= nnz) return;
+  const int co = cx * ld + cz;
+  const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+  const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+  if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l2(E + s1x * ld + s1z);
+  if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l2(E + s2x * ld + s2z);
+  if (d == 0) prefetch_l2(E + co);
+  else if (d == 1) prefetch_l2(hpos + co);
+  else if (d == 2) prefetch_l2(slow + co);
+}
+
+__device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int ld, const float dnx, const float dnz,
+                            const float earth, const float* __restrict__ slow, const float* __restrict__ risti_tab,
+                            unsigned* E, const int* hpos, const int sl) {
+  const int d = sl & 3;
   const float inv_ld = 1.0f / (float)ld;
+  int spec = -2;                                       // node the registers below were computed for
 #ifdef DAZIM_DUO_PROF
-  long long prof_wait_local = 0;
-  const long long tq0 = clock64();
+  long long q_hit = 0, q_miss = 0;
 #endif
+  QRes r;
+  r.cst = -2; r.cval = 0; r.trav = 0.0f; r.co = 0;
   for (;;) {
-#ifdef DAZIM_DUO_PROF
-    const long long ta0 = clock64();
-#endif
-    __syncthreads();                                  // A
-#ifdef DAZIM_DUO_PROF
-    g_prof_wait += clock64() - ta0;
-#endif
-    const int pn = comm[0];
+    duo_sync(DUO_X);
+    const int pn = comm[0], pred = comm[2];
 #ifdef DAZIM_DUO_PROF
     if (pn < 0 && ld != REF_LD && blockIdx.x == 0 && threadIdx.x == 32)
-      printf("[duo prof] Q: march cycles %lld, waiting at A %lld (%.1f%%)\n", clock64() - tq0, prof_wait_local,
-             100.0 * prof_wait_local / (double)(clock64() - tq0));
+      printf("[duo prof] Q: speculation hits %lld misses %lld; per call cycles: issue %.0f loadwait %.0f shfl %.0f quadrant %.0f reduce %.0f\n",
+             q_hit, q_miss, (double)g_q_t[0] / (q_hit + q_miss), (double)g_q_t[1] / (q_hit + q_miss), (double)g_q_t[2] / (q_hit + q_miss),
+             (double)g_q_t[3] / (q_hit + q_miss), (double)g_q_t[4] / (q_hit + q_miss));
 #endif
     if (pn < 0) break;
-    int ix = (int)((float)pn * inv_ld);
-    int iz = pn - ix * ld;
-    if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
-    const int cx = ix + ndx, cz = iz + ndz;
-    const bool cin = (cx >= 0 && cx < nnx && cz >= 0 && cz < nnz);
-    const int co = cx * ld + cz;
-    unsigned e1 = E_OUT, e2 = E_OUT;
-    {
-      const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
-      if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[s1x * ld + s1z];
-      if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[s2x * ld + s2z];
-    }
-    unsigned cval = 0;                                 // d=0: E[c], 1: hpos[c], 2: slowness, 3: R sin(theta)
-    if (cin) {
-      if (d == 0) cval = E[co];
-      else if (d == 1) cval = (unsigned)hpos[co];
-      else if (d == 2) cval = __float_as_uint(slow[co]);
-      else cval = __float_as_uint(risti_tab[cx]);
-    }
-    const unsigned cE = __shfl_sync(DUO_FULL, cval, base + 0, 16);
-    const float slown = __uint_as_float(__shfl_sync(DUO_FULL, cval, base + 2, 16));
-    const float risti = __uint_as_float(__shfl_sync(DUO_FULL, cval, base + 3, 16));
-    const int cst = !cin ? -2 : (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
-    const int js = (sl >> 1) & 1, ks = sl & 1;
-    const unsigned ej1 = __shfl_sync(DUO_FULL, e1, base + js, 16), ej2 = __shfl_sync(DUO_FULL, e2, base + js, 16);
-    const unsigned ek1 = __shfl_sync(DUO_FULL, e1, base + 2 + ks, 16), ek2 = __shfl_sync(DUO_FULL, e2, base + 2 + ks, 16);
-    bool ok = false;
-    float trav = quadrant(e_status(ej1), e_status(ej2), __uint_as_float(ej1), __uint_as_float(ej2), e_status(ek1),
-                          e_status(ek2), __uint_as_float(ek1), __uint_as_float(ek2), slown, earth, risti, dnx, dnz, ok);
-    if (!ok) trav = __int_as_float(0x7f800000);
-    trav = fminf(trav, __shfl_xor_sync(DUO_FULL, trav, 1, 16));
-    trav = fminf(trav, __shfl_xor_sync(DUO_FULL, trav, 2, 16));
-    // hand the four (status, position-before-pop, trial time, offset) records to H; mark the
-    // neighbours close with their new trial time (nothing reads E between here and the next gather)
-    int out = cst;
-    if (d == 1) out = (int)cval;
-    else if (d == 2) out = __float_as_int(trav);
-    else if (d == 3) out = co;
+#ifdef DAZIM_DUO_PROF
+    if (pn != spec) ++q_miss; else ++q_hit;
+#endif
+    if (pn != spec)                                    // first step, or a sift-up put another node on top
+      r = duo_stencil(pn, -1, nnx, nnz, ld, inv_ld, dnx, dnz, earth, slow, risti_tab, E, hpos, sl);
+    // hand the four (status, heap position as read, trial time, offset) records to H; mark the
+    // neighbours close with their new trial time (only this warp reads or writes E from here on)
+    int out = r.cst;
+    if (d == 1) out = (int)r.cval;
+    else if (d == 2) out = __float_as_int(r.trav);
+    else if (d == 3) out = r.co;
     if (threadIdx.x - 32 < 16) comm[16 + sl] = out;
-    if (d == 0 && (cst == -1 || cst == 1) && threadIdx.x - 32 < 16) E[co] = __float_as_uint(trav) | E_SIGN;
-    __syncthreads();                                  // B
-    // while H applies the four sift-ups: pull the stencil lines of the predicted next node towards the SM
-    const int pp = comm[2];
-    if (pp >= 0) {
-      int px = (int)((float)pp * inv_ld);
-      int pz = pp - px * ld;
-      if (pz < 0) { px -= 1; pz += ld; } else if (pz >= ld) { px += 1; pz -= ld; }
-      const int qx = px + ndx, qz = pz + ndz;
-      if (qx >= 0 && qx < nnx && qz >= 0 && qz < nnz) {
-        const int qo = qx * ld + qz;
-        const int s1x = qx + ddx, s1z = qz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
-        if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l1(E + s1x * ld + s1z);
-        if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l1(E + s2x * ld + s2z);
-        if (d == 0) prefetch_l1(E + qo);
-        else if (d == 1) prefetch_l1(hpos + qo);
-        else if (d == 2) prefetch_l1(slow + qo);
-      }
+    if (d == 0 && (r.cst == -1 || r.cst == 1) && threadIdx.x - 32 < 16) E[r.co] = __float_as_uint(r.trav) | E_SIGN;
+    duo_arrive(DUO_Y);
+    // pull the stencil lines of the nodes that can be accepted two steps from now towards the L2
+    // (lanes 0-15 take one candidate, the mirror lanes 16-31 another)
+#ifdef DAZIM_DUO_CANDPF
+    duo_prefetch(comm[3 + ((threadIdx.x >> 4) & 1)], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+    duo_prefetch(((threadIdx.x >> 4) & 1) ? -1 : comm[5], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+#endif
+    // speculate on the next node while H pops this one and sifts its neighbours
+    spec = -2;
+    if (pred >= 0) {
+      r = duo_stencil(pred, pred, nnx, nnz, ld, inv_ld, dnx, dnz, earth, slow, risti_tab, E, hpos, sl);
+      spec = pred;
     }
   }
 }
