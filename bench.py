@@ -102,6 +102,10 @@ def workload(args):
         return synthetic.s200()
     if args.workload == "S200-lite":
         return synthetic.s200(src_per_period=125)
+    if args.workload.startswith("S200-") and args.workload[5:].isdigit():
+        return synthetic.s200(src_per_period=int(args.workload[5:]))      # S200 grid, fewer sources per period
+    if args.workload == "YN":
+        return synthetic.yunnan_shaped()
     if args.workload == "S40":
         return synthetic.s200(src_per_period=64, n=42, nz=5, nsta=200, nrec=16, kmax=4)
     raise SystemExit("unknown workload " + args.workload)
