@@ -244,10 +244,31 @@ __device__ __forceinline__ float quadrant(int sj, int sj2, float tj, float tj2, 
 
 __device__ __forceinline__ int e_status(unsigned e) { return e == E_OUT ? -2 : ((int)e >= 0 ? 0 : 1); }
 
+// Software prefetch of the words an accept step of node pn will gather (hint only).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void stencil_prefetch(const int pn, const int nnx, const int nnz, const int ld, const float inv_ld,
+                                             const float* slow, const unsigned* E, const int* hpos, const int sl) {
+  if (pn < 0) return;
+  const int nb = sl >> 2, d = sl & 3;
+  int ix = (int)((float)pn * inv_ld);
+  int iz = pn - ix * ld;
+  if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+  const int cx = ix + ((nb == 0) ? -1 : (nb == 1 ? 1 : 0)), cz = iz + ((nb == 2) ? -1 : (nb == 3 ? 1 : 0));
+  if (cx < 0 || cx >= nnx || cz < 0 || cz >= nnz) return;
+  const int co = cx * ld + cz;
+  const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+  const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+  if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l2(E + s1x * ld + s1z);
+  if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l2(E + s2x * ld + s2z);
+  if (d == 0) prefetch_l2(E + co);
+  else if (d == 1) prefetch_l2(hpos + co);
+  else if (d == 2) prefetch_l2(slow + co);
+}
+
 // The narrow-band march (travel's DO WHILE, CalSurfG.f90:356-456) on one grid,
 // executed by one half-warp: sl = lane within the half, hm = its shuffle mask.
 // URG==1: refined grid with the early exit of :362-382.
-template <int URG, unsigned CM>
+template <int URG, unsigned CM, bool PF>
 __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const float dnx,
                       const float dnz, const float earth, const float* __restrict__ slow,
                       const float* __restrict__ risti_tab, unsigned* __restrict__ E, int* __restrict__ hpos,
@@ -274,6 +295,22 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
     const int pn = root.y;
     // the element that will be sifted down from the root (may live in the spill part: fetch it now)
     const int2 last = hget(h, h.ntr);
+    if (PF) {
+      // the root after this pop (first level of downtree, decided now) is almost always the next node to be
+      // accepted: start pulling its stencil lines towards the L2 one full accept step ahead
+      const int n1 = h.ntr - 1;
+      int pred = -1;
+      if (n1 == 1) pred = last.y;
+      else if (n1 >= 2) {
+        int2 c = h.sm[2];
+        if (n1 >= 3) {
+          const int2 c3 = h.sm[3];
+          if (HKEY(c) > HKEY(c3)) c = c3;
+        }
+        pred = (HKEY(c) < HKEY(last)) ? c.y : last.y;
+      }
+      stencil_prefetch(pred, nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+    }
     // (ix, iz) 0-based from the linear offset: float quotient, exact after one correction
     int ix = (int)((float)pn * inv_ld);
     int iz = pn - ix * ld;
@@ -532,7 +569,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
       }
     }
     // ---- refined march; exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz) ----
-    march<1, CM>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
+    march<1, CM, false>(h, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r,
                  A.risti_r + (size_t)sc * REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
                  sr.vnb != sr.nnzr, sl, hm, nacc, overflow, active);
     if (active) {
@@ -596,7 +633,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
       }
       __syncwarp(hm);
     }
-    march<2, CM>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
+    march<2, CM, (SPC == 2)>(h, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c,
                  false, false, false, false, sl, hm, nacc, overflow, active && !overflow);
     pair = -1;
   }
@@ -869,26 +906,6 @@ __device__ __forceinline__ QRes duo_stencil(const int pn, const int patch, const
   return r;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void duo_prefetch(const int pn, const int nnx, const int nnz, const int ld, const float inv_ld,
-                                             const float* slow, const unsigned* E, const int* hpos, const int sl) {
-  if (pn < 0) return;
-  const int nb = sl >> 2, d = sl & 3;
-  int ix = (int)((float)pn * inv_ld);
-  int iz = pn - ix * ld;
-  if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
-  const int cx = ix + ((nb == 0) ? -1 : (nb == 1 ? 1 : 0)), cz = iz + ((nb == 2) ? -1 : (nb == 3 ? 1 : 0));
-  if (cx < 0 || cx >= nnx || cz < 0 || cz >= nnz) return;
-  const int co = cx * ld + cz;
-  const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
-  const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
-  if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l2(E + s1x * ld + s1z);
-  if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l2(E + s2x * ld + s2z);
-  if (d == 0) prefetch_l2(E + co);
-  else if (d == 1) prefetch_l2(hpos + co);
-  else if (d == 2) prefetch_l2(slow + co);
-}
-
 __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int ld, const float dnx, const float dnz,
                             const float earth, const float* __restrict__ slow, const float* __restrict__ risti_tab,
                             unsigned* E, const int* hpos, const int sl) {
@@ -927,8 +944,8 @@ __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int l
     // pull the stencil lines of the nodes that can be accepted two steps from now towards the L2
     // (lanes 0-15 take one candidate, the mirror lanes 16-31 another)
 #ifdef DAZIM_DUO_CANDPF
-    duo_prefetch(comm[3 + ((threadIdx.x >> 4) & 1)], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
-    duo_prefetch(((threadIdx.x >> 4) & 1) ? -1 : comm[5], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+    stencil_prefetch(comm[3 + ((threadIdx.x >> 4) & 1)], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+    stencil_prefetch(((threadIdx.x >> 4) & 1) ? -1 : comm[5], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
 #endif
     // speculate on the next node while H pops this one and sifts its neighbours
     spec = -2;
