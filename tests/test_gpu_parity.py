@@ -298,3 +298,28 @@ def test_empty_and_ragged_surveys(gpu, oracle, test1, test1_tables):
     o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, one,
                       test1["gc"], test1["gs"], tables=test1_tables)
     assert one.dall == 1 and np.array_equal(r["dsurf"], o["dsurf"]) and np.array_equal(r["obsTaa"], o["obsTaa"])
+
+
+def test_limits_mirror_reference_caps(gpu, test1):
+    """surfdisp96's hard caps (NL=200 layers, NP=60 periods, surfdisp96.f:57-59) come back as DAZIM_ELAYERS."""
+    p = test1["para"]
+    vs = np.asfortranarray(test1["vs"][:3, :3, :])
+    with pytest.raises(gpu.DazimError) as e:
+        gpu.depthkernelTI(vs, test1["depz"], np.arange(1, 62, dtype=float), p.sublayers)      # 61 periods
+    assert e.value.code == 5
+    deep = np.asfortranarray(np.repeat(vs, 30, axis=2)[:, :, :100])                              # 99 intervals x 3 sub-layers
+    depz = np.arange(100, dtype=np.float32) * 2.0
+    with pytest.raises(gpu.DazimError) as e:
+        gpu.depthkernel(deep, depz, p.tRc[:2], 2.0)
+    assert e.value.code == 5
+
+
+def test_nnz_overflow_is_reported(gpu, oracle, test1, test1_tables):
+    """maxnar too small: the reference overruns and stops at Main_Jt.f90:523; we return DAZIM_ENNZ_OVERFLOW."""
+    p = test1["para"]
+    pv, svs, svp, srho, _ = oracle.depthkernel(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    tb = dict(test1_tables, sen_vs=svs, sen_vp=svp, sen_rho=srho)
+    with pytest.raises(gpu.DazimError) as e:
+        gpu.CalSurfG(test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"],
+                     tables=tb, maxnar=100)
+    assert e.value.code == 3
