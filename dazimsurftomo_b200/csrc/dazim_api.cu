@@ -344,13 +344,14 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
       CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
     }
   }
-  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC") || getenv("DAZIM_DUO")) {
+  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC") || getenv("DAZIM_DUO") || getenv("DAZIM_NCTAS")) {
     if (const char* e = getenv("DAZIM_DUO")) P->duo = atoi(e) ? 1 : 0;
     if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
     if (P->duo) P->spc = 1;
-    if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, pow2ceil(atoi(e)));
+    if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, (atoi(e) + 1) & ~1);
     if (P->duo) CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
     else CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
+    if (const char* e = getenv("DAZIM_NCTAS")) nctas = std::max(1, std::min(nctas, atoi(e)));
   }
   if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
   const long long npairs_all = (nsrc + P->spc - 1) / P->spc;
