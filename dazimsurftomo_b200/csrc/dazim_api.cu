@@ -21,7 +21,8 @@ cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
 cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas);
 cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st);
-cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, float* ttn, int* nsts, cudaStream_t st);
+cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, int nnz_tiled, float* ttn, int* nsts,
+                                 cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
 cudaError_t launch_coef(int nx, int ny, int nz, const float* vels, float* ca, float* cr, cudaStream_t st);
 cudaError_t launch_assemble(const AsmArgs& A, bool fill, cudaStream_t st);
@@ -360,8 +361,9 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   CK(available_bytes(h->dev, &free_b));
   double budget = 0.60 * (double)free_b;
   if (const char* e = getenv("DAZIM_WS_GB")) budget = std::min(budget, atof(e) * 1e9);
-  const double per_src = (double)ncoarse * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
-  const double per_slot = (double)ncoarse * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
+  const size_t ncf = coarse_field_size(g.nnx, g.nnz);     // E_c / hpos_c in the interleaved layout
+  const double per_src = (double)ncf * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
+  const double per_slot = (double)ncf * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
   nctas = (int)std::min<long long>(nctas, std::max<long long>(npairs_all, 1));
   long long maxB = (long long)((budget - 2.0 * nctas * per_slot) / per_src);   // 2 slots per CTA are always laid out
   if (maxB < 2) maxB = 2;
@@ -469,8 +471,8 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     CK(P->d_slow_c.alloc(ncoarse * p->kmaxRc));
     const size_t B = (size_t)P->maxB, nslot = 2 * (size_t)P->nctas;
     CK(P->d_E_r.alloc(B * REF_N));
-    CK(P->d_E_c.alloc(B * ncoarse));
-    CK(P->d_hpos_c.alloc(nslot * ncoarse));
+    CK(P->d_E_c.alloc(B * coarse_field_size(g.nnx, g.nnz)));
+    CK(P->d_hpos_c.alloc(nslot * coarse_field_size(g.nnx, g.nnz)));
     CK(P->d_hpos_r.alloc(nslot * REF_N));
     CK(P->d_slow_r.alloc(nslot * REF_N));
     CK(P->d_hspill.alloc(nslot * P->hspill));
@@ -546,7 +548,7 @@ static int plan_run(dazim_plan* P) {
     F.flags = P->d_icnt.p + 1; F.n_accept = P->d_counters.p + 1;
     if (F.nsrc > 0) {
       // far = 0xFFFFFFFF everywhere on the coarse grids of this batch; the refined boxes reset themselves
-      CK(cudaMemsetAsync(P->d_E_c.p, 0xFF, (size_t)F.nsrc * ncoarse * sizeof(unsigned), st));
+      CK(cudaMemsetAsync(P->d_E_c.p, 0xFF, (size_t)F.nsrc * coarse_field_size(g.nnx, g.nnz) * sizeof(unsigned), st));
       CK(cudaMemsetAsync(P->d_icnt.p + 2, 0, sizeof(int), st));
       if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
       else CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + P->spc - 1) / P->spc), st));
@@ -832,14 +834,15 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
     if (e == cudaSuccess) e = d_s.alloc(std::max(nc, (size_t)REF_N));
     for (int i = 0; i < n && e == cudaSuccess; ++i) {
       // the coarse hpos of a slot is only valid for the LAST solve it ran; the final coarse field is all alive anyway
-      e = launch_decode_status(P->d_E_c.p + (size_t)i * nc, nullptr, nc, d_t.p, d_s.p, h->st);
+      e = launch_decode_status(P->d_E_c.p + (size_t)i * coarse_field_size(P->g.nnx, P->g.nnz), nullptr, nc, P->g.nnz,
+                               d_t.p, d_s.p, h->st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
       if (ttn && e == cudaSuccess) e = cudaMemcpy(ttn + (size_t)i * nc, d_t.p, nc * 4, cudaMemcpyDeviceToHost);
       if (nsts && e == cudaSuccess) e = cudaMemcpy(nsts + (size_t)i * nc, d_s.p, nc * 4, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) break;
       const bool own_slot = ((size_t)P->spc * (size_t)P->nctas >= (size_t)n);   // one solve per slot: refined heap slots are intact
       e = launch_decode_status(P->d_E_r.p + (size_t)i * REF_N,
-                               own_slot ? P->d_hpos_r.p + (size_t)slot_of[i] * REF_N : nullptr, REF_N, d_t.p, d_s.p, h->st);
+                               own_slot ? P->d_hpos_r.p + (size_t)slot_of[i] * REF_N : nullptr, REF_N, 0, d_t.p, d_s.p, h->st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
       if (ttnr && e == cudaSuccess) e = cudaMemcpy(ttnr + (size_t)i * REF_N, d_t.p, (size_t)REF_N * 4, cudaMemcpyDeviceToHost);
       if (nstsr && e == cudaSuccess) e = cudaMemcpy(nstsr + (size_t)i * REF_N, d_s.p, (size_t)REF_N * 4, cudaMemcpyDeviceToHost);

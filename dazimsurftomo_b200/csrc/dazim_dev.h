@@ -44,6 +44,15 @@ struct RayRec {
   int row;          // global 0-based row id (count1-1)
 };
 
+// Layout of the per-solve COARSE fields (E_c: status + travel time, hpos_c: heap back pointers).
+// 8 x-columns are interleaved per z row: offset(ix, iz) = ((ix >> 3) * nnz + iz) * 8 + (ix & 7), 0-based.
+// One 32-byte sector then holds the 8 x-neighbours of a node and the z-neighbours sit in the adjacent
+// sectors, so the 7 x 7 diamond an accept step gathers comes from 1-2 contiguous 224-byte runs (one or
+// two DRAM rows) instead of 7 columns 4 KB apart.  The eikonal stage at full occupancy is bound by the
+// rate of random DRAM accesses, which is what this layout attacks.
+__host__ __device__ inline size_t coarse_field_size(int nnx, int nnz) { return (size_t)((nnx + 7) >> 3) * (size_t)nnz * 8; }
+__host__ __device__ inline int cidx(int ix, int iz, int nnz) { return (((ix >> 3) * nnz + iz) << 3) + (ix & 7); }
+
 static const int REF_LD = 129;           // leading dimension of refined fields: 2*sgs*sgdl+1
 static const int REF_N = REF_LD * REF_LD;
 

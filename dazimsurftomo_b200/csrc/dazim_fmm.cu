@@ -244,25 +244,40 @@ __device__ __forceinline__ float quadrant(int sj, int sj2, float tj, float tj2, 
 
 __device__ __forceinline__ int e_status(unsigned e) { return e == E_OUT ? -2 : ((int)e >= 0 ? 0 : 1); }
 
+// Node offset of (ix, iz) in a per-solve field: the refined box (URG == 1) is plain column-major with
+// leading dimension ld; the coarse grid (URG == 2, ld == nnz) uses the interleaved layout of dazim_dev.h.
+template <int URG>
+__device__ __forceinline__ int nidx(int ix, int iz, int ld) { return URG == 2 ? cidx(ix, iz, ld) : ix * ld + iz; }
+// inverse: float quotient, exact after one correction (offsets < 2^30, ld <= 32767)
+template <int URG>
+__device__ __forceinline__ void ndecode(int o, int ld, float inv_ld, int& ix, int& iz) {
+  const int b = (URG == 2) ? (o >> 3) : o;
+  int q = (int)((float)b * inv_ld);
+  int r = b - q * ld;
+  if (r < 0) { q -= 1; r += ld; } else if (r >= ld) { q += 1; r -= ld; }
+  ix = (URG == 2) ? (q * 8 + (o & 7)) : q;
+  iz = r;
+}
+
 // Software prefetch of the words an accept step of node pn will gather (hint only).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int URG>
 __device__ __forceinline__ void stencil_prefetch(const int pn, const int nnx, const int nnz, const int ld, const float inv_ld,
                                              const float* slow, const unsigned* E, const int* hpos, const int sl) {
   if (pn < 0) return;
   const int nb = sl >> 2, d = sl & 3;
-  int ix = (int)((float)pn * inv_ld);
-  int iz = pn - ix * ld;
-  if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+  int ix, iz;
+  ndecode<URG>(pn, ld, inv_ld, ix, iz);
   const int cx = ix + ((nb == 0) ? -1 : (nb == 1 ? 1 : 0)), cz = iz + ((nb == 2) ? -1 : (nb == 3 ? 1 : 0));
   if (cx < 0 || cx >= nnx || cz < 0 || cz >= nnz) return;
-  const int co = cx * ld + cz;
+  const int co = nidx<URG>(cx, cz, ld);
   const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
   const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
-  if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l2(E + s1x * ld + s1z);
-  if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l2(E + s2x * ld + s2z);
+  if (s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) prefetch_l2(E + nidx<URG>(s1x, s1z, ld));
+  if (s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) prefetch_l2(E + nidx<URG>(s2x, s2z, ld));
   if (d == 0) prefetch_l2(E + co);
   else if (d == 1) prefetch_l2(hpos + co);
-  else if (d == 2) prefetch_l2(slow + co);
+  else if (d == 2) prefetch_l2(slow + cx * ld + cz);
 }
 
 // The narrow-band march (travel's DO WHILE, CalSurfG.f90:356-456) on one grid,
@@ -309,12 +324,10 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
         }
         pred = (HKEY(c) < HKEY(last)) ? c.y : last.y;
       }
-      stencil_prefetch(pred, nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+      stencil_prefetch<URG>(pred, nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
     }
-    // (ix, iz) 0-based from the linear offset: float quotient, exact after one correction
-    int ix = (int)((float)pn * inv_ld);
-    int iz = pn - ix * ld;
-    if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+    int ix, iz;                                        // 0-based grid coordinates of the node
+    ndecode<URG>(pn, ld, inv_ld, ix, iz);
     // the popped node becomes alive with its trial value (= its heap key)
     E[pn] = (unsigned)root.x & ~E_SIGN;
     if (URG == 1) {
@@ -327,18 +340,18 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
     // ---- issue the gather: 4 neighbours x 4 directions x (first, second) stencil node ----
     const int cx = ix + ndx, cz = iz + ndz;            // neighbour handled by this lane group
     const bool cin = (cx >= 0 && cx < nnx && cz >= 0 && cz < nnz);
-    const int co = cx * ld + cz;
+    const int co = nidx<URG>(cx, cz, ld);
     unsigned e1 = E_OUT, e2 = E_OUT;
     {
       const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
-      if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[s1x * ld + s1z];
-      if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[s2x * ld + s2z];
+      if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[nidx<URG>(s1x, s1z, ld)];
+      if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[nidx<URG>(s2x, s2z, ld)];
     }
     unsigned cval = 0;                                 // d=0: E[c], 1: hpos[c], 2: slowness, 3: R sin(theta)
     if (cin) {
       if (d == 0) cval = E[co];
       else if (d == 1) cval = (unsigned)hpos[co];
-      else if (d == 2) cval = __float_as_uint(slow[co]);
+      else if (d == 2) cval = __float_as_uint(slow[cx * ld + cz]);
       else cval = __float_as_uint(risti_tab[cx]);
     }
     // ---- pop the root while the loads are in flight ----
@@ -367,7 +380,7 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
       qst[q] = __shfl_sync(hm, cst, q * 4, 16);
       qt[q] = __shfl_sync(hm, trav, q * 4, 16);
       const int hl = (int)__shfl_sync(hm, cval, q * 4 + 1, 16);      // hpos[neighbour] as of before the pop
-      qo[q] = (ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0))) * ld + (iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0)));
+      qo[q] = nidx<URG>(ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0)), iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0)), ld);
       spos[q] = 0;
       if (qst[q] == -1) spos[q] = h.ntr + (++nins);
       else if (qst[q] == 1) spos[q] = hl;
@@ -493,14 +506,15 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
   const int half = lane >> 4, sl = lane & 15;
   const unsigned hm = CM ? CM : (0xffffu << (half * 16));
   const GridC& g = A.g;
-  const size_t ncoarse = (size_t)g.nnx * g.nnz;
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;          // slow_c / veln_c (plain column-major)
+  const size_t ncf = coarse_field_size(g.nnx, g.nnz);    // E_c / hpos_c (interleaved layout)
   const int slot = blockIdx.x * 2 + half;
   Heap h;
   h.sm = reinterpret_cast<int2*>(smem_raw) + (size_t)half * A.hcap;
   h.gl = A.hspill + (size_t)slot * A.hspill_n;
   h.hcap = A.hcap;
   h.hspill = A.hspill_n;
-  int* hpos_c = A.hpos_c + (size_t)slot * ncoarse;
+  int* hpos_c = A.hpos_c + (size_t)slot * ncf;
   int* hpos_r = A.hpos_r + (size_t)slot * REF_N;
   float* slow_r = A.slow_r + (size_t)slot * REF_N;
   unsigned long long nacc = 0;
@@ -519,7 +533,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
     const int sc = min(s, A.nsrc - 1);                 // inactive half: valid addresses, no side effects
     const SrcRec sr = A.src[sc];
     unsigned* E_r = A.E_r + (size_t)sc * REF_N;
-    unsigned* E_c = A.E_c + (size_t)sc * ncoarse;
+    unsigned* E_c = A.E_c + (size_t)sc * ncf;
     const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
     const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
     if (active) {
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
         for (int e = sl; e < nkx * nkz; e += 16) {
           const int kz = e % nkz, kx = e / nkz;
           const int orf = (kx * g.sgdl) * REF_LD + (kz * g.sgdl);
-          const int oc = (sr.vnl + kx - 1) * g.nnz + (sr.vnt + kz - 1);
+          const int oc = cidx(sr.vnl + kx - 1, sr.vnt + kz - 1, g.nnz);
           E_c[oc] = E_r[orf];
         }
       }
@@ -597,12 +611,12 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
           int o = 0;
           if (e < nb_tot) {
             const int l = sr.vnt + e % nz_b, k = sr.vnl + e / nz_b;
-            o = (k - 1) * g.nnz + (l - 1);
+            o = cidx(k - 1, l - 1, g.nnz);
             if ((int)E_c[o] >= 0) {
-              if (l - 1 >= 1 && E_c[o - 1] == E_FAR) mk = true;
-              if (l + 1 <= g.nnz && E_c[o + 1] == E_FAR) mk = true;
-              if (k - 1 >= 1 && E_c[o - g.nnz] == E_FAR) mk = true;
-              if (k + 1 <= g.nnx && E_c[o + g.nnz] == E_FAR) mk = true;
+              if (l - 1 >= 1 && E_c[cidx(k - 1, l - 2, g.nnz)] == E_FAR) mk = true;
+              if (l + 1 <= g.nnz && E_c[cidx(k - 1, l, g.nnz)] == E_FAR) mk = true;
+              if (k - 1 >= 1 && E_c[cidx(k - 2, l - 1, g.nnz)] == E_FAR) mk = true;
+              if (k + 1 <= g.nnx && E_c[cidx(k, l - 1, g.nnz)] == E_FAR) mk = true;
             }
           }
           __syncwarp(hm);
@@ -617,8 +631,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
           for (int l0 = sr.vnt; l0 <= sr.vnb; l0 += 16) {
             const int l = l0 + sl;
             unsigned ev = E_FAR;
-            const int o = (k - 1) * g.nnz + (l - 1);
-            if (l <= sr.vnb) ev = E_c[o];
+            if (l <= sr.vnb) ev = E_c[cidx(k - 1, l - 1, g.nnz)];
             unsigned msk = __ballot_sync(hm, (int)ev < 0 && ev != E_FAR) >> (half * 16);
             while (msk) {
               const int b = __ffs(msk) - 1;
@@ -626,7 +639,7 @@ __global__ void __launch_bounds__(32, 20) k_fmm(FmmArgs A) {
               const float tb = __uint_as_float(__shfl_sync(hm, ev, b, 16) & ~E_SIGN);
               if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; break; }
               h.ntr += 1;
-              sift_up(h, hpos_c, h.ntr, tb, (k - 1) * g.nnz + (l0 + b - 1), nullptr);
+              sift_up(h, hpos_c, h.ntr, tb, cidx(k - 1, l0 + b - 1, g.nnz), nullptr);
             }
           }
         }
@@ -846,6 +859,7 @@ __device__ long long g_q_t[6];
 #else
 #define QT(i)
 #endif
+template <int URG>
 __device__ __forceinline__ QRes duo_stencil(const int pn, const int patch, const int nnx, const int nnz, const int ld,
                                             const float inv_ld, const float dnx, const float dnz, const float earth,
                                             const float* __restrict__ slow, const float* __restrict__ risti_tab,
@@ -859,16 +873,15 @@ __device__ __forceinline__ QRes duo_stencil(const int pn, const int patch, const
 #ifdef DAZIM_DUO_PROF
   long long tq_ = clock64();
 #endif
-  int ix = (int)((float)pn * inv_ld);
-  int iz = pn - ix * ld;
-  if (iz < 0) { ix -= 1; iz += ld; } else if (iz >= ld) { ix += 1; iz -= ld; }
+  int ix, iz;
+  ndecode<URG>(pn, ld, inv_ld, ix, iz);
   const int cx = ix + ndx, cz = iz + ndz;
   const bool cin = (cx >= 0 && cx < nnx && cz >= 0 && cz < nnz);
-  const int co = cx * ld + cz;
+  const int co = nidx<URG>(cx, cz, ld);
   unsigned e1 = E_OUT, e2 = E_OUT;
   {
     const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
-    const int o1 = s1x * ld + s1z, o2 = s2x * ld + s2z;
+    const int o1 = nidx<URG>(s1x, s1z, ld), o2 = nidx<URG>(s2x, s2z, ld);
     if (cin && s1x >= 0 && s1x < nnx && s1z >= 0 && s1z < nnz) e1 = E[o1];
     if (cin && s2x >= 0 && s2x < nnx && s2z >= 0 && s2z < nnz) e2 = E[o2];
     if (o1 == patch && e1 != E_OUT) e1 &= ~E_SIGN;
@@ -878,7 +891,7 @@ __device__ __forceinline__ QRes duo_stencil(const int pn, const int patch, const
   if (cin) {
     if (d == 0) cval = E[co];
     else if (d == 1) cval = (unsigned)hpos[co];
-    else if (d == 2) cval = __float_as_uint(slow[co]);
+    else if (d == 2) cval = __float_as_uint(slow[cx * ld + cz]);
     else cval = __float_as_uint(risti_tab[cx]);
   }
   QT(0);
@@ -906,6 +919,7 @@ __device__ __forceinline__ QRes duo_stencil(const int pn, const int patch, const
   return r;
 }
 
+template <int URG>
 __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int ld, const float dnx, const float dnz,
                             const float earth, const float* __restrict__ slow, const float* __restrict__ risti_tab,
                             unsigned* E, const int* hpos, const int sl) {
@@ -931,7 +945,7 @@ __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int l
     if (pn != spec) ++q_miss; else ++q_hit;
 #endif
     if (pn != spec)                                    // first step, or a sift-up put another node on top
-      r = duo_stencil(pn, -1, nnx, nnz, ld, inv_ld, dnx, dnz, earth, slow, risti_tab, E, hpos, sl);
+      r = duo_stencil<URG>(pn, -1, nnx, nnz, ld, inv_ld, dnx, dnz, earth, slow, risti_tab, E, hpos, sl);
     // hand the four (status, heap position as read, trial time, offset) records to H; mark the
     // neighbours close with their new trial time (only this warp reads or writes E from here on)
     int out = r.cst;
@@ -944,13 +958,13 @@ __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int l
     // pull the stencil lines of the nodes that can be accepted two steps from now towards the L2
     // (lanes 0-15 take one candidate, the mirror lanes 16-31 another)
 #ifdef DAZIM_DUO_CANDPF
-    stencil_prefetch(comm[3 + ((threadIdx.x >> 4) & 1)], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
-    stencil_prefetch(((threadIdx.x >> 4) & 1) ? -1 : comm[5], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+    stencil_prefetch<URG>(comm[3 + ((threadIdx.x >> 4) & 1)], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
+    stencil_prefetch<URG>(((threadIdx.x >> 4) & 1) ? -1 : comm[5], nnx, nnz, ld, inv_ld, slow, E, hpos, sl);
 #endif
     // speculate on the next node while H pops this one and sifts its neighbours
     spec = -2;
     if (pred >= 0) {
-      r = duo_stencil(pred, pred, nnx, nnz, ld, inv_ld, dnx, dnz, earth, slow, risti_tab, E, hpos, sl);
+      r = duo_stencil<URG>(pred, pred, nnx, nnz, ld, inv_ld, dnx, dnz, earth, slow, risti_tab, E, hpos, sl);
       spec = pred;
     }
   }
@@ -961,6 +975,7 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sl = lane & 15;
   const GridC& g = A.g;
   const size_t ncoarse = (size_t)g.nnx * g.nnz;
+  const size_t ncf = coarse_field_size(g.nnx, g.nnz);
   const int slot = blockIdx.x * 2;
   Heap h;
   h.sm = reinterpret_cast<int2*>(smem_raw);
@@ -969,7 +984,7 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
   h.hspill = A.hspill_n;
   h.ntr = 0;
   int* comm = reinterpret_cast<int*>(smem_raw + (size_t)A.hcap * 8);       // 32 ints
-  int* hpos_c = A.hpos_c + (size_t)slot * ncoarse;
+  int* hpos_c = A.hpos_c + (size_t)slot * ncf;
   int* hpos_r = A.hpos_r + (size_t)slot * REF_N;
   float* slow_r = A.slow_r + (size_t)slot * REF_N;
   unsigned long long nacc = 0;
@@ -978,7 +993,7 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
     const SrcRec sr = A.src[s];
     if (A.slot_of && tid == 0) A.slot_of[s] = slot;
     unsigned* E_r = A.E_r + (size_t)s * REF_N;
-    unsigned* E_c = A.E_c + (size_t)s * ncoarse;
+    unsigned* E_c = A.E_c + (size_t)s * ncf;
     const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
     const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
     // ---- refined slowness nodes (bsplrefine) + status reset: all 64 threads ----
@@ -1025,7 +1040,7 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
       march_duo_H<1>(h, comm, sr.nnxr, sr.nnzr, REF_LD, E_r, hpos_r, sr.vnl != 1, sr.vnr != sr.nnxr, sr.vnt != 1,
                      sr.vnb != sr.nnzr, sl, nacc, overflow);
     } else {
-      march_duo_Q(comm, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r, A.risti_r + (size_t)s * REF_LD, E_r,
+      march_duo_Q<1>(comm, sr.nnxr, sr.nnzr, REF_LD, sr.dnxr, sr.dnzr, g.earth, slow_r, A.risti_r + (size_t)s * REF_LD, E_r,
                   hpos_r, sl);
     }
     __syncthreads();
@@ -1034,7 +1049,7 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
       const int nkx = (sr.nnxr - 1) / g.sgdl + 1, nkz = (sr.nnzr - 1) / g.sgdl + 1;
       for (int e = tid; e < nkx * nkz; e += 64) {
         const int kz = e % nkz, kx = e / nkz;
-        E_c[(sr.vnl + kx - 1) * g.nnz + (sr.vnt + kz - 1)] = E_r[(kx * g.sgdl) * REF_LD + (kz * g.sgdl)];
+        E_c[cidx(sr.vnl + kx - 1, sr.vnt + kz - 1, g.nnz)] = E_r[(kx * g.sgdl) * REF_LD + (kz * g.sgdl)];
       }
     }
     __syncthreads();
@@ -1047,12 +1062,12 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
         int o = 0;
         if (e < nb_tot) {
           const int l = sr.vnt + e % nz_b, k = sr.vnl + e / nz_b;
-          o = (k - 1) * g.nnz + (l - 1);
+          o = cidx(k - 1, l - 1, g.nnz);
           if ((int)E_c[o] >= 0) {
-            if (l - 1 >= 1 && E_c[o - 1] == E_FAR) mk = true;
-            if (l + 1 <= g.nnz && E_c[o + 1] == E_FAR) mk = true;
-            if (k - 1 >= 1 && E_c[o - g.nnz] == E_FAR) mk = true;
-            if (k + 1 <= g.nnx && E_c[o + g.nnz] == E_FAR) mk = true;
+            if (l - 1 >= 1 && E_c[cidx(k - 1, l - 2, g.nnz)] == E_FAR) mk = true;
+            if (l + 1 <= g.nnz && E_c[cidx(k - 1, l, g.nnz)] == E_FAR) mk = true;
+            if (k - 1 >= 1 && E_c[cidx(k - 2, l - 1, g.nnz)] == E_FAR) mk = true;
+            if (k + 1 <= g.nnx && E_c[cidx(k, l - 1, g.nnz)] == E_FAR) mk = true;
           }
         }
         __syncthreads();
@@ -1067,7 +1082,7 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
         for (int l0 = sr.vnt; l0 <= sr.vnb; l0 += 16) {
           const int l = l0 + sl;
           unsigned ev = E_FAR;
-          if (l <= sr.vnb) ev = E_c[(k - 1) * g.nnz + (l - 1)];
+          if (l <= sr.vnb) ev = E_c[cidx(k - 1, l - 1, g.nnz)];
           unsigned msk = __ballot_sync(DUO_FULL, (int)ev < 0 && ev != E_FAR) & 0xffffu;
           while (msk) {
             const int b = __ffs(msk) - 1;
@@ -1075,13 +1090,13 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
             const float tb = __uint_as_float(__shfl_sync(DUO_FULL, ev, b, 16) & ~E_SIGN);
             if (h.ntr + 1 >= h.hcap + h.hspill) { overflow = 1; break; }
             h.ntr += 1;
-            sift_up(h, hpos_c, h.ntr, tb, (k - 1) * g.nnz + (l0 + b - 1), nullptr);
+            sift_up(h, hpos_c, h.ntr, tb, cidx(k - 1, l0 + b - 1, g.nnz), nullptr);
           }
         }
       }
       march_duo_H<2>(h, comm, g.nnx, g.nnz, g.nnz, E_c, hpos_c, false, false, false, false, sl, nacc, overflow);
     } else {
-      march_duo_Q(comm, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c, sl);
+      march_duo_Q<2>(comm, g.nnx, g.nnz, g.nnz, g.dnx, g.dnz, g.earth, slow_c, A.risti_c, E_c, hpos_c, sl);
     }
     __syncthreads();
     // next solve: first one = own CTA index, later ones from the queue
@@ -1116,23 +1131,26 @@ cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st) {
 }
 
 // test seam: (E, hpos) -> the reference's (ttn, nsts) pair
-__global__ void k_decode_status(const unsigned* __restrict__ E, const int* __restrict__ hpos, size_t n,
+__global__ void k_decode_status(const unsigned* __restrict__ E, const int* __restrict__ hpos, size_t n, int nnz_tiled,
                                 float* __restrict__ ttn, int* __restrict__ nsts) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // output index: plain column-major
   if (i >= n) return;
-  const unsigned e = E[i];
+  // nnz_tiled > 0: the input is a coarse field in the interleaved layout
+  const size_t j = nnz_tiled > 0 ? (size_t)cidx((int)(i / nnz_tiled), (int)(i % nnz_tiled), nnz_tiled) : i;
+  const unsigned e = E[j];
   int st;
   float t;
   if (e == E_FAR) { st = -1; t = 0.0f; }
   else if ((int)e >= 0) { st = 0; t = __uint_as_float(e); }
-  else { st = hpos ? hpos[i] : 1; t = __uint_as_float(e & ~E_SIGN); }
+  else { st = hpos ? hpos[j] : 1; t = __uint_as_float(e & ~E_SIGN); }
   if (ttn) ttn[i] = t;
   if (nsts) nsts[i] = st;
 }
 
-cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, float* ttn, int* nsts, cudaStream_t st) {
+cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, int nnz_tiled, float* ttn, int* nsts,
+                                 cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  k_decode_status<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, hpos, n, ttn, nsts);
+  k_decode_status<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, hpos, n, nnz_tiled, ttn, nsts);
   return cudaGetLastError();
 }
 

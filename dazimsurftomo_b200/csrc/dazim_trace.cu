@@ -136,12 +136,12 @@ __device__ void trace_one(const TraceArgs& A, const RayRec rr, Foot& f, int& fla
   const SrcRec sr = A.src[rr.src];
   const size_t ncoarse = (size_t)g.nnx * g.nnz;
   const float* __restrict__ veln = A.veln_c + (size_t)sr.period * ncoarse;
-  const float* __restrict__ ttn = A.ttn_c + (size_t)rr.src * ncoarse;
+  const float* __restrict__ ttn = A.ttn_c + (size_t)rr.src * coarse_field_size(g.nnx, g.nnz);
   const float* __restrict__ ttnr = A.ttn_r + (size_t)rr.src * REF_N;
   const float scx = sr.scx, scz = sr.scz, earth = g.earth;
   const float rcx = rr.rcx, rcz = rr.rcz;
   const int nnx = g.nnx, nnz = g.nnz;
-#define TTN(iz, ix) ttn[(size_t)((ix)-1) * nnz + ((iz)-1)]
+#define TTN(iz, ix) ttn[cidx((ix)-1, (iz)-1, nnz)]
 #define TTNR(iz, ix) ttnr[((ix)-1) * REF_LD + ((iz)-1)]
 // nstsr(iz,ix) /= 0  <=>  not alive  <=>  sign bit of the encoded refined field
 #define NSTSR(iz, ix) (__float_as_int(ttnr[((ix)-1) * REF_LD + ((iz)-1)]) >> 31)
