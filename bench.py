@@ -90,7 +90,10 @@ def _measured_traffic(workload_name, solves):
     p = os.path.join(ROOT, "profiles", "k3_dram_traffic.json")
     try:
         d = json.load(open(p))
-        per_solve = d["bytes_per_solve"].get(workload_name.split("-")[0])
+        key = workload_name.split("-")[0]
+        if solves <= 1480 and key + "_duo" in d["bytes_per_solve"]:
+            key += "_duo"          # every solve resident: the library runs the two-warp latency kernel
+        per_solve = d["bytes_per_solve"].get(key)
         return None if per_solve is None else float(per_solve) * solves
     except Exception:
         return None
