@@ -26,6 +26,7 @@
 //    global read-after-write sits on the critical path.
 #include "dazim_dev.h"
 #include <cstdio>
+#include <cstdlib>
 
 namespace dz {
 
@@ -970,7 +971,8 @@ __device__ void march_duo_Q(int* comm, const int nnx, const int nnz, const int l
   }
 }
 
-__global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_fmm_duo(FmmArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sl = lane & 15;
   const GridC& g = A.g;
@@ -1111,12 +1113,19 @@ __global__ void __launch_bounds__(64, 10) k_fmm_duo(FmmArgs A) {
   }
 }
 
+// MINB = 10: 96 registers (fastest single solve); MINB = 16: 64 registers, more solves per SM
+static int duo_minb() {
+  const char* e = getenv("DAZIM_DUO_MINB");
+  return (e && atoi(e) >= 16) ? 16 : 10;
+}
+
 cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas) {
   const size_t smem = (size_t)hcap * 8 + 128;
-  cudaError_t e = cudaFuncSetAttribute(k_fmm_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const void* fn = duo_minb() == 16 ? (const void*)k_fmm_duo<16> : (const void*)k_fmm_duo<10>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fmm_duo, 64, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 64, smem);
   if (e != cudaSuccess) return e;
   *nctas = per_sm * nsm;
   return cudaSuccess;
@@ -1124,9 +1133,12 @@ cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas) {
 
 cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st) {
   const size_t smem = (size_t)A.hcap * 8 + 128;
-  cudaError_t e = cudaFuncSetAttribute(k_fmm_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool wide = duo_minb() == 16;
+  const void* fn = wide ? (const void*)k_fmm_duo<16> : (const void*)k_fmm_duo<10>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_fmm_duo<<<nctas, 64, smem, st>>>(A);
+  if (wide) k_fmm_duo<16><<<nctas, 64, smem, st>>>(A);
+  else k_fmm_duo<10><<<nctas, 64, smem, st>>>(A);
   return cudaGetLastError();
 }
 
