@@ -305,7 +305,10 @@ __device__ void march(Heap& h, const int nnx, const int nnz, const int ld, const
   for (;;) {
     const bool act = !done && h.ntr > 0;
     if (CM == 0) { if (!__any_sync(0xffffffffu, act)) break; }
-    else if (!act) break;
+    else {
+      if (!act) break;
+      __syncwarp(CM);        // the lanes of the solve run the scalar heap code redundantly: re-align them every step
+    }
     if (!act) continue;
     const int2 root = h.sm[1];
     const int pn = root.y;
@@ -693,6 +696,7 @@ __device__ void march_duo_H(Heap& h, int* comm, const int nnx, const int nnz, co
     const long long t0 = clock64();
     if (p_open) { p_apply += t0; p_open = 0; }
 #endif
+    __syncwarp();            // the 32 lanes run the scalar heap code redundantly: re-align them every step
     bool stop = (h.ntr == 0) || overflow;
     int2 root = make_int2(0, 0), last = make_int2(0, 0);
     int pred = -1, cand0 = -1, cand1 = -1, cand2 = -1;
