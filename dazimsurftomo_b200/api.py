@@ -286,6 +286,26 @@ def CalSurfGAnisoJoint(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Surv
     return _gbuild(2, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle)
 
 
+class LsmrInfo(C.Structure):
+    _fields_ = [("istop", C.c_int), ("itn", C.c_int), ("normA", C.c_float), ("condA", C.c_float), ("normr", C.c_float),
+                ("normAr", C.c_float), ("normx", C.c_float), ("setup_ms", C.c_float), ("solve_ms", C.c_float)]
+
+
+def LSMR(m, n, row, col, rw, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, itnlim=500, localSize=10,
+         handle: Optional[Handle] = None):
+    """lsmrModule.f90:36 on the reference's COO system (row = iw(2:nar+1), col = iw(nar+2:), rw; 1-based).
+    Defaults are the joint-inversion controls of Main_Jt.f90:548-553.  Returns (x, info dict)."""
+    h = handle or default_handle()
+    row = np.ascontiguousarray(row, np.int32); col = np.ascontiguousarray(col, np.int32)
+    rw = np.ascontiguousarray(rw, np.float32); b = np.ascontiguousarray(b, np.float32)
+    x = np.zeros(n, np.float32)
+    info = LsmrInfo()
+    _chk(load().dazim_lsmr(h._h, C.c_int(m), C.c_int(n), C.c_longlong(len(rw)), _p(row), _p(col), _p(rw), _p(b),
+                           C.c_float(damp), C.c_float(atol), C.c_float(btol), C.c_float(conlim), C.c_int(itnlim),
+                           C.c_int(localSize), _p(x), C.byref(info)))
+    return x, {k: getattr(info, k) for k, _ in info._fields_}
+
+
 def fmm_solve(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, handle: Optional[Handle] = None):
     """Test seam: eikonal fields of n sources on one phase-velocity map."""
     h = handle or default_handle()

@@ -38,6 +38,11 @@ int th_depthkernel_ti(cudaStream_t st, int nx, int ny, int nz, const float* vel,
 int th_surfdisp96(cudaStream_t st, int nprof, int nlayer, const float* thk, const float* vp, const float* vs,
                   const float* rho, int kmax, const double* t, double* cg);
 }  // namespace dz
+namespace dzl {
+int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, const int* col, const float* rw,
+               const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize, float* x,
+               dazim_lsmr_info* info);
+}
 
 using namespace dz;
 
@@ -788,6 +793,14 @@ extern "C" int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, d
               tb.pvRc[(size_t)jj * nx + ii + (size_t)(tt - 1) * nxy];
   }
   return DAZIM_OK;
+}
+
+extern "C" int dazim_lsmr(dazim_handle* h, int m, int n, long long nnz, const int* iw_row, const int* col,
+                          const float* rw, const float* b, float damp, float atol, float btol, float conlim, int itnlim,
+                          int localSize, float* x, dazim_lsmr_info* info) {
+  if (!h) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  return dzl::lsmr_solve(h->st, m, n, nnz, iw_row, col, rw, b, damp, atol, btol, conlim, itnlim, localSize, x, info);
 }
 
 // ---------------------------------------------------------------------------

@@ -133,3 +133,18 @@ extern "C" void calsurfganisojoint_(int* nx, int* ny, int* nz, int* nparpi, floa
   if (GVs || GGc || GGs) densify(c, *dall, *nparpi, GVs, GGc, GGs);
   if (dazim_last_times(handle())->rbint) printf(" ray path along the boundary, dangerous!!\n");
 }
+
+// LSMRmodule::LSMR (lsmrModule.f90:36): iw(1) = nnz, iw(2:nnz+1) = rows, iw(nnz+2:2nnz+1) = columns (aprod.f90:22-27)
+extern "C" void __lsmrmodule_MOD_lsmr(int* m, int* n, int* leniw, int* lenrw, int* iw, float* rw, float* b, float* damp,
+                                      float* atol, float* btol, float* conlim, int* itnlim, int* localSize, int* nout,
+                                      float* x, int* istop, int* itn, float* normA, float* condA, float* normr,
+                                      float* normAr, float* normx) {
+  (void)leniw; (void)lenrw; (void)nout;
+  const long long nnz = iw[0];
+  dazim_lsmr_info info;
+  std::memset(&info, 0, sizeof(info));
+  stop_on(dazim_lsmr(handle(), *m, *n, nnz, iw + 1, iw + 1 + nnz, rw, b, *damp, *atol, *btol, *conlim, *itnlim,
+                     *localSize, x, &info), "LSMR");
+  *istop = info.istop; *itn = info.itn; *normA = info.normA; *condA = info.condA; *normr = info.normr;
+  *normAr = info.normAr; *normx = info.normx;
+}

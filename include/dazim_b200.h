@@ -160,6 +160,22 @@ int dazim_plan_device_ptrs(dazim_plan* plan, void** dsurf, void** obsTaa, void**
                            void** val);
 void dazim_plan_destroy(dazim_plan* plan);
 
+/* --- next stage: the sparse least-squares solve that consumes G ------------------
+ * LSMR (src/src_inv_iso_joint/lsmrModule.f90:36) with the reference's COO products (aprod.f90:7), single
+ * precision like the reference (lsmrDataModule.f90:21).  A is m x n, given as nnz triplets
+ * (iw_row[k], col[k], rw[k]) with 1-based indices in any order -- exactly iw(2:nar+1), iw(nar+2:2nar+1), rw of the
+ * reference (Main_Jt.f90:529-532).  x (n) is the output.  Stopping rules, istop codes and the norm / condition
+ * estimates are the reference's. */
+typedef struct dazim_lsmr_info {
+  int istop, itn;
+  float normA, condA, normr, normAr, normx;
+  float setup_ms;            /* upload + CSR/CSC construction (device time) */
+  float solve_ms;            /* the iterations (device time) */
+} dazim_lsmr_info;
+int dazim_lsmr(dazim_handle* h, int m, int n, long long nnz, const int* iw_row, const int* col, const float* rw,
+               const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize,
+               float* x, dazim_lsmr_info* info);
+
 /* --- gfortran-ABI drop-in symbols (lower case + underscore, all by reference) --- */
 void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, float* vels, float* Gctrue,
                           float* Gstrue, float* dsurf, float* obsTaa, int* dall, int* rmax,
@@ -185,6 +201,11 @@ void depthkernel_(int* nx, int* ny, int* nz, float* vel, double* pvRc, double* s
                   double* tRc, float* depz, float* minthk);
 void depthkernelti_(int* nx, int* ny, int* nz, float* vel, double* pvRc, int* iwave, int* igr,
                     int* kmaxRc, double* tRc, float* depz, float* minthk, float* Lsen_Gsc);
+/* module procedure LSMRmodule::LSMR as gfortran mangles it (lsmrModule.f90:36; called at Main_Jt.f90:562) */
+void __lsmrmodule_MOD_lsmr(int* m, int* n, int* leniw, int* lenrw, int* iw, float* rw, float* b, float* damp,
+                           float* atol, float* btol, float* conlim, int* itnlim, int* localSize, int* nout,
+                           float* x, int* istop, int* itn, float* normA, float* condA, float* normr,
+                           float* normAr, float* normx);
 
 #ifdef __cplusplus
 }

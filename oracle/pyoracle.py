@@ -210,3 +210,22 @@ def gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc=None, g
                 Lsen_Gsc=L, rw=rw[:n], row=iw[:n], col=col[:n], nar=n, rbint=a.rbint,
                 times=dict(kernels=a.t_kernels, dice_fmm=a.t_dice_fmm, trace=a.t_trace, assemble=a.t_assemble),
                 n_accept=a.n_accept, n_steps=a.n_steps)
+
+
+class LsmrOut(C.Structure):
+    _fields_ = [("istop", C.c_int), ("itn", C.c_int), ("normA", C.c_float), ("condA", C.c_float),
+                ("normr", C.c_float), ("normAr", C.c_float), ("normx", C.c_float)]
+
+
+def lsmr(m, n, row, col, rw, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, itnlim=500, localSize=10):
+    """LSMR (lsmrModule.f90:36) + aprod (aprod.f90:7) in single precision on a COO system (1-based indices)."""
+    row = np.ascontiguousarray(row, np.int32); col = np.ascontiguousarray(col, np.int32)
+    rw = np.ascontiguousarray(rw, np.float32); b = np.ascontiguousarray(b, np.float32)
+    x = np.zeros(n, np.float32)
+    out = LsmrOut()
+    st = lib().orc_lsmr(C.c_int(m), C.c_int(n), C.c_longlong(len(rw)), _p(row), _p(col), _p(rw), _p(b), C.c_float(damp),
+                        C.c_float(atol), C.c_float(btol), C.c_float(conlim), C.c_int(itnlim), C.c_int(localSize), _p(x),
+                        C.byref(out))
+    if st:
+        raise RuntimeError(f"orc_lsmr status {st}")
+    return x, {k: getattr(out, k) for k, _ in out._fields_}

@@ -2,6 +2,7 @@
 fields, ray footprints, sparsity pattern and G values (float32 arithmetic is reproduced
 operation by operation); tolerances are written where floating-point libraries differ."""
 import numpy as np
+import os
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -323,3 +324,33 @@ def test_nnz_overflow_is_reported(gpu, oracle, test1, test1_tables):
         gpu.CalSurfG(test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"],
                      tables=tb, maxnar=100)
     assert e.value.code == 3
+
+
+def test_forward_driver_reproduces_reference_files(gpu, test1, tmp_path):
+    """SurfAAForward replacement on the reference's own inputs (subset of example/test1_syn_foward): the
+    surfphase_forward.dat it writes matches the reference's shipped output line by line (coordinates
+    exactly, velocities to the printed f9.5 +- 1.5e-5) and period_Azm_tomo.real matches the golden table."""
+    import shutil
+    from conftest import GOLD
+    from dazimsurftomo_b200 import forward
+    for f in ("para.in", "MODVs.true", "MODGc.true", "MODGs.true"):
+        shutil.copy(os.path.join(GOLD, f), tmp_path / f)
+    shutil.copy(os.path.join(GOLD, "surfdata_subset.dat"), tmp_path / "Surfphase_RV3_5_40s_1s.dat")
+    out = forward.run(str(tmp_path / "para.in"))
+    mine = open(tmp_path / "surfphase_forward.dat").read().split("\n")
+    gold = open(os.path.join(GOLD, "surfphase_subset.dat")).read().split("\n")
+    assert len(mine) == len(gold)
+    for a, b in zip(mine, gold):
+        if not b.strip():
+            continue
+        if b.startswith("#"):
+            assert a.split() == b.split()
+        else:
+            ta, tb = a.split(), b.split()
+            assert ta[:2] == tb[:2] and abs(float(ta[2]) - float(tb[2])) < 1.5e-5
+    g = test1["azm"]                       # period_Azm_tomo.real of the reference (36 periods x 225 nodes x 9 cols)
+    t = out["azim"]
+    n = min(len(g), len(t))
+    assert n == 8100
+    assert np.abs(t[:n, 3] - g[:n, 3]).max() < 6e-6                  # isotropic phase velocity (col 4)
+    assert np.abs(t[:n, 7:9] - g[:n, 7:9]).max() < 2e-5              # Sum Lsen*Gc, Sum Lsen*Gs (cols 8-9)
