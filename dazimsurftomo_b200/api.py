@@ -381,6 +381,17 @@ class Plan:
         _chk(load().dazim_plan_device_ptrs(self._plan, *[C.byref(p) for p in ptrs]))
         return dict(zip(("dsurf", "obsTaa", "rowptr", "col", "val"), [p.value for p in ptrs]))
 
+    def lsmr(self, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, itnlim=500, localSize=10):
+        """LSMR on the G row block of the last run, resident in HBM (dazim_plan_lsmr): returns (x, info)."""
+        b = np.ascontiguousarray(b, np.float32)
+        nx, ny, nz = self._pr.shape
+        n = (3 if self.mode == 2 else 1) * (nx - 2) * (ny - 2) * (nz - 1)
+        x = np.zeros(n, np.float32)
+        info = LsmrInfo()
+        _chk(load().dazim_plan_lsmr(self._plan, _p(b), C.c_float(damp), C.c_float(atol), C.c_float(btol), C.c_float(conlim),
+                                    C.c_int(itnlim), C.c_int(localSize), _p(x), C.byref(info)))
+        return x, {k: getattr(info, k) for k, _ in info._fields_}
+
     def device_tensors(self):
         """Zero-copy torch views of the last run's outputs in HBM (for NCCL exchanges without a host hop).
         plan.run() has synchronised the library stream, so the views are safe on torch's current stream."""

@@ -41,7 +41,7 @@ int th_surfdisp96(cudaStream_t st, int nprof, int nlayer, const float* thk, cons
 namespace dzl {
 int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, const int* col, const float* rw,
                const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize, float* x,
-               dazim_lsmr_info* info);
+               dazim_lsmr_info* info, bool coo_on_device);
 }
 
 using namespace dz;
@@ -800,7 +800,18 @@ extern "C" int dazim_lsmr(dazim_handle* h, int m, int n, long long nnz, const in
                           int localSize, float* x, dazim_lsmr_info* info) {
   if (!h) return DAZIM_EBADARG;
   CK(cudaSetDevice(h->dev));
-  return dzl::lsmr_solve(h->st, m, n, nnz, iw_row, col, rw, b, damp, atol, btol, conlim, itnlim, localSize, x, info);
+  return dzl::lsmr_solve(h->st, m, n, nnz, iw_row, col, rw, b, damp, atol, btol, conlim, itnlim, localSize, x, info, false);
+}
+
+extern "C" int dazim_plan_lsmr(dazim_plan* P, const float* b, float damp, float atol, float btol, float conlim,
+                               int itnlim, int localSize, float* x, dazim_lsmr_info* info) {
+  if (!P || P->mode == 0 || P->nnz <= 0) return DAZIM_EBADARG;
+  dazim_handle* h = P->h;
+  CK(cudaSetDevice(h->dev));
+  const int nblk = (P->mode == 2) ? 3 : 1;
+  const long long ncol = (long long)nblk * P->g.nvx * P->g.nvz * (P->nz - 1);
+  return dzl::lsmr_solve(h->st, (int)P->nrow, (int)ncol, P->nnz, P->d_rowid.p, P->d_col.p, P->d_val.p, b, damp, atol, btol,
+                         conlim, itnlim, localSize, x, info, true);
 }
 
 // ---------------------------------------------------------------------------

@@ -176,9 +176,10 @@ static int compress(cudaStream_t st, long long nnz, int nkey, const int* d_key, 
   return 0;
 }
 
+// coo_on_device: row/col/rw already live in HBM (the G row block of a plan): no upload, G never leaves the GPU
 int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, const int* col, const float* rw,
                const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize, float* x,
-               dazim_lsmr_info* info) {
+               dazim_lsmr_info* info, bool coo_on_device) {
   if (m < 1 || n < 1 || nnz < 0 || nnz >= (1ll << 31) || !row || !col || !rw || !b || !x || !info) return DAZIM_EBADARG;
   cudaEvent_t e0, e1, e2;
   LCK(cudaEventCreate(&e0)); LCK(cudaEventCreate(&e1)); LCK(cudaEventCreate(&e2));
@@ -186,18 +187,21 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   Buf<int> d_row, d_col, csr_idx, csc_idx;
   Buf<float> d_val, csr_val, csc_val;
   Buf<long long> csr_ptr, csc_ptr;
-  LCK(d_row.alloc(nnz, st)); LCK(d_col.alloc(nnz, st)); LCK(d_val.alloc(nnz, st));
+  if (!coo_on_device) { LCK(d_row.alloc(nnz, st)); LCK(d_col.alloc(nnz, st)); LCK(d_val.alloc(nnz, st)); }
   LCK(csr_idx.alloc(nnz, st)); LCK(csc_idx.alloc(nnz, st)); LCK(csr_val.alloc(nnz, st)); LCK(csc_val.alloc(nnz, st));
   LCK(csr_ptr.alloc((size_t)m + 1, st)); LCK(csc_ptr.alloc((size_t)n + 1, st));
   LCK(cudaEventRecord(e0, st));
-  if (nnz > 0) {
+  if (nnz > 0 && !coo_on_device) {
     LCK(cudaMemcpyAsync(d_row.p, row, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
     LCK(cudaMemcpyAsync(d_col.p, col, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
     LCK(cudaMemcpyAsync(d_val.p, rw, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
   }
-  int rc = compress(st, nnz, m, d_row.p, d_col.p, d_val.p, csr_ptr.p, csr_idx.p, csr_val.p);
+  const int* k_row = coo_on_device ? row : d_row.p;
+  const int* k_col = coo_on_device ? col : d_col.p;
+  const float* k_val = coo_on_device ? rw : d_val.p;
+  int rc = compress(st, nnz, m, k_row, k_col, k_val, csr_ptr.p, csr_idx.p, csr_val.p);
   if (rc) return rc;
-  rc = compress(st, nnz, n, d_col.p, d_row.p, d_val.p, csc_ptr.p, csc_idx.p, csc_val.p);
+  rc = compress(st, nnz, n, k_col, k_row, k_val, csc_ptr.p, csc_idx.p, csc_val.p);
   if (rc) return rc;
   // ---- vectors ----
   const int localVecs = std::max(0, std::min(localSize, std::min(m, n)));

@@ -176,6 +176,11 @@ int dazim_lsmr(dazim_handle* h, int m, int n, long long nnz, const int* iw_row, 
                const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize,
                float* x, dazim_lsmr_info* info);
 
+/* the same solve on the G row block of a plan's last run: the matrix never leaves the GPU (b has plan rows entries,
+ * x has nparpi (iso) or 3*nparpi (joint) entries) */
+int dazim_plan_lsmr(dazim_plan* plan, const float* b, float damp, float atol, float btol, float conlim, int itnlim,
+                    int localSize, float* x, dazim_lsmr_info* info);
+
 /* --- gfortran-ABI drop-in symbols (lower case + underscore, all by reference) --- */
 void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, float* vels, float* Gctrue,
                           float* Gstrue, float* dsurf, float* obsTaa, int* dall, int* rmax,

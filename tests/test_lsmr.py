@@ -77,3 +77,21 @@ def test_cuda_lsmr_on_g_matrix(gpu, oracle, test1, test1_tables):
     assert np.linalg.norm(G @ x - G @ ox) <= 2e-3 * np.linalg.norm(b)
     assert abs(info["normx"] - oi["normx"]) <= 2e-2 * oi["normx"]        # null-space components differ with the iteration count
     assert info["solve_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_plan_lsmr_keeps_g_on_device(gpu, oracle, test1, test1_tables):
+    """dazim_plan_lsmr (G stays in HBM) == dazim_lsmr on the fetched triplets, bit for bit."""
+    p = test1["para"]; sv = test1["sv"]
+    pv, svs, svp, srho, _ = oracle.depthkernel(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    tb = dict(test1_tables, sen_vs=svs, sen_vp=svp, sen_rho=srho)
+    plan = gpu.Plan(2, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, tb)
+    plan.run()
+    out = plan.fetch()
+    m = plan.rows; n = 3 * (p.nx - 2) * (p.ny - 2) * (p.nz - 1)
+    rows = np.repeat(np.arange(1, m + 1, dtype=np.int32), np.diff(out["rowptr"]))
+    b = np.random.default_rng(3).standard_normal(m).astype(np.float32)
+    x1, i1 = plan.lsmr(b, damp=0.3, itnlim=30)
+    x2, i2 = gpu.LSMR(m, n, rows, out["col"], out["val"], b, damp=0.3, itnlim=30)
+    plan.close()
+    assert i1["itn"] == i2["itn"] and i1["istop"] == i2["istop"] and np.array_equal(x1, x2)
