@@ -28,6 +28,16 @@ static dazim_handle* handle() {
   return g_handle;
 }
 
+// writepath (FwdTraveltimeCPS.f90:673-686, rpathsAzim.f90:617-625) dumps every ray's nodes to
+// raypath_refmdl_<T>s.dat; all shipped examples run with it off.  It is a diagnostic, not an input of the
+// inversion: say so loudly instead of silently ignoring the request.
+static void warn_writepath(int flag) {
+  if (flag) {
+    printf(" dazim_b200: writepath requested -- ray-path files (raypath_refmdl_*s.dat) are NOT written by the GPU path\n");
+    fflush(stdout);
+  }
+}
+
 static void stop_on(int st, const char* where) {
   if (st == DAZIM_OK) return;
   fprintf(stdout, " %s\n TERMINATING PROGRAM!!! (%s)\n", dazim_strerror(st), where);
@@ -81,7 +91,8 @@ extern "C" void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, flo
                                      int* kmaxRc, double* tRc, int* periods, float* depz, float* minthk, float* scxf,
                                      float* sczf, float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1, int* kmax,
                                      int* nsrcsurf, int* nrcf, int* writepath) {
-  (void)nparpi; (void)dall; (void)rmax; (void)writepath;
+  (void)nparpi; (void)dall; (void)rmax;
+  warn_writepath(*writepath);
   dazim_problem p;
   fill_problem(p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, tRc, periods, depz, minthk, scxf, sczf, rcxf,
                rczf, nrc1, nsrcsurf1, kmax, nsrcsurf, nrcf);
@@ -118,7 +129,8 @@ extern "C" void calsurfganisojoint_(int* nx, int* ny, int* nz, int* nparpi, floa
                                     int* kmaxRc, double* tRc, int* periods, float* depz, float* minthk, float* scxf,
                                     float* sczf, float* rcxf, float* rczf, int* nrc1, int* nsrcsurf1, int* kmax,
                                     int* nsrcsurf, int* nrcf, int* nar, int* writepath) {
-  (void)rmax; (void)writepath;
+  (void)rmax;
+  warn_writepath(*writepath);
   dazim_problem p;
   fill_problem(p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, tRc, periods, depz, minthk, scxf, sczf, rcxf,
                rczf, nrc1, nsrcsurf1, kmax, nsrcsurf, nrcf);
