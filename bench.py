@@ -109,6 +109,8 @@ def workload(args):
         return synthetic.s200(src_per_period=int(args.workload[5:]))      # S200 grid, fewer sources per period
     if args.workload == "YN":
         return synthetic.yunnan_shaped()
+    if args.workload.startswith("YN-") and args.workload[3:].isdigit():
+        return synthetic.yunnan_shaped(nsta=int(args.workload[3:]))
     if args.workload == "S40":
         return synthetic.s200(src_per_period=64, n=42, nz=5, nsta=200, nrec=16, kmax=4)
     raise SystemExit("unknown workload " + args.workload)

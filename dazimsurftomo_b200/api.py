@@ -371,7 +371,9 @@ class Plan:
         dsurf = np.zeros(n, np.float32)
         taa = np.zeros(n, np.float32) if self.mode == 0 else None
         rowptr = col = val = None
-        if self.mode != 0 and csr:
+        if self.mode != 0 and csr == "rowptr":          # row pointers only (the triplets of a big job are tens of GB)
+            rowptr = np.zeros(n + 1, np.int64)
+        elif self.mode != 0 and csr:
             rowptr = np.zeros(n + 1, np.int64); col = np.zeros(self.nnz, np.int32); val = np.zeros(self.nnz, np.float32)
         _chk(load().dazim_plan_fetch(self._plan, _p(dsurf), _p(taa), _p(rowptr), _p(col), _p(val)))
         return dict(dsurf=dsurf, obsTaa=taa, rowptr=rowptr, col=col, val=val)

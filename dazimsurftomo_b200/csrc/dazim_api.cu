@@ -27,7 +27,7 @@ cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_
 cudaError_t launch_coef(int nx, int ny, int nz, const float* vels, float* ca, float* cr, cudaStream_t st);
 cudaError_t launch_assemble(const AsmArgs& A, bool fill, cudaStream_t st);
 cudaError_t launch_taa(const TaaArgs& A, cudaStream_t st);
-cudaError_t scan_rowptr(const int* counts, long long* rowptr, int n, void* tmp, size_t* tmp_bytes, cudaStream_t st);
+cudaError_t scan_rowptr(const long long* counts, long long* rowptr, int n, void* tmp, size_t* tmp_bytes, cudaStream_t st);
 // Thomson-Haskell stage (dazim_th.cu)
 int th_depthkernel(cudaStream_t st, int nx, int ny, int nz, const float* vel, double* pvRc, double* sen_vs,
                    double* sen_vp, double* sen_rho, int kmaxRc, const double* tRc, const float* depz, float minthk,
@@ -196,7 +196,7 @@ struct dazim_plan {
   unsigned long long pool_cap = 0;
   DBuf<unsigned long long> d_counters;   // [0] pool_used [1] n_accept [2] n_steps
   DBuf<int> d_icnt;                       // [0] work counter [1] flags
-  DBuf<float> d_dsurf, d_taa, d_val; DBuf<int> d_col, d_rowid, d_nnz_row; DBuf<long long> d_rowptr;
+  DBuf<float> d_dsurf, d_taa, d_val; DBuf<int> d_col, d_rowid; DBuf<long long> d_nnz_row, d_rowptr;
   DBuf<unsigned char> d_scan_tmp; size_t scan_tmp_bytes = 0;
   long long val_cap = 0;
   cudaEvent_t ev[8];
@@ -619,9 +619,9 @@ static int plan_run(dazim_plan* P) {
       size_t tb = P->scan_tmp_bytes;
       CK(scan_rowptr(P->d_nnz_row.p, P->d_rowptr.p, (int)P->nrow, P->d_scan_tmp.p, &tb, st));
       long long last_off = 0;
-      int last_cnt = 0;
+      long long last_cnt = 0;
       CK(cudaMemcpyAsync(&last_off, P->d_rowptr.p + (P->nrow - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(&last_cnt, P->d_nnz_row.p + (P->nrow - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&last_cnt, P->d_nnz_row.p + (P->nrow - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       P->nnz = last_off + last_cnt;
       CK(cudaMemcpyAsync(P->d_rowptr.p + P->nrow, &P->nnz, sizeof(long long), cudaMemcpyHostToDevice, st));

@@ -120,7 +120,7 @@ struct AsmArgs {
   const double* sen_vs; const double* sen_vp; const double* sen_rho;   // (nx*ny,kmax,nz)
   const float* lsen;        // (nx*ny,kmax,nz-1)
   const float* coe_a; const float* coe_rho;   // (nx*ny, nz-1) at node index jj*nx+kk (vels(kk+1,jj+1,k))
-  int* nnz_row;             // [nrow] counts (pass 1)
+  long long* nnz_row;       // [nrow] counts (pass 1); 64-bit so that the row-pointer scan cannot wrap at 2^31 non-zeros
   const long long* rowptr;  // [nrow+1] (pass 2)
   float* val; int* col;     // CSR outputs (pass 2)
   int* rowid;               // optional COO row ids, 1-based (pass 2)

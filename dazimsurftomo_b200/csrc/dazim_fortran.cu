@@ -119,6 +119,7 @@ extern "C" void calsurfg_(int* nx, int* ny, int* nz, int* nparpi, float* vels, i
   // the caller sized rw/col by spfra (Main_Jt.f90:325); the bound is not passed down, so trust it like the reference
   c.maxnar = (long long)1 << 62;
   stop_on(dazim_gbuild(handle(), 1, &p, &tb, 0, nullptr, nullptr, dsurf, nullptr, nullptr, &c), "CalSurfG");
+  if (c.nar > 2147483647ll) stop_on(DAZIM_ENNZ_OVERFLOW, "CalSurfG: nar exceeds the reference's default INTEGER");
   *nar = (int)c.nar;
   if (GVs) densify(c, *dall, *nparpi, GVs, nullptr, nullptr);
 }
@@ -141,6 +142,7 @@ extern "C" void calsurfganisojoint_(int* nx, int* ny, int* nz, int* nparpi, floa
   c.rw = rw; c.iw_row = iw + 1; c.col = col; c.nar = 0;
   c.maxnar = (long long)1 << 62;
   stop_on(dazim_gbuild(handle(), 2, &p, &tb, 0, nullptr, nullptr, dsurf, nullptr, tRcV, &c), "CalSurfGAnisoJoint");
+  if (c.nar > 2147483647ll) stop_on(DAZIM_ENNZ_OVERFLOW, "CalSurfGAnisoJoint: nar exceeds the reference's default INTEGER");
   *nar = (int)c.nar;
   if (GVs || GGc || GGs) densify(c, *dall, *nparpi, GVs, GGc, GGs);
   if (dazim_last_times(handle())->rbint) printf(" ray path along the boundary, dangerous!!\n");

@@ -616,8 +616,9 @@ cudaError_t launch_taa(const TaaArgs& A, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// exclusive scan of int counts -> long long row pointers (n+1 entries, last = total)
-cudaError_t scan_rowptr(const int* counts, long long* rowptr, int n, void* tmp, size_t* tmp_bytes, cudaStream_t st) {
+// exclusive scan of 64-bit counts -> row pointers.  (An int input would make cub accumulate in int: a joint G
+// of the Yunnan-shaped survey has 4.8e9 non-zeros.)
+cudaError_t scan_rowptr(const long long* counts, long long* rowptr, int n, void* tmp, size_t* tmp_bytes, cudaStream_t st) {
   // rowptr[0..n-1] = exclusive sum; the caller adds the last element
   return cub::DeviceScan::ExclusiveSum(tmp, *tmp_bytes, counts, rowptr, n, st);
 }

@@ -354,3 +354,22 @@ def test_forward_driver_reproduces_reference_files(gpu, test1, tmp_path):
     assert n == 8100
     assert np.abs(t[:n, 3] - g[:n, 3]).max() < 6e-6                  # isotropic phase velocity (col 4)
     assert np.abs(t[:n, 7:9] - g[:n, 7:9]).max() < 2e-5              # Sum Lsen*Gc, Sum Lsen*Gs (cols 8-9)
+
+
+def test_more_than_2_31_nonzeros(gpu):
+    """BASELINE config 5 (Yunnan-shaped grid, 300 stations, all pairs, 36 periods): the joint G has 5.4e9
+    non-zeros.  Row pointers must stay monotone past 2^31 (regression: the count scan accumulated in int)."""
+    from dazimsurftomo_b200 import synthetic
+    w = synthetic.yunnan_shaped()
+    pv, svs, svp, srho = gpu.depthkernel(w.vs, w.depz, w.tRc, w.sublayers)
+    pv2, L = gpu.depthkernelTI(w.vs, w.depz, w.tRc, w.sublayers)
+    tb = dict(pvRc=pv, sen_vs=svs, sen_vp=svp, sen_rho=srho, Lsen_Gsc=L)
+    plan = gpu.Plan(2, w.vs, w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv, tb)
+    plan.run()
+    nnz = plan.nnz
+    out = plan.fetch(csr="rowptr")
+    plan.close()
+    rp = out["rowptr"]
+    assert nnz > 2 ** 31 and rp[0] == 0 and rp[-1] == nnz
+    d = np.diff(rp)
+    assert d.min() >= 0 and d.max() < 3 * 36 * 40 * 17 and np.isfinite(out["dsurf"]).all() and out["dsurf"].min() > 0
