@@ -107,6 +107,8 @@ def workload(args):
         return synthetic.s200(src_per_period=125)
     if args.workload.startswith("S200-") and args.workload[5:].isdigit():
         return synthetic.s200(src_per_period=int(args.workload[5:]))      # S200 grid, fewer sources per period
+    if args.workload == "T1":
+        return synthetic.t1_shaped()
     if args.workload == "YN":
         return synthetic.yunnan_shaped()
     if args.workload.startswith("YN-") and args.workload[3:].isdigit():

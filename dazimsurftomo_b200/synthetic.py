@@ -172,3 +172,35 @@ def yunnan_shaped(nsta=300, src_per_period=None, nrec=None, kmax=36, seed=4242) 
                 np.zeros(dall, F32), np.zeros(dall, F32), dall)
     return Workload(f"YN-{nsta}sta" + ("" if src_per_period is None else f"-{src_per_period}src"), nx, ny, nz, goxd, gozd,
                     dv, dv, 4.0, depz, tRc, vs, gc, gs, sv)
+
+
+def t1_shaped(nsta=121, kmax=36, seed=99) -> Workload:
+    """BASELINE config 1 shape (example/test1_syn_foward): 17 x 17 x 4 model (71 x 71 propagation grid, refined
+    source boxes that cover most of it), 36 periods 5..40 s, sublayers 2, ~120 sources per period with all other
+    stations as receivers -- with a seeded synthetic model and geometry (the shipped files stay in /root/reference)."""
+    nx = ny = 17; nz = 4
+    goxd, gozd, dv = 26.5, 101.0, 0.25          # any origin works; spacing like the example
+    depz = np.array([0, 10, 35, 60], F32)
+    _, vs, gc, gs = make_model(nx, ny, nz, cells=4, seed=seed)
+    rng = np.random.default_rng(seed)
+    lat = rng.uniform(goxd - (nx - 3) * dv + 0.2, goxd - 0.2, nsta).astype(F32)
+    lon = rng.uniform(gozd + 0.2, gozd + (ny - 3) * dv - 0.2, nsta).astype(F32)
+    colat = ((F32(90.0) - lat) * PI32 / F32(180.0)).astype(F32)
+    lonr = (lon * PI32 / F32(180.0)).astype(F32)
+    ns = nsta - 1
+    nrcf = nsta - 1
+    periods = np.zeros((ns, kmax), np.int32, order="F"); nrc1 = np.zeros((ns, kmax), np.int32, order="F")
+    scxf = np.zeros((ns, kmax), F32, order="F"); sczf = np.zeros((ns, kmax), F32, order="F")
+    rcxf = np.zeros((nrcf, ns, kmax), F32, order="F"); rczf = np.zeros((nrcf, ns, kmax), F32, order="F")
+    for k in range(kmax):
+        for s in range(ns):
+            n = nsta - 1 - s
+            periods[s, k] = k + 1; nrc1[s, k] = n
+            scxf[s, k] = colat[s]; sczf[s, k] = lonr[s]
+            rcxf[:n, s, k] = colat[s + 1:]; rczf[:n, s, k] = lonr[s + 1:]
+    dall = int(nrc1.sum())
+    wave = np.full((ns, kmax), 2, np.int32, order="F"); igrt = np.zeros((ns, kmax), np.int32, order="F")
+    sv = Survey(kmax, ns, nrcf, periods, nrc1, np.full(kmax, ns, np.int32), scxf, sczf, rcxf, rczf, wave, igrt,
+                np.zeros(dall, F32), np.zeros(dall, F32), dall)
+    tRc = (5.0 + np.arange(kmax)).astype(np.float64)
+    return Workload(f"T1-{nsta}sta", nx, ny, nz, goxd, gozd, dv, dv, 2.0, depz, tRc, vs, gc, gs, sv)

@@ -373,3 +373,30 @@ def test_more_than_2_31_nonzeros(gpu):
     assert nnz > 2 ** 31 and rp[0] == 0 and rp[-1] == nnz
     d = np.diff(rp)
     assert d.min() >= 0 and d.max() < 3 * 36 * 40 * 17 and np.isfinite(out["dsurf"]).all() and out["dsurf"].min() > 0
+
+
+@pytest.mark.parametrize("env", [dict(DAZIM_DUO="0", DAZIM_SPC="2"), dict(DAZIM_DUO="0", DAZIM_SPC="2", DAZIM_HCAP="64"),
+                                 dict(DAZIM_DUO="0", DAZIM_SPC="1"), dict(DAZIM_DUO="1", DAZIM_DUO_MINB="16"),
+                                 dict(DAZIM_DUO="1", DAZIM_HCAP="64")])
+def test_every_eikonal_kernel_variant_is_bit_identical(gpu, oracle, test1, test1_tables, monkeypatch, env):
+    """The library picks the eikonal kernel from the number of solves (two-warp latency kernel, half-warp
+    throughput kernel, shared / spilled heap).  Force each variant on the same inputs: fields and G must not change."""
+    p = test1["para"]
+    pv = np.ascontiguousarray(test1_tables["pvRc"][:, 3])
+    sv = test1["sv"]
+    src = [(float(sv.scxf[s, 0]), float(sv.sczf[s, 0])) for s in range(int(sv.nsrcsurf1[0]))]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    r = gpu.fmm_solve(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, [s[0] for s in src], [s[1] for s in src])
+    for i, (x, z) in enumerate(src):
+        o = oracle.fmm_source(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, x, z)
+        nzr, nxr = o["geom"][0], o["geom"][1]
+        assert np.array_equal(r["ttn"][:, :, i], o["ttn"])
+        assert np.array_equal(r["nstsr"][:nzr, :nxr, i] == 0, o["nstsr"][:nzr, :nxr] == 0)
+        alive = o["nstsr"][:nzr, :nxr] >= 0
+        assert np.array_equal(r["ttnr"][:nzr, :nxr, i][alive], o["ttnr"][:nzr, :nxr][alive])
+    a = gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, sv, tables=test1_tables)
+    o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv,
+                      test1["gc"], test1["gs"], tables=test1_tables)
+    assert np.array_equal(a["dsurf"], o["dsurf"]) and np.array_equal(a["obsTaa"], o["obsTaa"])
