@@ -5,6 +5,7 @@
 // scalar code (grid constants, per-source box bounds, sin() of grid rows).
 #include "../../include/dazim_b200.h"
 #include "dazim_dev.h"
+#include "dazim_inv.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -174,6 +175,7 @@ struct dazim_plan {
   GridC g;
   std::vector<SrcRec> src;            // owned units, loop order; ray0 = global row
   std::vector<RayRec> ray;            // batch-ordered rays (src index batch-local)
+  std::vector<float> h_velv;          // staging of real(pvRc) (kept so that a model update can reuse it)
   std::vector<long long> batch_src0;  // batch boundaries in src (size nb+1)
   std::vector<long long> batch_ray0;  // batch boundaries in ray
   long long row0 = 0, nrow = 0;
@@ -445,9 +447,9 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     UP(P->d_ray, P->ray.data(), P->ray.size());
     UP(P->d_row_knumi, row_knumi.data(), row_knumi.size());
     // velv(i,j) = real(pv(i*(nvx+2)+j+1)) (CalSurfG.f90:1455) for every period
-    std::vector<float> velv(nxy * p->kmaxRc);
-    for (size_t i = 0; i < velv.size(); ++i) velv[i] = (float)tb->pvRc[i];
-    UP(P->d_velv, velv.data(), velv.size());
+    P->h_velv.resize(nxy * p->kmaxRc);
+    for (size_t i = 0; i < P->h_velv.size(); ++i) P->h_velv[i] = (float)tb->pvRc[i];
+    UP(P->d_velv, P->h_velv.data(), P->h_velv.size());
     std::vector<float> ric(g.nnx);
     for (int ix = 1; ix <= g.nnx; ++ix) ric[ix - 1] = g.earth * sin_r(g.gox + (float)(ix - 1) * g.dnx);
     UP(P->d_risti_c, ric.data(), ric.size());
@@ -625,8 +627,10 @@ static int plan_run(dazim_plan* P) {
       CK(cudaStreamSynchronize(st));
       P->nnz = last_off + last_cnt;
       CK(cudaMemcpyAsync(P->d_rowptr.p + P->nrow, &P->nnz, sizeof(long long), cudaMemcpyHostToDevice, st));
-      if (P->nnz > P->val_cap) {
-        P->val_cap = P->nnz + P->nnz / 8 + 1024;
+      // headroom: the Tikhonov rows of dazim_plan_iterate are appended behind G (at most 7 entries per model cell)
+      const long long reg_room = 21ll * g.nvx * g.nvz * (P->nz - 1);
+      if (P->nnz + reg_room > P->val_cap) {
+        P->val_cap = P->nnz + P->nnz / 8 + 1024 + reg_room;
         CK(P->d_val.alloc(P->val_cap));
         CK(P->d_col.alloc(P->val_cap));
         CK(P->d_rowid.alloc(P->val_cap));
@@ -812,6 +816,265 @@ extern "C" int dazim_plan_lsmr(dazim_plan* P, const float* b, float damp, float 
   const long long ncol = (long long)nblk * P->g.nvx * P->g.nvz * (P->nz - 1);
   return dzl::lsmr_solve(h->st, (int)P->nrow, (int)ncol, P->nnz, P->d_rowid.p, P->d_col.p, P->d_val.p, b, damp, atol, btol,
                          conlim, itnlim, localSize, x, info, true);
+}
+
+// ---------------------------------------------------------------------------
+// Outer-iteration tail: Main_Jt.f90:416-727 on the device-resident G of a plan.
+
+extern "C" int dazim_plan_update_model(dazim_plan* P, const float* vels, const dazim_tables* tb) {
+  if (!P || !tb || !tb->pvRc) return DAZIM_EBADARG;
+  const int mode = P->mode;
+  if ((mode == 0 || mode == 2) && !tb->Lsen_Gsc) return DAZIM_EBADARG;
+  if ((mode == 1 || mode == 2) && (!tb->sen_vs || !tb->sen_vp || !tb->sen_rho || !vels)) return DAZIM_EBADARG;
+  dazim_handle* h = P->h;
+  CK(cudaSetDevice(h->dev));
+  cudaStream_t st = h->st;
+  const size_t nxy = (size_t)P->nx * P->ny, nlay = (size_t)P->nz - 1, k = (size_t)P->kmaxRc;
+  h->times.h2d_bytes = 0;
+  P->h_velv.resize(nxy * k);
+  for (size_t i = 0; i < P->h_velv.size(); ++i) P->h_velv[i] = (float)tb->pvRc[i];
+  CK(cudaMemcpyAsync(P->d_velv.p, P->h_velv.data(), nxy * k * sizeof(float), cudaMemcpyHostToDevice, st));
+  h->times.h2d_bytes += (long long)(nxy * k * sizeof(float));
+  if (mode == 1 || mode == 2) {
+    const size_t nb = nxy * k * P->nz * sizeof(double);
+    CK(cudaMemcpyAsync(P->d_sen_vs.p, tb->sen_vs, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(P->d_sen_vp.p, tb->sen_vp, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(P->d_sen_rho.p, tb->sen_rho, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(P->d_vels.p, vels, nxy * P->nz * sizeof(float), cudaMemcpyHostToDevice, st));
+    h->times.h2d_bytes += (long long)(3 * nb + nxy * P->nz * sizeof(float));
+  }
+  if (mode == 0 || mode == 2) {
+    CK(cudaMemcpyAsync(P->d_lsen.p, tb->Lsen_Gsc, nxy * k * nlay * sizeof(float), cudaMemcpyHostToDevice, st));
+    h->times.h2d_bytes += (long long)(nxy * k * nlay * sizeof(float));
+  }
+  CK(cudaStreamSynchronize(st));
+  return DAZIM_OK;
+}
+
+extern "C" long long dazim_tikh_offset(int i, int j, int k, int nvx, int nvz, int nzm1) {
+  return dzi::tikh_offset(i, j, k, nvx, nvz, nzm1);
+}
+extern "C" long long dazim_tikh_block_entries(int nvx, int nvz, int nzm1) {
+  return dzi::tikh_block_entries(nvx, nvz, nzm1);
+}
+
+// Tikhonov rows behind `base` entries of (val, col, rowid); returns entries appended, rows appended and the entry
+// count after the dVs block (joint).  TikhRegul.f90:2-105 (joint = 0) / :108-209 (joint = 1).
+static int tikh_append(cudaStream_t st, int joint, int iso_inv, int nx, int ny, int nz, int maxvp, int dall, long long base,
+                       float weightGcs, float weightVs, float* val, int* col, int* rowid, long long* appended,
+                       int* count3, long long* after_vs) {
+  const int nvx = nx - 2, nvz = ny - 2, nzm1 = nz - 1;
+  const int ncell = nvx * nvz * nzm1;
+  const long long per = dzi::tikh_block_entries(nvx, nvz, nzm1);
+  long long o = base;
+  int rows = 0;
+  *after_vs = -1;
+  if (joint) {
+    CK(dzi::launch_tikh(nvx, nvz, nzm1, o, dall + rows + 1, 0, weightVs, val, col, rowid, st));
+    o += per; rows += ncell;
+    *after_vs = o;
+    for (int sc = 1; sc <= 2; ++sc) {
+      CK(dzi::launch_tikh(nvx, nvz, nzm1, o, dall + rows + 1, sc * maxvp, weightGcs, val, col, rowid, st));
+      o += per; rows += ncell;
+    }
+  } else if (iso_inv) {
+    CK(dzi::launch_tikh(nvx, nvz, nzm1, o, dall + rows + 1, 0, weightVs, val, col, rowid, st));
+    o += per; rows += ncell;
+  } else {
+    for (int sc = 1; sc <= 2; ++sc) {
+      CK(dzi::launch_tikh(nvx, nvz, nzm1, o, dall + rows + 1, (sc - 1) * maxvp, weightGcs, val, col, rowid, st));
+      o += per; rows += ncell;
+    }
+  }
+  *appended = o - base;
+  *count3 = rows;
+  return DAZIM_OK;
+}
+
+extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_iter_params* prm, float* vsf, float* dv,
+                                  float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
+                                  float* fwdTaa, dazim_iter_stats* S) {
+  if (!P || !obst || !prm || !vsf || !dv || !S) return DAZIM_EBADARG;
+  if (P->mode != 1 && P->mode != 2) return DAZIM_EBADARG;
+  if ((P->mode == 1) != (prm->iso_inv != 0)) return DAZIM_EBADARG;
+  if (P->row0 != 0 || P->nrow < 1 || P->nnz < 1) return DAZIM_EBADARG;
+  dazim_handle* h = P->h;
+  CK(cudaSetDevice(h->dev));
+  g_alloc_stream = h->st;
+  cudaStream_t st = h->st;
+  const int iso = prm->iso_inv ? 1 : 0;
+  const int nx = P->nx, ny = P->ny, nz = P->nz;
+  const int maxvp = (nx - 2) * (ny - 2) * (nz - 1);
+  const int nblk = iso ? 1 : 3;
+  const int n = nblk * maxvp;
+  if (P->nrow > 0x7fffffffll - 3ll * maxvp) return DAZIM_EBADARG;
+  const int dall = (int)P->nrow;
+  std::memset(S, 0, sizeof(*S));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  DBuf<float> d_obst, d_cbst, d_tdata, d_dt, d_sig, d_w, d_stats, d_b, d_dv, d_gcf, d_gsf, d_tvs, d_taa, d_res, d_resw,
+      d_lm, d_lmw, d_dws;
+  DBuf<double> d_partial, d_dwsacc;
+  const long long reg_entries = (long long)nblk * dzi::tikh_block_entries(nx - 2, ny - 2, nz - 1);
+  if (P->nnz + reg_entries > P->val_cap) return DAZIM_ENNZ_OVERFLOW;   // plan_run reserves this room
+  CK(d_obst.alloc(dall)); CK(d_cbst.alloc(dall)); CK(d_tdata.alloc(dall)); CK(d_dt.alloc(dall)); CK(d_sig.alloc(dall));
+  CK(d_w.alloc(dall)); CK(d_stats.alloc(64)); CK(d_b.alloc((size_t)dall + (size_t)nblk * maxvp)); CK(d_dv.alloc(n));
+  CK(d_gcf.alloc(maxvp)); CK(d_gsf.alloc(maxvp)); CK(d_tvs.alloc(dall)); CK(d_taa.alloc(dall)); CK(d_res.alloc(dall));
+  CK(d_resw.alloc(dall)); CK(d_lm.alloc(reg_entries)); CK(d_lmw.alloc(reg_entries)); CK(d_partial.alloc(1024));
+  if (iso && dws) { CK(d_dws.alloc(maxvp)); CK(d_dwsacc.alloc(maxvp)); }
+  float hs[64];
+  std::memset(hs, 0, sizeof(hs));
+  CK(cudaMemcpyAsync(d_obst.p, obst, sizeof(float) * dall, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(e0, st));
+  // ---- residual of the reference model, CalDdatSigma, weights (Main_Jt.f90:425-469) ----
+  CK(dzi::launch_resid(dall, d_obst.p, P->d_dsurf.p, d_cbst.p, d_tdata.p, d_dt.p, st));
+  {
+    const float* arrs[2] = {d_cbst.p, d_dt.p};
+    CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p, st));                       // [0..2] cbst, [3..5] deltaT
+  }
+  CK(dzi::launch_norm2(d_cbst.p, dall, d_partial.p, d_stats.p + 42, st));          // ||cbst|| before weighting
+  CK(dzi::launch_sigma(dall, d_dt.p, d_obst.p, d_stats.p + 3, d_sig.p, d_w.p, d_cbst.p, st));
+  {
+    const float* arrs[2] = {d_w.p, d_cbst.p};
+    CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p + 6, st));                   // [6] sum w, [10] sum |cbst_w|
+  }
+  CK(dzi::launch_scale_rows(P->nrow, P->d_rowptr.p, d_w.p, P->d_val.p, st));
+  if (iso && dws) CK(dzi::launch_dws(P->nnz, P->d_col.p, P->d_val.p, maxvp, d_dwsacc.p, d_dws.p, st));
+  // ---- regularisation rows behind G (Main_Jt.f90:507-520) ----
+  long long appended = 0, after_vs = -1;
+  int count3 = 0;
+  {
+    int rc = tikh_append(st, iso ? 0 : 1, iso, nx, ny, nz, maxvp, dall, P->nnz, prm->weightGcs, prm->weightVs, P->d_val.p,
+                         P->d_col.p, P->d_rowid.p, &appended, &count3, &after_vs);
+    if (rc) return rc;
+  }
+  const long long nar1 = P->nnz, nar = P->nnz + appended;
+  const int m = dall + count3;
+  CK(cudaMemcpyAsync(d_b.p, d_cbst.p, sizeof(float) * dall, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(d_b.p + dall, 0, sizeof(float) * (size_t)count3, st));
+  // ---- LSMR on [W G ; L] (Main_Jt.f90:527-564) ----
+  float atol = prm->atol, btol = prm->btol, conlim = prm->conlim;
+  int itnlim = prm->itnlim, localSize = prm->localSize;
+  if (prm->use_ref_controls) {
+    if (iso) { atol = 1e-3f; btol = 1e-3f; conlim = 1200.0f; itnlim = 1000; localSize = n / 4; }
+    else { atol = 1e-5f; btol = 1e-4f; conlim = 200.0f; itnlim = 500; localSize = 10; }
+  }
+  {
+    int rc = dzl::lsmr_solve(st, m, n, nar, P->d_rowid.p, P->d_col.p, P->d_val.p, d_b.p, prm->damp, atol, btol, conlim,
+                             itnlim, localSize, d_dv.p, &S->lsmr, true);
+    if (rc) return rc;
+  }
+  // ---- model update (Main_Jt.f90:582-620) ----
+  CK(cudaMemcpyAsync(P->d_vels.p, vsf, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyHostToDevice, st));
+  CK(dzi::launch_model_update(nx, ny, nz, iso, d_dv.p, P->d_vels.p, prm->minvel, prm->maxvel, d_gcf.p, d_gsf.p, st));
+  // ---- ||Lm|| and the residual of the solution from the sparse rows (CalSigamNorm.f90) ----
+  const long long nre = nar - nar1, nre_vs = iso ? nre : after_vs - nar1;
+  CK(dzi::launch_lm_terms(nre, nre_vs, P->d_val.p + nar1, P->d_col.p + nar1, d_dv.p, prm->weightVs, prm->weightGcs, d_lm.p,
+                          d_lmw.p, st));
+  if (iso) {
+    CK(dzi::launch_norm2(d_lm.p, nre, d_partial.p, d_stats.p + 36, st));
+    CK(dzi::launch_norm2(d_lmw.p, nre, d_partial.p, d_stats.p + 37, st));
+  } else {
+    CK(dzi::launch_norm2(d_lm.p, nre_vs, d_partial.p, d_stats.p + 32, st));
+    CK(dzi::launch_norm2(d_lmw.p, nre_vs, d_partial.p, d_stats.p + 33, st));
+    CK(dzi::launch_norm2(d_lm.p + nre_vs, nre - nre_vs, d_partial.p, d_stats.p + 34, st));
+    CK(dzi::launch_norm2(d_lmw.p + nre_vs, nre - nre_vs, d_partial.p, d_stats.p + 35, st));
+    CK(dzi::launch_norm2(d_lm.p, nre, d_partial.p, d_stats.p + 36, st));
+    CK(dzi::launch_norm2(d_lmw.p, nre, d_partial.p, d_stats.p + 37, st));
+  }
+  CK(dzi::launch_resid_rows(P->nrow, P->d_rowptr.p, P->d_col.p, P->d_val.p, d_dv.p, d_w.p, maxvp, nblk, d_tdata.p, d_tvs.p,
+                            d_taa.p, d_res.p, d_resw.p, st));
+  {
+    const float* arrs[3] = {d_res.p, d_taa.p, d_tvs.p};
+    CK(dzi::launch_seq_stats(3, arrs, dall, d_stats.p + 12, st));                  // [12..14] res, [16] |taa|, [19] |tvs|
+  }
+  CK(dzi::launch_norm2(d_res.p, dall, d_partial.p, d_stats.p + 40, st));
+  CK(dzi::launch_norm2(d_resw.p, dall, d_partial.p, d_stats.p + 41, st));
+  CK(cudaEventRecord(e1, st));
+  // ---- results to the host ----
+  CK(cudaMemcpyAsync(hs, d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(vsf, P->d_vels.p, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(dv, d_dv.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  if (!iso && gcf) CK(cudaMemcpyAsync(gcf, d_gcf.p, sizeof(float) * maxvp, cudaMemcpyDeviceToHost, st));
+  if (!iso && gsf) CK(cudaMemcpyAsync(gsf, d_gsf.p, sizeof(float) * maxvp, cudaMemcpyDeviceToHost, st));
+  if (iso && dws) CK(cudaMemcpyAsync(dws, d_dws.p, sizeof(float) * maxvp, cudaMemcpyDeviceToHost, st));
+  if (sigmaT) CK(cudaMemcpyAsync(sigmaT, d_sig.p, sizeof(float) * dall, cudaMemcpyDeviceToHost, st));
+  if (resbst) CK(cudaMemcpyAsync(resbst, d_res.p, sizeof(float) * dall, cudaMemcpyDeviceToHost, st));
+  if (fwdTvs) CK(cudaMemcpyAsync(fwdTvs, d_tvs.p, sizeof(float) * dall, cudaMemcpyDeviceToHost, st));
+  if (fwdTaa) CK(cudaMemcpyAsync(fwdTaa, d_taa.p, sizeof(float) * dall, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  const float fd = (float)dall;
+  S->before[0] = hs[1] / fd;                     // abs mean
+  S->before[1] = std::sqrt(hs[2] / fd);          // std
+  S->before[2] = hs[42] / std::sqrt(fd);         // RMS = dnrm2/sqrt(real(dall))
+  S->before[3] = hs[0] / fd;                     // mean
+  S->meandeltaT = hs[3] / fd;
+  S->mean_weight = hs[6] / fd;
+  S->meanabs_weighted = hs[10] / fd;
+  S->after[0] = hs[13] / fd;
+  S->after[1] = std::sqrt(hs[14] / fd);
+  S->after[2] = hs[40] / std::sqrt(fd);
+  S->after[3] = hs[12] / fd;
+  S->meanabs_Taa = hs[16] / fd;
+  S->meanabs_Tvs = hs[19] / fd;
+  for (int q = 0; q < 6; ++q) S->norms[q] = hs[32 + q];
+  S->res2Nm = hs[40];
+  S->resW2Nm = hs[41];
+  S->nar1 = nar1; S->nar = nar; S->count3 = count3;
+  cudaEventElapsedTime(&S->step_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return DAZIM_OK;
+}
+
+extern "C" int dazim_cal_ddat_sigma(dazim_handle* h, int dall, const float* obst, const float* cbst, float* sigmaT,
+                                    float* meandeltaT) {
+  if (!h || dall < 1 || !obst || !cbst || !sigmaT || !meandeltaT) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  g_alloc_stream = h->st;
+  cudaStream_t st = h->st;
+  DBuf<float> d_obst, d_cbst, d_dt, d_sig, d_w, d_stats;
+  CK(d_obst.alloc(dall)); CK(d_cbst.alloc(dall)); CK(d_dt.alloc(dall)); CK(d_sig.alloc(dall)); CK(d_w.alloc(dall));
+  CK(d_stats.alloc(8));
+  CK(cudaMemcpyAsync(d_obst.p, obst, sizeof(float) * dall, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_cbst.p, cbst, sizeof(float) * dall, cudaMemcpyHostToDevice, st));
+  CK(dzi::launch_delta(dall, d_cbst.p, d_obst.p, d_dt.p, st));
+  const float* arrs[1] = {d_dt.p};
+  CK(dzi::launch_seq_stats(1, arrs, dall, d_stats.p, st));
+  CK(dzi::launch_sigma(dall, d_dt.p, d_obst.p, d_stats.p, d_sig.p, d_w.p, d_cbst.p, st));
+  float hs[3];
+  CK(cudaMemcpyAsync(hs, d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(sigmaT, d_sig.p, sizeof(float) * dall, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  *meandeltaT = hs[0] / (float)dall;
+  return DAZIM_OK;
+}
+
+extern "C" int dazim_tikhonov(dazim_handle* h, int joint, int nx, int ny, int nz, int maxvp, int dall, long long* nar,
+                              float* rw, int* iw_row, int* col, long long* narVs, int* count3, int iso_inv,
+                              float weightGcs, float weightVs) {
+  if (!h || !nar || !rw || !iw_row || !col || !count3 || nx < 3 || ny < 3 || nz < 2 || *nar < 0) return DAZIM_EBADARG;
+  if (maxvp != (nx - 2) * (ny - 2) * (nz - 1)) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  g_alloc_stream = h->st;
+  cudaStream_t st = h->st;
+  const int nblk = joint ? 3 : (iso_inv ? 1 : 2);
+  const long long tot = (long long)nblk * dzi::tikh_block_entries(nx - 2, ny - 2, nz - 1);
+  DBuf<float> d_val; DBuf<int> d_col, d_row;
+  CK(d_val.alloc(tot)); CK(d_col.alloc(tot)); CK(d_row.alloc(tot));
+  long long appended = 0, after_vs = -1;
+  int rc = tikh_append(st, joint, iso_inv, nx, ny, nz, maxvp, dall, 0, weightGcs, weightVs, d_val.p, d_col.p, d_row.p,
+                       &appended, count3, &after_vs);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(rw + *nar, d_val.p, sizeof(float) * appended, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(col + *nar, d_col.p, sizeof(int) * appended, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(iw_row + *nar, d_row.p, sizeof(int) * appended, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (narVs) *narVs = joint ? *nar + after_vs : -1;
+  *nar += appended;
+  return DAZIM_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -162,3 +162,29 @@ extern "C" void __lsmrmodule_MOD_lsmr(int* m, int* n, int* leniw, int* lenrw, in
   *istop = info.istop; *itn = info.itn; *normA = info.normA; *condA = info.condA; *normr = info.normr;
   *normAr = info.normAr; *normx = info.normx;
 }
+
+// CalDdatSigma (CalSigamNorm.f90:2; called at Main_Jt.f90:460)
+extern "C" void calddatsigma_(int* dall, float* obst, float* cbst, float* sigmaT, float* meandeltaT) {
+  stop_on(dazim_cal_ddat_sigma(handle(), *dall, obst, cbst, sigmaT, meandeltaT), "CalDdatSigma");
+}
+
+// TikhonovRegularization (TikhRegul.f90:2; Main_Jt.f90:513): rows live at iw(2:), iso_inv is a LOGICAL (4-byte)
+extern "C" void tikhonovregularization_(int* nx, int* ny, int* nz, int* maxvp, int* dall, int* nar, float* rw, int* iw,
+                                        int* col, int* count3, int* iso_inv, float* weightGcs, float* weightVs) {
+  long long n = *nar;
+  stop_on(dazim_tikhonov(handle(), 0, *nx, *ny, *nz, *maxvp, *dall, &n, rw, iw + 1, col, nullptr, count3, *iso_inv != 0,
+                         *weightGcs, *weightVs), "TikhonovRegularization");
+  if (n > 2147483647ll) stop_on(DAZIM_ENNZ_OVERFLOW, "TikhonovRegularization: nar exceeds the reference's default INTEGER");
+  *nar = (int)n;
+}
+
+// TikhRegul_joint (TikhRegul.f90:108; Main_Jt.f90:515)
+extern "C" void tikhregul_joint_(int* nx, int* ny, int* nz, int* maxvp, int* dall, int* nar, float* rw, int* iw, int* col,
+                                 int* narVs, int* count3, float* weightGcs, float* weightVs) {
+  long long n = *nar, nvs = -1;
+  stop_on(dazim_tikhonov(handle(), 1, *nx, *ny, *nz, *maxvp, *dall, &n, rw, iw + 1, col, &nvs, count3, 0, *weightGcs,
+                         *weightVs), "TikhRegul_joint");
+  if (n > 2147483647ll) stop_on(DAZIM_ENNZ_OVERFLOW, "TikhRegul_joint: nar exceeds the reference's default INTEGER");
+  *nar = (int)n;
+  *narVs = (int)nvs;
+}

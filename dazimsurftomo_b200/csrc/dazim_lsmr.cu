@@ -212,7 +212,7 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   Ctx c{st, partial.p, scal.p, 592};
   const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256);
   const unsigned gwm = (unsigned)(((long long)m * 32 + 255) / 256), gwn = (unsigned)(((long long)n * 32 + 255) / 256);
-  LCK(cudaMemcpyAsync(u.p, b, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+  LCK(cudaMemcpyAsync(u.p, b, sizeof(float) * m, cudaMemcpyDefault, st));     // b may live on the host or in HBM
   LCK(cudaMemsetAsync(v.p, 0, sizeof(float) * n, st));
   LCK(cudaMemsetAsync(dx.p, 0, sizeof(float) * n, st));
   LCK(cudaMemsetAsync(hbar.p, 0, sizeof(float) * n, st));
@@ -323,7 +323,7 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
     if (damp > 0.0f && istop == 2) istop = 3;
   }
   LCK(cudaEventRecord(e2, st));
-  LCK(cudaMemcpyAsync(x, dx.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  LCK(cudaMemcpyAsync(x, dx.p, sizeof(float) * n, cudaMemcpyDefault, st));    // so may x
   LCK(cudaStreamSynchronize(st));
   LCK(cudaGetLastError());
   info->istop = istop; info->itn = itn; info->normA = normA; info->condA = condA; info->normr = normr;

@@ -181,6 +181,61 @@ int dazim_lsmr(dazim_handle* h, int m, int n, long long nnz, const int* iw_row, 
 int dazim_plan_lsmr(dazim_plan* plan, const float* b, float damp, float atol, float btol, float conlim, int itnlim,
                     int localSize, float* x, dazim_lsmr_info* info);
 
+/* --- next stage: the rest of one outer iteration of Main_Jt.f90 ----------------------------
+ * Everything the reference does between two G builds (Main_Jt.f90:416-727), on the device-resident G of a plan:
+ * residual and its statistics, CalDdatSigma, data weighting of b and of the rows of G, DWS sums, Tikhonov rows
+ * appended behind G, LSMR, model update with clamps, model norms and the residual of the solution computed from the
+ * sparse rows (no dense GVs/GGc/GGs).  G never leaves the GPU. */
+typedef struct dazim_iter_params {
+  int iso_inv;               /* 1: CalSurfG system (plan mode 1), TikhonovRegularization; 0: joint (plan mode 2), TikhRegul_joint */
+  float weightVs, weightGcs; /* para.in smoothing weights (Main_Jt.f90:174-175, :508-510) */
+  float damp;                /* LSMR damping (Main_Jt.f90:176) */
+  float minvel, maxvel;      /* Vs clamps (Main_Jt.f90:168, :593-594) */
+  int use_ref_controls;      /* 1: atol/btol/conlim/itnlim/localSize of Main_Jt.f90:542-554; 0: the five fields below */
+  float atol, btol, conlim;
+  int itnlim, localSize;
+} dazim_iter_params;
+
+typedef struct dazim_iter_stats {
+  float before[4];           /* abs mean, std, RMS, mean of obst - dsyn        (Main_Jt.f90:432-437) */
+  float after[4];            /* the same of the residual after the solve       (Main_Jt.f90:720-725) */
+  float meandeltaT;          /* CalDdatSigma's mean |dT/T| */
+  float mean_weight;         /* sum(datweight)/dall */
+  float meanabs_weighted;    /* sum(|cbst|)/dall after weighting */
+  float norms[6];            /* VsNorm2, VswNorm2, GcsNorm2, GcswNorm2, Mnorm2, MwNorm2 (Calmodel2Norm / ...Joint) */
+  float res2Nm, resW2Nm;     /* ||Gm-d||, ||W(Gm-d)||                         (CalVsReslNorm / CalReslNormJoint) */
+  float meanabs_Taa, meanabs_Tvs;
+  long long nar1, nar;       /* non-zeros before / after the regularisation rows */
+  int count3;                /* regularisation rows */
+  dazim_lsmr_info lsmr;
+  float step_ms;             /* device time of the whole step */
+} dazim_iter_stats;
+
+/* New model for an existing plan (same geometry): re-uploads vels and the depth-kernel tables; the work list,
+ * workspaces and ray order are kept.  Call between outer iterations instead of destroying the plan. */
+int dazim_plan_update_model(dazim_plan* plan, const float* vels, const dazim_tables* tables);
+
+/* One outer-iteration tail on the G of the plan's last run (the plan must own every row: src range 0,-1).
+ * obst (rows) observed travel times in row order.  vsf (nx,ny,nz) is updated in place; dv (nparpi or 3*nparpi)
+ * receives the clipped LSMR solution; gcf/gsf ((nx-2),(ny-2),(nz-1); joint only), dws (nparpi; iso only) and the
+ * per-row arrays sigmaT, resbst, fwdTvs, fwdTaa may be NULL.  Afterwards the plan's val[] holds the WEIGHTED
+ * rows until the next dazim_plan_run. */
+int dazim_plan_iterate(dazim_plan* plan, const float* obst, const dazim_iter_params* prm, float* vsf, float* dv,
+                       float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
+                       float* fwdTaa, dazim_iter_stats* stats);
+
+/* The two small subroutines on their own (host arrays), for callers that keep the stock Fortran loop:
+ * CalDdatSigma (CalSigamNorm.f90:2) and TikhonovRegularization / TikhRegul_joint (TikhRegul.f90:2 / :108).
+ * dazim_tikhonov appends to rw / iw_row (= iw+1) / col behind *nar entries and advances *nar; joint != 0 selects
+ * TikhRegul_joint (narVs is then set, iso_inv ignored). */
+int dazim_cal_ddat_sigma(dazim_handle* h, int dall, const float* obst, const float* cbst, float* sigmaT,
+                         float* meandeltaT);
+int dazim_tikhonov(dazim_handle* h, int joint, int nx, int ny, int nz, int maxvp, int dall, long long* nar, float* rw,
+                   int* iw_row, int* col, long long* narVs, int* count3, int iso_inv, float weightGcs, float weightVs);
+/* test seam (no GPU needed): offset of cell (i,j,k)'s row inside one Tikhonov block and the block's entry count */
+long long dazim_tikh_offset(int i, int j, int k, int nvx, int nvz, int nzm1);
+long long dazim_tikh_block_entries(int nvx, int nvz, int nzm1);
+
 /* --- gfortran-ABI drop-in symbols (lower case + underscore, all by reference) --- */
 void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, float* vels, float* Gctrue,
                           float* Gstrue, float* dsurf, float* obsTaa, int* dall, int* rmax,
@@ -211,6 +266,14 @@ void __lsmrmodule_MOD_lsmr(int* m, int* n, int* leniw, int* lenrw, int* iw, floa
                            float* atol, float* btol, float* conlim, int* itnlim, int* localSize, int* nout,
                            float* x, int* istop, int* itn, float* normA, float* condA, float* normr,
                            float* normAr, float* normx);
+
+/* CalDdatSigma (CalSigamNorm.f90:2; called at Main_Jt.f90:460), TikhonovRegularization (TikhRegul.f90:2; Main_Jt.f90:513)
+ * and TikhRegul_joint (TikhRegul.f90:108; Main_Jt.f90:515) -- external (non-module) subroutines */
+void calddatsigma_(int* dall, float* obst, float* cbst, float* sigmaT, float* meandeltaT);
+void tikhonovregularization_(int* nx, int* ny, int* nz, int* maxvp, int* dall, int* nar, float* rw, int* iw, int* col,
+                             int* count3, int* iso_inv, float* weightGcs, float* weightVs);
+void tikhregul_joint_(int* nx, int* ny, int* nz, int* maxvp, int* dall, int* nar, float* rw, int* iw, int* col,
+                      int* narVs, int* count3, float* weightGcs, float* weightVs);
 
 #ifdef __cplusplus
 }

@@ -229,3 +229,138 @@ def lsmr(m, n, row, col, rw, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, it
     if st:
         raise RuntimeError(f"orc_lsmr status {st}")
     return x, {k: getattr(out, k) for k, _ in out._fields_}
+
+
+# ---- outer inversion iteration: oracle/inversion.cpp ---------------------------------------------
+
+def cal_ddat_sigma(obst, cbst):
+    """CalDdatSigma (CalSigamNorm.f90:2-42) -> (sigmaT, meandeltaT)."""
+    obst = np.ascontiguousarray(obst, np.float32); cbst = np.ascontiguousarray(cbst, np.float32)
+    sig = np.zeros(len(obst), np.float32)
+    mean = C.c_float(0)
+    lib().orc_cal_ddat_sigma(C.c_int(len(obst)), _p(obst), _p(cbst), _p(sig), C.byref(mean))
+    return sig, mean.value
+
+
+def apply_weights(sigmaT, cbst, row, rw):
+    """Main_Jt.f90:461-469 -> (datweight, weighted cbst, weighted rw); inputs are not modified."""
+    sigmaT = np.ascontiguousarray(sigmaT, np.float32)
+    cb = np.array(cbst, np.float32); w = np.zeros(len(sigmaT), np.float32)
+    row = np.ascontiguousarray(row, np.int32); r = np.array(rw, np.float32)
+    lib().orc_apply_weights(C.c_int(len(sigmaT)), _p(sigmaT), _p(w), _p(cb), C.c_long(len(r)), _p(row), _p(r))
+    return w, cb, r
+
+
+def tikhonov(nx, ny, nz, dall, iso_inv, weightGcs, weightVs, joint=False):
+    """TikhonovRegularization (TikhRegul.f90:2) or, joint=True, TikhRegul_joint (:108): the appended triplets only.
+    Returns dict(rw, row, col, count3, narVs) with narVs = entries of the dVs block (joint) or None."""
+    maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+    cap = 7 * 3 * maxvp
+    rw = np.zeros(cap, np.float32); row = np.zeros(cap, np.int32); col = np.zeros(cap, np.int32)
+    nar = C.c_long(0); cnt = C.c_int(0); narvs = C.c_long(-1)
+    if joint:
+        lib().orc_tikh_joint(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(maxvp), C.c_int(dall), C.byref(nar), _p(rw),
+                             _p(row), _p(col), C.byref(narvs), C.byref(cnt), C.c_float(weightGcs), C.c_float(weightVs))
+    else:
+        lib().orc_tikhonov(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(maxvp), C.c_int(dall), C.byref(nar), _p(rw),
+                           _p(row), _p(col), C.byref(cnt), C.c_int(int(iso_inv)), C.c_float(weightGcs),
+                           C.c_float(weightVs))
+    n = nar.value
+    return dict(rw=rw[:n], row=row[:n], col=col[:n], count3=cnt.value, narVs=narvs.value if joint else None)
+
+
+def model_update(dv, vsf, iso_inv, minvel, maxvel):
+    """Main_Jt.f90:582-620 -> (clipped dv, new vsf, gcf, gsf)."""
+    nx, ny, nz = vsf.shape
+    dv = np.array(dv, np.float32); v = np.array(vsf, np.float32, order="F")
+    g = (nx - 2, ny - 2, nz - 1)
+    gcf = np.zeros(g, np.float32, order="F"); gsf = np.zeros(g, np.float32, order="F")
+    lib().orc_model_update(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(int(iso_inv)), _p(dv), _p(v),
+                           C.c_float(minvel), C.c_float(maxvel), _p(gcf), _p(gsf))
+    return dv, v, gcf, gsf
+
+
+def model_norms(nar1, narVs, rw, col, dv, lameGcs, lameVs):
+    rw = np.ascontiguousarray(rw, np.float32); col = np.ascontiguousarray(col, np.int32)
+    dv = np.ascontiguousarray(dv, np.float32)
+    out = np.zeros(6, np.float32)
+    lib().orc_model_norms(C.c_long(nar1), C.c_long(len(rw)), C.c_long(-1 if narVs is None else narVs), _p(rw), _p(col),
+                          _p(dv), C.c_float(lameGcs), C.c_float(lameVs), _p(out))
+    return dict(zip(("VsNorm2", "VswNorm2", "GcsNorm2", "GcswNorm2", "Mnorm2", "MwNorm2"), map(float, out)))
+
+
+def residuals(maxvp, nblk, rw, row, col, dv, datweight, Tdata):
+    dall = len(Tdata)
+    rw = np.ascontiguousarray(rw, np.float32); row = np.ascontiguousarray(row, np.int32)
+    col = np.ascontiguousarray(col, np.int32); dv = np.ascontiguousarray(dv, np.float32)
+    datweight = np.ascontiguousarray(datweight, np.float32); Tdata = np.ascontiguousarray(Tdata, np.float32)
+    tvs = np.zeros(dall, np.float32); taa = np.zeros(dall, np.float32); res = np.zeros(dall, np.float32)
+    nrm = np.zeros(2, np.float32)
+    lib().orc_residuals(C.c_int(dall), C.c_long(maxvp), C.c_int(nblk), C.c_long(len(rw)), _p(rw), _p(row), _p(col),
+                        _p(dv), _p(datweight), _p(Tdata), _p(tvs), _p(taa), _p(res), _p(nrm))
+    return dict(fwdTvs=tvs, fwdTaa=taa, resbst=res, res2Nm=float(nrm[0]), resW2Nm=float(nrm[1]))
+
+
+def res_stats(r):
+    r = np.ascontiguousarray(r, np.float32)
+    out = np.zeros(4, np.float32)
+    lib().orc_res_stats(C.c_int(len(r)), _p(r), _p(out))
+    return dict(meanabs=float(out[0]), std=float(out[1]), rms=float(out[2]), mean=float(out[3]))
+
+
+def lsmr_controls(iso_inv, n):
+    """Main_Jt.f90:542-554."""
+    if iso_inv:
+        return dict(atol=1e-3, btol=1e-3, conlim=1200.0, itnlim=1000, localSize=n // 4)
+    return dict(atol=1e-5, btol=1e-4, conlim=200.0, itnlim=500, localSize=10)
+
+
+def invert(vsf, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, obst, iso_mod, weightVs, weightGcs, damp, minvel,
+           maxvel, maxiter, spfra=None, nthreads=1, log=None, on_iter=None):
+    """The outer loop of DAzimSurfTomo (Main_Jt.f90:364-750) on the oracle's pieces.  Returns the final vsf, gcf, gsf,
+    the per-iteration statistics and the last iteration's tables (for period_Azm_tomo.inv)."""
+    nx, ny, nz = vsf.shape
+    maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+    dall = int(sv.dall)
+    vsf = np.array(vsf, np.float32, order="F")
+    obst = np.ascontiguousarray(obst, np.float32)
+    gcf = np.zeros((nx - 2, ny - 2, nz - 1), np.float32, order="F"); gsf = np.zeros_like(gcf)
+    hist = []
+    last = None
+    for it in range(1, maxiter + 1):
+        iso_inv = bool(iso_mod)
+        n = maxvp if iso_inv else 3 * maxvp
+        maxnar = None if spfra is None else int(np.float32(spfra) * dall * nx * ny * nz * 3)
+        g = gbuild(1 if iso_inv else 2, vsf, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, nthreads=nthreads,
+                   maxnar=maxnar)
+        dsyn = g["dsurf"]
+        cbst = (obst - dsyn).astype(np.float32)
+        Tdata = cbst.copy()
+        before = res_stats(cbst)
+        sigmaT, meandeltaT = cal_ddat_sigma(obst, cbst)
+        datweight, cbw, rww = apply_weights(sigmaT, cbst, g["row"], g["rw"])
+        nar1 = int(g["nar"])
+        tk = tikhonov(nx, ny, nz, dall, iso_inv, weightGcs, weightVs, joint=not iso_inv)
+        rw_all = np.concatenate([rww, tk["rw"]]); row_all = np.concatenate([g["row"], tk["row"]])
+        col_all = np.concatenate([g["col"], tk["col"]])
+        m = dall + tk["count3"]
+        b = np.concatenate([cbw, np.zeros(tk["count3"], np.float32)])
+        dv, info = lsmr(m, n, row_all, col_all, rw_all, b, damp=damp, **lsmr_controls(iso_inv, n))
+        dv, vsf, gc_new, gs_new = model_update(dv, vsf, iso_inv, minvel, maxvel)
+        if not iso_inv:
+            gcf, gsf = gc_new, gs_new
+        mn = model_norms(nar1, None if iso_inv else nar1 + tk["narVs"], rw_all, col_all, dv, weightGcs, weightVs)
+        rs = residuals(maxvp, 1 if iso_inv else 3, g["rw"], g["row"], g["col"], dv, datweight, Tdata)
+        after = res_stats(rs["resbst"])
+        rec = dict(iter=it, before=before, after=after, meandeltaT=meandeltaT, mean_weight=float(datweight.mean()),
+                   lsmr=info, norms=mn, res2Nm=rs["res2Nm"], resW2Nm=rs["resW2Nm"], nar1=nar1, nar=len(rw_all),
+                   dv_absmean=float(np.abs(dv[:maxvp]).mean()))
+        hist.append(rec)
+        last = dict(tRcV=g["tRcV"], Lsen_Gsc=g["Lsen_Gsc"], dsyn=dsyn, dv=dv, sigmaT=sigmaT, datweight=datweight,
+                    resbst=rs["resbst"], fwdTvs=rs["fwdTvs"], fwdTaa=rs["fwdTaa"], Tdata=Tdata)
+        if log:
+            log("iter %d: before rms %.4f after rms %.4f itn %d istop %d |dv| %.5f" %
+                (it, before["rms"], after["rms"], info["itn"], info["istop"], rec["dv_absmean"]))
+        if on_iter:
+            on_iter(it, vsf, gcf, gsf, rec)
+    return dict(vsf=vsf, gcf=gcf, gsf=gsf, history=hist, last=last)
