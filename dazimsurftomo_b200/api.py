@@ -338,6 +338,64 @@ def raytrace(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, rcx, rcz, azim=True, 
     return tt, fdm, fdmc, fdms
 
 
+class IterParams(C.Structure):
+    _fields_ = [("iso_inv", C.c_int), ("weightVs", C.c_float), ("weightGcs", C.c_float), ("damp", C.c_float),
+                ("minvel", C.c_float), ("maxvel", C.c_float), ("use_ref_controls", C.c_int), ("atol", C.c_float),
+                ("btol", C.c_float), ("conlim", C.c_float), ("itnlim", C.c_int), ("localSize", C.c_int)]
+
+
+class IterStats(C.Structure):
+    _fields_ = [("before", C.c_float * 4), ("after", C.c_float * 4), ("meandeltaT", C.c_float),
+                ("mean_weight", C.c_float), ("meanabs_weighted", C.c_float), ("norms", C.c_float * 6),
+                ("res2Nm", C.c_float), ("resW2Nm", C.c_float), ("meanabs_Taa", C.c_float), ("meanabs_Tvs", C.c_float),
+                ("nar1", C.c_longlong), ("nar", C.c_longlong), ("count3", C.c_int), ("lsmr", LsmrInfo),
+                ("step_ms", C.c_float), ("scale_ms", C.c_float)]
+
+    def as_dict(self):
+        st = ("meanabs", "std", "rms", "mean")
+        d = dict(before=dict(zip(st, map(float, self.before))), after=dict(zip(st, map(float, self.after))),
+                 norms=dict(zip(("VsNorm2", "VswNorm2", "GcsNorm2", "GcswNorm2", "Mnorm2", "MwNorm2"),
+                                map(float, self.norms))),
+                 lsmr={k: getattr(self.lsmr, k) for k, _ in self.lsmr._fields_})
+        for k in ("meandeltaT", "mean_weight", "meanabs_weighted", "res2Nm", "resW2Nm", "meanabs_Taa", "meanabs_Tvs",
+                  "nar1", "nar", "count3", "step_ms", "scale_ms"):
+            d[k] = getattr(self, k)
+        return d
+
+
+def CalDdatSigma(obst, cbst, handle: Optional[Handle] = None):
+    """CalSigamNorm.f90:2 -> (sigmaT, meandeltaT)."""
+    h = handle or default_handle()
+    obst = np.ascontiguousarray(obst, np.float32); cbst = np.ascontiguousarray(cbst, np.float32)
+    sig = np.zeros(len(obst), np.float32)
+    mean = C.c_float(0)
+    _chk(load().dazim_cal_ddat_sigma(h._h, C.c_int(len(obst)), _p(obst), _p(cbst), _p(sig), C.byref(mean)))
+    return sig, mean.value
+
+
+def _tikh(joint, nx, ny, nz, dall, iso_inv, weightGcs, weightVs, handle):
+    h = handle or default_handle()
+    maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+    cap = 7 * 3 * maxvp
+    rw = np.zeros(cap, np.float32); row = np.zeros(cap, np.int32); col = np.zeros(cap, np.int32)
+    nar = C.c_longlong(0); narvs = C.c_longlong(-1); cnt = C.c_int(0)
+    _chk(load().dazim_tikhonov(h._h, C.c_int(joint), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(maxvp), C.c_int(dall),
+                               C.byref(nar), _p(rw), _p(row), _p(col), C.byref(narvs), C.byref(cnt), C.c_int(int(iso_inv)),
+                               C.c_float(weightGcs), C.c_float(weightVs)))
+    n = nar.value
+    return dict(rw=rw[:n], row=row[:n], col=col[:n], count3=cnt.value, narVs=narvs.value if joint else None)
+
+
+def TikhonovRegularization(nx, ny, nz, dall, iso_inv, weightGcs, weightVs, handle: Optional[Handle] = None):
+    """TikhRegul.f90:2: the appended triplets (rw, row = iw(2:), col; 1-based) and count3."""
+    return _tikh(0, nx, ny, nz, dall, iso_inv, weightGcs, weightVs, handle)
+
+
+def TikhRegul_joint(nx, ny, nz, dall, weightGcs, weightVs, handle: Optional[Handle] = None):
+    """TikhRegul.f90:108: dVs block then Gc and Gs blocks; narVs = entries after the dVs block."""
+    return _tikh(1, nx, ny, nz, dall, False, weightGcs, weightVs, handle)
+
+
 class Plan:
     """Device-resident plan (dazim_plan_*): inputs uploaded once, run() leaves results in HBM."""
 
@@ -393,6 +451,45 @@ class Plan:
         _chk(load().dazim_plan_lsmr(self._plan, _p(b), C.c_float(damp), C.c_float(atol), C.c_float(btol), C.c_float(conlim),
                                     C.c_int(itnlim), C.c_int(localSize), _p(x), C.byref(info)))
         return x, {k: getattr(info, k) for k, _ in info._fields_}
+
+    def update_model(self, vels, tables: dict):
+        """New model, same geometry (dazim_plan_update_model): re-uploads vels and the depth-kernel tables."""
+        nx, ny, nz = self._pr.shape
+        self._vels = np.asfortranarray(vels, np.float32)
+        self._tb = _Tab(self._pr.shape, len(self._pr.tRc), tables)
+        _chk(load().dazim_plan_update_model(self._plan, _p(self._vels), C.byref(self._tb.c)))
+
+    def iterate(self, obst, vsf, iso_inv, weightVs, weightGcs, damp, minvel, maxvel, controls: Optional[dict] = None,
+                want_rows=False):
+        """The rest of one outer iteration of Main_Jt.f90 (:416-727) on the G of the last run, resident in HBM
+        (dazim_plan_iterate).  Returns dict(vsf, dv, gcf, gsf, dws, stats[, sigmaT, resbst, fwdTvs, fwdTaa])."""
+        nx, ny, nz = self._pr.shape
+        maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+        n = maxvp if iso_inv else 3 * maxvp
+        obst = np.ascontiguousarray(obst, np.float32)
+        if len(obst) != self.rows:
+            raise ValueError("obst must have one entry per row of the plan")
+        v = np.array(vsf, np.float32, order="F")
+        dv = np.zeros(n, np.float32)
+        g = (nx - 2, ny - 2, nz - 1)
+        gcf = None if iso_inv else np.zeros(g, np.float32, order="F")
+        gsf = None if iso_inv else np.zeros(g, np.float32, order="F")
+        dws = np.zeros(maxvp, np.float32) if iso_inv else None
+        rows = [np.zeros(self.rows, np.float32) if want_rows else None for _ in range(4)]
+        prm = IterParams()
+        prm.iso_inv = int(bool(iso_inv)); prm.weightVs = weightVs; prm.weightGcs = weightGcs; prm.damp = damp
+        prm.minvel = minvel; prm.maxvel = maxvel
+        prm.use_ref_controls = 1 if controls is None else 0
+        if controls is not None:
+            prm.atol, prm.btol, prm.conlim = controls["atol"], controls["btol"], controls["conlim"]
+            prm.itnlim, prm.localSize = controls["itnlim"], controls["localSize"]
+        st = IterStats()
+        _chk(load().dazim_plan_iterate(self._plan, _p(obst), C.byref(prm), _p(v), _p(dv), _p(gcf), _p(gsf), _p(dws),
+                                       _p(rows[0]), _p(rows[1]), _p(rows[2]), _p(rows[3]), C.byref(st)))
+        out = dict(vsf=v, dv=dv, gcf=gcf, gsf=gsf, dws=dws, stats=st.as_dict())
+        if want_rows:
+            out.update(sigmaT=rows[0], resbst=rows[1], fwdTvs=rows[2], fwdTaa=rows[3])
+        return out
 
     def device_tensors(self):
         """Zero-copy torch views of the last run's outputs in HBM (for NCCL exchanges without a host hop).

@@ -910,8 +910,8 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   if (P->nrow > 0x7fffffffll - 3ll * maxvp) return DAZIM_EBADARG;
   const int dall = (int)P->nrow;
   std::memset(S, 0, sizeof(*S));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  cudaEvent_t e0, e1, e2, e3;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
   DBuf<float> d_obst, d_cbst, d_tdata, d_dt, d_sig, d_w, d_stats, d_b, d_dv, d_gcf, d_gsf, d_tvs, d_taa, d_res, d_resw,
       d_lm, d_lmw, d_dws;
   DBuf<double> d_partial, d_dwsacc;
@@ -924,6 +924,7 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   if (iso && dws) { CK(d_dws.alloc(maxvp)); CK(d_dwsacc.alloc(maxvp)); }
   float hs[64];
   std::memset(hs, 0, sizeof(hs));
+  CK(cudaMemsetAsync(d_stats.p, 0, sizeof(float) * 64, st));     // slots a mode does not use read back as zero
   CK(cudaMemcpyAsync(d_obst.p, obst, sizeof(float) * dall, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(e0, st));
   // ---- residual of the reference model, CalDdatSigma, weights (Main_Jt.f90:425-469) ----
@@ -938,7 +939,9 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
     const float* arrs[2] = {d_w.p, d_cbst.p};
     CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p + 6, st));                   // [6] sum w, [10] sum |cbst_w|
   }
+  CK(cudaEventRecord(e2, st));
   CK(dzi::launch_scale_rows(P->nrow, P->d_rowptr.p, d_w.p, P->d_val.p, st));
+  CK(cudaEventRecord(e3, st));
   if (iso && dws) CK(dzi::launch_dws(P->nnz, P->d_col.p, P->d_val.p, maxvp, d_dwsacc.p, d_dws.p, st));
   // ---- regularisation rows behind G (Main_Jt.f90:507-520) ----
   long long appended = 0, after_vs = -1;
@@ -1023,7 +1026,8 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   S->resW2Nm = hs[41];
   S->nar1 = nar1; S->nar = nar; S->count3 = count3;
   cudaEventElapsedTime(&S->step_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaEventElapsedTime(&S->scale_ms, e2, e3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   return DAZIM_OK;
 }
 

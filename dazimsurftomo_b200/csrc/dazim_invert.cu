@@ -37,52 +37,75 @@ __global__ void k_delta(int n, const float* __restrict__ cbst, const float* __re
 
 // Sequential float32 statistics of up to gridDim.x arrays (one CTA each): out[3*b+0] = sum x(i), +1 = sum |x(i)|,
 // +2 = sum (x(i) - sum/n)^2, each accumulated in index order like the Fortran loops / SUM intrinsics
-// (gfortran -O3 without -ffast-math does not reassociate).  Warp 0 and warp 1 run the two first sums side by side.
+// (gfortran -O3 without -ffast-math does not reassociate).  The order is what makes the chain serial; the memory
+// side is not: a warp streams the array through shared memory in 1024-element chunks (coalesced loads, the next
+// chunk already in flight in registers) and lane 0 adds the staged values in order, so a pass costs the float add
+// latency per element (~4 cycles) instead of a global-load round trip per few elements.  Warp 0 accumulates
+// sum x, warp 1 sum |x| side by side; warp 0 then makes the second pass for the squared deviations.
 struct SeqArrays { const float* x[6]; };
+static constexpr int SEQ_CHUNK = 1024;
+
+// kind 0: x ; 1: |x| ; 2: (x - mean)^2
+template <int KIND>
+__device__ __forceinline__ float seq_pass(const float* __restrict__ x, int n, float mean, float* __restrict__ stage) {
+  const int lane = threadIdx.x & 31;
+  float acc = 0.0f;
+  float r[SEQ_CHUNK / 32];
+#pragma unroll
+  for (int q = 0; q < SEQ_CHUNK / 32; ++q) { const int i = q * 32 + lane; r[q] = i < n ? x[i] : 0.0f; }
+  for (int base = 0; base < n; base += SEQ_CHUNK) {
+#pragma unroll
+    for (int q = 0; q < SEQ_CHUNK / 32; ++q) stage[q * 32 + lane] = r[q];
+    const int nb = base + SEQ_CHUNK;
+    if (nb < n) {
+#pragma unroll
+      for (int q = 0; q < SEQ_CHUNK / 32; ++q) { const int i = nb + q * 32 + lane; r[q] = i < n ? x[i] : 0.0f; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int cnt = min(SEQ_CHUNK, n - base);
+      int i = 0;
+      for (; i + 8 <= cnt; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float t = stage[i + q];
+          if (KIND == 0) v[q] = t;
+          else if (KIND == 1) v[q] = fabsf(t);
+          else { const float d = t - mean; v[q] = d * d; }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = acc + v[q];
+      }
+      for (; i < cnt; ++i) {
+        const float t = stage[i];
+        if (KIND == 0) acc = acc + t;
+        else if (KIND == 1) acc = acc + fabsf(t);
+        else { const float d = t - mean; acc = acc + d * d; }
+      }
+    }
+    __syncwarp();
+  }
+  return acc;      // valid in lane 0
+}
+
 __global__ void __launch_bounds__(64) k_seq_stats(SeqArrays a, int n, float* __restrict__ out) {
   const float* __restrict__ x = a.x[blockIdx.x];
+  __shared__ float stage[2][SEQ_CHUNK];
   __shared__ float sh_sum;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    float s = 0.0f;
-    int i = 0;
-    if (warp == 0) {
-      for (; i + 8 <= n; i += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = x[i + q];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s = s + v[q];
-      }
-      for (; i < n; ++i) s = s + x[i];
-      out[3 * blockIdx.x + 0] = s;
-      sh_sum = s;
-    } else {
-      for (; i + 8 <= n; i += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = fabsf(x[i + q]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s = s + v[q];
-      }
-      for (; i < n; ++i) s = s + fabsf(x[i]);
-      out[3 * blockIdx.x + 1] = s;
-    }
+  if (warp == 0) {
+    const float s = seq_pass<0>(x, n, 0.0f, stage[0]);
+    if (lane == 0) { out[3 * blockIdx.x + 0] = s; sh_sum = s; }
+  } else {
+    const float s = seq_pass<1>(x, n, 0.0f, stage[1]);
+    if (lane == 0) out[3 * blockIdx.x + 1] = s;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     const float mean = sh_sum / (float)n;
-    float q2 = 0.0f;
-    int i = 0;
-    for (; i + 8 <= n; i += 8) {
-      float v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { const float d = x[i + q] - mean; v[q] = d * d; }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) q2 = q2 + v[q];
-    }
-    for (; i < n; ++i) { const float d = x[i] - mean; q2 = q2 + d * d; }
-    out[3 * blockIdx.x + 2] = q2;
+    const float q2 = seq_pass<2>(x, n, mean, stage[0]);
+    if (lane == 0) out[3 * blockIdx.x + 2] = q2;
   }
 }
 

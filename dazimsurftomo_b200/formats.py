@@ -356,3 +356,91 @@ def azim_map(nx, ny, nz, goxd, gozd, dvxd, dvzd, tRc, gcf, gsf, lsen_gsc, tRcV):
                 rows.append((F32(gozd) + F32(jj - 1) * F32(dvzd), F32(goxd) - F32(ii - 1) * F32(dvxd),
                              tRc[tt], isoc, ang, rel, amp, ct, st))
     return np.array(rows, dtype=np.float64)
+
+
+# ---- writers of the inversion driver (Main_Jt.f90:752-908) ----------------------------------------------------
+
+def fortran_e(x: float, w: int = 12, d: int = 3) -> str:
+    """Fortran Ew.d edit descriptor (mantissa 0.ddd, two-digit exponent), e.g. e12.3 -> '   0.123E+01'."""
+    x = float(x)
+    if x == 0.0 or not np.isfinite(x):
+        body = "0." + "0" * d + "E+00" if x == 0.0 else ("NaN" if x != x else "Infinity")
+        s = ("-" if (x < 0 or (x == 0.0 and np.signbit(x))) else "") + body
+        return s.rjust(w)
+    m, e = ("%.*e" % (d - 1, abs(x))).split("e")          # d significant digits: m = 'D.DD..'
+    e = int(e) + 1
+    digits = m.replace(".", "")
+    s = ("-" if x < 0 else "") + "0." + digits + "E%+03d" % e
+    return s.rjust(w) if len(s) <= w else "*" * w
+
+
+def write_vs_model(path: str, nx, ny, nz, gozd, goxd, dvzd, dvxd, depz, vsf) -> None:
+    """writeVsmodel (Main_Jt.f90:838-856): '(5f8.4)' lon lat depth Vs, k outer, j, i fastest."""
+    gozd, goxd, dvzd, dvxd = F32(gozd), F32(goxd), F32(dvzd), F32(dvxd)
+    with open(path, "w") as f:
+        for k in range(nz):
+            for j in range(1, ny + 1):
+                lon = gozd + F32(j - 2) * dvzd
+                for i in range(1, nx + 1):
+                    lat = goxd - F32(i - 2) * dvxd
+                    f.write("%8.4f%8.4f%8.4f%8.4f\n" % (lon, lat, depz[k], vsf[i - 1, j - 1, k]))
+
+
+def azimuthal_rows(nx, ny, nz, gozd, goxd, dvzd, dvxd, depz, gcf, gsf, vsf) -> np.ndarray:
+    """The 8 columns of writeAzimuthal (Main_Jt.f90:859-887): lon lat depth(lower) Vs(mid) angle amp Gc% Gs%."""
+    gozd, goxd, dvzd, dvxd = F32(gozd), F32(goxd), F32(dvzd), F32(dvxd)
+    pi8 = np.float64(3.1415926535898)
+    rows = []
+    for k in range(nz - 1):
+        for j in range(1, ny - 1):
+            for i in range(1, nx - 1):
+                c = F32(gcf[i - 1, j - 1, k]); s = F32(gsf[i - 1, j - 1, k])
+                amp = F32(0.5) * F32(np.sqrt(F32(c * c + s * s)))
+                ang = F32(np.arctan2(s, c).astype(np.float64) / pi8 * 180)
+                if ang < 0:
+                    ang = F32(ang + F32(360))
+                ang = F32(0.5) * ang
+                vsref = F32(F32(vsf[i, j, k] + vsf[i, j, k + 1]) / F32(2))
+                rows.append((gozd + F32(j - 1) * dvzd, goxd - F32(i - 1) * dvxd, depz[k + 1], vsref, ang, amp,
+                             c * F32(100), s * F32(100)))
+    return np.array(rows, dtype=np.float64)
+
+
+def write_azimuthal(path: str, nx, ny, nz, gozd, goxd, dvzd, dvxd, depz, gcf, gsf, vsf) -> None:
+    """Gc_Gs_model.inv, '(8f10.4)'."""
+    with open(path, "w") as f:
+        for r in azimuthal_rows(nx, ny, nz, gozd, goxd, dvzd, dvxd, depz, gcf, gsf, vsf):
+            f.write("".join("%10.4f" % x for x in r) + "\n")
+
+
+def write_period_phasev(path: str, nx, ny, gozd, goxd, dvzd, dvxd, tRc, tRcV) -> None:
+    """WTPeriodPhaseV (Main_Jt.f90:889-908): '(5f10.4)' lon lat period c over the interior nodes."""
+    gozd, goxd, dvzd, dvxd = F32(gozd), F32(goxd), F32(dvzd), F32(dvxd)
+    tv = np.asarray(tRcV).reshape(((nx - 2) * (ny - 2), len(tRc)), order="F")
+    with open(path, "w") as f:
+        for tt in range(len(tRc)):
+            for jj in range(1, ny - 1):
+                for ii in range(1, nx - 1):
+                    f.write("%10.4f%10.4f%10.4f%10.4f\n" % (gozd + F32(jj - 1) * dvzd, goxd - F32(ii - 1) * dvxd, tRc[tt],
+                                                           tv[(jj - 1) * (nx - 2) + ii - 1, tt]))
+
+
+def write_mod_ref(path: str, depz, vsf) -> None:
+    """MOD_Ref (Main_Jt.f90:753-769): depths f7.1 on the first record, then one record of nx f8.4 per (k, j)."""
+    nx, ny, nz = vsf.shape
+    with open(path, "w") as f:
+        f.write("".join("%7.1f" % float(d) for d in depz))
+        for k in range(nz):
+            for j in range(ny):
+                f.write("\n" + "".join("%8.4f" % float(vsf[i, j, k]) for i in range(nx)))
+        f.write("\n")
+
+
+def interior_phase_velocity(pvRc, nx, ny) -> np.ndarray:
+    """tRcV((nx-2)(ny-2),kmax) from pvRc(nx*ny,kmax) (FwdTraveltimeCPS.f90:771-778)."""
+    pv = np.asarray(pvRc)
+    k = pv.shape[1]
+    out = np.zeros(((nx - 2) * (ny - 2), k), np.float64, order="F")
+    for jj in range(1, ny - 1):
+        out[(jj - 1) * (nx - 2):(jj) * (nx - 2), :] = pv[jj * nx + 1:jj * nx + nx - 1, :]
+    return out

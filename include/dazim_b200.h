@@ -209,6 +209,7 @@ typedef struct dazim_iter_stats {
   int count3;                /* regularisation rows */
   dazim_lsmr_info lsmr;
   float step_ms;             /* device time of the whole step */
+  float scale_ms;            /* of which: the row scaling of G by the data weights (8 B per non-zero) */
 } dazim_iter_stats;
 
 /* New model for an existing plan (same geometry): re-uploads vels and the depth-kernel tables; the work list,

@@ -7,6 +7,8 @@ outputs (example/test1_syn_foward), cut down so they stay small:
   test1/surfphase_subset.dat                              the matching blocks of the reference's
                                                           output/surfphase_forward_RV3th.dat
   test1/period_Azm_tomo.npz                               output/period_Azm_tomo.real as an array
+  inv/test2_para.in, test2_MOD, test3_para.in, test3_MOD  verbatim inputs of the two inversion examples
+  (inv/test2_iter.npz, test3_iter.npz are written by scripts/pin_inversion.py)
 """
 import os
 import shutil
@@ -57,6 +59,14 @@ def main():
             fg.writelines(gold[i])
     g = np.loadtxt(os.path.join(REF, "output", "period_Azm_tomo.real"))
     np.savez_compressed(os.path.join(OUT, "period_Azm_tomo.npz"), table=g.astype(np.float32))
+    # inversion examples: control files and start models only (the data file of test2/test3 is test1's output)
+    inv = os.path.join(OUT, "..", "inv")
+    os.makedirs(inv, exist_ok=True)
+    for case, tag in (("test2_syn_iso_inv", "test2"), ("test3_syn_joint_inv", "test3")):
+        for f in ("para.in", "MOD"):
+            dst = os.path.join(inv, "%s_%s" % (tag, f))
+            shutil.copy(os.path.join(REF, "..", case, f), dst)
+            os.chmod(dst, 0o644)
     print("units kept:", len(keep), "rays:", sum(len(inp[i]) - 1 for i in keep))
 
 

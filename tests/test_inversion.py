@@ -1,0 +1,206 @@
+"""Outer-iteration stage, CPU side: the oracle's restatement against independent numpy
+restatements and against the reference's shipped inversion results, the closed-form Tikhonov offsets exported
+by the C-ABI library (no GPU needed), and the writers of the inversion driver."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+INV = os.path.join(ROOT, "tests", "golden", "inv")
+F32 = np.float32
+
+
+def _seq_sum32(x):
+    """float32 sum in index order (np.cumsum accumulates sequentially in the array's dtype)."""
+    return np.cumsum(np.asarray(x, F32), dtype=F32)[-1]
+
+
+def test_cal_ddat_sigma_matches_sequential_float32(oracle):
+    rng = np.random.default_rng(3)
+    n = 5000
+    obst = rng.uniform(5, 120, n).astype(F32)
+    cbst = (rng.standard_normal(n) * 0.8).astype(F32)
+    cbst[::97] *= 9                                            # outliers take the exp() branch
+    sig, mean = oracle.cal_ddat_sigma(obst, cbst)
+    d = np.abs(cbst / obst).astype(F32)
+    m = F32(_seq_sum32(d) / F32(n))
+    s = F32(np.sqrt(F32(_seq_sum32(((d - m) * (d - m)).astype(F32)) / F32(n))))
+    ratio = np.abs(d / F32(F32(1.5) * s)).astype(F32)
+    want = (s * obst).astype(F32)
+    big = ratio > 1
+    want[big] = (want[big] * np.exp((ratio[big] - F32(1)).astype(F32)).astype(F32)).astype(F32)
+    assert F32(mean) == m
+    assert big.sum() > 10
+    assert np.array_equal(sig[~big], want[~big])
+    assert np.allclose(sig[big], want[big], rtol=3e-7, atol=0)    # libm expf vs numpy's
+
+
+@pytest.mark.parametrize("shape", [(17, 17, 4), (6, 5, 3), (5, 5, 2), (9, 7, 6)])
+def test_tikhonov_rows_are_a_laplacian(oracle, shape):
+    nx, ny, nz = shape
+    nvx, nvz, nl = nx - 2, ny - 2, nz - 1
+    maxvp = nvx * nvz * nl
+    dall = 1234
+    iso = oracle.tikhonov(nx, ny, nz, dall, True, 35.0, 240.0)
+    assert iso["count3"] == maxvp
+    assert np.array_equal(np.unique(iso["row"]), np.arange(dall + 1, dall + maxvp + 1))
+    # dense L: interior rows sum to zero with 6w on the diagonal, face rows are 2w on the diagonal alone
+    L = np.zeros((maxvp, maxvp))
+    np.add.at(L, (iso["row"] - dall - 1, iso["col"] - 1), iso["rw"])
+    ii, jj, kk = np.meshgrid(np.arange(nvx), np.arange(nvz), np.arange(nl), indexing="ij")
+    face = ((ii == 0) | (ii == nvx - 1) | (jj == 0) | (jj == nvz - 1) | (kk == 0) | (kk == nl - 1)).ravel(order="F")
+    assert np.allclose(np.diag(L)[face], 2 * 240.0) and np.allclose(np.diag(L)[~face], 6 * 240.0)
+    assert np.allclose(L[~face].sum(1), 0) and np.allclose(np.abs(L[face]).sum(1), 2 * 240.0)
+    for r in np.flatnonzero(~face):                          # the six neighbours, i fastest
+        nb = sorted(np.flatnonzero(L[r] == -240.0) - r)
+        assert nb == sorted([-1, 1, -nvx, nvx, -nvx * nvz, nvx * nvz])
+    # Gc,Gs-only variant (iso_inv = F) and the joint variant place the same block at the reference's column offsets
+    aa = oracle.tikhonov(nx, ny, nz, dall, False, 35.0, 240.0)
+    assert aa["count3"] == 2 * maxvp and aa["col"].max() <= 2 * maxvp
+    assert np.allclose(np.abs(aa["rw"]).max(), (2 if face.all() else 6) * 35.0)
+    jt = oracle.tikhonov(nx, ny, nz, dall, False, 35.0, 240.0, joint=True)
+    n1 = len(iso["rw"])
+    assert jt["narVs"] == n1 and jt["count3"] == 3 * maxvp and len(jt["rw"]) == 3 * n1
+    assert np.array_equal(jt["rw"][:n1], iso["rw"]) and np.array_equal(jt["col"][:n1], iso["col"])
+    assert np.array_equal(jt["col"][n1:2 * n1], iso["col"] + maxvp) and np.array_equal(jt["col"][2 * n1:], iso["col"] + 2 * maxvp)
+    assert np.allclose(jt["rw"][n1:2 * n1] * (240.0 / 35.0), iso["rw"], rtol=1e-6)
+    assert np.array_equal(jt["row"], np.concatenate([iso["row"], iso["row"] + maxvp, iso["row"] + 2 * maxvp]))
+
+
+@pytest.mark.parametrize("shape", [(17, 17, 4), (5, 5, 2), (6, 5, 3), (7, 9, 5), (38, 42, 18), (4, 4, 4), (3, 3, 2)])
+def test_library_tikhonov_offsets_match_oracle(oracle, shape):
+    """The CUDA kernel writes every regularisation row independently at a closed-form offset; the same
+    __host__ __device__ function is exported by the library, so it can be checked without a GPU."""
+    from dazimsurftomo_b200 import build
+    lib = C.CDLL(build.build())
+    lib.dazim_tikh_offset.restype = C.c_longlong
+    lib.dazim_tikh_block_entries.restype = C.c_longlong
+    nx, ny, nz = shape
+    nvx, nvz, nl = nx - 2, ny - 2, nz - 1
+    t = oracle.tikhonov(nx, ny, nz, 10, True, 1.0, 2.0)
+    first = np.r_[0, np.flatnonzero(np.diff(t["row"])) + 1]
+    got = [lib.dazim_tikh_offset(i, j, k, nvx, nvz, nl) for k in range(1, nl + 1) for j in range(1, nvz + 1)
+           for i in range(1, nvx + 1)]
+    assert list(first) == got
+    assert lib.dazim_tikh_block_entries(nvx, nvz, nl) == len(t["row"])
+
+
+def test_model_update_clips_and_clamps(oracle):
+    nx, ny, nz = 6, 5, 4
+    maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+    rng = np.random.default_rng(0)
+    vsf = np.asfortranarray(rng.uniform(2.9, 4.2, (nx, ny, nz)).astype(F32))
+    dv = (rng.standard_normal(3 * maxvp) * 0.4).astype(F32)
+    dv[3] = 5e-6; dv[4] = -0.7; dv[5] = 0.9
+    d2, v2, gc, gs = oracle.model_update(dv, vsf, False, 3.0, 4.1)
+    assert d2[3] == 0 and d2[4] == F32(-0.5) and d2[5] == F32(0.5)
+    assert np.array_equal(d2[maxvp:], dv[maxvp:])                      # only the dVs block is clipped
+    assert np.array_equal(gc.ravel(order="F"), dv[maxvp:2 * maxvp]) and np.array_equal(gs.ravel(order="F"), dv[2 * maxvp:])
+    want = vsf.copy()
+    want[1:-1, 1:-1, :nz - 1] = np.clip(vsf[1:-1, 1:-1, :nz - 1] + d2[:maxvp].reshape((nx - 2, ny - 2, nz - 1), order="F"),
+                                        F32(3.0), F32(4.1))
+    assert np.array_equal(v2, want)
+    assert np.array_equal(v2[:, :, nz - 1], vsf[:, :, nz - 1])          # the deepest grid plane never moves
+    d1, v1, _, _ = oracle.model_update(dv[:maxvp], vsf, True, 3.0, 4.1)
+    assert np.array_equal(v1, v2) and np.array_equal(d1, d2[:maxvp])
+
+
+def test_residuals_and_norms_against_dense(oracle):
+    rng = np.random.default_rng(5)
+    dall, maxvp = 40, 12
+    n = 3 * maxvp
+    G = (rng.standard_normal((dall, n)) * (rng.random((dall, n)) < 0.3)).astype(F32)
+    row, col = np.nonzero(G)                                            # row-major: rows ascending, columns ascending
+    rw = G[row, col]
+    dv = rng.standard_normal(n).astype(F32); w = rng.uniform(0.5, 2, dall).astype(F32)
+    td = rng.standard_normal(dall).astype(F32)
+    r = oracle.residuals(maxvp, 3, rw, row + 1, col + 1, dv, w, td)
+    tvs = G[:, :maxvp].astype(np.float64) @ dv[:maxvp]; taa = G[:, maxvp:].astype(np.float64) @ dv[maxvp:]
+    assert np.allclose(r["fwdTvs"], tvs, atol=1e-5) and np.allclose(r["fwdTaa"], taa, atol=1e-5)
+    assert np.allclose(r["resbst"], td - taa - tvs, atol=1e-5)
+    assert np.isclose(r["res2Nm"], np.linalg.norm(td - taa - tvs), rtol=1e-5)
+    assert np.isclose(r["resW2Nm"], np.linalg.norm((td - taa - tvs) * w), rtol=1e-5)
+    s = oracle.res_stats(td)
+    assert np.isclose(s["meanabs"], np.abs(td).mean(), rtol=1e-5) and np.isclose(s["std"], td.std(), rtol=1e-5)
+    assert np.isclose(s["rms"], np.sqrt((td.astype(np.float64) ** 2).mean()), rtol=1e-5)
+    tk = oracle.tikhonov(6, 5, 3, dall, False, 3.0, 7.0, joint=True)   # (4,3,2) cells = 24 != maxvp: only the norms' algebra is used
+    dv2 = rng.standard_normal(3 * 24).astype(F32)
+    nm = oracle.model_norms(0, tk["narVs"], tk["rw"], tk["col"], dv2, 3.0, 7.0)
+    terms = tk["rw"].astype(np.float64) * dv2[tk["col"] - 1]
+    k = tk["narVs"]
+    assert np.isclose(nm["VswNorm2"], np.linalg.norm(terms[:k]), rtol=1e-5)
+    assert np.isclose(nm["VsNorm2"], np.linalg.norm(terms[:k]) / 7.0, rtol=1e-5)
+    assert np.isclose(nm["GcsNorm2"], np.linalg.norm(terms[k:]) / 3.0, rtol=1e-5)
+    assert np.isclose(nm["MwNorm2"], np.linalg.norm(terms), rtol=1e-5)
+
+
+def test_oracle_inversion_reproduces_the_reference_shipped_models():
+    """scripts/pin_inversion.py ran the oracle's full outer loop on the reference's test2 (20 iterations, iso) and
+    test3 (5 iterations, joint) examples; the fixtures hold its final models next to the shipped
+    plot_script/DSurfTomo.inv and Gc_Gs_model.inv columns.  This pins, end to end, what no other shipped artefact
+    pins: the finite-difference kernels sen_vs/vp/rho and the G triplets, CalDdatSigma, the Tikhonov
+    rows, LSMR and the model update."""
+    t2 = np.load(os.path.join(INV, "test2_iter.npz"))
+    ours = t2["final"].ravel(order="F")                       # i fastest, then j, then k = the file's order
+    assert ours.shape == t2["shipped"].shape == (17 * 17 * 4,)
+    assert np.abs(ours - t2["shipped"]).max() <= 1.0e-4 + 1e-6      # f8.4 print precision
+    assert np.abs(t2["shipped"] - t2["shipped"].mean()).max() > 0.3  # the model did move: the agreement is not trivial
+    assert t2["hist"].shape == (20, 4) and t2["hist"][-1, 1] < 0.27 and t2["hist"][0, 0] > 1.8
+    t3 = np.load(os.path.join(INV, "test3_iter.npz"))
+    gc = t3["final_gcf"].ravel(order="F") * 100; gs = t3["final_gsf"].ravel(order="F") * 100
+    v = t3["final_vsf"]
+    vs_mid = ((v[1:-1, 1:-1, :-1] + v[1:-1, 1:-1, 1:]) / 2).ravel(order="F")
+    sh = t3["shipped"]
+    assert np.abs(vs_mid - sh[:, 0]).max() <= 1.5e-4
+    assert np.abs(gc - sh[:, 1]).max() < 0.01 and np.abs(gs - sh[:, 2]).max() < 0.01     # percent; amplitudes reach 12 %
+    assert np.abs(sh[:, 1]).max() > 10
+
+
+def test_oracle_inversion_two_iterations_on_the_subset(oracle, test1):
+    """The loop itself (small: 1 240 rays of the reference's own data, 2 outer iterations, seconds)."""
+    from dazimsurftomo_b200 import formats as fm
+    p = fm.read_para_inv(os.path.join(INV, "test2_para.in"))
+    depz, vs = fm.read_model(os.path.join(INV, "test2_MOD"), p.nx, p.ny, p.nz)
+    sv = fm.read_surfdata(os.path.join(ROOT, "tests", "golden", "test1", "surfphase_subset.dat"), p.kmaxRc)
+    obst = (sv.dist / sv.obsvel).astype(F32)
+    # para.in's smoothing (240) is sized for 261 360 rays; 8 lets 1 240 rays move the model
+    r = oracle.invert(vs, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, obst, True, 8.0,
+                      p.weightGcs, p.damp, p.minvel, p.maxvel, 2, nthreads=8)
+    h = r["history"]
+    assert h[0]["after"]["rms"] < h[0]["before"]["rms"] and h[1]["before"]["rms"] < h[0]["before"]["rms"]
+    assert h[0]["lsmr"]["istop"] in (1, 2) and h[0]["nar"] - h[0]["nar1"] == len(oracle.tikhonov(17, 17, 4, 1, True, 0, 1)["rw"])
+    upd = r["vsf"][1:-1, 1:-1, :-1]                      # edge nodes and the deepest plane are never touched
+    assert np.abs(r["vsf"] - vs).max() > 1e-3 and upd.min() >= F32(p.minvel) and upd.max() <= F32(p.maxvel)
+    assert np.array_equal(r["vsf"][:, :, -1], vs[:, :, -1]) and np.array_equal(r["vsf"][0], vs[0])
+
+
+def test_fortran_e_and_writers(tmp_path):
+    from dazimsurftomo_b200 import formats as fm
+    assert fm.fortran_e(1.2345) == "   0.123E+01" and fm.fortran_e(-0.000123456) == "  -0.123E-03"
+    assert fm.fortran_e(0.0) == "   0.000E+00" and fm.fortran_e(9.9996) == "   0.100E+02"
+    nx, ny, nz = 5, 6, 3
+    rng = np.random.default_rng(1)
+    vs = np.asfortranarray(rng.uniform(3, 4, (nx, ny, nz)).astype(F32))
+    depz = np.array([0, 10, 35], F32)
+    fm.write_vs_model(tmp_path / "DSurfTomo.inv", nx, ny, nz, 101.25, 26.5, 0.25, 0.25, depz, vs)
+    lines = open(tmp_path / "DSurfTomo.inv").read().splitlines()
+    assert len(lines) == nx * ny * nz and all(len(l) == 32 for l in lines)
+    assert lines[0] == "101.0000 26.7500  0.0000%8.4f" % vs[0, 0, 0]          # the reference's own first record layout
+    assert lines[nx] == "101.2500 26.7500  0.0000%8.4f" % vs[0, 1, 0]
+    fm.write_mod_ref(tmp_path / "MOD_Ref", depz, vs)
+    d2, v2 = fm.read_model(str(tmp_path / "MOD_Ref"), nx, ny, nz)          # the reference re-reads MOD_Ref as a MOD
+    assert np.array_equal(d2, depz) and np.abs(v2 - vs).max() <= 5.1e-5
+    gc = np.asfortranarray(rng.uniform(-0.05, 0.05, (nx - 2, ny - 2, nz - 1)).astype(F32)); gs = gc[::-1].copy(order="F")
+    rows = fm.azimuthal_rows(nx, ny, nz, 101.25, 26.5, 0.25, 0.25, depz, gc, gs, vs)
+    assert rows.shape == ((nx - 2) * (ny - 2) * (nz - 1), 8)
+    assert np.allclose(rows[:, 5], 0.5 * np.hypot(gc, gs).ravel(order="F"), rtol=1e-6)
+    ang = np.degrees(np.arctan2(gs.ravel(order="F").astype(np.float64), gc.ravel(order="F"))) % 360 / 2
+    assert np.allclose(rows[:, 4], ang, atol=1e-3) and rows[0, 0] == 101.25 and rows[0, 1] == 26.5 and rows[0, 2] == 10
+    pv = rng.uniform(3, 4, (nx * ny, 2))
+    tv = fm.interior_phase_velocity(pv, nx, ny)
+    assert tv.shape == ((nx - 2) * (ny - 2), 2) and tv[0, 0] == pv[nx + 1, 0] and tv[-1, 1] == pv[(ny - 2) * nx + nx - 2, 1]
+    fm.write_period_phasev(tmp_path / "phaseV_FWD.dat", nx, ny, 101.25, 26.5, 0.25, 0.25, [5.0, 6.0], tv)
+    assert len(open(tmp_path / "phaseV_FWD.dat").read().splitlines()) == 2 * (nx - 2) * (ny - 2)
