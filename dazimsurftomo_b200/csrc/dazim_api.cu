@@ -393,7 +393,6 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     for (int knumi = 1; knumi <= p->kmax; ++knumi)
       for (int srcnum = 1; srcnum <= p->nsrcsurf1[knumi - 1]; ++srcnum, ++unit2) {
         if (!(unit2 >= sb && (se < 0 || unit2 < se))) continue;
-        const size_t sk = (size_t)(srcnum - 1) + (size_t)(knumi - 1) * p->nsrc;
         const SrcRec& sr = P->src[si];
         const int b = (int)(si / maxB);
         for (int i = 0; i < sr.nray; ++i) {
@@ -523,7 +522,6 @@ static int plan_run(dazim_plan* P) {
   g_alloc_stream = h->st;
   cudaStream_t st = h->st;
   const GridC& g = P->g;
-  const size_t ncoarse = (size_t)g.nnx * g.nnz;
   dazim_times& T = h->times;
   T.dice_ms = T.fmm_ms = T.trace_ms = T.assemble_ms = T.total_ms = 0;
   T.n_fmm_launch = T.n_trace_launch = T.n_launch = 0;
@@ -910,8 +908,12 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   if (P->nrow > 0x7fffffffll - 3ll * maxvp) return DAZIM_EBADARG;
   const int dall = (int)P->nrow;
   std::memset(S, 0, sizeof(*S));
-  cudaEvent_t e0, e1, e2, e3;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+  struct Events {                               // destroyed on every return path
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+  } ev;
+  for (auto& x : ev.e) CK(cudaEventCreate(&x));
+  cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2], e3 = ev.e[3];
   DBuf<float> d_obst, d_cbst, d_tdata, d_dt, d_sig, d_w, d_stats, d_b, d_dv, d_gcf, d_gsf, d_tvs, d_taa, d_res, d_resw,
       d_lm, d_lmw, d_dws;
   DBuf<double> d_partial, d_dwsacc;
@@ -1027,7 +1029,6 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   S->nar1 = nar1; S->nar = nar; S->count3 = count3;
   cudaEventElapsedTime(&S->step_ms, e0, e1);
   cudaEventElapsedTime(&S->scale_ms, e2, e3);
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   return DAZIM_OK;
 }
 

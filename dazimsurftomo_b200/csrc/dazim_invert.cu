@@ -65,17 +65,20 @@ __device__ __forceinline__ float seq_pass(const float* __restrict__ x, int n, fl
     if (lane == 0) {
       const int cnt = min(SEQ_CHUNK, n - base);
       int i = 0;
-      for (; i + 8 <= cnt; i += 8) {
-        float v[8];
+      for (; i + 32 <= cnt; i += 32) {           // 8 x LDS.128 in flight, then 32 dependent adds
+        float v[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float t = stage[i + q];
-          if (KIND == 0) v[q] = t;
-          else if (KIND == 1) v[q] = fabsf(t);
-          else { const float d = t - mean; v[q] = d * d; }
+          const float4 t4 = *reinterpret_cast<const float4*>(stage + i + 4 * q);
+          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc = acc + v[q];
+        for (int q = 0; q < 32; ++q) {
+          if (KIND == 1) v[q] = fabsf(v[q]);
+          else if (KIND == 2) { const float d = v[q] - mean; v[q] = d * d; }
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc = acc + v[q];
       }
       for (; i < cnt; ++i) {
         const float t = stage[i];
@@ -91,7 +94,7 @@ __device__ __forceinline__ float seq_pass(const float* __restrict__ x, int n, fl
 
 __global__ void __launch_bounds__(64) k_seq_stats(SeqArrays a, int n, float* __restrict__ out) {
   const float* __restrict__ x = a.x[blockIdx.x];
-  __shared__ float stage[2][SEQ_CHUNK];
+  __shared__ __align__(16) float stage[2][SEQ_CHUNK];
   __shared__ float sh_sum;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {

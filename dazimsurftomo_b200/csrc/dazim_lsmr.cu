@@ -109,11 +109,34 @@ __global__ void k_scal(float* __restrict__ x, int n, float a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = a * x[i];
 }
-// v = v - d * q with d read from device memory (local reorthogonalisation, lsmrModule.f90:743-746)
-__global__ void k_axpy_dev(float* __restrict__ v, const float* __restrict__ q, int n, const float* __restrict__ d) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = v[i] - d[0] * q[i];
+// Local reorthogonalisation (lsmrModule.f90:740-747): for q = 1..lim, in order, d = v . V_q ; v = v - d V_q.
+// The steps depend on each other, n is the model size (10^3 - 10^5) and lim reaches n/4 in the isotropic
+// inversion (Main_Jt.f90:547), so three launches per step are pure launch latency: one CTA runs the whole chain,
+// every thread owning the same elements of v in all steps (dot products accumulated in double, fixed tree).
+__global__ void __launch_bounds__(1024) k_reorth(float* __restrict__ v, const float* __restrict__ localV, int n, int lim) {
+  __shared__ double sh[32];
+  __shared__ float sh_d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < lim; ++q) {
+    const float* __restrict__ lq = localV + (size_t)q * n;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) acc += (double)v[i] * (double)lq[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double t = sh[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sh_d = (float)t;
+    }
+    __syncthreads();
+    const float d = sh_d;
+    for (int i = threadIdx.x; i < n; i += 1024) v[i] = v[i] - d * lq[i];
+  }
 }
+
 // hbar = h - c1*hbar ; x = x + c2*hbar ; h = v - c3*h   (lsmrModule.f90:539-541)
 __global__ void k_update(float* __restrict__ hbar, float* __restrict__ h, float* __restrict__ x,
                          const float* __restrict__ v, int n, float c1, float c2, float c3) {
@@ -260,13 +283,7 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
         k_spmv_add<<<gwn, 256, 0, st>>>(n, csc_ptr.p, csc_idx.p, csc_val.p, u.p, v.p);  // v = v + A^T u
         if (localOrtho) {
           const int lim = queueFull ? localVecs : localPointer;
-          const int nb = std::min(c.nb, std::max(1, (n + 255) / 256));
-          for (int q = 0; q < lim; ++q) {
-            const float* lq = localV.p + (size_t)q * n;
-            k_dot_partial<<<nb, 256, 0, st>>>(v.p, lq, n, partial.p);
-            k_dot_final<<<1, 32, 0, st>>>(partial.p, nb, 0, scal.p + 1);
-            k_axpy_dev<<<gn, 256, 0, st>>>(v.p, lq, n, scal.p + 1);
-          }
+          k_reorth<<<1, 1024, 0, st>>>(v.p, localV.p, n, lim);
         }
         if ((rc = norm2(c, v.p, n, &alpha))) return rc;
         if (alpha > 0.0f) k_scal<<<gn, 256, 0, st>>>(v.p, n, 1.0f / alpha);

@@ -43,15 +43,67 @@ cccccccccc periods
 """
 
 
+def real_example(tag, h, cpu_iters):
+    """BASELINE configs 3 / 4 for real: the reference's example/test2_syn_iso_inv or test3_syn_joint_inv (fixture copies
+    of para.in, MOD and the data file), all outer iterations, compared with the model the reference shipped."""
+    import lzma
+    from dazimsurftomo_b200 import formats as fm, invert
+    from oracle import pyoracle as po
+    inv = os.path.join(ROOT, "tests", "golden", "inv")
+    tmp = tempfile.mkdtemp(prefix="dazim_%s_" % tag)
+    for f in ("para.in", "MOD"):
+        open(os.path.join(tmp, f), "w").write(open(os.path.join(inv, "%s_%s" % (tag, f))).read())
+    with lzma.open(os.path.join(inv, "surfphase_forward_RV3th.dat.xz"), "rb") as f:
+        open(os.path.join(tmp, "surfphase_forward_RV3th.dat"), "wb").write(f.read())
+    t0 = time.time()
+    out = invert.run(os.path.join(tmp, "para.in"), handle=h, log_stream=open(os.devnull, "w"))
+    wall = time.time() - t0
+    hist = out["history"]; p = out["para"]; sv = out["survey"]; g = out["gpu_ms"]; n = len(hist)
+    fix = np.load(os.path.join(inv, "%s_iter.npz" % tag))
+    depz, vs0 = fm.read_model(os.path.join(tmp, "MOD"), p.nx, p.ny, p.nz)
+    if tag == "test2":
+        ours = np.array([float(l[24:32]) for l in open(os.path.join(tmp, "DSurfTomo.inv")).read().splitlines()])
+        vs_ref = {"file": "plot_script/DSurfTomo.inv", "max_abs_dVs_km_s": float(np.abs(ours - fix["shipped"]).max()),
+                  "rms_dVs_km_s": float(np.sqrt(((ours - fix["shipped"]) ** 2).mean())),
+                  "model_moved_km_s": float(np.abs(fix["shipped"] - vs0.ravel(order="F")).max())}
+    else:
+        tab = np.loadtxt(os.path.join(tmp, "Gc_Gs_model.inv"))
+        vs_ref = {"file": "plot_script/Gc_Gs_model.inv", "max_abs_dVs_mid_km_s": float(np.abs(tab[:, 3] - fix["shipped"][:, 0]).max()),
+                  "max_abs_dGc_percent": float(np.abs(tab[:, 6] - fix["shipped"][:, 1]).max()),
+                  "max_abs_dGs_percent": float(np.abs(tab[:, 7] - fix["shipped"][:, 2]).max()),
+                  "shipped_max_Gc_percent": float(np.abs(fix["shipped"][:, 1]).max())}
+    obst = (sv.dist / sv.obsvel).astype(np.float32)
+    t0 = time.time()
+    po.invert(vs0, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, obst, p.iso_mod, p.weightVs, p.weightGcs,
+              p.damp, p.minvel, p.maxvel, cpu_iters, spfra=p.spfra, nthreads=os.cpu_count() or 1)
+    cpu_s = (time.time() - t0) / cpu_iters
+    dev_s = (g["kernels"] + g["gbuild"] + g["iterate"]) * 1e-3
+    print(json.dumps({
+        "stage": "DAzimSurfTomo para.in on the reference's example/%s (BASELINE config %d), file-based GPU driver" %
+                 ("test2_syn_iso_inv" if tag == "test2" else "test3_syn_joint_inv", 3 if tag == "test2" else 4),
+        "rays": int(sv.dall), "outer_iterations": n, "nnz_G": int(np.mean([s["nar1"] for s in hist])),
+        "vs_reference_shipped_model": vs_ref,
+        "device_s_total": dev_s, "wall_s_total_incl_file_io": wall,
+        "gpu_ms_per_iteration": {"depth_kernels": g["kernels"] / n, "g_build": g["gbuild"] / n, "iteration_tail": g["iterate"] / n,
+                                 "of_which_lsmr": g["lsmr"] / n},
+        "per_iteration_ms": {"tail": [round(s["step_ms"], 1) for s in hist], "lsmr_solve": [round(s["lsmr"]["solve_ms"], 1) for s in hist]},
+        "lsmr_itn": [s["lsmr"]["itn"] for s in hist],
+        "rms_before_first_after_last": [hist[0]["before"]["rms"], hist[-1]["after"]["rms"]],
+        "cpu_port_s_per_iteration": cpu_s, "cpu_cores": os.cpu_count(),
+        "speedup_device_vs_cpu_port_per_iteration": cpu_s / (dev_s / n)}))
+
+
 def main():
     from dazimsurftomo_b200 import api, formats as fm, invert, synthetic
     from oracle import pyoracle as po
     mode = sys.argv[1] if len(sys.argv) > 1 else "iso"
     maxiter = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     cpu_iters = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    h = api.Handle(0)
+    if mode in ("test2", "test3"):
+        return real_example(mode, h, cpu_iters)
     iso = mode == "iso"
     w = synthetic.t1_shaped()
-    h = api.Handle(0)
     # observations: T_iso (+ T_aa) of the true model through the forward path
     fwd = api.FwdObsTraveltimeCPS(w.vs, w.gc if not iso else np.zeros_like(w.gc), w.gs if not iso else np.zeros_like(w.gs),
                                   w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv, handle=h)

@@ -8,6 +8,7 @@ outputs (example/test1_syn_foward), cut down so they stay small:
                                                           output/surfphase_forward_RV3th.dat
   test1/period_Azm_tomo.npz                               output/period_Azm_tomo.real as an array
   inv/test2_para.in, test2_MOD, test3_para.in, test3_MOD  verbatim inputs of the two inversion examples
+  inv/surfphase_forward_RV3th.dat.xz                      the data file of test2 and test3 (identical), xz -9
   (inv/test2_iter.npz, test3_iter.npz are written by scripts/pin_inversion.py)
 """
 import os
@@ -67,6 +68,14 @@ def main():
             dst = os.path.join(inv, "%s_%s" % (tag, f))
             shutil.copy(os.path.join(REF, "..", case, f), dst)
             os.chmod(dst, 0o644)
+    # the data file of both inversion examples (byte-identical in test2 and test3; = test1's shipped output), xz'd:
+    # with it the GPU box can run BASELINE configs 3 and 4 for real and compare with the shipped models
+    import filecmp
+    import lzma
+    d2 = os.path.join(REF, "..", "test2_syn_iso_inv", "surfphase_forward_RV3th.dat")
+    assert filecmp.cmp(d2, os.path.join(REF, "..", "test3_syn_joint_inv", "surfphase_forward_RV3th.dat"), shallow=False)
+    with open(d2, "rb") as f, lzma.open(os.path.join(inv, "surfphase_forward_RV3th.dat.xz"), "wb", preset=9) as g:
+        g.write(f.read())
     print("units kept:", len(keep), "rays:", sum(len(inp[i]) - 1 for i in keep))
 
 

@@ -102,3 +102,42 @@ def test_calsurfganisojoint_and_lsmr_symbols(gpu, test1):
     x2, info = gpu.LSMR(m, ncol, row_ref, col_ref, rw_ref, b, damp=0.5, atol=1e-5, btol=1e-4, conlim=200.0, itnlim=40, localSize=10)
     assert istop.value == info["istop"] and itn.value == info["itn"]
     assert np.array_equal(x, x2) and fl[2].value == info["normr"]
+
+
+def test_calddatsigma_and_tikhonov_symbols(gpu, oracle):
+    """CalDdatSigma, TikhonovRegularization and TikhRegul_joint the way Main_Jt.f90:460,513,515 calls them: rows behind
+    iw(1), nar advanced in place, LOGICAL iso_inv as a 4-byte integer."""
+    lib = gpu.load()
+    rng = np.random.default_rng(8)
+    dall = 3001
+    obst = rng.uniform(5, 90, dall).astype(np.float32); cbst = (rng.standard_normal(dall) * 0.5).astype(np.float32)
+    sig = np.zeros(dall, np.float32); mean = C.c_float(0)
+    lib.calddatsigma_(_ref(dall, C.c_int), _ptr(obst), _ptr(cbst), _ptr(sig), C.byref(mean))
+    s2, m2 = gpu.CalDdatSigma(obst, cbst)
+    assert np.array_equal(sig, s2) and mean.value == np.float32(m2)
+    osig, omean = oracle.cal_ddat_sigma(obst, cbst)
+    assert np.float32(omean) == np.float32(mean.value) and np.allclose(sig, osig, rtol=2.5e-7, atol=0)
+    nx, ny, nz = 9, 8, 5
+    maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+    nar0 = 57                                                  # entries of "G" already there
+    cap = nar0 + 21 * maxvp
+    for joint in (False, True):
+        iw = np.zeros(2 * cap + 1, np.int32); rw = np.zeros(cap, np.float32); col = np.zeros(cap, np.int32)
+        rw[:nar0] = 1.5; col[:nar0] = 3; iw[1:nar0 + 1] = 7
+        nar = C.c_int(nar0); count3 = C.c_int(0); narvs = C.c_int(0)
+        if joint:
+            lib.tikhregul_joint_(_ref(nx, C.c_int), _ref(ny, C.c_int), _ref(nz, C.c_int), _ref(maxvp, C.c_int),
+                                 _ref(dall, C.c_int), C.byref(nar), _ptr(rw), _ptr(iw), _ptr(col), C.byref(narvs),
+                                 C.byref(count3), _ref(35.0, C.c_float), _ref(240.0, C.c_float))
+        else:
+            lib.tikhonovregularization_(_ref(nx, C.c_int), _ref(ny, C.c_int), _ref(nz, C.c_int), _ref(maxvp, C.c_int),
+                                        _ref(dall, C.c_int), C.byref(nar), _ptr(rw), _ptr(iw), _ptr(col), C.byref(count3),
+                                        _ref(1, C.c_int), _ref(35.0, C.c_float), _ref(240.0, C.c_float))
+        o = oracle.tikhonov(nx, ny, nz, dall, True, 35.0, 240.0, joint=joint)
+        n = nar.value
+        assert n == nar0 + len(o["rw"]) and count3.value == o["count3"]
+        assert np.all(rw[:nar0] == 1.5) and np.all(col[:nar0] == 3) and np.all(iw[1:nar0 + 1] == 7) and iw[0] == 0
+        assert np.array_equal(rw[nar0:n], o["rw"]) and np.array_equal(col[nar0:n], o["col"])
+        assert np.array_equal(iw[1 + nar0:1 + n], o["row"])
+        if joint:
+            assert narvs.value == nar0 + o["narVs"]
