@@ -5,8 +5,10 @@
 //
 // Parity pinning: the restatement is checked against the golden files the
 // reference ships in example/test1_syn_foward/output/ (see tests/golden/ and
-// tests/test_oracle_golden.py).  What those files do NOT pin: the
-// isotropic finite-difference kernels sen_vs/vp/rho and the COO triplets.
+// tests/test_oracle_golden.py).  What those files do not pin -- the
+// isotropic finite-difference kernels sen_vs/vp/rho and the COO triplets -- is
+// pinned end to end by the inversion results the reference ships for test2 /
+// test3 (inversion.cpp header, scripts/pin_inversion.py, tests/test_inversion.py).
 #pragma once
 #include "fmm2d.hpp"
 
