@@ -396,6 +396,55 @@ def TikhRegul_joint(nx, ny, nz, dall, weightGcs, weightVs, handle: Optional[Hand
     return _tikh(1, nx, ny, nz, dall, False, weightGcs, weightVs, handle)
 
 
+def _iterate(call, shape, nrow, obst, vsf, iso_inv, weightVs, weightGcs, damp, minvel, maxvel, controls, want_rows):
+    """Host-side marshalling shared by Plan.iterate and iterate_device: `call` receives the common argument tail
+    (obst, prm, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa, stats)."""
+    nx, ny, nz = shape
+    maxvp = (nx - 2) * (ny - 2) * (nz - 1)
+    n = maxvp if iso_inv else 3 * maxvp
+    obst = np.ascontiguousarray(obst, np.float32)
+    if len(obst) != nrow:
+        raise ValueError("obst must have one entry per row of the system")
+    v = np.array(vsf, np.float32, order="F")
+    dv = np.zeros(n, np.float32)
+    g = (nx - 2, ny - 2, nz - 1)
+    gcf = None if iso_inv else np.zeros(g, np.float32, order="F")
+    gsf = None if iso_inv else np.zeros(g, np.float32, order="F")
+    dws = np.zeros(maxvp, np.float32) if iso_inv else None
+    rows = [np.zeros(nrow, np.float32) if want_rows else None for _ in range(4)]
+    prm = IterParams()
+    prm.iso_inv = int(bool(iso_inv)); prm.weightVs = weightVs; prm.weightGcs = weightGcs; prm.damp = damp
+    prm.minvel = minvel; prm.maxvel = maxvel
+    prm.use_ref_controls = 1 if controls is None else 0
+    if controls is not None:
+        prm.atol, prm.btol, prm.conlim = controls["atol"], controls["btol"], controls["conlim"]
+        prm.itnlim, prm.localSize = controls["itnlim"], controls["localSize"]
+    st = IterStats()
+    _chk(call(_p(obst), C.byref(prm), _p(v), _p(dv), _p(gcf), _p(gsf), _p(dws), _p(rows[0]), _p(rows[1]), _p(rows[2]),
+              _p(rows[3]), C.byref(st)))
+    out = dict(vsf=v, dv=dv, gcf=gcf, gsf=gsf, dws=dws, stats=st.as_dict())
+    if want_rows:
+        out.update(sigmaT=rows[0], resbst=rows[1], fwdTvs=rows[2], fwdTaa=rows[3])
+    return out
+
+
+def iterate_device(shape, system: dict, obst, vsf, iso_inv, weightVs, weightGcs, damp, minvel, maxvel,
+                   controls: Optional[dict] = None, want_rows=False, handle: Optional[Handle] = None):
+    """dazim_iterate_device: the iteration tail on a system held in HBM by the caller -- `system` is what
+    partition.assemble_system() makes of the all-gathered row blocks: torch CUDA tensors rowptr (int64, rows+1),
+    col / val / row (capacity >= nnz + regularisation entries), dsurf, and the ints nrow, nnz, cap.  The tensors'
+    producing stream is synchronised here; val / col / row are modified (rows weighted, regularisation appended)."""
+    import torch
+    h = handle or default_handle()
+    torch.cuda.synchronize(system["val"].device)
+    ptr = lambda name: C.c_void_p(system[name].data_ptr())
+    nx, ny, nz = shape
+    return _iterate(lambda *tail: load().dazim_iterate_device(
+        h._h, C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_longlong(system["nrow"]), C.c_longlong(system["nnz"]),
+        C.c_longlong(system["cap"]), ptr("rowptr"), ptr("col"), ptr("val"), ptr("row"), ptr("dsurf"), *tail),
+        shape, int(system["nrow"]), obst, vsf, iso_inv, weightVs, weightGcs, damp, minvel, maxvel, controls, want_rows)
+
+
 class Plan:
     """Device-resident plan (dazim_plan_*): inputs uploaded once, run() leaves results in HBM."""
 
@@ -463,33 +512,8 @@ class Plan:
                 want_rows=False):
         """The rest of one outer iteration of Main_Jt.f90 (:416-727) on the G of the last run, resident in HBM
         (dazim_plan_iterate).  Returns dict(vsf, dv, gcf, gsf, dws, stats[, sigmaT, resbst, fwdTvs, fwdTaa])."""
-        nx, ny, nz = self._pr.shape
-        maxvp = (nx - 2) * (ny - 2) * (nz - 1)
-        n = maxvp if iso_inv else 3 * maxvp
-        obst = np.ascontiguousarray(obst, np.float32)
-        if len(obst) != self.rows:
-            raise ValueError("obst must have one entry per row of the plan")
-        v = np.array(vsf, np.float32, order="F")
-        dv = np.zeros(n, np.float32)
-        g = (nx - 2, ny - 2, nz - 1)
-        gcf = None if iso_inv else np.zeros(g, np.float32, order="F")
-        gsf = None if iso_inv else np.zeros(g, np.float32, order="F")
-        dws = np.zeros(maxvp, np.float32) if iso_inv else None
-        rows = [np.zeros(self.rows, np.float32) if want_rows else None for _ in range(4)]
-        prm = IterParams()
-        prm.iso_inv = int(bool(iso_inv)); prm.weightVs = weightVs; prm.weightGcs = weightGcs; prm.damp = damp
-        prm.minvel = minvel; prm.maxvel = maxvel
-        prm.use_ref_controls = 1 if controls is None else 0
-        if controls is not None:
-            prm.atol, prm.btol, prm.conlim = controls["atol"], controls["btol"], controls["conlim"]
-            prm.itnlim, prm.localSize = controls["itnlim"], controls["localSize"]
-        st = IterStats()
-        _chk(load().dazim_plan_iterate(self._plan, _p(obst), C.byref(prm), _p(v), _p(dv), _p(gcf), _p(gsf), _p(dws),
-                                       _p(rows[0]), _p(rows[1]), _p(rows[2]), _p(rows[3]), C.byref(st)))
-        out = dict(vsf=v, dv=dv, gcf=gcf, gsf=gsf, dws=dws, stats=st.as_dict())
-        if want_rows:
-            out.update(sigmaT=rows[0], resbst=rows[1], fwdTvs=rows[2], fwdTaa=rows[3])
-        return out
+        return _iterate(lambda *tail: load().dazim_plan_iterate(self._plan, *tail), self._pr.shape, self.rows, obst, vsf,
+                        iso_inv, weightVs, weightGcs, damp, minvel, maxvel, controls, want_rows)
 
     def device_tensors(self):
         """Zero-copy torch views of the last run's outputs in HBM (for NCCL exchanges without a host hop).

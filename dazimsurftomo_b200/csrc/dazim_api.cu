@@ -889,24 +889,30 @@ static int tikh_append(cudaStream_t st, int joint, int iso_inv, int nx, int ny, 
   return DAZIM_OK;
 }
 
-extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_iter_params* prm, float* vsf, float* dv,
-                                  float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
-                                  float* fwdTaa, dazim_iter_stats* S) {
-  if (!P || !obst || !prm || !vsf || !dv || !S) return DAZIM_EBADARG;
-  if (P->mode != 1 && P->mode != 2) return DAZIM_EBADARG;
-  if ((P->mode == 1) != (prm->iso_inv != 0)) return DAZIM_EBADARG;
-  if (P->row0 != 0 || P->nrow < 1 || P->nnz < 1) return DAZIM_EBADARG;
-  dazim_handle* h = P->h;
+// The system the iteration tail works on: CSR rows of G in HBM (all rows, global row ids 1..nrow in rowid), with
+// room behind the nnz entries of val/col/rowid for the regularisation rows, and the reference travel times.
+struct IterSystem {
+  int nx, ny, nz;
+  long long nrow, nnz, cap;
+  const long long* rowptr;   // [nrow+1]
+  int* col; float* val; int* rowid;   // [cap]
+  const float* dsurf;        // [nrow]
+  float* vels;               // [nx*ny*nz] device workspace for the model update
+};
+
+static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst, const dazim_iter_params* prm, float* vsf,
+                        float* dv, float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
+                        float* fwdTaa, dazim_iter_stats* S) {
   CK(cudaSetDevice(h->dev));
   g_alloc_stream = h->st;
   cudaStream_t st = h->st;
   const int iso = prm->iso_inv ? 1 : 0;
-  const int nx = P->nx, ny = P->ny, nz = P->nz;
+  const int nx = Y.nx, ny = Y.ny, nz = Y.nz;
   const int maxvp = (nx - 2) * (ny - 2) * (nz - 1);
   const int nblk = iso ? 1 : 3;
   const int n = nblk * maxvp;
-  if (P->nrow > 0x7fffffffll - 3ll * maxvp) return DAZIM_EBADARG;
-  const int dall = (int)P->nrow;
+  if (Y.nrow > 0x7fffffffll - 3ll * maxvp) return DAZIM_EBADARG;
+  const int dall = (int)Y.nrow;
   std::memset(S, 0, sizeof(*S));
   struct Events {                               // destroyed on every return path
     cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -918,7 +924,7 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
       d_lm, d_lmw, d_dws;
   DBuf<double> d_partial, d_dwsacc;
   const long long reg_entries = (long long)nblk * dzi::tikh_block_entries(nx - 2, ny - 2, nz - 1);
-  if (P->nnz + reg_entries > P->val_cap) return DAZIM_ENNZ_OVERFLOW;   // plan_run reserves this room
+  if (Y.nnz + reg_entries > Y.cap) return DAZIM_ENNZ_OVERFLOW;   // the caller reserves this room (plan_run does)
   CK(d_obst.alloc(dall)); CK(d_cbst.alloc(dall)); CK(d_tdata.alloc(dall)); CK(d_dt.alloc(dall)); CK(d_sig.alloc(dall));
   CK(d_w.alloc(dall)); CK(d_stats.alloc(64)); CK(d_b.alloc((size_t)dall + (size_t)nblk * maxvp)); CK(d_dv.alloc(n));
   CK(d_gcf.alloc(maxvp)); CK(d_gsf.alloc(maxvp)); CK(d_tvs.alloc(dall)); CK(d_taa.alloc(dall)); CK(d_res.alloc(dall));
@@ -930,7 +936,7 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   CK(cudaMemcpyAsync(d_obst.p, obst, sizeof(float) * dall, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(e0, st));
   // ---- residual of the reference model, CalDdatSigma, weights (Main_Jt.f90:425-469) ----
-  CK(dzi::launch_resid(dall, d_obst.p, P->d_dsurf.p, d_cbst.p, d_tdata.p, d_dt.p, st));
+  CK(dzi::launch_resid(dall, d_obst.p, Y.dsurf, d_cbst.p, d_tdata.p, d_dt.p, st));
   {
     const float* arrs[2] = {d_cbst.p, d_dt.p};
     CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p, st));                       // [0..2] cbst, [3..5] deltaT
@@ -942,18 +948,18 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
     CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p + 6, st));                   // [6] sum w, [10] sum |cbst_w|
   }
   CK(cudaEventRecord(e2, st));
-  CK(dzi::launch_scale_rows(P->nrow, P->d_rowptr.p, d_w.p, P->d_val.p, st));
+  CK(dzi::launch_scale_rows(Y.nrow, Y.rowptr, d_w.p, Y.val, st));
   CK(cudaEventRecord(e3, st));
-  if (iso && dws) CK(dzi::launch_dws(P->nnz, P->d_col.p, P->d_val.p, maxvp, d_dwsacc.p, d_dws.p, st));
+  if (iso && dws) CK(dzi::launch_dws(Y.nnz, Y.col, Y.val, maxvp, d_dwsacc.p, d_dws.p, st));
   // ---- regularisation rows behind G (Main_Jt.f90:507-520) ----
   long long appended = 0, after_vs = -1;
   int count3 = 0;
   {
-    int rc = tikh_append(st, iso ? 0 : 1, iso, nx, ny, nz, maxvp, dall, P->nnz, prm->weightGcs, prm->weightVs, P->d_val.p,
-                         P->d_col.p, P->d_rowid.p, &appended, &count3, &after_vs);
+    int rc = tikh_append(st, iso ? 0 : 1, iso, nx, ny, nz, maxvp, dall, Y.nnz, prm->weightGcs, prm->weightVs, Y.val,
+                         Y.col, Y.rowid, &appended, &count3, &after_vs);
     if (rc) return rc;
   }
-  const long long nar1 = P->nnz, nar = P->nnz + appended;
+  const long long nar1 = Y.nnz, nar = Y.nnz + appended;
   const int m = dall + count3;
   CK(cudaMemcpyAsync(d_b.p, d_cbst.p, sizeof(float) * dall, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(d_b.p + dall, 0, sizeof(float) * (size_t)count3, st));
@@ -965,16 +971,16 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
     else { atol = 1e-5f; btol = 1e-4f; conlim = 200.0f; itnlim = 500; localSize = 10; }
   }
   {
-    int rc = dzl::lsmr_solve(st, m, n, nar, P->d_rowid.p, P->d_col.p, P->d_val.p, d_b.p, prm->damp, atol, btol, conlim,
+    int rc = dzl::lsmr_solve(st, m, n, nar, Y.rowid, Y.col, Y.val, d_b.p, prm->damp, atol, btol, conlim,
                              itnlim, localSize, d_dv.p, &S->lsmr, true);
     if (rc) return rc;
   }
   // ---- model update (Main_Jt.f90:582-620) ----
-  CK(cudaMemcpyAsync(P->d_vels.p, vsf, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyHostToDevice, st));
-  CK(dzi::launch_model_update(nx, ny, nz, iso, d_dv.p, P->d_vels.p, prm->minvel, prm->maxvel, d_gcf.p, d_gsf.p, st));
+  CK(cudaMemcpyAsync(Y.vels, vsf, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyHostToDevice, st));
+  CK(dzi::launch_model_update(nx, ny, nz, iso, d_dv.p, Y.vels, prm->minvel, prm->maxvel, d_gcf.p, d_gsf.p, st));
   // ---- ||Lm|| and the residual of the solution from the sparse rows (CalSigamNorm.f90) ----
   const long long nre = nar - nar1, nre_vs = iso ? nre : after_vs - nar1;
-  CK(dzi::launch_lm_terms(nre, nre_vs, P->d_val.p + nar1, P->d_col.p + nar1, d_dv.p, prm->weightVs, prm->weightGcs, d_lm.p,
+  CK(dzi::launch_lm_terms(nre, nre_vs, Y.val + nar1, Y.col + nar1, d_dv.p, prm->weightVs, prm->weightGcs, d_lm.p,
                           d_lmw.p, st));
   if (iso) {
     CK(dzi::launch_norm2(d_lm.p, nre, d_partial.p, d_stats.p + 36, st));
@@ -987,7 +993,7 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
     CK(dzi::launch_norm2(d_lm.p, nre, d_partial.p, d_stats.p + 36, st));
     CK(dzi::launch_norm2(d_lmw.p, nre, d_partial.p, d_stats.p + 37, st));
   }
-  CK(dzi::launch_resid_rows(P->nrow, P->d_rowptr.p, P->d_col.p, P->d_val.p, d_dv.p, d_w.p, maxvp, nblk, d_tdata.p, d_tvs.p,
+  CK(dzi::launch_resid_rows(Y.nrow, Y.rowptr, Y.col, Y.val, d_dv.p, d_w.p, maxvp, nblk, d_tdata.p, d_tvs.p,
                             d_taa.p, d_res.p, d_resw.p, st));
   {
     const float* arrs[3] = {d_res.p, d_taa.p, d_tvs.p};
@@ -998,7 +1004,7 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   CK(cudaEventRecord(e1, st));
   // ---- results to the host ----
   CK(cudaMemcpyAsync(hs, d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(vsf, P->d_vels.p, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(vsf, Y.vels, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(dv, d_dv.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
   if (!iso && gcf) CK(cudaMemcpyAsync(gcf, d_gcf.p, sizeof(float) * maxvp, cudaMemcpyDeviceToHost, st));
   if (!iso && gsf) CK(cudaMemcpyAsync(gsf, d_gsf.p, sizeof(float) * maxvp, cudaMemcpyDeviceToHost, st));
@@ -1030,6 +1036,41 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   cudaEventElapsedTime(&S->step_ms, e0, e1);
   cudaEventElapsedTime(&S->scale_ms, e2, e3);
   return DAZIM_OK;
+}
+
+extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_iter_params* prm, float* vsf, float* dv,
+                                  float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
+                                  float* fwdTaa, dazim_iter_stats* S) {
+  if (!P || !obst || !prm || !vsf || !dv || !S) return DAZIM_EBADARG;
+  if (P->mode != 1 && P->mode != 2) return DAZIM_EBADARG;
+  if ((P->mode == 1) != (prm->iso_inv != 0)) return DAZIM_EBADARG;
+  if (P->row0 != 0 || P->nrow < 1 || P->nnz < 1) return DAZIM_EBADARG;
+  IterSystem Y;
+  Y.nx = P->nx; Y.ny = P->ny; Y.nz = P->nz; Y.nrow = P->nrow; Y.nnz = P->nnz; Y.cap = P->val_cap;
+  Y.rowptr = P->d_rowptr.p; Y.col = P->d_col.p; Y.val = P->d_val.p; Y.rowid = P->d_rowid.p; Y.dsurf = P->d_dsurf.p;
+  Y.vels = P->d_vels.p;
+  return iterate_core(P->h, Y, obst, prm, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa, S);
+}
+
+// The same tail on a system the caller holds in HBM -- the row blocks of several ranks after the NCCL all-gather
+// ("exchange before the solver").  All d_* are DEVICE pointers on the handle's device, complete before the
+// call (synchronise the producing stream); d_val / d_col / d_rowid have cap >= nnz + regularisation entries
+// (dazim_tikh_block_entries x 1 or 3); they are modified (weighted, rows appended).
+extern "C" int dazim_iterate_device(dazim_handle* h, int nx, int ny, int nz, long long nrow, long long nnz, long long cap,
+                                    const long long* d_rowptr, int* d_col, float* d_val, int* d_rowid,
+                                    const float* d_dsurf, const float* obst, const dazim_iter_params* prm, float* vsf,
+                                    float* dv, float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst,
+                                    float* fwdTvs, float* fwdTaa, dazim_iter_stats* S) {
+  if (!h || !d_rowptr || !d_col || !d_val || !d_rowid || !d_dsurf || !obst || !prm || !vsf || !dv || !S) return DAZIM_EBADARG;
+  if (nx < 5 || ny < 5 || nz < 2 || nrow < 1 || nnz < 1 || cap < nnz) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  g_alloc_stream = h->st;
+  DBuf<float> d_vels;
+  CK(d_vels.alloc((size_t)nx * ny * nz));
+  IterSystem Y;
+  Y.nx = nx; Y.ny = ny; Y.nz = nz; Y.nrow = nrow; Y.nnz = nnz; Y.cap = cap;
+  Y.rowptr = d_rowptr; Y.col = d_col; Y.val = d_val; Y.rowid = d_rowid; Y.dsurf = d_dsurf; Y.vels = d_vels.p;
+  return iterate_core(h, Y, obst, prm, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa, S);
 }
 
 extern "C" int dazim_cal_ddat_sigma(dazim_handle* h, int dall, const float* obst, const float* cbst, float* sigmaT,

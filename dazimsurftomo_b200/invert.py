@@ -1,6 +1,7 @@
 """Thin inversion driver with the reference's command line and file formats:
 
     python -m dazimsurftomo_b200.invert para.in [outdir]       (reference: DAzimSurfTomo para.in)
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 -m dazimsurftomo_b200.invert para.in
 
 Reads para.in (inversion layout, Main_Jt.f90:158-211), the '#'-block data file (:274-315) and MOD (:345-353) from
 the directory of para.in and runs the outer loop of Main_Jt.f90 (:364-750) with every numerical stage on the GPU:
@@ -8,6 +9,8 @@ the directory of para.in and runs the outer loop of Main_Jt.f90 (:364-750) with 
     depthkernel / depthkernelTI  ->  plan.run (dice, eikonal, rays, G rows; CalSurfG / CalSurfGAnisoJoint)
     ->  plan.iterate (residual, CalDdatSigma, weights, Tikhonov rows, LSMR, model update, norms)
 
+With N ranks the depth kernels are cut into strips of grid rows, the G build into period-aligned (period, source)
+ranges, the row blocks are all-gathered over NCCL from HBM to HBM and every rank solves the gathered system.
 G stays in HBM for the whole iteration; the host sees the model (nx*ny*nz floats), the solution vector and the
 per-row travel-time columns.  Files written (same names and formats as the reference):
 
@@ -24,7 +27,7 @@ import time
 
 import numpy as np
 
-from . import api, formats as fm
+from . import api, formats as fm, partition
 
 
 def loop_order_obst(sv: fm.Survey) -> np.ndarray:
@@ -38,12 +41,35 @@ def loop_order_obst(sv: fm.Survey) -> np.ndarray:
     return (sv.dist / sv.obsvel).astype(np.float32)
 
 
-def tables_for(iso_inv: bool, vsf, depz, tRc, minthk, handle):
-    """The depth-kernel tables one G build needs (CalSurfG.f90:1004, CalSurfGAniso_Joint.f90:321-333)."""
+def _ranks():
+    """(rank, world, torch device or None).  Under torchrun (WORLD_SIZE > 1) one process per GPU over NCCL: the depth
+    kernels are cut into strips of grid rows, the G build into contiguous (period, source) ranges aligned to periods
+    ("period-sharded", BASELINE config 4), and the row blocks are all-gathered before the solve -- the one place the
+    inversion needs the full system."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world, torch.device("cuda", local)
+
+
+def tables_for(iso_inv: bool, vsf, depz, tRc, minthk, handle, rank=0, world=1, device=None):
+    """The depth-kernel tables one G build needs (CalSurfG.f90:1004, CalSurfGAniso_Joint.f90:321-333); with several
+    ranks each computes a strip of grid rows and one all-gather hands every rank the full tables."""
+    nx, ny, nz = vsf.shape
+    strips = partition.node_strips(ny, world)
+    part = vsf if world == 1 else partition.strip_model(vsf, strips[rank], strips[rank + 1])
     t = {}
     if not iso_inv:
-        _, t["Lsen_Gsc"] = api.depthkernelTI(vsf, depz, tRc, minthk, handle=handle)
-    t["pvRc"], t["sen_vs"], t["sen_vp"], t["sen_rho"] = api.depthkernel(vsf, depz, tRc, minthk, handle=handle)
+        _, t["Lsen_Gsc"] = api.depthkernelTI(part, depz, tRc, minthk, handle=handle)
+    t["pvRc"], t["sen_vs"], t["sen_vp"], t["sen_rho"] = api.depthkernel(part, depz, tRc, minthk, handle=handle)
+    if world > 1:
+        t = partition.gather_tables(t, nx, ny, strips, rank, device=device)
     return t
 
 
@@ -57,6 +83,10 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
     if sv is None:
         sv = fm.read_surfdata(os.path.join(base, p.datafile), p.kmaxRc)
     obst = loop_order_obst(sv)
+    rank, world, device = _ranks()
+    write_files = write_files and rank == 0
+    if rank != 0 and log_stream is None:
+        log_stream = open(os.devnull, "w")
     h = handle or api.default_handle()
     nx, ny, nz = p.nx, p.ny, p.nz
     maxvp = (nx - 2) * (ny - 2) * (nz - 1)
@@ -98,24 +128,46 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
             say("%12d%s" % (it, "th iteration, invert for isotropic Vs para." if iso_inv else
                             "th iteration, invert for dVs, Gc, Gs "))
             say(" -----------------------------------------------------------")
-            tables = tables_for(iso_inv, vsf, depz, p.tRc, p.sublayers, h)
+            tables = tables_for(iso_inv, vsf, depz, p.tRc, p.sublayers, h, rank, world, device)
             gpu_ms["kernels"] += h.times["kernels_ms"]
             if plan is None:
+                sb, se = 0, -1
+                if world > 1:
+                    bounds = partition.split_units(sv, world, align_periods=True)
+                    sb, se = bounds[rank], bounds[rank + 1]
                 plan = api.Plan(1 if iso_inv else 2, vsf, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv,
-                                tables, handle=h)
+                                tables, src_begin=sb, src_end=se, handle=h)
             else:
                 plan.update_model(vsf, tables)
             tm = plan.run()
             gpu_ms["gbuild"] += tm["total_ms"]
+            system = None
+            nnz_all = plan.nnz
+            if world > 1:
+                # the exchange step: all-gather-v of the CSR row blocks and dsurf over NCCL, straight from HBM
+                import torch
+                t = plan.device_tensors()
+                t0 = time.perf_counter()
+                full = partition.gather_rows(dict(dsurf=t["dsurf"], nnz_row=t["rowptr"][1:] - t["rowptr"][:-1], col=t["col"],
+                                                  val=t["val"]), plan.row0)
+                system = partition.assemble_system(full, nx, ny, nz, joint=not iso_inv)
+                torch.cuda.synchronize()
+                gpu_ms["gather"] = gpu_ms.get("gather", 0.0) + (time.perf_counter() - t0) * 1e3
+                nnz_all = system["nnz"]
             maxnar = int(np.float32(p.spfra) * sv.dall * nx * ny * nz * 3)
-            if plan.nnz > maxnar:                      # Main_Jt.f90:523
+            if nnz_all > maxnar:                       # Main_Jt.f90:523
                 raise api.DazimError(3, "increase sparsity fraction(spfra)")
             tRcV = fm.interior_phase_velocity(tables["pvRc"], nx, ny)
             if it == 1:
                 tRcV_first = tRcV
             last = it == niter
-            r = plan.iterate(obst, vsf, iso_inv, p.weightVs, p.weightGcs, p.damp, p.minvel, p.maxvel,
-                             want_rows=(it == 1 or last))
+            if world == 1:
+                r = plan.iterate(obst, vsf, iso_inv, p.weightVs, p.weightGcs, p.damp, p.minvel, p.maxvel,
+                                 want_rows=(it == 1 or last))
+            else:
+                # every rank solves the gathered system (same data, same kernels: identical models, no broadcast needed)
+                r = api.iterate_device((nx, ny, nz), system, obst, vsf, iso_inv, p.weightVs, p.weightGcs, p.damp, p.minvel,
+                                       p.maxvel, want_rows=(it == 1 or last), handle=h)
             s = r["stats"]
             gpu_ms["iterate"] += s["step_ms"]; gpu_ms["lsmr"] += s["lsmr"]["solve_ms"] + s["lsmr"]["setup_ms"]
             vsf = r["vsf"]
@@ -174,7 +226,7 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
                     for j in range(ny - 2):
                         iterf.write("".join("%10.3f" % dws[i, j, k] for i in range(nx - 2)) + "\n")
             if r.get("resbst") is not None:
-                dsyn = plan.fetch(csr=False)["dsurf"]
+                dsyn = plan.fetch(csr=False)["dsurf"] if world == 1 else system["dsurf"].cpu().numpy()
                 rows_out = dict(dsyn=dsyn, Tdata=(obst - dsyn).astype(np.float32), fwdTvs=r["fwdTvs"], fwdTaa=r["fwdTaa"],
                                 resbst=r["resbst"], sigmaT=r["sigmaT"])
                 if write_files:                        # Main_Jt.f90:701-717 (id stays '00': its write is commented out)
@@ -213,7 +265,8 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
     for f in (logf, iterf, lsmrf):
         if f:
             f.close()
-    return dict(para=p, survey=sv, vsf=vsf, gcf=gcf, gsf=gsf, history=history, rows=rows_out, gpu_ms=gpu_ms, depz=depz)
+    return dict(para=p, survey=sv, vsf=vsf, gcf=gcf, gsf=gsf, history=history, rows=rows_out, gpu_ms=gpu_ms, depz=depz,
+                rank=rank, world=world)
 
 
 def main(argv=None):

@@ -127,6 +127,35 @@ def gather_rows(block: Dict[str, "object"], row0: int, group=None) -> Dict[str, 
     return dict(dsurf=dsurf, rw=val, col=col, row=rows, nar=int(val.numel()), nnz_row=nnz_row)
 
 
+def tikh_block_entries(nx: int, ny: int, nz: int) -> int:
+    """Entries of one Tikhonov block (TikhRegul.f90:22-56): one per cell + six more per interior cell."""
+    nvx, nvz, nl = nx - 2, ny - 2, nz - 1
+    return nvx * nvz * nl + 6 * max(nvx - 2, 0) * max(nvz - 2, 0) * max(nl - 2, 0)
+
+
+def assemble_system(full: Dict[str, "object"], nx: int, ny: int, nz: int, joint: bool) -> Dict[str, "object"]:
+    """What the solver stage needs from the all-gathered row blocks (gather_rows output): CSR row pointers and the
+    val / col / row arrays re-housed with room for the regularisation rows that dazim_iterate_device appends
+    (1 block in iso mode, 3 in joint mode).  Pure torch: runs on CUDA tensors on the box, on CPU tensors in the tests."""
+    import torch
+    nnz = int(full["rw"].numel())
+    nrow = int(full["dsurf"].numel())
+    cap = nnz + (3 if joint else 1) * tikh_block_entries(nx, ny, nz)
+    dev = full["rw"].device
+    rowptr = torch.zeros(nrow + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(full["nnz_row"].to(torch.int64), 0, out=rowptr[1:])
+    if int(rowptr[-1]) != nnz:
+        raise RuntimeError("row counts and triplets disagree")
+
+    def housed(t):
+        out = torch.empty(cap, dtype=t.dtype, device=dev)
+        out[:nnz].copy_(t)
+        return out
+
+    return dict(nrow=nrow, nnz=nnz, cap=cap, rowptr=rowptr, col=housed(full["col"]), val=housed(full["rw"]),
+                row=housed(full["row"]), dsurf=full["dsurf"].contiguous())
+
+
 def misfit_sums(obst, dsurf, group=None):
     """mean / std / rms inputs of Main_Jt.f90:432-434 as three float64 partial sums reduced over ranks:
     returns (n, sum(r), sum(r^2)) of r = obst - dsurf over all ranks."""

@@ -225,6 +225,15 @@ int dazim_plan_iterate(dazim_plan* plan, const float* obst, const dazim_iter_par
                        float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
                        float* fwdTaa, dazim_iter_stats* stats);
 
+/* The same on a system the caller holds in HBM: the CSR row blocks of several ranks after the NCCL all-gather
+ * (all rows; d_rowid = 1-based global row id of every entry).  d_* are DEVICE pointers on the handle's device and
+ * must be complete before the call; d_val / d_col / d_rowid need cap >= nnz + (1 or 3) x dazim_tikh_block_entries and
+ * are modified (rows weighted, regularisation rows appended).  Host arrays as in dazim_plan_iterate. */
+int dazim_iterate_device(dazim_handle* h, int nx, int ny, int nz, long long nrow, long long nnz, long long cap,
+                         const long long* d_rowptr, int* d_col, float* d_val, int* d_rowid, const float* d_dsurf,
+                         const float* obst, const dazim_iter_params* prm, float* vsf, float* dv, float* gcf, float* gsf,
+                         float* dws, float* sigmaT, float* resbst, float* fwdTvs, float* fwdTaa, dazim_iter_stats* stats);
+
 /* The two small subroutines on their own (host arrays), for callers that keep the stock Fortran loop:
  * CalDdatSigma (CalSigamNorm.f90:2) and TikhonovRegularization / TikhRegul_joint (TikhRegul.f90:2 / :108).
  * dazim_tikhonov appends to rw / iw_row (= iw+1) / col behind *nar entries and advances *nar; joint != 0 selects

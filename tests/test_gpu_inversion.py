@@ -237,3 +237,43 @@ def test_test3_inversion_reproduces_the_reference_shipped_model(gpu, tmp_path):
     assert np.abs(shipped[:, 1]).max() > 10                                    # amplitudes reach 12 %
     assert np.abs(tab[:, 6] - shipped[:, 1]).max() <= 0.03 and np.abs(tab[:, 7] - shipped[:, 2]).max() <= 0.03
     assert (tmp_path / "period_Azm_tomo.inv").stat().st_size > 0
+
+
+@pytest.mark.parametrize("iso", [True, False])
+def test_iterate_device_equals_plan_iterate(gpu, oracle, test1, iso):
+    """dazim_iterate_device (the N>1 path: row blocks all-gathered into caller-held HBM arrays, re-housed by
+    partition.assemble_system) on a copy of a plan's own G must give exactly what dazim_plan_iterate gives."""
+    import torch
+    from dazimsurftomo_b200 import partition
+    p, depz, vs, sv, obst = _subset_problem(test1)
+    nx, ny, nz = p.nx, p.ny, p.nz
+    tb = dict(zip(("pvRc", "sen_vs", "sen_vp", "sen_rho"), gpu.depthkernel(vs, depz, p.tRc, p.sublayers)))
+    if not iso:
+        _, tb["Lsen_Gsc"] = gpu.depthkernelTI(vs, depz, p.tRc, p.sublayers)
+    plan = gpu.Plan(1 if iso else 2, vs, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, tables=tb)
+    plan.run()
+    t = plan.device_tensors()
+    nnz_row = t["rowptr"][1:] - t["rowptr"][:-1]
+    rows = torch.repeat_interleave(torch.arange(1, plan.rows + 1, device=nnz_row.device, dtype=torch.int32), nnz_row)
+    full = dict(dsurf=t["dsurf"].clone(), rw=t["val"].clone(), col=t["col"].clone(), row=rows, nnz_row=nnz_row,
+                nar=int(t["val"].numel()))
+    system = partition.assemble_system(full, nx, ny, nz, joint=not iso)
+    assert system["nnz"] == plan.nnz and system["nrow"] == plan.rows
+    a = gpu.iterate_device((nx, ny, nz), system, obst, vs, iso, 8.0, 3.0, 0.0, p.minvel, p.maxvel, want_rows=True)
+    b = plan.iterate(obst, vs, iso, 8.0, 3.0, 0.0, p.minvel, p.maxvel, want_rows=True)
+    plan.close()
+    for k in ("vsf", "dv", "sigmaT", "resbst", "fwdTvs", "fwdTaa"):
+        assert np.array_equal(a[k], b[k]), k
+    if iso:
+        assert np.allclose(a["dws"], b["dws"], rtol=1e-6)       # double atomics: order-independent to the last float bit or so
+    else:
+        assert np.array_equal(a["gcf"], b["gcf"]) and np.array_equal(a["gsf"], b["gsf"])
+    sa, sb = a["stats"], b["stats"]
+    assert sa["lsmr"]["itn"] == sb["lsmr"]["itn"] and sa["lsmr"]["istop"] == sb["lsmr"]["istop"]
+    assert (sa["nar1"], sa["nar"], sa["count3"]) == (sb["nar1"], sb["nar"], sb["count3"])
+    assert sa["before"] == sb["before"] and sa["after"] == sb["after"] and sa["norms"] == sb["norms"]
+    # the weighted rows and the appended regularisation rows sit in the caller's arrays afterwards
+    n1, n2 = sa["nar1"], sa["nar"]
+    tk = oracle.tikhonov(nx, ny, nz, sv.dall, iso, 3.0, 8.0, joint=not iso)
+    assert np.array_equal(system["val"][n1:n2].cpu().numpy(), tk["rw"]) and np.array_equal(system["col"][n1:n2].cpu().numpy(), tk["col"])
+    assert np.array_equal(system["row"][n1:n2].cpu().numpy(), tk["row"])

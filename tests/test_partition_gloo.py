@@ -54,9 +54,14 @@ def _worker(rank, world, port, align, q):
     full = pt.gather_rows(blk, row0)
     obst = torch.from_numpy(sub.dist / np.maximum(sub.obsvel, 1e-3))
     ms = pt.misfit_sums(obst, blk["dsurf"])
+    # what the solver stage (dazim_iterate_device) is handed on every rank
+    sysd = pt.assemble_system(full, vs.shape[0], vs.shape[1], vs.shape[2], joint=True)
     if rank == 0:
         q.put(dict(bounds=b, dsurf=full["dsurf"].numpy(), rw=full["rw"].numpy(), col=full["col"].numpy(),
-                   row=full["row"].numpy(), nar=full["nar"], misfit=ms.numpy()))
+                   row=full["row"].numpy(), nar=full["nar"], misfit=ms.numpy(),
+                   sys=dict(nrow=sysd["nrow"], nnz=sysd["nnz"], cap=sysd["cap"], rowptr=sysd["rowptr"].numpy(),
+                            col=sysd["col"].numpy(), val=sysd["val"].numpy(), row=sysd["row"].numpy(),
+                            dsurf=sysd["dsurf"].numpy())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -89,6 +94,15 @@ def test_partition_and_gather_match_single_rank(oracle, world, align):
     assert np.array_equal(got["row"], ref["row"])
     assert np.array_equal(got["col"], ref["col"])
     assert np.array_equal(got["rw"], ref["rw"])
+    # the assembled solver input: CSR pointers of the global rows, triplets re-housed with room for 3 Tikhonov blocks
+    sy = got["sys"]
+    n = ref["nar"]
+    assert (sy["nrow"], sy["nnz"]) == (sv.dall, n)
+    assert sy["cap"] == n + 3 * len(oracle.tikhonov(vs.shape[0], vs.shape[1], vs.shape[2], 1, True, 1.0, 1.0)["rw"])
+    assert all(len(sy[k]) == sy["cap"] for k in ("col", "val", "row"))
+    assert np.array_equal(sy["rowptr"], np.concatenate([[0], np.cumsum(np.bincount(ref["row"] - 1, minlength=sv.dall))]))
+    assert np.array_equal(sy["col"][:n], ref["col"]) and np.array_equal(sy["val"][:n], ref["rw"])
+    assert np.array_equal(sy["row"][:n], ref["row"]) and np.array_equal(sy["dsurf"], ref["dsurf"])
     obst = sv.dist / np.maximum(sv.obsvel, 1e-3)
     r = obst.astype(np.float64) - ref["dsurf"].astype(np.float64)
     assert got["misfit"][0] == len(r)
