@@ -260,8 +260,9 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
                     f.write("".join("%10.5f" % x for x in row) + "\n")
     say("  -----------------------------------------------------------")
     say("   Program finishes successfully")
-    say("   All time cost= %13.1fs   (GPU: depth kernels %.0f ms, G build %.0f ms, iteration tail %.0f ms of which LSMR %.0f ms)" %
-        (time.time() - t_start, gpu_ms["kernels"], gpu_ms["gbuild"], gpu_ms["iterate"], gpu_ms["lsmr"]))
+    say("   All time cost= %13.1fs   (GPU: depth kernels %.0f ms, G build %.0f ms, iteration tail %.0f ms of which LSMR %.0f ms%s)" %
+        (time.time() - t_start, gpu_ms["kernels"], gpu_ms["gbuild"], gpu_ms["iterate"], gpu_ms["lsmr"],
+         "" if world == 1 else "; %d ranks, all-gather of the row blocks %.0f ms" % (world, gpu_ms.get("gather", 0.0))))
     for f in (logf, iterf, lsmrf):
         if f:
             f.close()
