@@ -332,30 +332,33 @@ def read_surfphase_velocities(path: str) -> np.ndarray:
 
 
 def azim_map(nx, ny, nz, goxd, gozd, dvxd, dvzd, tRc, gcf, gsf, lsen_gsc, tRcV):
-    """FwdAzimuthalAniMap.f90:41-79 -> array (kmax*(ny-2)*(nx-2), 9) as printed by '(10f10.5)'."""
+    """FwdAzimuthalAniMap.f90:41-79 -> array (kmax*(ny-2)*(nx-2), 9) as printed by '(10f10.5)'.
+    Vectorised over (period, jj, ii); the float32 accumulation over layers keeps the reference's order."""
     kmax = len(tRc)
-    nvx = nx - 2
-    rows = []
-    L = np.asarray(lsen_gsc, F32).reshape((nx * ny, kmax, nz - 1), order="F")
-    tv = np.asarray(tRcV).reshape(((nx - 2) * (ny - 2), kmax), order="F")
-    for tt in range(kmax):
-        for jj in range(1, ny - 1):
-            for ii in range(1, nx - 1):
-                ct = F32(0); st = F32(0)
-                node = jj * (nvx + 2) + ii  # 0-based of jj*(nvx+2)+ii+1
-                for kk in range(nz - 1):
-                    ct = F32(ct + L[node, tt, kk] * gcf[ii - 1, jj - 1, kk])
-                    st = F32(st + L[node, tt, kk] * gsf[ii - 1, jj - 1, kk])
-                amp = F32(np.sqrt(F32(ct * ct + st * st)))
-                isoc = F32(tv[(jj - 1) * (nx - 2) + ii - 1, tt])
-                rel = F32(amp / isoc) if isoc != 0 else F32(0)
-                ang = F32(np.arctan2(st, ct) / np.float64(F32(3.1415926535898)) * 180)
-                if ang < 0:
-                    ang = F32(ang + 360)
-                ang = F32(0.5) * ang
-                rows.append((F32(gozd) + F32(jj - 1) * F32(dvzd), F32(goxd) - F32(ii - 1) * F32(dvxd),
-                             tRc[tt], isoc, ang, rel, amp, ct, st))
-    return np.array(rows, dtype=np.float64)
+    nvx, nvz = nx - 2, ny - 2
+    L = np.asarray(lsen_gsc, F32).reshape((nx, ny, kmax, nz - 1), order="F")[1:-1, 1:-1]      # node = jj*nx + ii
+    tv = np.asarray(tRcV).reshape((nvx, nvz, kmax), order="F")
+    gc = np.asarray(gcf, F32); gs = np.asarray(gsf, F32)
+    ct = np.zeros((nvx, nvz, kmax), F32); st = np.zeros((nvx, nvz, kmax), F32)
+    for kk in range(nz - 1):
+        ct = (ct + L[:, :, :, kk] * gc[:, :, kk, None]).astype(F32)
+        st = (st + L[:, :, :, kk] * gs[:, :, kk, None]).astype(F32)
+    amp = np.sqrt((ct * ct + st * st).astype(F32)).astype(F32)
+    isoc = tv.astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(isoc != 0, (amp / isoc).astype(F32), F32(0)).astype(F32)
+    ang = (np.arctan2(st, ct).astype(np.float64) / np.float64(F32(3.1415926535898)) * 180).astype(F32)
+    ang = np.where(ang < 0, (ang + F32(360)).astype(F32), ang).astype(F32)
+    ang = (F32(0.5) * ang).astype(F32)
+    lon = (F32(gozd) + np.arange(nvz, dtype=F32) * F32(dvzd)).astype(F32)          # gozd+(jj-1)*dvzd
+    lat = (F32(goxd) - np.arange(nvx, dtype=F32) * F32(dvxd)).astype(F32)
+    out = np.zeros((kmax, nvz, nvx, 9), np.float64)                                  # period outer, jj, ii fastest
+    out[..., 0] = lon[None, :, None]
+    out[..., 1] = lat[None, None, :]
+    out[..., 2] = np.asarray(tRc, np.float64)[:, None, None]
+    for c, a in ((3, isoc), (4, ang), (5, rel), (6, amp), (7, ct), (8, st)):
+        out[..., c] = np.transpose(a, (2, 1, 0))
+    return out.reshape(-1, 9)
 
 
 # ---- writers of the inversion driver (Main_Jt.f90:752-908) ----------------------------------------------------
@@ -444,3 +447,20 @@ def interior_phase_velocity(pvRc, nx, ny) -> np.ndarray:
     for jj in range(1, ny - 1):
         out[(jj - 1) * (nx - 2):(jj) * (nx - 2), :] = pv[jj * nx + 1:jj * nx + nx - 1, :]
     return out
+
+
+def stage_reference_example(fixture_dir: str, tag: str, outdir: str) -> str:
+    """Unpack the fixture copy of one of the reference's inversion examples (tests/golden/inv: test2 = test2_syn_iso_inv,
+    test3 = test3_syn_joint_inv, test4 = test4_Yunnan) into outdir as para.in / MOD / <data file>; returns para.in's path."""
+    import lzma
+    os.makedirs(outdir, exist_ok=True)
+    with open(os.path.join(outdir, "para.in"), "w") as f:
+        f.write(open(os.path.join(fixture_dir, "%s_para.in" % tag)).read())
+    datafile = read_para_inv(os.path.join(outdir, "para.in")).datafile
+    mod = os.path.join(fixture_dir, "%s_MOD" % tag)
+    with open(os.path.join(outdir, "MOD"), "wb") as f:
+        f.write(lzma.open(mod + ".xz", "rb").read() if os.path.exists(mod + ".xz") else open(mod, "rb").read())
+    data = "test4_data.dat.xz" if tag == "test4" else "surfphase_forward_RV3th.dat.xz"
+    with open(os.path.join(outdir, datafile), "wb") as f:
+        f.write(lzma.open(os.path.join(fixture_dir, data), "rb").read())
+    return os.path.join(outdir, "para.in")

@@ -229,7 +229,9 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
                 dsyn = plan.fetch(csr=False)["dsurf"] if world == 1 else system["dsurf"].cpu().numpy()
                 rows_out = dict(dsyn=dsyn, Tdata=(obst - dsyn).astype(np.float32), fwdTvs=r["fwdTvs"], fwdTaa=r["fwdTaa"],
                                 resbst=r["resbst"], sigmaT=r["sigmaT"])
-                if write_files:                        # Main_Jt.f90:701-717 (id stays '00': its write is commented out)
+                # Main_Jt.f90:701-717: written at iteration 1 and at the last one under the same name (id stays '00': its
+                # write is commented out), so only the last one survives -- write that one
+                if write_files and last:
                     with open(os.path.join(outdir, "Traveltime_statis_00th.dat"), "w") as f:
                         if p.iso_mod:
                             f.write("   Dist(km)   T_obs(s)  T_ref_iso   Res(in)   dT(dvs)   Res(out)\n")

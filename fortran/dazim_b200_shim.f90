@@ -10,6 +10,10 @@
 !!      FwdTraveltimeCPS.f90 / depthkernelTI.f90 (any Fortran 2003 compiler); it binds the plain C
 !!      entry points dazim_create / dazim_gbuild / dazim_depthkernel* by name.
 !!
+!!  (3) G resident in HBM for the whole outer iteration: subroutine DazimOuterIteration at the end of this file is the
+!!      body a maintainer puts inside Main_Jt.f90's `do iter=1,maxiter` (it binds dazim_plan_create / _update_model /
+!!      _run / _iterate); python -m dazimsurftomo_b200.invert is the tested twin of that loop.
+!!
 !! NOTE: no Fortran compiler exists in the build image or on the GPU box, so this file is shipped
 !! untested; the tested boundary is the C ABI underneath (tests/test_cabi.py, tests/test_gpu_parity.py).
 module dazim_b200
@@ -37,7 +41,59 @@ module dazim_b200
     integer(c_long_long) :: maxnar, nar
   end type
 
+  !> struct dazim_lsmr_info / dazim_iter_params / dazim_iter_stats (device-resident outer iteration, Main_Jt.f90:416-727)
+  type, bind(C) :: dazim_lsmr_info
+    integer(c_int) :: istop, itn
+    real(c_float) :: normA, condA, normr, normAr, normx, setup_ms, solve_ms
+  end type
+  type, bind(C) :: dazim_iter_params
+    integer(c_int) :: iso_inv
+    real(c_float) :: weightVs, weightGcs, damp, minvel, maxvel
+    integer(c_int) :: use_ref_controls
+    real(c_float) :: atol, btol, conlim
+    integer(c_int) :: itnlim, localSize
+  end type
+  type, bind(C) :: dazim_iter_stats
+    real(c_float) :: before(4), after(4), meandeltaT, mean_weight, meanabs_weighted, norms(6), res2Nm, resW2Nm
+    real(c_float) :: meanabs_Taa, meanabs_Tvs
+    integer(c_long_long) :: nar1, nar
+    integer(c_int) :: count3
+    type(dazim_lsmr_info) :: lsmr
+    real(c_float) :: step_ms, scale_ms
+  end type
+
   interface
+    !> plan API: G stays in HBM between the G build and the solve (include/dazim_b200.h)
+    integer(c_int) function dazim_plan_create(h, mode, p, tables, Gctrue, Gstrue, src_begin, src_end, plan) &
+        bind(C, name='dazim_plan_create')
+      import :: c_ptr, c_int, c_long_long, dazim_problem, dazim_tables
+      type(c_ptr), value :: h, Gctrue, Gstrue
+      integer(c_int), value :: mode
+      type(dazim_problem), intent(in) :: p
+      type(dazim_tables), intent(in) :: tables
+      integer(c_long_long), value :: src_begin, src_end
+      type(c_ptr), intent(out) :: plan
+    end function
+    integer(c_int) function dazim_plan_update_model(plan, vels, tables) bind(C, name='dazim_plan_update_model')
+      import :: c_ptr, c_int, dazim_tables
+      type(c_ptr), value :: plan, vels
+      type(dazim_tables), intent(in) :: tables
+    end function
+    integer(c_int) function dazim_plan_run(plan) bind(C, name='dazim_plan_run')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: plan
+    end function
+    integer(c_int) function dazim_plan_iterate(plan, obst, prm, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa, &
+                                               stats) bind(C, name='dazim_plan_iterate')
+      import :: c_ptr, c_int, dazim_iter_params, dazim_iter_stats
+      type(c_ptr), value :: plan, obst, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa
+      type(dazim_iter_params), intent(in) :: prm
+      type(dazim_iter_stats), intent(out) :: stats
+    end function
+    subroutine dazim_plan_destroy(plan) bind(C, name='dazim_plan_destroy')
+      import :: c_ptr
+      type(c_ptr), value :: plan
+    end subroutine
     integer(c_int) function dazim_create(h, device) bind(C, name='dazim_create')
       import :: c_ptr, c_int
       type(c_ptr), intent(out) :: h
@@ -244,4 +300,65 @@ subroutine depthkernelTI(nx, ny, nz, vel, pvRc, iwave, igr, kmaxRc, tRc, depz, m
   st = dazim_depthkernel_ti(dz_handle, nx, ny, nz, c_loc(vel), c_loc(pvRc), kmaxRc, c_loc(tRc), c_loc(depz), minthk, &
                             c_loc(Lsen_Gsc))
   if (st /= 0) call dz_stop(st, 'depthkernelTI')
+end subroutine
+
+
+!> Body of the outer iteration (Main_Jt.f90:384-727) with G resident in HBM: what a maintainer puts inside
+!! `do iter=1,maxiter` instead of CalSurfG / CalSurfGAnisoJoint + CalDdatSigma + the weighting loops + Tikhonov + LSMR +
+!! the model update + the CalSigamNorm diagnostics.  `plan` is kept across iterations (c_null_ptr before the first).
+subroutine DazimOuterIteration(plan, iter, iso_inv, nx, ny, nz, vsf, obst, dall, goxd, gozd, dvxd, dvzd, kmaxRc, tRc, &
+                               periods, depz, minthk, scxf, sczf, rcxf, rczf, nrc1, nsrc1, kmax, nsrc, nrc, &
+                               weightVs, weightGcs, damp, Minvel, Maxvel, dv, gcf, gsf, stats)
+  use dazim_b200
+  implicit none
+  type(c_ptr), intent(inout) :: plan
+  integer, intent(in) :: iter, nx, ny, nz, dall, kmaxRc, kmax, nsrc, nrc
+  logical, intent(in) :: iso_inv
+  real, target, intent(inout) :: vsf(nx, ny, nz)
+  real, target, intent(in) :: obst(dall), depz(nz), scxf(nsrc, kmax), sczf(nsrc, kmax), rcxf(nrc, nsrc, kmax), &
+                              rczf(nrc, nsrc, kmax)
+  real, intent(in) :: goxd, gozd, dvxd, dvzd, minthk, weightVs, weightGcs, damp, Minvel, Maxvel
+  real*8, target, intent(in) :: tRc(kmaxRc)
+  integer, target, intent(in) :: periods(nsrc, kmax), nrc1(nsrc, kmax), nsrc1(kmax)
+  real, target, intent(out) :: dv(*), gcf(nx-2, ny-2, nz-1), gsf(nx-2, ny-2, nz-1)
+  type(dazim_iter_stats), intent(out) :: stats
+  type(dazim_problem) :: p
+  type(dazim_tables) :: tb
+  type(dazim_iter_params) :: prm
+  real*8, allocatable, target, save :: pvRc(:,:), svs(:,:,:), svp(:,:,:), srho(:,:,:)
+  real, allocatable, target, save :: Lsen(:,:,:)
+  integer(c_int) :: st, mode
+  call dz_init()
+  if (.not. allocated(pvRc)) then
+    allocate(pvRc(nx*ny, kmaxRc), svs(nx*ny, kmaxRc, nz), svp(nx*ny, kmaxRc, nz), srho(nx*ny, kmaxRc, nz), &
+             Lsen(nx*ny, kmaxRc, nz-1))
+  end if
+  if (.not. iso_inv) then
+    st = dazim_depthkernel_ti(dz_handle, nx, ny, nz, c_loc(vsf), c_loc(pvRc), kmaxRc, c_loc(tRc), c_loc(depz), minthk, &
+                              c_loc(Lsen))
+    if (st /= 0) call dz_stop(st, 'depthkernelTI')
+  end if
+  st = dazim_depthkernel(dz_handle, nx, ny, nz, c_loc(vsf), c_loc(pvRc), c_loc(svs), c_loc(svp), c_loc(srho), kmaxRc, &
+                         c_loc(tRc), c_loc(depz), minthk)
+  if (st /= 0) call dz_stop(st, 'depthkernel')
+  tb%pvRc = c_loc(pvRc); tb%sen_vs = c_loc(svs); tb%sen_vp = c_loc(svp); tb%sen_rho = c_loc(srho); tb%Lsen_Gsc = c_loc(Lsen)
+  mode = 2
+  if (iso_inv) mode = 1
+  if (iter == 1 .or. .not. c_associated(plan)) then
+    call dz_problem(p, nx, ny, nz, vsf, goxd, gozd, dvxd, dvzd, kmaxRc, tRc, periods, depz, minthk, scxf, sczf, rcxf, &
+                    rczf, nrc1, nsrc1, kmax, nsrc, nrc)
+    st = dazim_plan_create(dz_handle, mode, p, tb, c_null_ptr, c_null_ptr, 0_c_long_long, -1_c_long_long, plan)
+  else
+    st = dazim_plan_update_model(plan, c_loc(vsf), tb)
+  end if
+  if (st /= 0) call dz_stop(st, 'plan')
+  st = dazim_plan_run(plan)                        ! CalSurfG / CalSurfGAnisoJoint: G stays on the GPU
+  if (st /= 0) call dz_stop(st, 'G build')
+  prm%iso_inv = 0
+  if (iso_inv) prm%iso_inv = 1
+  prm%weightVs = weightVs; prm%weightGcs = weightGcs; prm%damp = damp; prm%minvel = Minvel; prm%maxvel = Maxvel
+  prm%use_ref_controls = 1                         ! atol/btol/conlim/itnlim/localSize of Main_Jt.f90:542-554
+  st = dazim_plan_iterate(plan, c_loc(obst), prm, c_loc(vsf), c_loc(dv), c_loc(gcf), c_loc(gsf), c_null_ptr, c_null_ptr, &
+                          c_null_ptr, c_null_ptr, c_null_ptr, stats)
+  if (st /= 0) call dz_stop(st, 'outer iteration')
 end subroutine

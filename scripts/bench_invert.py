@@ -46,15 +46,11 @@ cccccccccc periods
 def real_example(tag, h, cpu_iters):
     """BASELINE configs 3 / 4 for real: the reference's example/test2_syn_iso_inv or test3_syn_joint_inv (fixture copies
     of para.in, MOD and the data file), all outer iterations, compared with the model the reference shipped."""
-    import lzma
     from dazimsurftomo_b200 import formats as fm, invert
     from oracle import pyoracle as po
     inv = os.path.join(ROOT, "tests", "golden", "inv")
     tmp = tempfile.mkdtemp(prefix="dazim_%s_" % tag)
-    for f in ("para.in", "MOD"):
-        open(os.path.join(tmp, f), "w").write(open(os.path.join(inv, "%s_%s" % (tag, f))).read())
-    with lzma.open(os.path.join(inv, "surfphase_forward_RV3th.dat.xz"), "rb") as f:
-        open(os.path.join(tmp, "surfphase_forward_RV3th.dat"), "wb").write(f.read())
+    fm.stage_reference_example(inv, tag, tmp)
     t0 = time.time()
     out = invert.run(os.path.join(tmp, "para.in"), handle=h, log_stream=open(os.devnull, "w"))
     wall = time.time() - t0
@@ -80,7 +76,7 @@ def real_example(tag, h, cpu_iters):
     dev_s = (g["kernels"] + g["gbuild"] + g["iterate"]) * 1e-3
     print(json.dumps({
         "stage": "DAzimSurfTomo para.in on the reference's example/%s (BASELINE config %d), file-based GPU driver" %
-                 ("test2_syn_iso_inv" if tag == "test2" else "test3_syn_joint_inv", 3 if tag == "test2" else 4),
+                 {"test2": ("test2_syn_iso_inv", 3), "test3": ("test3_syn_joint_inv", 4), "test4": ("test4_Yunnan, real data", 5)}[tag],
         "rays": int(sv.dall), "outer_iterations": n, "nnz_G": int(np.mean([s["nar1"] for s in hist])),
         "vs_reference_shipped_model": vs_ref,
         "device_s_total": dev_s, "wall_s_total_incl_file_io": wall,
@@ -100,7 +96,7 @@ def main():
     maxiter = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     cpu_iters = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     h = api.Handle(0)
-    if mode in ("test2", "test3"):
+    if mode in ("test2", "test3", "test4"):
         return real_example(mode, h, cpu_iters)
     iso = mode == "iso"
     w = synthetic.t1_shaped()

@@ -9,6 +9,7 @@ outputs (example/test1_syn_foward), cut down so they stay small:
   test1/period_Azm_tomo.npz                               output/period_Azm_tomo.real as an array
   inv/test2_para.in, test2_MOD, test3_para.in, test3_MOD  verbatim inputs of the two inversion examples
   inv/surfphase_forward_RV3th.dat.xz                      the data file of test2 and test3 (identical), xz -9
+  inv/test4_para.in, test4_MOD.xz, test4_data.dat.xz      example/test4_Yunnan inputs (real data), xz -9
   (inv/test2_iter.npz, test3_iter.npz are written by scripts/pin_inversion.py)
 """
 import os
@@ -76,6 +77,13 @@ def main():
     assert filecmp.cmp(d2, os.path.join(REF, "..", "test3_syn_joint_inv", "surfphase_forward_RV3th.dat"), shallow=False)
     with open(d2, "rb") as f, lzma.open(os.path.join(inv, "surfphase_forward_RV3th.dat.xz"), "wb", preset=9) as g:
         g.write(f.read())
+    # example/test4_Yunnan (real data; BASELINE config 5's real counterpart): control file verbatim, MOD and data xz'd
+    t4 = os.path.join(REF, "..", "test4_Yunnan")
+    shutil.copy(os.path.join(t4, "para.in"), os.path.join(inv, "test4_para.in"))
+    os.chmod(os.path.join(inv, "test4_para.in"), 0o644)
+    for src, dst in (("MOD", "test4_MOD.xz"), ("China_YN_Rayleigh_RS_5-40s.dat", "test4_data.dat.xz")):
+        with open(os.path.join(t4, src), "rb") as f, lzma.open(os.path.join(inv, dst), "wb", preset=9) as g:
+            g.write(f.read())
     print("units kept:", len(keep), "rays:", sum(len(inp[i]) - 1 for i in keep))
 
 

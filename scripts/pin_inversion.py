@@ -92,5 +92,29 @@ def main():
                                            for h in r["history"]], np.float32), **snaps)
 
 
+def main_test4(mi=None):
+    """example/test4_Yunnan (real data, 38x42x18, 86 refined layers, joint, 5 outer iterations) vs the shipped
+    plot_script/Gc_Gs_model.inv and period_Azm_tomo.inv."""
+    p, depz, r, snaps = run("test4_Yunnan", mi)
+    ref = np.loadtxt(os.path.join(REF, "test4_Yunnan/plot_script/Gc_Gs_model.inv"))
+    nvx, nvz = p.nx - 2, p.ny - 2
+    f = lambda a: a.ravel(order="F")
+    gc = f(r["gcf"]) * 100; gs = f(r["gsf"]) * 100
+    v = r["vsf"]
+    vsm = f((v[1:-1, 1:-1, :-1] + v[1:-1, 1:-1, 1:]) / 2)
+    print("test4: oracle vs shipped Gc_Gs_model.inv: max |dVs_mid| %.4f km/s (rms %.5f), max |dGc| %.4f %% (rms %.5f), "
+          "max |dGs| %.4f %% (rms %.5f); shipped max |Gc| %.3f %%, |Gs| %.3f %%" %
+          (np.abs(vsm - ref[:, 3]).max(), np.sqrt(((vsm - ref[:, 3]) ** 2).mean()), np.abs(gc - ref[:, 6]).max(),
+           np.sqrt(((gc - ref[:, 6]) ** 2).mean()), np.abs(gs - ref[:, 7]).max(), np.sqrt(((gs - ref[:, 7]) ** 2).mean()),
+           np.abs(ref[:, 6]).max(), np.abs(ref[:, 7]).max()))
+    np.savez_compressed(os.path.join(OUT, "test4_iter.npz"), final_vsf=r["vsf"], final_gcf=r["gcf"], final_gsf=r["gsf"],
+                        shipped=ref[:, [3, 6, 7]].astype(np.float32),
+                        hist=np.array([[h["before"]["rms"], h["after"]["rms"], h["lsmr"]["itn"], h["lsmr"]["istop"]]
+                                       for h in r["history"]], np.float32), **snaps)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "test4":
+        main_test4(int(sys.argv[2]) if len(sys.argv) > 2 else None)
+        sys.exit(0)
     main()

@@ -193,12 +193,9 @@ def test_inversion_driver_matches_oracle_loop(gpu, oracle, tmp_path, tag):
 
 
 def _real_case(tmp_path, tag):
-    """The reference's example/test2_syn_iso_inv or test3_syn_joint_inv, verbatim (para.in, MOD, data file)."""
-    import lzma
-    (tmp_path / "para.in").write_text(open(os.path.join(INV, "%s_para.in" % tag)).read())
-    (tmp_path / "MOD").write_text(open(os.path.join(INV, "%s_MOD" % tag)).read())
-    with lzma.open(os.path.join(INV, "surfphase_forward_RV3th.dat.xz"), "rb") as f:
-        (tmp_path / "surfphase_forward_RV3th.dat").write_bytes(f.read())
+    """The reference's example/test2_syn_iso_inv, test3_syn_joint_inv or test4_Yunnan, verbatim (para.in, MOD, data)."""
+    from dazimsurftomo_b200 import formats as fm
+    fm.stage_reference_example(INV, tag, str(tmp_path))
 
 
 def test_test2_inversion_reproduces_the_reference_shipped_model(gpu, tmp_path):
