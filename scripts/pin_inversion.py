@@ -34,7 +34,7 @@ def fixed(path, w, ncol):
     return np.array(rows)
 
 
-def run(case, maxiter=None):
+def run(case, maxiter=None, track=None):
     base = os.path.join(REF, case)
     p = fm.read_para_inv(os.path.join(base, "para.in"))
     depz, vs = fm.read_model(os.path.join(base, "MOD"), p.nx, p.ny, p.nz)
@@ -45,6 +45,13 @@ def run(case, maxiter=None):
     def on_iter(it, vsf, gcf, gsf, rec):
         if it <= 2:
             snaps["vsf%d" % it] = vsf.copy(); snaps["gcf%d" % it] = gcf.copy(); snaps["gsf%d" % it] = gsf.copy()
+        if track is not None:                      # distance to the shipped model after every outer iteration
+            f = lambda a: a.ravel(order="F")
+            vsm = f((vsf[1:-1, 1:-1, :-1] + vsf[1:-1, 1:-1, 1:]) / 2)
+            print("  [%s] after iteration %d: vs shipped  Vs_mid max %.4f rms %.5f | Gc max %.4f rms %.5f %% | Gs max %.4f rms %.5f %%"
+                  % (case, it, np.abs(vsm - track[:, 3]).max(), np.sqrt(((vsm - track[:, 3]) ** 2).mean()),
+                     np.abs(f(gcf) * 100 - track[:, 6]).max(), np.sqrt(((f(gcf) * 100 - track[:, 6]) ** 2).mean()),
+                     np.abs(f(gsf) * 100 - track[:, 7]).max(), np.sqrt(((f(gsf) * 100 - track[:, 7]) ** 2).mean())), flush=True)
 
     t0 = time.time()
     r = po.invert(vs, depz, p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, obst, p.iso_mod, p.weightVs,
@@ -95,8 +102,8 @@ def main():
 def main_test4(mi=None):
     """example/test4_Yunnan (real data, 38x42x18, 86 refined layers, joint, 5 outer iterations) vs the shipped
     plot_script/Gc_Gs_model.inv and period_Azm_tomo.inv."""
-    p, depz, r, snaps = run("test4_Yunnan", mi)
     ref = np.loadtxt(os.path.join(REF, "test4_Yunnan/plot_script/Gc_Gs_model.inv"))
+    p, depz, r, snaps = run("test4_Yunnan", mi, track=ref)
     nvx, nvz = p.nx - 2, p.ny - 2
     f = lambda a: a.ravel(order="F")
     gc = f(r["gcf"]) * 100; gs = f(r["gsf"]) * 100
