@@ -117,7 +117,7 @@ def main_test4(mi=None):
     np.savez_compressed(os.path.join(OUT, "test4_iter.npz"), final_vsf=r["vsf"], final_gcf=r["gcf"], final_gsf=r["gsf"],
                         shipped=ref[:, [3, 6, 7]].astype(np.float32),
                         hist=np.array([[h["before"]["rms"], h["after"]["rms"], h["lsmr"]["itn"], h["lsmr"]["istop"]]
-                                       for h in r["history"]], np.float32), **snaps)
+                                       for h in r["history"]], np.float32))
 
 
 if __name__ == "__main__":
