@@ -218,3 +218,48 @@ def test_test4_yunnan_shipped_model_is_not_a_pin():
     assert np.corrcoef(gc, sh[:, 1])[0, 1] > 0.98 and np.corrcoef(gs, sh[:, 2])[0, 1] > 0.97
     assert 0.05 < np.sqrt(((gc - sh[:, 1]) ** 2).mean()) < 0.2          # per cent: related, not identical
     assert np.all(z["hist"][:, 3] == 2) and np.all(z["hist"][:, 1] < z["hist"][:, 0])
+
+
+def test_reference_example_fixtures_stage_and_parse(tmp_path):
+    """The fixture copies of the reference's three inversion examples unpack to files its parsers accept, with the
+    sizes SURVEY 8 quotes (test2/test3: T1 shape, 4 320 sources, 261 360 rays; test4: 1 469 sources, 20 877 rays)."""
+    from dazimsurftomo_b200 import formats as fm, invert
+    for tag, shape, nsrc, dall, iso, niter in (("test2", (17, 17, 4), 4320, 261360, True, 20),
+                                               ("test3", (17, 17, 4), 4320, 261360, False, 5),
+                                               ("test4", (38, 42, 18), 1469, 20877, False, 5)):
+        d = tmp_path / tag
+        para = fm.stage_reference_example(INV, tag, str(d))
+        p = fm.read_para_inv(para)
+        assert (p.nx, p.ny, p.nz) == shape and p.iso_mod == iso and p.maxiter == niter and p.kmaxRc == 36
+        depz, vs = fm.read_model(str(d / "MOD"), p.nx, p.ny, p.nz)
+        assert vs.shape == shape and depz[0] == 0 and vs.min() > 2.5 and vs.max() < 5.0
+        if tag == "test3":
+            continue                                   # same data file as test2 (byte-identical in the reference)
+        sv = fm.read_surfdata(str(d / p.datafile), p.kmaxRc)
+        assert int(sv.nsrcsurf1.sum()) == nsrc and sv.dall == dall
+        obst = invert.loop_order_obst(sv)              # period-sorted: file order == row order (SURVEY Q7)
+        assert obst.shape == (dall,) and obst.min() > 0
+
+
+def test_unsorted_data_file_is_refused(tmp_path):
+    """Rows are numbered in (period, source, receiver) loop order while the reference keeps obst in file order
+    (Main_Jt.f90:301-308 vs CalSurfGAniso_Joint.f90:693): a file whose periods are interleaved would silently pair the
+    wrong observation with every row.  The driver refuses it."""
+    from dazimsurftomo_b200 import formats as fm, invert
+    src = os.path.join(ROOT, "tests", "golden", "test1", "surfphase_subset.dat")
+    blocks, cur = [], None
+    for line in open(src):
+        if line.startswith("#"):
+            cur = [line]; blocks.append(cur)
+        elif line.strip():
+            cur.append(line)
+    per = [int(b[0].split()[3]) for b in blocks]
+    assert per == sorted(per) and len(set(per)) > 1
+    good = fm.read_surfdata(src, 36)
+    assert invert.loop_order_obst(good).shape == (good.dall,)
+    mixed = tmp_path / "mixed.dat"
+    order = sorted(range(len(blocks)), key=lambda i: (i % 2, i))          # interleave the periods
+    mixed.write_text("".join("".join(blocks[i]) for i in order))
+    bad = fm.read_surfdata(str(mixed), 36)
+    with pytest.raises(ValueError, match="not sorted by period"):
+        invert.loop_order_obst(bad)
