@@ -526,6 +526,7 @@ int Fmm::solve_source(const double* pv, float x, float z) {
         if (k + 1 <= nnx) { if (NSTS(l, k + 1) == -1) NSTS(l, k) = 1; }
       }
     }
+  if (fim_coarse) return travel_fim();     // experiment only (fim_experiment.cpp)
   return travel(x, z, 2);
 }
 

@@ -46,6 +46,11 @@ struct Fmm {
   // ---- binary heap ----
   int ntr = 0;
   std::vector<int> btg_px, btg_pz;
+  // ---- EXPERIMENT switch (fim_experiment.cpp; never set by tests of the reference path) ----
+  // 1: the coarse-grid continuation is solved as a fast-iterative fixed point instead of the heap march
+  int fim_coarse = 0;
+  long fim_sweeps = 0;   // Gauss-Seidel passes the last fixed-point solve took
+  int fim_converged = 0;
   // ---- statistics for the bench (not in the reference) ----
   long n_accept = 0;   // nodes set alive
   long n_steps = 0;    // ray steps taken
@@ -71,6 +76,8 @@ struct Fmm {
   // the per-source block of the orchestrators (FwdTraveltimeCPS.f90:467-645):
   // gridder + refined solve + hand-off + coarse solve
   int solve_source(const double* pv, float x, float z);
+  int travel_fim();                       // fim_experiment.cpp (experiment, not the reference's algorithm)
+  float fouds2_values(int iz, int ix, float tcur, bool second_order);   // fim_experiment.cpp
   int srtimes(float scx, float scz, float rcx1, float rcz1, float* cbst1);  // CalSurfG.f90:1599
   // rpathsAzim.f90:16 (azim=true) / rpaths CalSurfG.f90:1735 (azim=false)
   int rpaths(float scx, float scz, float* fdm, float* fdmc, float* fdms,

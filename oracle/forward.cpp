@@ -11,6 +11,7 @@
 // not depend on the thread count.
 #include "oracle.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <chrono>
@@ -281,6 +282,7 @@ int gbuild(GBuild& g) {
   auto worker = [&](int t) {
     Fmm f;
     f.init(nx, ny, g.goxd, g.gozd, g.dvxd, g.dvzd);
+    if (const char* e = std::getenv("ORC_FIM_EXPERIMENT")) f.fim_coarse = std::atoi(e);   // fim_experiment.cpp
     const size_t nf = (size_t)(nvz + 2) * (nvx + 2);
     const int ldf = nvz + 2;
     std::vector<float> fdm(nf), fdmc(nf), fdms(nf);

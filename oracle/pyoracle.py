@@ -364,3 +364,20 @@ def invert(vsf, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, obst, iso_mod, we
         if on_iter:
             on_iter(it, vsf, gcf, gsf, rec)
     return dict(vsf=vsf, gcf=gcf, gsf=gsf, history=hist, last=last)
+
+
+# ---- EXPERIMENT (oracle/fim_experiment.cpp): order-free fixed point of the reference's local eikonal solver ---------
+
+def fmm_source_fim(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz):
+    """Coarse travel-time field of one source with the coarse-grid continuation solved as a fast-iterative fixed point
+    instead of the reference's heap march (refined source box and hand-off unchanged).  Returns (ttn (nnz,nnx), passes);
+    passes < 0 means the overwrite phase hit its pass limit."""
+    nnx = (nx - 3) * 5 + 1; nnz = (ny - 3) * 5 + 1
+    pv = np.ascontiguousarray(pv, np.float64)
+    ttn = np.zeros((nnz, nnx), np.float32, order="F")
+    sw = C.c_long(0)
+    st = lib().orc_fmm_source_fim(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+                                  C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), _p(ttn), C.byref(sw))
+    if st:
+        raise RuntimeError(f"orc_fmm_source_fim status {st}")
+    return ttn, sw.value
