@@ -23,13 +23,19 @@ static const float FIM_INF = 1.0e30f;
 
 // fouds2 with the alive tests replaced by the causal test against tcur (the node's current value); returns the minimum
 // over the quadrants that have a usable neighbour, or FIM_INF.  Arithmetic is the reference's, operation for operation.
+// (defined after fouds2_pred's declaration in the header; the template body follows)
 float Fmm::fouds2_values(int iz, int ix, float tcur, bool second_order) {
+  return fouds2_pred(iz, ix, second_order, [&](int z, int x) { return TTN(z, x) < tcur; });
+}
+
+// The reference's quadrant solver with its "alive" tests answered by a caller-supplied predicate.
+template <class Pred>
+float Fmm::fouds2_pred(int iz, int ix, bool second_order, Pred usable) {
   int tsw1 = 0;
   float travm = FIM_INF, trav;
   const float slown = 1.0f / VELN(iz, ix);
   const float ri = earth;
   const float risti = ri * sin_rf(gox + (float)(ix - 1) * dnx);
-  auto usable = [&](int z, int x) { return TTN(z, x) < tcur; };
   for (int j = ix - 1; j <= ix + 1; j += 2) {
     if (j < 1 || j > nnx) continue;
     int swj = -1, j2 = (j == ix - 1) ? j - 1 : j + 1;
@@ -211,6 +217,240 @@ int Fmm::travel_fim() {
 }
 
 }  // namespace orc
+
+namespace orc {
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORDER EXPERIMENT.  In the reference's march the value a node ends with is a function of the acceptance ORDER only:
+// it is fouds2 evaluated when the last of its direct neighbours was accepted before its own pop, with exactly the nodes
+// accepted up to that moment alive (CalSurfG.f90:394-417, 557-729).  If that rule is right (checked bit for bit below),
+// a solve can be REPLAYED from a rank per node with purely local work -- parallel over the dependency wavefronts
+// instead of serial over the heap -- provided the ranks can be predicted.  This measures how well "rank = position in
+// the sorted list of (approximate) arrival times" predicts them, and how deep the dependency graph is.
+struct OrderStats {
+  long popped, rule_mismatch;             // nodes accepted by the coarse march; nodes where the rank rule != reference
+  long pairs, pair_ties, pair_inversions; // interacting (stencil) pairs: equal final keys / order contradicts the keys
+  long sorted_exact_mismatch;             // replay with rank = sort(final reference values): nodes != reference
+  long sorted_fim_mismatch;               // replay with rank = sort(fixed-point values): nodes != reference
+  long sorted_fim_rank_errors;            // ... replay steps that found no accepted direct neighbour (impossible order)
+  long dag_levels;                        // longest dependency chain of the replay
+  long fim_passes;
+  // local, order-free checks on the replay made from the fixed-point ranks (what a GPU path could run per node):
+  long verify_order_flags;                // interacting pairs whose replayed values are tied or contradict the ranks
+  long verify_key_increase_flags;         // nodes inside a key-increase window that interact with a node later in that window
+  long key_increase_events;               // overwrites of a heap key by a larger value
+};
+
+namespace {
+struct Replay {
+  Fmm& f;
+  const std::vector<int>& s0;        // status handed to the coarse march
+  const std::vector<float>& t0;      // values handed to it
+  size_t id(int iz, int ix) const { return (size_t)(ix - 1) * f.ld + (iz - 1); }
+  // values from ranks; returns replay steps that had no accepted direct neighbour although the node was far
+  long run(const std::vector<int>& rank, std::vector<int>* level_out) {
+    const int nnx = f.nnx, nnz = f.nnz;
+    std::vector<std::pair<int, int>> order;     // (rank, linear id)
+    for (int ix = 1; ix <= nnx; ++ix)
+      for (int iz = 1; iz <= nnz; ++iz) {
+        const size_t k = id(iz, ix);
+        if (s0[k] >= 0) f.ttn[k] = t0[k]; else f.ttn[k] = FIM_INF;
+        if (rank[k] >= 0) order.push_back({rank[k], (int)k});
+      }
+    std::sort(order.begin(), order.end());
+    std::vector<int> level;
+    if (level_out) level.assign(f.ttn.size(), 0);
+    long impossible = 0;
+    for (const auto& e : order) {
+      const int k = e.second, r = e.first;
+      const int ix = k / f.ld + 1, iz = k % f.ld + 1;
+      int tstar = -1;
+      bool any = false;
+      const int dz[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
+      for (int q = 0; q < 4; ++q) {
+        const int z = iz + dz[q], x = ix + dx[q];
+        if (z < 1 || z > nnz || x < 1 || x > nnx) continue;
+        const int rn = rank[id(z, x)];
+        if (rn >= 0 && rn < r) { any = true; tstar = std::max(tstar, rn); }
+      }
+      if (!any) {                         // never recomputed by the coarse march: a band node keeps its injected value
+        if (s0[k] < 0) ++impossible;
+        continue;
+      }
+      auto alive = [&](int z, int x) {
+        const size_t n = id(z, x);
+        return s0[n] == 0 || (rank[n] >= 0 && rank[n] <= tstar);
+      };
+      f.ttn[k] = f.fouds2_pred(iz, ix, true, alive);
+      if (level_out) {
+        int lv = 0;
+        const int sz[8] = {-1, -2, 1, 2, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, -1, -2, 1, 2};
+        for (int q = 0; q < 8; ++q) {
+          const int z = iz + sz[q], x = ix + sx[q];
+          if (z < 1 || z > nnz || x < 1 || x > nnx) continue;
+          if (rank[id(z, x)] >= 0 && alive(z, x)) lv = std::max(lv, level[id(z, x)]);
+        }
+        level[k] = lv + 1;
+      }
+    }
+    if (level_out) *level_out = level;
+    return impossible;
+  }
+};
+
+// Checks on a finished replay (f.ttn = replayed values, rank = the ranks it used); every step is local to a node or a
+// sort, nothing walks the heap.
+//  (a) every interacting pair must be STRICTLY ordered by value the way the ranks say (ties between interacting nodes
+//      are broken by heap position in the reference: not predictable);
+//  (b) the keys a node had in the heap -- its injected value if it was in the initial band, then one trial per direct
+//      neighbour accepted before it -- normally only decrease.  When a trial is LARGER than the key it overwrites
+//      (CalSurfG.f90:728 assigns, updtree :864 only sifts up) the node keeps a heap slot justified by the old key: the
+//      edge to its children may be invalid, and nodes below it with keys in the window [old, new) are popped late, at
+//      the latest when the frontier reaches `new`.  Such a delay changes values only if a node whose key lies in a
+//      window interacts with a node whose key lies between its own and the end of the (merged) window.  Windows are
+//      merged transitively (a delayed node may itself hide others).
+void verify_replay(Fmm& f, const std::vector<int>& s0, const std::vector<float>& t0, const std::vector<int>& rank,
+                   long* order_flags, long* increase_flags, long* increase_events) {
+  auto id = [&](int iz, int ix) { return (size_t)(ix - 1) * f.ld + (iz - 1); };
+  *order_flags = 0; *increase_flags = 0; *increase_events = 0;
+  const int sz[8] = {-1, -2, 1, 2, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, -1, -2, 1, 2};
+  std::vector<std::pair<float, float>> win;
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz) {
+      const size_t k = id(iz, ix);
+      const int r = rank[k];
+      if (r < 0) continue;
+      for (int q = 0; q < 8; ++q) {
+        const int z = iz + sz[q], x = ix + sx[q];
+        if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+        const int rn = rank[id(z, x)];
+        if (rn < 0 || rn > r) continue;
+        if (!(f.ttn[id(z, x)] < f.ttn[k])) ++*order_flags;
+      }
+      int trig[4] = {0, 0, 0, 0}, nt = 0;
+      const int dz[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
+      for (int q = 0; q < 4; ++q) {
+        const int z = iz + dz[q], x = ix + dx[q];
+        if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+        const int rn = rank[id(z, x)];
+        if (rn >= 0 && rn < r) trig[nt++] = rn;
+      }
+      for (int a = 1; a < nt; ++a)                      // insertion sort of <= 4 entries
+        for (int b = a; b > 0 && trig[b - 1] > trig[b]; --b) std::swap(trig[b - 1], trig[b]);
+      float prev = s0[k] > 0 ? t0[k] : FIM_INF;          // key already in the heap at the hand-off, if any
+      for (int t = 0; t < nt; ++t) {
+        const int ts = trig[t];
+        const float trial = f.fouds2_pred(iz, ix, true, [&](int z, int x) {
+          const size_t n = id(z, x);
+          return s0[n] == 0 || (rank[n] >= 0 && rank[n] <= ts);
+        });
+        if (trial > prev) { win.push_back({prev, trial}); ++*increase_events; }
+        prev = trial;
+      }
+    }
+  if (win.empty()) return;
+  std::sort(win.begin(), win.end());
+  std::vector<std::pair<float, float>> merged;
+  for (const auto& w : win) {
+    if (!merged.empty() && w.first <= merged.back().second) merged.back().second = std::max(merged.back().second, w.second);
+    else merged.push_back(w);
+  }
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz) {
+      const size_t k = id(iz, ix);
+      if (rank[k] < 0) continue;
+      const float v = f.ttn[k];
+      auto it = std::upper_bound(merged.begin(), merged.end(), std::make_pair(v, FIM_INF));
+      if (it == merged.begin()) continue;
+      --it;
+      if (!(v >= it->first && v < it->second)) continue;      // this node's key lies in no hazard window
+      const float end = it->second;
+      for (int q = 0; q < 8; ++q) {
+        const int z = iz + sz[q], x = ix + sx[q];
+        if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+        if (rank[id(z, x)] < 0) continue;
+        const float vn = f.ttn[id(z, x)];
+        if (vn >= v && vn < end) { ++*increase_flags; break; }
+      }
+    }
+}
+
+std::vector<int> ranks_by_value(const Fmm& f, const std::vector<float>& val, const std::vector<int>& true_rank) {
+  std::vector<std::pair<float, int>> v;
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz) {
+      const size_t k = (size_t)(ix - 1) * f.ld + (iz - 1);
+      if (true_rank[k] >= 0) v.push_back({val[k], (int)k});       // the set of nodes the march accepts is known a priori
+    }
+  std::stable_sort(v.begin(), v.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  std::vector<int> r(true_rank.size(), -1);
+  for (size_t i = 0; i < v.size(); ++i) r[v[i].second] = (int)i;
+  return r;
+}
+}  // namespace
+}  // namespace orc
+
+extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                                   float scx, float scz, orc::OrderStats* out) {
+  using namespace orc;
+  Fmm f;
+  f.init(nx, ny, goxd, gozd, dvxd, dvzd);
+  std::vector<int> rank(f.ttn.size(), -1), s0;
+  std::vector<float> t0;
+  f.rec_rank = &rank; f.rec_init_nsts = &s0; f.rec_init_ttn = &t0;
+  int st = f.solve_source(pv, scx, scz);
+  if (st) return st;
+  f.rec_rank = nullptr; f.rec_init_nsts = nullptr; f.rec_init_ttn = nullptr;
+  const std::vector<float> ref = f.ttn;
+  OrderStats S{};
+  auto idx = [&](int iz, int ix) { return (size_t)(ix - 1) * f.ld + (iz - 1); };
+  auto count_mismatch = [&]() {
+    long m = 0;
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz)
+        if (f.ttn[idx(iz, ix)] != ref[idx(iz, ix)]) ++m;
+    return m;
+  };
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz)
+      if (rank[idx(iz, ix)] >= 0) ++S.popped;
+  Replay R{f, s0, t0};
+  // (1) the rank rule itself, with the reference's own order
+  std::vector<int> level;
+  R.run(rank, &level);
+  S.rule_mismatch = count_mismatch();
+  for (int v : level) S.dag_levels = std::max<long>(S.dag_levels, v);
+  // (2) interacting pairs: do the final keys tell the order?
+  const int sz[8] = {-1, -2, 1, 2, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, -1, -2, 1, 2};
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz) {
+      const int r = rank[idx(iz, ix)];
+      if (r < 0) continue;
+      for (int q = 0; q < 8; ++q) {
+        const int z = iz + sz[q], x = ix + sx[q];
+        if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+        const int rn = rank[idx(z, x)];
+        if (rn < 0 || rn > r) continue;                 // each unordered pair once: N accepted before X
+        ++S.pairs;
+        if (ref[idx(z, x)] == ref[idx(iz, ix)]) ++S.pair_ties;
+        else if (ref[idx(z, x)] > ref[idx(iz, ix)]) ++S.pair_inversions;
+      }
+    }
+  // (3) ranks predicted from the exact final values
+  R.run(ranks_by_value(f, ref, rank), nullptr);
+  S.sorted_exact_mismatch = count_mismatch();
+  // (4) ranks predicted from the fixed-point (fast-iterative) values
+  f.nsts = s0; f.ttn = t0;
+  f.travel_fim();
+  S.fim_passes = f.fim_sweeps;
+  const std::vector<float> fimv = f.ttn;
+  const std::vector<int> prank = ranks_by_value(f, fimv, rank);
+  S.sorted_fim_rank_errors = R.run(prank, nullptr);
+  S.sorted_fim_mismatch = count_mismatch();
+  verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events);
+  *out = S;
+  return 0;
+}
 
 extern "C" {
 // coarse travel-time field of one source from the fixed-point experiment: ttn (nnz,nnx) column-major; returns the

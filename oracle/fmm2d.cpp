@@ -219,6 +219,7 @@ int Fmm::travel(float scx, float scz, int urg) {
     iz = btg_pz[1];
     NSTS(iz, ix) = 0;
     ++n_accept;
+    if (rec_rank) (*rec_rank)[(size_t)(ix - 1) * ld + (iz - 1)] = rec_count++;   // experiment hook (order_experiment)
     downtree();
     for (int i = ix - 1; i <= ix + 1; i += 2) {
       if (i >= 1 && i <= nnx) {
@@ -526,6 +527,12 @@ int Fmm::solve_source(const double* pv, float x, float z) {
         if (k + 1 <= nnx) { if (NSTS(l, k + 1) == -1) NSTS(l, k) = 1; }
       }
     }
+  if (rec_rank) {                          // experiment only: record the coarse march alone (fim_experiment.cpp)
+    rec_rank->assign(rec_rank->size(), -1);
+    rec_count = 0;
+    if (rec_init_nsts) *rec_init_nsts = nsts;
+    if (rec_init_ttn) *rec_init_ttn = ttn;
+  }
   if (fim_coarse) return travel_fim();     // experiment only (fim_experiment.cpp)
   return travel(x, z, 2);
 }

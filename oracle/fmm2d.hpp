@@ -48,6 +48,10 @@ struct Fmm {
   std::vector<int> btg_px, btg_pz;
   // ---- EXPERIMENT switch (fim_experiment.cpp; never set by tests of the reference path) ----
   // 1: the coarse-grid continuation is solved as a fast-iterative fixed point instead of the heap march
+  std::vector<int>* rec_rank = nullptr;   // experiment: if set, rec_rank[(ix-1)*ld+(iz-1)] = pop counter of travel()
+  int rec_count = 0;
+  std::vector<int>* rec_init_nsts = nullptr;   // experiment: status / values handed to the coarse march
+  std::vector<float>* rec_init_ttn = nullptr;
   int fim_coarse = 0;
   long fim_sweeps = 0;   // Gauss-Seidel passes the last fixed-point solve took
   int fim_converged = 0;
@@ -78,6 +82,7 @@ struct Fmm {
   int solve_source(const double* pv, float x, float z);
   int travel_fim();                       // fim_experiment.cpp (experiment, not the reference's algorithm)
   float fouds2_values(int iz, int ix, float tcur, bool second_order);   // fim_experiment.cpp
+  template <class Pred> float fouds2_pred(int iz, int ix, bool second_order, Pred usable);   // fim_experiment.cpp
   int srtimes(float scx, float scz, float rcx1, float rcz1, float* cbst1);  // CalSurfG.f90:1599
   // rpathsAzim.f90:16 (azim=true) / rpaths CalSurfG.f90:1735 (azim=false)
   int rpaths(float scx, float scz, float* fdm, float* fdmc, float* fdms,

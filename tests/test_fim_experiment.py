@@ -32,3 +32,20 @@ def test_default_path_ignores_the_experiment_switch(oracle, test1, test1_tables,
     monkeypatch.setenv("ORC_FIM_EXPERIMENT", "0")
     b = oracle.gbuild(*args, tables=test1_tables)
     assert np.array_equal(a["dsurf"], b["dsurf"]) and np.array_equal(a["obsTaa"], b["obsTaa"])
+
+
+def test_values_are_a_local_function_of_the_acceptance_order(oracle, test1, test1_tables):
+    """ORDER EXPERIMENT (scripts/order_experiment.py): the rule 'a node's value = the quadrant solver at the acceptance
+    of its last direct neighbour before its own pop, with the nodes accepted up to then alive' reproduces the
+    reference's coarse march bit for bit, a replay fed with ranks predicted from the order-free fixed point does too on
+    this model, and the local hazard checks never pass a wrong replay."""
+    p = test1["para"]; sv = test1["sv"]
+    for k in (0, 20):
+        pv = np.ascontiguousarray(test1_tables["pvRc"][:, k])
+        for s in range(int(sv.nsrcsurf1[0])):
+            r = oracle.fmm_order_stats(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, float(sv.scxf[s, 0]), float(sv.sczf[s, 0]))
+            assert r["popped"] > 4000 and r["rule_mismatch"] == 0
+            assert r["sorted_exact_mismatch"] == 0 and r["sorted_fim_mismatch"] == 0 and r["sorted_fim_rank_errors"] == 0
+            assert 50 < r["dag_levels"] < 200                    # ~40-60 nodes per wavefront on a 71 x 71 grid
+            flagged = r["verify_order_flags"] + r["verify_key_increase_flags"] > 0
+            assert flagged or r["sorted_fim_mismatch"] == 0      # soundness: wrong => flagged
