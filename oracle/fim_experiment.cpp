@@ -248,8 +248,13 @@ struct Replay {
   const std::vector<float>& t0;      // values handed to it
   size_t id(int iz, int ix) const { return (size_t)(ix - 1) * f.ld + (iz - 1); }
   // values from ranks; returns replay steps that had no accepted direct neighbour although the node was far
-  long run(const std::vector<int>& rank, std::vector<int>* level_out) {
+  // exit_rank >= 0 (refined source box): the node with that rank is the one the march stopped at -- it is alive with
+  // the value of its last trial but never updated its neighbours (CalSurfG.f90:362-382); nodes without a rank that
+  // touch an accepted node are CLOSE and keep the trial of their last update (their status is returned in close_out).
+  long run(const std::vector<int>& rank, std::vector<int>* level_out, int exit_rank = -1,
+           std::vector<char>* close_out = nullptr) {
     const int nnx = f.nnx, nnz = f.nnz;
+    const int trig_limit = exit_rank >= 0 ? exit_rank : 0x7fffffff;     // ranks below this update their neighbours
     std::vector<std::pair<int, int>> order;     // (rank, linear id)
     for (int ix = 1; ix <= nnx; ++ix)
       for (int iz = 1; iz <= nnz; ++iz) {
@@ -271,9 +276,9 @@ struct Replay {
         const int z = iz + dz[q], x = ix + dx[q];
         if (z < 1 || z > nnz || x < 1 || x > nnx) continue;
         const int rn = rank[id(z, x)];
-        if (rn >= 0 && rn < r) { any = true; tstar = std::max(tstar, rn); }
+        if (rn >= 0 && rn < r && rn < trig_limit) { any = true; tstar = std::max(tstar, rn); }
       }
-      if (!any) {                         // never recomputed by the coarse march: a band node keeps its injected value
+      if (!any) {                         // never recomputed by the march: a band node keeps its injected value
         if (s0[k] < 0) ++impossible;
         continue;
       }
@@ -292,6 +297,28 @@ struct Replay {
         }
         level[k] = lv + 1;
       }
+    }
+    if (close_out) {
+      close_out->assign(f.ttn.size(), 0);
+      const int dz[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
+      for (int ix = 1; ix <= nnx; ++ix)
+        for (int iz = 1; iz <= nnz; ++iz) {
+          const size_t k = id(iz, ix);
+          if (rank[k] >= 0 || s0[k] == 0) continue;        // accepted in this march / before it began
+          int tstar = -1;
+          for (int q = 0; q < 4; ++q) {
+            const int z = iz + dz[q], x = ix + dx[q];
+            if (z < 1 || z > nnz || x < 1 || x > nnx) continue;
+            const int rn = rank[id(z, x)];
+            if (rn >= 0 && rn < trig_limit) tstar = std::max(tstar, rn);
+          }
+          if (tstar < 0) { if (s0[k] > 0) (*close_out)[k] = 1; continue; }     // untouched band node stays close
+          (*close_out)[k] = 1;
+          f.ttn[k] = f.fouds2_pred(iz, ix, true, [&](int z, int x) {
+            const size_t n = id(z, x);
+            return s0[n] == 0 || (rank[n] >= 0 && rank[n] <= tstar);
+          });
+        }
     }
     if (level_out) *level_out = level;
     return impossible;
@@ -447,6 +474,167 @@ extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float
   const std::vector<int> prank = ranks_by_value(f, fimv, rank);
   S.sorted_fim_rank_errors = R.run(prank, nullptr);
   S.sorted_fim_mismatch = count_mismatch();
+  verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events);
+  *out = S;
+  return 0;
+}
+
+namespace orc {
+namespace {
+// the refined source box exactly as solve_source sets it up (FwdTraveltimeCPS.f90:493-560), without the march
+int setup_refined(Fmm& f, const double* pv, float x, float z) {
+  f.nnx = f.nnx_c; f.nnz = f.nnz_c; f.dnx = f.dnx_c; f.dnz = f.dnz_c; f.gox = f.gox_c; f.goz = f.goz_c;
+  f.gridder(pv);
+  int isx = (int)((x - f.gox) / f.dnx) + 1;
+  int isz = (int)((z - f.goz) / f.dnz) + 1;
+  if (isx < 1 || isx > f.nnx || isz < 1 || isz > f.nnz) return ERR_SOURCE_OUTSIDE;
+  if (isx == f.nnx) isx = isx - 1;
+  if (isz == f.nnz) isz = isz - 1;
+  f.vnl = isx - f.sgs; if (f.vnl < 1) f.vnl = 1;
+  f.vnr = isx + f.sgs; if (f.vnr > f.nnx) f.vnr = f.nnx;
+  f.vnt = isz - f.sgs; if (f.vnt < 1) f.vnt = 1;
+  f.vnb = isz + f.sgs; if (f.vnb > f.nnz) f.vnb = f.nnz;
+  f.nrnx = (f.vnr - f.vnl) * f.sgdl + 1;
+  f.nrnz = (f.vnb - f.vnt) * f.sgdl + 1;
+  f.drnx = f.dvx / (float)(f.gdx * f.sgdl);
+  f.drnz = f.dvz / (float)(f.gdz * f.sgdl);
+  f.gorx = f.gox + f.dnx * (float)(f.vnl - 1);
+  f.gorz = f.goz + f.dnz * (float)(f.vnt - 1);
+  f.nnx = f.nrnx; f.nnz = f.nrnz; f.dnx = f.drnx; f.dnz = f.drnz; f.gox = f.gorx; f.goz = f.gorz;
+  f.bsplrefine();
+  return OK;
+}
+// the march stops when a node on an edge of the box that is not an edge of the model reaches the heap root
+bool is_exit_node(const Fmm& f, int iz, int ix) {
+  if (ix == 1 && f.vnl != 1) return true;
+  if (ix == f.nnx && f.vnr != f.nnx) return true;      // literal (CalSurfG.f90:369-371)
+  if (iz == 1 && f.vnt != 1) return true;
+  if (iz == f.nnz && f.vnb != f.nnz) return true;
+  return false;
+}
+}  // namespace
+}  // namespace orc
+
+// ORDER EXPERIMENT on the refined source box (129 x 129 around the source, 40x finer than the model grid), including
+// its stopping rule and the trial values of the close nodes it hands to the coarse grid.
+// prefix > 0: the first `prefix` accepts are taken from the reference (= marched serially with the heap, as today) and
+// only the rest of the box is predicted and replayed -- the hazards of this stage sit around the source cell.
+extern "C" int orc_fmm_order_stats_refined(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                                           float scx, float scz, int prefix, orc::OrderStats* out) {
+  using namespace orc;
+  Fmm f;
+  f.init(nx, ny, goxd, gozd, dvxd, dvzd);
+  int st = setup_refined(f, pv, scx, scz);
+  if (st) return st;
+  std::vector<int> rank(f.ttn.size(), -1);
+  f.rec_rank = &rank; f.rec_count = 0;
+  st = f.travel(scx, scz, 1);
+  if (st) return st;
+  f.rec_rank = nullptr;
+  const int npop = f.rec_count;
+  const std::vector<float> ref = f.ttn;
+  const std::vector<int> refs = f.nsts;
+  auto idx = [&](int iz, int ix) { return (size_t)(ix - 1) * f.ld + (iz - 1); };
+  // initial state of this march: everything far except the four corners of the source cell (close, analytic times)
+  std::vector<int> s0(f.ttn.size(), -1);
+  std::vector<float> t0(f.ttn.size(), 0.0f);
+  {
+    int isx = (int)((scx - f.gox) / f.dnx) + 1, isz = (int)((scz - f.goz) / f.dnz) + 1;
+    if (isx == f.nnx) isx = isx - 1;
+    if (isz == f.nnz) isz = isz - 1;
+    float vss[2][2];
+    for (int i = 1; i <= 2; ++i)
+      for (int j = 1; j <= 2; ++j) vss[i - 1][j - 1] = f.VELN(isz - 1 + j, isx - 1 + i);
+    const float dsx = (scx - f.gox) - (float)(isx - 1) * f.dnx, dsz = (scz - f.goz) - (float)(isz - 1) * f.dnz;
+    const float vsrc = f.bilinear(vss, dsx, dsz);
+    for (int i = 1; i <= 2; ++i)
+      for (int j = 1; j <= 2; ++j) {
+        const float ax = dsx - (float)(i - 1) * f.dnx, az = dsz - (float)(j - 1) * f.dnz;
+        const float ds = std::sqrt(ax * ax + az * az);
+        s0[idx(isz - 1 + j, isx - 1 + i)] = 1;
+        t0[idx(isz - 1 + j, isx - 1 + i)] = 2.0f * ds / (vss[i - 1][j - 1] + vsrc);
+      }
+  }
+  // the node the march stopped at is alive but was never counted by the hook: give it the last rank
+  int exit_rank = -1;
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz)
+      if (refs[idx(iz, ix)] == 0 && rank[idx(iz, ix)] < 0) { rank[idx(iz, ix)] = npop; exit_rank = npop; }
+  OrderStats S{};
+  auto compare = [&](const std::vector<int>& rk, const std::vector<char>& close) {
+    long m = 0;
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz) {
+        const size_t k = idx(iz, ix);
+        const int want = refs[k] == 0 ? 0 : (refs[k] > 0 ? 1 : -1);
+        const int got = (rk[k] >= 0 || s0[k] == 0) ? 0 : (close[k] ? 1 : -1);
+        if (want != got) { ++m; continue; }
+        if (want >= 0 && f.ttn[k] != ref[k]) ++m;          // alive values and the trial values of close nodes
+      }
+    return m;
+  };
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz)
+      if (rank[idx(iz, ix)] >= 0) ++S.popped;
+  Replay R{f, s0, t0};
+  std::vector<int> level;
+  std::vector<char> close;
+  R.run(rank, &level, exit_rank, &close);
+  S.rule_mismatch = compare(rank, close);
+  for (int v : level) S.dag_levels = std::max<long>(S.dag_levels, v);
+  const int sz[8] = {-1, -2, 1, 2, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, -1, -2, 1, 2};
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz) {
+      const int r = rank[idx(iz, ix)];
+      if (r < 0) continue;
+      for (int q = 0; q < 8; ++q) {
+        const int z = iz + sz[q], x = ix + sx[q];
+        if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+        const int rn = rank[idx(z, x)];
+        if (rn < 0 || rn > r) continue;
+        ++S.pairs;
+        if (ref[idx(z, x)] == ref[idx(iz, ix)]) ++S.pair_ties;
+        else if (ref[idx(z, x)] > ref[idx(iz, ix)]) ++S.pair_inversions;
+      }
+    }
+  // optional serial prefix: state of the march after `prefix` accepts, by the (exact) rule
+  if (prefix > 0 && prefix < npop) {
+    std::vector<int> rcut(rank.size(), -1);
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] >= 0 && rank[k] < prefix) rcut[k] = rank[k];
+    R.run(rcut, nullptr, prefix, &close);
+    std::vector<int> s1(rank.size(), -1);
+    std::vector<float> t1(rank.size(), 0.0f);
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz) {
+        const size_t k = idx(iz, ix);
+        if (rcut[k] >= 0) { s1[k] = 0; t1[k] = f.ttn[k]; }
+        else if (close[k]) { s1[k] = 1; t1[k] = f.ttn[k]; }
+      }
+    s0 = s1; t0 = t1;          // Replay R refers to s0 / t0: from here on the march starts at this state
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] >= 0 && rank[k] < prefix) rank[k] = -2;      // accepted before the replayed part began
+  }
+  // ranks predicted from the order-free fixed point on the whole box, cut at the first exit node in sorted order
+  f.nsts = s0; f.ttn = t0;
+  f.travel_fim();
+  S.fim_passes = f.fim_sweeps;
+  std::vector<std::pair<float, int>> v;
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz)
+      if (f.ttn[idx(iz, ix)] < FIM_INF && s0[idx(iz, ix)] != 0) v.push_back({f.ttn[idx(iz, ix)], (int)idx(iz, ix)});
+  std::stable_sort(v.begin(), v.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  std::vector<int> prank(f.ttn.size(), -1);
+  int pexit = -1;
+  for (size_t i = 0; i < v.size(); ++i) {
+    const int k = v[i].second;
+    prank[k] = (int)i;
+    if (is_exit_node(f, k % f.ld + 1, k / f.ld + 1)) { pexit = (int)i; break; }
+  }
+  f.nsts = s0;
+  S.sorted_fim_rank_errors = R.run(prank, nullptr, pexit, &close);
+  S.sorted_fim_mismatch = compare(prank, close);
+  S.sorted_exact_mismatch = -1;                          // not evaluated for this stage
   verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events);
   *out = S;
   return 0;

@@ -389,14 +389,18 @@ class OrderStats(C.Structure):
                                         "dag_levels", "fim_passes", "verify_order_flags", "verify_key_increase_flags", "key_increase_events")]
 
 
-def fmm_order_stats(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz):
+def fmm_order_stats(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, refined=False, prefix=0):
     """EXPERIMENT (oracle/fim_experiment.cpp, ORDER EXPERIMENT): statistics of the coarse march of one source --
     is the final value a local function of the acceptance order (rule_mismatch == 0), do sorted arrival times predict
     that order (pair_ties / pair_inversions, sorted_*_mismatch), how deep is the dependency graph (dag_levels)."""
     pv = np.ascontiguousarray(pv, np.float64)
     s = OrderStats()
-    st = lib().orc_fmm_order_stats(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
-                                   C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), C.byref(s))
+    head = (C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd), C.c_float(dvzd), _p(pv),
+            C.c_float(scx), C.c_float(scz))
+    if refined:
+        st = lib().orc_fmm_order_stats_refined(*head, C.c_int(prefix), C.byref(s))
+    else:
+        st = lib().orc_fmm_order_stats(*head, C.byref(s))
     if st:
         raise RuntimeError(f"orc_fmm_order_stats status {st}")
     return {k: getattr(s, k) for k, _ in s._fields_}

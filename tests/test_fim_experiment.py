@@ -49,3 +49,17 @@ def test_values_are_a_local_function_of_the_acceptance_order(oracle, test1, test
             assert 50 < r["dag_levels"] < 200                    # ~40-60 nodes per wavefront on a 71 x 71 grid
             flagged = r["verify_order_flags"] + r["verify_key_increase_flags"] > 0
             assert flagged or r["sorted_fim_mismatch"] == 0      # soundness: wrong => flagged
+
+
+def test_order_rule_holds_on_the_refined_source_box(oracle, test1, test1_tables):
+    """Same rule on the refined box, with its stopping rule (the node the march stops at is alive but never updates its
+    neighbours) and the trial values / statuses of the close nodes it hands to the coarse grid: bit for bit."""
+    p = test1["para"]; sv = test1["sv"]
+    pv = np.ascontiguousarray(test1_tables["pvRc"][:, 7])
+    for s in range(int(sv.nsrcsurf1[0])):
+        for prefix in (0, 4):
+            r = oracle.fmm_order_stats(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, float(sv.scxf[s, 0]), float(sv.sczf[s, 0]),
+                                       refined=True, prefix=prefix)
+            assert r["popped"] > 3000 and r["rule_mismatch"] == 0
+            flagged = r["verify_order_flags"] + r["verify_key_increase_flags"] > 0
+            assert flagged or r["sorted_fim_mismatch"] == 0      # soundness of the local checks
