@@ -417,8 +417,10 @@ std::vector<int> ranks_by_value(const Fmm& f, const std::vector<float>& val, con
 }  // namespace
 }  // namespace orc
 
+// prefix > 0: the first `prefix` accepts of the coarse march are taken from the reference (= marched serially) and only
+// the rest is predicted and replayed.
 extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
-                                   float scx, float scz, orc::OrderStats* out) {
+                                   float scx, float scz, int prefix, orc::OrderStats* out) {
   using namespace orc;
   Fmm f;
   f.init(nx, ny, goxd, gozd, dvxd, dvzd);
@@ -466,6 +468,25 @@ extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float
   // (3) ranks predicted from the exact final values
   R.run(ranks_by_value(f, ref, rank), nullptr);
   S.sorted_exact_mismatch = count_mismatch();
+  // optional serial prefix: state of the march after `prefix` accepts, by the (exact) rule
+  if (prefix > 0 && prefix < S.popped) {
+    std::vector<int> rcut(rank.size(), -1);
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] >= 0 && rank[k] < prefix) rcut[k] = rank[k];
+    std::vector<char> close;
+    R.run(rcut, nullptr, prefix, &close);
+    std::vector<int> s1(rank.size(), -1);
+    std::vector<float> t1(rank.size(), 0.0f);
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz) {
+        const size_t k = idx(iz, ix);
+        if (s0[k] == 0 || rcut[k] >= 0) { s1[k] = 0; t1[k] = f.ttn[k]; }
+        else if (close[k]) { s1[k] = 1; t1[k] = f.ttn[k]; }
+      }
+    s0 = s1; t0 = t1;
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] >= 0 && rank[k] < prefix) rank[k] = -1;     // accepted before the replayed part began
+  }
   // (4) ranks predicted from the fixed-point (fast-iterative) values
   f.nsts = s0; f.ttn = t0;
   f.travel_fim();

@@ -400,7 +400,7 @@ def fmm_order_stats(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, refined=False,
     if refined:
         st = lib().orc_fmm_order_stats_refined(*head, C.c_int(prefix), C.byref(s))
     else:
-        st = lib().orc_fmm_order_stats(*head, C.byref(s))
+        st = lib().orc_fmm_order_stats(*head, C.c_int(prefix), C.byref(s))
     if st:
         raise RuntimeError(f"orc_fmm_order_stats status {st}")
     return {k: getattr(s, k) for k, _ in s._fields_}

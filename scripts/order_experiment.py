@@ -53,6 +53,11 @@ def main():
     rs = [po.fmm_order_stats(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv[:, k], float(sv.scxf[s, 0]), float(sv.sczf[s, 0]))
           for k in (0, 7, 20, 35) for s in range(int(sv.nsrcsurf1[0]))]
     summarize("test1 model (71 x 71 nodes), 4 periods x 5 sources", rs)
+    # the key-increase hazards of the coarse march sit where the refined box hands over (band nodes whose injected keys
+    # get overwritten): taking the first 64 accepts from the serial march removes them
+    rs = [po.fmm_order_stats(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv[:, k], float(sv.scxf[s, 0]), float(sv.sczf[s, 0]),
+                             prefix=64) for k in (0, 7, 20, 35) for s in range(int(sv.nsrcsurf1[0]))]
+    summarize("test1 model (71 x 71 nodes), serial prefix of 64 accepts", rs)
     # the refined source box (129 x 129, stopping rule and close-node hand-off included); the first 4 accepts -- the
     # corners of the source cell, whose analytic keys get overwritten -- are taken from the serial march
     for pre in (0, 4):
@@ -64,6 +69,9 @@ def main():
                              float(w.sv.sczf[s, 0])) for s in range(24)]
     summarize("Yunnan-shaped model (176 x 196 nodes), 24 solves", rs)
     rs = [po.fmm_order_stats(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, tb["pvRc"][:, (3 * s) % 36], float(w.sv.scxf[s, 0]),
+                             float(w.sv.sczf[s, 0]), prefix=64) for s in range(24)]
+    summarize("Yunnan-shaped model (176 x 196 nodes), serial prefix of 64 accepts", rs)
+    rs = [po.fmm_order_stats(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, tb["pvRc"][:, (3 * s) % 36], float(w.sv.scxf[s, 0]),
                              float(w.sv.sczf[s, 0]), refined=True, prefix=4) for s in range(24)]
     summarize("Yunnan-shaped model, REFINED source box, serial prefix of 4 accepts", rs)
     if "--s200" in sys.argv:
@@ -71,6 +79,9 @@ def main():
         rs = [po.fmm_order_stats(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, tb["pvRc"][:, s], float(w.sv.scxf[s, 0]),
                                  float(w.sv.sczf[s, 0])) for s in range(4)]
         summarize("S200 model (996 x 996 nodes), 4 solves", rs)
+        rs = [po.fmm_order_stats(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, tb["pvRc"][:, s], float(w.sv.scxf[s, 0]),
+                                 float(w.sv.sczf[s, 0]), prefix=64) for s in range(4)]
+        summarize("S200 model (996 x 996 nodes), serial prefix of 64 accepts", rs)
 
 
 if __name__ == "__main__":
