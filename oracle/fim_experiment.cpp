@@ -239,6 +239,7 @@ struct OrderStats {
   long verify_order_flags;                // interacting pairs whose replayed values are tied or contradict the ranks
   long verify_key_increase_flags;         // nodes inside a key-increase window that interact with a node later in that window
   long key_increase_events;               // overwrites of a heap key by a larger value
+  long harmless_tie_groups;               // groups of exactly tied interacting nodes whose order provably does not matter
 };
 
 namespace {
@@ -337,10 +338,33 @@ struct Replay {
 //      window interacts with a node whose key lies between its own and the end of the (merged) window.  Windows are
 //      merged transitively (a delayed node may itself hide others).
 void verify_replay(Fmm& f, const std::vector<int>& s0, const std::vector<float>& t0, const std::vector<int>& rank,
-                   long* order_flags, long* increase_flags, long* increase_events) {
+                   long* order_flags, long* increase_flags, long* increase_events, int exit_rank = -1,
+                   long* harmless_tie_groups = nullptr) {
   auto id = [&](int iz, int ix) { return (size_t)(ix - 1) * f.ld + (iz - 1); };
   *order_flags = 0; *increase_flags = 0; *increase_events = 0;
+  if (harmless_tie_groups) *harmless_tie_groups = 0;
   const int sz[8] = {-1, -2, 1, 2, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, -1, -2, 1, 2};
+  const int trig_limit = exit_rank >= 0 ? exit_rank : 0x7fffffff;
+  std::vector<int> rk = rank;                     // mutable copy for the tie permutations
+  // the rule for one node under the ranks rk (what Replay::run computes, without writing)
+  auto rule_value = [&](size_t k) -> float {
+    const int ix = (int)(k / f.ld) + 1, iz = (int)(k % f.ld) + 1;
+    const int r = rk[k] >= 0 ? rk[k] : 0x7fffffff;
+    int tstar = -1;
+    const int dz[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
+    for (int q = 0; q < 4; ++q) {
+      const int z = iz + dz[q], x = ix + dx[q];
+      if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+      const int rn = rk[id(z, x)];
+      if (rn >= 0 && rn < r && rn < trig_limit) tstar = std::max(tstar, rn);
+    }
+    if (tstar < 0) return s0[k] >= 0 ? t0[k] : FIM_INF;
+    return f.fouds2_pred(iz, ix, true, [&](int z, int x) {
+      const size_t n = id(z, x);
+      return s0[n] == 0 || (rk[n] >= 0 && rk[n] <= tstar);
+    });
+  };
+  std::vector<std::pair<float, int>> tied;         // (value, node) of every node in an exactly tied interacting pair
   std::vector<std::pair<float, float>> win;
   for (int ix = 1; ix <= f.nnx; ++ix)
     for (int iz = 1; iz <= f.nnz; ++iz) {
@@ -352,7 +376,8 @@ void verify_replay(Fmm& f, const std::vector<int>& s0, const std::vector<float>&
         if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
         const int rn = rank[id(z, x)];
         if (rn < 0 || rn > r) continue;
-        if (!(f.ttn[id(z, x)] < f.ttn[k])) ++*order_flags;
+        if (f.ttn[id(z, x)] == f.ttn[k]) { tied.push_back({f.ttn[k], (int)k}); tied.push_back({f.ttn[k], (int)id(z, x)}); }
+        else if (!(f.ttn[id(z, x)] < f.ttn[k])) ++*order_flags;
       }
       int trig[4] = {0, 0, 0, 0}, nt = 0;
       const int dz[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
@@ -375,6 +400,76 @@ void verify_replay(Fmm& f, const std::vector<int>& s0, const std::vector<float>&
         prev = trial;
       }
     }
+  // The stopping rule of the refined box is a GLOBAL event (the first edge node to reach the heap root): a key equal to
+  // the stopping node's key anywhere in the heap makes the accepted set depend on heap position.
+  if (exit_rank >= 0) {
+    float ve = FIM_INF;
+    size_t ke = 0;
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] == exit_rank) { ve = f.ttn[k]; ke = k; }
+    if (ve < FIM_INF)
+      for (int ix = 1; ix <= f.nnx; ++ix)
+        for (int iz = 1; iz <= f.nnz; ++iz)
+          if (id(iz, ix) != ke && f.ttn[id(iz, ix)] == ve) ++*order_flags;
+  }
+  // Exact ties between interacting nodes: the reference breaks them by heap position.  A tie is harmless if every order
+  // of the tied nodes gives the same values for them and for every node that can see them (their stencil neighbours
+  // accepted later, and close nodes): checked by brute force over the permutations of small groups, locally.
+  std::sort(tied.begin(), tied.end());
+  tied.erase(std::unique(tied.begin(), tied.end()), tied.end());
+  for (size_t a0 = 0; a0 < tied.size();) {
+    size_t a1 = a0;
+    while (a1 < tied.size() && tied[a1].first == tied[a0].first) ++a1;
+    const size_t g = a1 - a0;
+    bool hazard = g > 4;
+    if (!hazard) {
+      std::vector<int> mem, ranks0, watch;
+      for (size_t i = a0; i < a1; ++i) { mem.push_back(tied[i].second); ranks0.push_back(rk[tied[i].second]); }
+      int rmin = 0x7fffffff;
+      for (int r0 : ranks0) rmin = std::min(rmin, r0);
+      watch = mem;
+      for (int m : mem) {
+        const int ix = m / f.ld + 1, iz = m % f.ld + 1;
+        for (int q = 0; q < 8; ++q) {
+          const int z = iz + sz[q], x = ix + sx[q];
+          if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+          const size_t n = id(z, x);
+          if (s0[n] == 0) continue;
+          if (rk[n] >= 0 && rk[n] < rmin) continue;            // accepted before any of them: cannot see them
+          watch.push_back((int)n);
+        }
+      }
+      std::sort(watch.begin(), watch.end());
+      watch.erase(std::unique(watch.begin(), watch.end()), watch.end());
+      std::vector<int> perm(g);
+      for (size_t i = 0; i < g; ++i) perm[i] = (int)i;
+      std::sort(ranks0.begin(), ranks0.end());
+      // order the members by their current rank so that the identity permutation is the replay's own order
+      std::sort(mem.begin(), mem.end(), [&](int x, int y) { return rank[x] < rank[y]; });
+      do {
+        for (size_t i = 0; i < g; ++i) rk[mem[i]] = ranks0[perm[i]];
+        for (int n : watch) {
+          if (rk[n] < 0 && s0[n] < 0) {                         // unranked: only close nodes carry a value
+            bool touches = false;
+            const int ix = n / f.ld + 1, iz = n % f.ld + 1;
+            const int dz[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
+            for (int q = 0; q < 4; ++q) {
+              const int z = iz + dz[q], x = ix + dx[q];
+              if (z < 1 || z > f.nnz || x < 1 || x > f.nnx) continue;
+              if (rk[id(z, x)] >= 0 && rk[id(z, x)] < trig_limit) touches = true;
+            }
+            if (!touches) continue;
+          }
+          if (rule_value((size_t)n) != f.ttn[n]) { hazard = true; break; }
+        }
+        if (hazard) break;
+      } while (std::next_permutation(perm.begin(), perm.end()));
+      for (size_t i = 0; i < g; ++i) rk[mem[i]] = rank[mem[i]];
+    }
+    if (hazard) ++*order_flags;
+    else if (harmless_tie_groups) ++*harmless_tie_groups;
+    a0 = a1;
+  }
   if (win.empty()) return;
   std::sort(win.begin(), win.end());
   std::vector<std::pair<float, float>> merged;
@@ -495,7 +590,8 @@ extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float
   const std::vector<int> prank = ranks_by_value(f, fimv, rank);
   S.sorted_fim_rank_errors = R.run(prank, nullptr);
   S.sorted_fim_mismatch = count_mismatch();
-  verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events);
+  verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events, -1,
+                &S.harmless_tie_groups);
   *out = S;
   return 0;
 }
@@ -656,7 +752,8 @@ extern "C" int orc_fmm_order_stats_refined(int nx, int ny, float goxd, float goz
   S.sorted_fim_rank_errors = R.run(prank, nullptr, pexit, &close);
   S.sorted_fim_mismatch = compare(prank, close);
   S.sorted_exact_mismatch = -1;                          // not evaluated for this stage
-  verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events);
+  verify_replay(f, s0, t0, prank, &S.verify_order_flags, &S.verify_key_increase_flags, &S.key_increase_events, pexit,
+                &S.harmless_tie_groups);
   *out = S;
   return 0;
 }
