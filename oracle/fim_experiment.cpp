@@ -174,6 +174,7 @@ int Fmm::travel_fim() {
   };
   fim_sweeps = 0;
   fim_converged = 0;
+  fim_evals = 0;
   // Phase 1: first-order scheme, monotone (minimum) updates: an upper bound with the right causal structure.
   // Phase 2: the reference's mixed first/second-order solver, values OVERWRITTEN (a second-order extrapolation from
   // not-yet-converged neighbours can undershoot; with minimum-only updates such a transient would be frozen in),
@@ -193,6 +194,7 @@ int Fmm::travel_fim() {
               if (cur != injected[id(iz, ix)]) { TTN(iz, ix) = injected[id(iz, ix)]; ++changed; }
               continue;
             }
+            fim_evals += phase == 1 ? 1 : 2;
             if (phase == 1) {
               const float t = fouds2_values(iz, ix, cur, false);
               if (t < cur) { TTN(iz, ix) = t; ++changed; }
@@ -235,6 +237,7 @@ struct OrderStats {
   long sorted_fim_rank_errors;            // ... replay steps that found no accepted direct neighbour (impossible order)
   long dag_levels;                        // longest dependency chain of the replay
   long fim_passes;
+  long fim_evals;                         // quadrant-solver evaluations of the fixed-point solve (Gauss-Seidel upper bound)
   // local, order-free checks on the replay made from the fixed-point ranks (what a GPU path could run per node):
   long verify_order_flags;                // interacting pairs whose replayed values are tied or contradict the ranks
   long verify_key_increase_flags;         // nodes inside a key-increase window that interact with a node later in that window
@@ -586,6 +589,7 @@ extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float
   f.nsts = s0; f.ttn = t0;
   f.travel_fim();
   S.fim_passes = f.fim_sweeps;
+  S.fim_evals = f.fim_evals;
   const std::vector<float> fimv = f.ttn;
   const std::vector<int> prank = ranks_by_value(f, fimv, rank);
   S.sorted_fim_rank_errors = R.run(prank, nullptr);
@@ -736,6 +740,7 @@ extern "C" int orc_fmm_order_stats_refined(int nx, int ny, float goxd, float goz
   f.nsts = s0; f.ttn = t0;
   f.travel_fim();
   S.fim_passes = f.fim_sweeps;
+  S.fim_evals = f.fim_evals;
   std::vector<std::pair<float, int>> v;
   for (int ix = 1; ix <= f.nnx; ++ix)
     for (int iz = 1; iz <= f.nnz; ++iz)

@@ -55,6 +55,7 @@ struct Fmm {
   int fim_coarse = 0;
   long fim_sweeps = 0;   // Gauss-Seidel passes the last fixed-point solve took
   int fim_converged = 0;
+  long fim_evals = 0;    // quadrant-solver evaluations the last fixed-point solve made (cost model)
   // ---- statistics for the bench (not in the reference) ----
   long n_accept = 0;   // nodes set alive
   long n_steps = 0;    // ray steps taken

@@ -386,7 +386,7 @@ def fmm_source_fim(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz):
 class OrderStats(C.Structure):
     _fields_ = [(k, C.c_long) for k in ("popped", "rule_mismatch", "pairs", "pair_ties", "pair_inversions",
                                         "sorted_exact_mismatch", "sorted_fim_mismatch", "sorted_fim_rank_errors",
-                                        "dag_levels", "fim_passes", "verify_order_flags", "verify_key_increase_flags", "key_increase_events", "harmless_tie_groups")]
+                                        "dag_levels", "fim_passes", "fim_evals", "verify_order_flags", "verify_key_increase_flags", "key_increase_events", "harmless_tie_groups")]
 
 
 def fmm_order_stats(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, refined=False, prefix=0):
