@@ -15,6 +15,7 @@
 #include "fmm2d.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace orc {
 
@@ -179,6 +180,55 @@ int Fmm::travel_fim() {
   // Phase 2: the reference's mixed first/second-order solver, values OVERWRITTEN (a second-order extrapolation from
   // not-yet-converged neighbours can undershoot; with minimum-only updates such a transient would be frozen in),
   // repeated until a whole pass changes nothing bit for bit.
+  if (fim_coarse == 2) {
+    // ACTIVE-LIST variant (what a GPU fast-iterative kernel does): only nodes one of whose stencil neighbours changed
+    // are re-evaluated.  FIFO work lists, same update rules, same fixed point; counts the evaluations it needs.
+    std::vector<int> q;
+    std::vector<char> inq((size_t)nnx * nnz + (size_t)ld * nnx, 0);
+    auto push = [&](int iz, int ix) {
+      if (iz < 1 || iz > nnz || ix < 1 || ix > nnx) return;
+      if (fixed[id(iz, ix)] == 1) return;
+      const size_t k = (size_t)(ix - 1) * ld + (iz - 1);
+      if (!inq[k]) { inq[k] = 1; q.push_back((int)k); }
+    };
+    for (int phase = 1; phase <= 2; ++phase) {
+      q.clear(); std::fill(inq.begin(), inq.end(), 0);
+      for (int ix = 1; ix <= nnx; ++ix)
+        for (int iz = 1; iz <= nnz; ++iz) {
+          if (phase == 1) { if (TTN(iz, ix) < FIM_INF) { push(iz - 1, ix); push(iz + 1, ix); push(iz, ix - 1); push(iz, ix + 1); push(iz, ix); } }
+          else push(iz, ix);
+        }
+      size_t head = 0;
+      const size_t cap = (size_t)400 * nnx * nnz;
+      while (head < q.size() && q.size() < cap) {
+        const int k = q[head++];
+        inq[k] = 0;
+        const int ix = k / ld + 1, iz = k % ld + 1;
+        const char kind = fixed[id(iz, ix)];
+        const float cur = TTN(iz, ix);
+        float t;
+        if (kind == 2 && !band_is_recomputed(iz, ix, injected[id(iz, ix)])) t = injected[id(iz, ix)];
+        else if (phase == 1) { ++fim_evals; t = std::min(cur, fouds2_values(iz, ix, cur, false)); }
+        else {
+          fim_evals += 2;
+          t = fouds2_values(iz, ix, FIM_INF, true);
+          t = fouds2_values(iz, ix, t, true);
+          if (t >= FIM_INF) t = cur;
+        }
+        if (t != cur) {
+          TTN(iz, ix) = t;
+          for (int d = 1; d <= (phase == 1 ? 1 : 2); ++d) { push(iz - d, ix); push(iz + d, ix); push(iz, ix - d); push(iz, ix + d); }
+        }
+      }
+      if (phase == 2) fim_converged = head >= q.size();
+      if (head > 0x3fffffff) break;
+    }
+    fim_sweeps = 1;
+    for (int ix = 1; ix <= nnx; ++ix)
+      for (int iz = 1; iz <= nnz; ++iz) NSTS(iz, ix) = 0;
+    n_accept += (long)nnx * nnz;
+    return OK;
+  }
   for (int phase = 1; phase <= 2; ++phase) {
     for (int pass = 0; pass < 2000; ++pass) {
       long changed = 0;
@@ -587,6 +637,7 @@ extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float
   }
   // (4) ranks predicted from the fixed-point (fast-iterative) values
   f.nsts = s0; f.ttn = t0;
+  if (const char* e = std::getenv("ORC_FIM_ACTIVE_LIST")) f.fim_coarse = std::atoi(e) ? 2 : 0;
   f.travel_fim();
   S.fim_passes = f.fim_sweeps;
   S.fim_evals = f.fim_evals;
@@ -738,6 +789,7 @@ extern "C" int orc_fmm_order_stats_refined(int nx, int ny, float goxd, float goz
   }
   // ranks predicted from the order-free fixed point on the whole box, cut at the first exit node in sorted order
   f.nsts = s0; f.ttn = t0;
+  if (const char* e = std::getenv("ORC_FIM_ACTIVE_LIST")) f.fim_coarse = std::atoi(e) ? 2 : 0;
   f.travel_fim();
   S.fim_passes = f.fim_sweeps;
   S.fim_evals = f.fim_evals;
