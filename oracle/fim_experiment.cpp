@@ -651,6 +651,72 @@ extern "C" int orc_fmm_order_stats(int nx, int ny, float goxd, float gozd, float
   return 0;
 }
 
+// RANK ITERATION.  Instead of paying a whole fixed-point solve for the ranks, start from any cheap guess of the arrival
+// order (guess = a field whose sorted order is the first prediction: distance from the source, the same source's field
+// at the neighbouring period, ...) and iterate  ranks -> replay -> values -> sort -> ranks  until the ranks stop
+// changing; each round costs one solver evaluation per node plus a sort.  Reports the rounds needed and whether the
+// fixed point is the reference's field.
+extern "C" int orc_fmm_rank_iteration(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                                      float scx, float scz, int prefix, const float* guess /* (nnz,nnx) column-major */,
+                                      int max_rounds, long* rounds, long* mismatch, long* flags, long* popped) {
+  using namespace orc;
+  Fmm f;
+  f.init(nx, ny, goxd, gozd, dvxd, dvzd);
+  std::vector<int> rank(f.ttn.size(), -1), s0;
+  std::vector<float> t0;
+  f.rec_rank = &rank; f.rec_init_nsts = &s0; f.rec_init_ttn = &t0;
+  int st = f.solve_source(pv, scx, scz);
+  if (st) return st;
+  f.rec_rank = nullptr; f.rec_init_nsts = nullptr; f.rec_init_ttn = nullptr;
+  const std::vector<float> ref = f.ttn;
+  auto idx = [&](int iz, int ix) { return (size_t)(ix - 1) * f.ld + (iz - 1); };
+  long np = 0;
+  for (int v : rank) if (v >= 0) ++np;
+  *popped = np;
+  Replay R{f, s0, t0};
+  if (prefix > 0 && prefix < np) {
+    std::vector<int> rcut(rank.size(), -1);
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] >= 0 && rank[k] < prefix) rcut[k] = rank[k];
+    std::vector<char> close;
+    R.run(rcut, nullptr, prefix, &close);
+    std::vector<int> s1(rank.size(), -1);
+    std::vector<float> t1(rank.size(), 0.0f);
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz) {
+        const size_t k = idx(iz, ix);
+        if (s0[k] == 0 || rcut[k] >= 0) { s1[k] = 0; t1[k] = f.ttn[k]; }
+        else if (close[k]) { s1[k] = 1; t1[k] = f.ttn[k]; }
+      }
+    s0 = s1; t0 = t1;
+    for (size_t k = 0; k < rank.size(); ++k)
+      if (rank[k] >= 0 && rank[k] < prefix) rank[k] = -1;
+  }
+  std::vector<float> g(f.ttn.size(), 0.0f);
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz) g[idx(iz, ix)] = guess[(size_t)(ix - 1) * f.nnz + (iz - 1)];
+  std::vector<int> rk = ranks_by_value(f, g, rank);
+  *rounds = 0;
+  for (int it = 0; it < max_rounds; ++it) {
+    R.run(rk, nullptr);
+    ++*rounds;
+    const std::vector<float> v = f.ttn;
+    std::vector<int> nr = ranks_by_value(f, v, rank);
+    if (nr == rk) break;
+    rk = nr;
+  }
+  R.run(rk, nullptr);
+  long m = 0;
+  for (int ix = 1; ix <= f.nnx; ++ix)
+    for (int iz = 1; iz <= f.nnz; ++iz)
+      if (f.ttn[idx(iz, ix)] != ref[idx(iz, ix)]) ++m;
+  *mismatch = m;
+  long of = 0, kf = 0, ke = 0;
+  verify_replay(f, s0, t0, rk, &of, &kf, &ke);
+  *flags = of + kf;
+  return 0;
+}
+
 namespace orc {
 namespace {
 // the refined source box exactly as solve_source sets it up (FwdTraveltimeCPS.f90:493-560), without the march
@@ -694,6 +760,8 @@ bool is_exit_node(const Fmm& f, int iz, int ix) {
 extern "C" int orc_fmm_order_stats_refined(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
                                            float scx, float scz, int prefix, orc::OrderStats* out) {
   using namespace orc;
+  const bool guess_mode = prefix >= 1000;      // prefix = 1000 + p: rank iteration from the distance guess, serial prefix p
+  if (guess_mode) prefix -= 1000;
   Fmm f;
   f.init(nx, ny, goxd, gozd, dvxd, dvzd);
   int st = setup_refined(f, pv, scx, scz);
@@ -787,23 +855,58 @@ extern "C" int orc_fmm_order_stats_refined(int nx, int ny, float goxd, float goz
     for (size_t k = 0; k < rank.size(); ++k)
       if (rank[k] >= 0 && rank[k] < prefix) rank[k] = -2;      // accepted before the replayed part began
   }
-  // ranks predicted from the order-free fixed point on the whole box, cut at the first exit node in sorted order
-  f.nsts = s0; f.ttn = t0;
-  if (const char* e = std::getenv("ORC_FIM_ACTIVE_LIST")) f.fim_coarse = std::atoi(e) ? 2 : 0;
-  f.travel_fim();
-  S.fim_passes = f.fim_sweeps;
-  S.fim_evals = f.fim_evals;
-  std::vector<std::pair<float, int>> v;
-  for (int ix = 1; ix <= f.nnx; ++ix)
-    for (int iz = 1; iz <= f.nnz; ++iz)
-      if (f.ttn[idx(iz, ix)] < FIM_INF && s0[idx(iz, ix)] != 0) v.push_back({f.ttn[idx(iz, ix)], (int)idx(iz, ix)});
-  std::stable_sort(v.begin(), v.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
-  std::vector<int> prank(f.ttn.size(), -1);
+  // ranks: sorted order of a field, cut at the first stopping-edge node
+  std::vector<int> prank;
   int pexit = -1;
-  for (size_t i = 0; i < v.size(); ++i) {
-    const int k = v[i].second;
-    prank[k] = (int)i;
-    if (is_exit_node(f, k % f.ld + 1, k / f.ld + 1)) { pexit = (int)i; break; }
+  auto ranks_from = [&](const std::vector<float>& val) {
+    std::vector<std::pair<float, int>> v;
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz)
+        if (val[idx(iz, ix)] < FIM_INF && s0[idx(iz, ix)] != 0) v.push_back({val[idx(iz, ix)], (int)idx(iz, ix)});
+    std::stable_sort(v.begin(), v.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+    std::vector<int> r(f.ttn.size(), -1);
+    pexit = -1;
+    for (size_t i = 0; i < v.size(); ++i) {
+      const int k = v[i].second;
+      r[k] = (int)i;
+      if (is_exit_node(f, k % f.ld + 1, k / f.ld + 1)) { pexit = (int)i; break; }
+    }
+    return r;
+  };
+  if (guess_mode) {
+    // RANK ITERATION from a trivial guess (distance from the source in grid metric): ranks -> replay -> sort -> ranks.
+    // Close nodes enter the next sort with their trial keys (the keys the heap would hold), far nodes with +infinity.
+    int isx = (int)((scx - f.gox) / f.dnx), isz = (int)((scz - f.goz) / f.dnz);
+    std::vector<float> cur(f.ttn.size(), FIM_INF);
+    for (int ix = 1; ix <= f.nnx; ++ix)
+      for (int iz = 1; iz <= f.nnz; ++iz) {
+        const float ax = ((float)(ix - 1 - isx) - 0.5f) * f.dnx * f.earth;
+        const float az = ((float)(iz - 1 - isz) - 0.5f) * f.dnz * f.earth * sin_rf(f.gox + (float)(ix - 1) * f.dnx);
+        cur[idx(iz, ix)] = std::sqrt(ax * ax + az * az);
+      }
+    prank = ranks_from(cur);
+    for (int it = 0; it < 60; ++it) {
+      R.run(prank, nullptr, pexit, &close);
+      ++S.fim_passes;                                      // rounds of the rank iteration
+      for (int ix = 1; ix <= f.nnx; ++ix)
+        for (int iz = 1; iz <= f.nnz; ++iz) {
+          const size_t k = idx(iz, ix);
+          cur[k] = (prank[k] >= 0 || close[k]) ? f.ttn[k] : FIM_INF;
+        }
+      const int old_exit = pexit;
+      std::vector<int> nr = ranks_from(cur);
+      if (nr == prank && pexit == old_exit) break;
+      prank = nr;
+    }
+  } else {
+    // ranks predicted from the order-free fixed point on the whole box
+    f.nsts = s0; f.ttn = t0;
+    if (const char* e = std::getenv("ORC_FIM_ACTIVE_LIST")) f.fim_coarse = std::atoi(e) ? 2 : 0;
+    f.travel_fim();
+    S.fim_passes = f.fim_sweeps;
+    S.fim_evals = f.fim_evals;
+    const std::vector<float> fimv = f.ttn;
+    prank = ranks_from(fimv);
   }
   f.nsts = s0;
   S.sorted_fim_rank_errors = R.run(prank, nullptr, pexit, &close);

@@ -404,3 +404,17 @@ def fmm_order_stats(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, refined=False,
     if st:
         raise RuntimeError(f"orc_fmm_order_stats status {st}")
     return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+def fmm_rank_iteration(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, guess, prefix=64, max_rounds=200):
+    """EXPERIMENT: ranks -> replay -> sort iterated from the sorted order of `guess` (a (nnz,nnx) field) on the coarse
+    march of one source; returns dict(rounds, mismatch vs the reference, flags of the local checks, popped)."""
+    pv = np.ascontiguousarray(pv, np.float64)
+    g = np.asfortranarray(guess, np.float32)
+    out = [C.c_long(0) for _ in range(4)]
+    st = lib().orc_fmm_rank_iteration(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+                                      C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), C.c_int(prefix), _p(g),
+                                      C.c_int(max_rounds), *[C.byref(o) for o in out])
+    if st:
+        raise RuntimeError(f"orc_fmm_rank_iteration status {st}")
+    return dict(zip(("rounds", "mismatch", "flags", "popped"), [o.value for o in out]))

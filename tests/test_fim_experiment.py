@@ -63,3 +63,23 @@ def test_order_rule_holds_on_the_refined_source_box(oracle, test1, test1_tables)
             assert r["popped"] > 3000 and r["rule_mismatch"] == 0
             flagged = r["verify_order_flags"] + r["verify_key_increase_flags"] > 0
             assert flagged or r["sorted_fim_mismatch"] == 0      # soundness of the local checks
+
+
+def test_rank_iteration_from_a_distance_guess_reaches_the_reference_field(oracle, test1, test1_tables):
+    """RANK ITERATION (scripts/rank_iteration_experiment.py): starting from the order of plain geometric distance to the
+    source, ranks -> replay -> sort -> ranks settles within a few rounds on the reference's coarse field, bit for bit."""
+    p = test1["para"]; sv = test1["sv"]
+    pv = np.ascontiguousarray(test1_tables["pvRc"][:, 10])
+    nnx = (p.nx - 3) * 5 + 1; nnz = (p.ny - 3) * 5 + 1
+    gox = (90 - p.goxd) * np.pi / 180; goz = p.gozd * np.pi / 180
+    x = gox + np.arange(nnx) * (p.dvxd * np.pi / 180 / 5); z = goz + np.arange(nnz) * (p.dvzd * np.pi / 180 / 5)
+    X, Z = np.meshgrid(x, z)
+    for s in range(int(sv.nsrcsurf1[0])):
+        scx, scz = float(sv.scxf[s, 0]), float(sv.sczf[s, 0])
+        guess = np.hypot(X - scx, (Z - scz) * np.sin(X)).astype(np.float32)
+        r = oracle.fmm_rank_iteration(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, scx, scz, guess, prefix=64)
+        assert r["popped"] > 4000 and r["mismatch"] == 0 and r["flags"] == 0 and r["rounds"] <= 12
+        rr = oracle.fmm_order_stats(p.nx, p.ny, p.goxd, p.gozd, p.dvxd, p.dvzd, pv, scx, scz, refined=True, prefix=1004)
+        assert rr["rule_mismatch"] == 0 and rr["fim_passes"] <= 12
+        flagged = rr["verify_order_flags"] + rr["verify_key_increase_flags"] > 0
+        assert flagged or rr["sorted_fim_mismatch"] == 0
