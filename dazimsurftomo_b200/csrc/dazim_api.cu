@@ -516,7 +516,21 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   return DAZIM_OK;
 }
 
-static int plan_run(dazim_plan* P) {
+// events that are destroyed on every exit path
+struct EventList {
+  std::vector<cudaEvent_t> v;
+  cudaError_t make(cudaEvent_t* e) {
+    cudaError_t r = cudaEventCreate(e);
+    if (r == cudaSuccess) v.push_back(*e);
+    return r;
+  }
+  cudaEvent_t operator[](size_t i) const { return v[i]; }
+  ~EventList() { for (auto e : v) cudaEventDestroy(e); }
+};
+
+static const int ST_POOL_OVERFLOW = -1000;   // internal: ray-footprint pool too small, plan_run grows it and re-runs
+
+static int plan_run_once(dazim_plan* P) {
   dazim_handle* h = P->h;
   CK(cudaSetDevice(h->dev));
   g_alloc_stream = h->st;
@@ -536,13 +550,12 @@ static int plan_run(dazim_plan* P) {
   }
   CK(cudaEventRecord(P->ev[1], st));
   const size_t nb = P->batch_src0.size() - 1;
-  std::vector<cudaEvent_t> bev;   // per-batch fmm/trace boundaries
+  EventList bev;   // per-batch fmm/trace boundaries
   for (size_t b = 0; b < nb; ++b) {
     const long long s0 = P->batch_src0[b], s1 = P->batch_src0[b + 1];
     const long long r0 = P->batch_ray0[b], r1 = P->batch_ray0[b + 1];
     cudaEvent_t e0, e1, e2;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
-    bev.push_back(e0); bev.push_back(e1); bev.push_back(e2);
+    CK(bev.make(&e0)); CK(bev.make(&e1)); CK(bev.make(&e2));
     CK(cudaEventRecord(e0, st));
     FmmArgs F;
     F.g = g; F.src = P->d_src.p + s0; F.nsrc = (int)(s1 - s0); F.velv = P->d_velv.p; F.slow_c = P->d_slow_c.p;
@@ -588,14 +601,13 @@ static int plan_run(dazim_plan* P) {
     cudaEventElapsedTime(&ms, bev[3 * b], bev[3 * b + 1]); T.fmm_ms += ms;
     cudaEventElapsedTime(&ms, bev[3 * b + 1], bev[3 * b + 2]); T.trace_ms += ms;
   }
-  for (auto e : bev) cudaEventDestroy(e);
   T.n_accept = (long long)cnt[1];
   T.n_steps = (long long)cnt[2];
   T.rbint = icnt[1] & 1;
   if (icnt[1] & 16) return DAZIM_EHEAP;
   if (icnt[1] & 2) return DAZIM_ERECEIVER_OUTSIDE;
   if (icnt[1] & 4) return DAZIM_EFOOTPRINT;
-  if (icnt[1] & 8) return DAZIM_EFOOTPRINT + 1;   // pool overflow: caller retries with a bigger pool
+  if (icnt[1] & 8) return ST_POOL_OVERFLOW;       // pool overflow: plan_run retries with a bigger pool
   CK(cudaEventRecord(P->ev[3], st));
   P->nnz = 0;
   if (P->nrow > 0 && !P->emit_all) {
@@ -645,6 +657,25 @@ static int plan_run(dazim_plan* P) {
   cudaEventElapsedTime(&ms, P->ev[3], P->ev[4]); T.assemble_ms = ms;
   cudaEventElapsedTime(&ms, P->ev[0], P->ev[4]); T.total_ms = ms;
   return DAZIM_OK;
+}
+
+// The footprint pool is sized from a straight-line estimate at plan creation; rays of a later outer iteration can
+// bend more.  Grow it (x4, up to three times) and re-run instead of failing a plan that is reused across iterations.
+static int plan_run(dazim_plan* P) {
+  int st = DAZIM_OK;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    st = plan_run_once(P);
+    if (st != ST_POOL_OVERFLOW) return st;
+    if (attempt == 3) break;
+    CK(cudaSetDevice(P->h->dev));
+    g_alloc_stream = P->h->st;
+    if (P->pool_cap >= 2000000000ull) break;                       // fp_off is a 32-bit offset
+    P->pool_cap = std::min(P->pool_cap * 4ull, 2000000000ull);
+    CK(P->d_fp_cell.alloc(P->pool_cap));
+    CK(P->d_fp_fdm.alloc(P->pool_cap));
+    if (P->azim) { CK(P->d_fp_fdmc.alloc(P->pool_cap)); CK(P->d_fp_fdms.alloc(P->pool_cap)); }
+  }
+  return DAZIM_EFOOTPRINT;
 }
 
 extern "C" int dazim_plan_create(dazim_handle* h, int mode, const dazim_problem* p, const dazim_tables* tables,
@@ -751,26 +782,10 @@ extern "C" int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, d
   }
   dazim_plan* P = nullptr;
   int st = DAZIM_OK;
-  double pool_scale = 1.0;
-  for (int attempt = 0; attempt < 4; ++attempt) {
-    st = plan_build(h, mode, p, &tb, Gc, Gs, 0, -1, 0, &P);
-    if (st) return st;
-    if (pool_scale > 1.0) {
-      // grow the footprint pool after an overflow
-      P->pool_cap = (unsigned long long)(P->pool_cap * pool_scale);
-      cudaError_t e = P->d_fp_cell.alloc(P->pool_cap);
-      if (e == cudaSuccess) e = P->d_fp_fdm.alloc(P->pool_cap);
-      if (e == cudaSuccess && P->azim) e = P->d_fp_fdmc.alloc(P->pool_cap);
-      if (e == cudaSuccess && P->azim) e = P->d_fp_fdms.alloc(P->pool_cap);
-      if (e != cudaSuccess) { plan_free(P); return DAZIM_ECUDA + (int)e; }
-    }
-    st = plan_run(P);
-    if (st != DAZIM_EFOOTPRINT + 1) break;
-    plan_free(P);
-    P = nullptr;
-    pool_scale *= 4.0;
-  }
-  if (st) { if (P) plan_free(P); return st == DAZIM_EFOOTPRINT + 1 ? DAZIM_EFOOTPRINT : st; }
+  st = plan_build(h, mode, p, &tb, Gc, Gs, 0, -1, 0, &P);
+  if (st) return st;
+  st = plan_run(P);       // grows the ray-footprint pool and re-runs if the estimate was too small
+  if (st) { if (P) plan_free(P); return st; }
   h->times.kernels_ms = kms;
   h->times.n_launch += klaunch;
   if (coo && mode != 0) {

@@ -533,7 +533,9 @@ int Fmm::solve_source(const double* pv, float x, float z) {
     if (rec_init_nsts) *rec_init_nsts = nsts;
     if (rec_init_ttn) *rec_init_ttn = ttn;
   }
-  if (fim_coarse) return travel_fim();     // experiment only (fim_experiment.cpp)
+#ifdef ORC_WITH_EXPERIMENTS
+  if (fim_coarse) return travel_fim();     // experiment only (fim_experiment.cpp; liboracle_experiments.so)
+#endif
   return travel(x, z, 2);
 }
 

@@ -282,7 +282,9 @@ int gbuild(GBuild& g) {
   auto worker = [&](int t) {
     Fmm f;
     f.init(nx, ny, g.goxd, g.gozd, g.dvxd, g.dvzd);
+#ifdef ORC_WITH_EXPERIMENTS
     if (const char* e = std::getenv("ORC_FIM_EXPERIMENT")) f.fim_coarse = std::atoi(e);   // fim_experiment.cpp
+#endif
     const size_t nf = (size_t)(nvz + 2) * (nvx + 2);
     const int ldf = nvz + 2;
     std::vector<float> fdm(nf), fdmc(nf), fdms(nf);

@@ -13,7 +13,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_LIB_EXP = os.path.join(_HERE, "_build", "liboracle_experiments.so")
 _lib = None
+_lib_exp = None
 
 f32p = np.ctypeslib.ndpointer(np.float32, flags="F_CONTIGUOUS")
 f64p = np.ctypeslib.ndpointer(np.float64, flags="F_CONTIGUOUS")
@@ -22,7 +24,8 @@ i32p = np.ctypeslib.ndpointer(np.int32, flags="F_CONTIGUOUS")
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".h"))]
-    stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    stale = force or not (os.path.exists(_LIB) and os.path.exists(_LIB_EXP)) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(_LIB), os.path.getmtime(_LIB_EXP)) for s in srcs + [os.path.join(_HERE, "Makefile")])
     if stale:
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _LIB
@@ -33,10 +36,21 @@ def lib():
     if _lib is None:
         if not os.path.exists(_LIB):
             build()
-        _lib = C.CDLL(_LIB)
+        _lib = C.CDLL(_LIB_EXP if os.environ.get("ORC_USE_EXPERIMENTS_LIB") == "1" else _LIB)
         _lib.orc_delsph.restype = C.c_float
         _lib.orc_delsph.argtypes = [C.c_float] * 4
     return _lib
+
+
+def lib_exp():
+    """The analysis experiments (fim_experiment.cpp) live in their own library so that nothing of them is inside the
+    library the CPU baseline times."""
+    global _lib_exp
+    if _lib_exp is None:
+        if not os.path.exists(_LIB_EXP):
+            build()
+        _lib_exp = C.CDLL(_LIB_EXP)
+    return _lib_exp
 
 
 class GBuildArgs(C.Structure):
@@ -165,8 +179,9 @@ def ray(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, rcx, rcz, azim=True):
 
 
 def gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc=None, gs=None, tables=None,
-           nthreads=1, maxnar=None):
-    """Run the oracle orchestrator.  mode 0 forward, 1 iso G, 2 joint G.  Returns a dict."""
+           nthreads=1, maxnar=None, experiments=False):
+    """Run the oracle orchestrator.  mode 0 forward, 1 iso G, 2 joint G.  Returns a dict.
+    experiments=True runs the copy inside liboracle_experiments.so (the only build in which ORC_FIM_EXPERIMENT acts)."""
     nx, ny, nz = vels.shape
     vels = np.asfortranarray(vels, np.float32); depz = np.ascontiguousarray(depz, np.float32)
     tRc = np.ascontiguousarray(tRc, np.float64); k = len(tRc)
@@ -202,7 +217,7 @@ def gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc=None, g
     rw = np.zeros(maxnar, np.float32); iw = np.zeros(maxnar, np.int32); col = np.zeros(maxnar, np.int32)
     a.rw = _p(rw); a.iw_row = _p(iw); a.col = _p(col); a.maxnar = maxnar
     a.nthreads = nthreads
-    st = lib().orc_gbuild(C.byref(a))
+    st = (lib_exp() if experiments else lib()).orc_gbuild(C.byref(a))
     if st:
         raise RuntimeError(f"orc_gbuild status {st}")
     n = a.nar
@@ -376,7 +391,7 @@ def fmm_source_fim(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz):
     pv = np.ascontiguousarray(pv, np.float64)
     ttn = np.zeros((nnz, nnx), np.float32, order="F")
     sw = C.c_long(0)
-    st = lib().orc_fmm_source_fim(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+    st = lib_exp().orc_fmm_source_fim(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
                                   C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), _p(ttn), C.byref(sw))
     if st:
         raise RuntimeError(f"orc_fmm_source_fim status {st}")
@@ -398,9 +413,9 @@ def fmm_order_stats(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, refined=False,
     head = (C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd), C.c_float(dvzd), _p(pv),
             C.c_float(scx), C.c_float(scz))
     if refined:
-        st = lib().orc_fmm_order_stats_refined(*head, C.c_int(prefix), C.byref(s))
+        st = lib_exp().orc_fmm_order_stats_refined(*head, C.c_int(prefix), C.byref(s))
     else:
-        st = lib().orc_fmm_order_stats(*head, C.c_int(prefix), C.byref(s))
+        st = lib_exp().orc_fmm_order_stats(*head, C.c_int(prefix), C.byref(s))
     if st:
         raise RuntimeError(f"orc_fmm_order_stats status {st}")
     return {k: getattr(s, k) for k, _ in s._fields_}
@@ -412,7 +427,7 @@ def fmm_rank_iteration(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, guess, pref
     pv = np.ascontiguousarray(pv, np.float64)
     g = np.asfortranarray(guess, np.float32)
     out = [C.c_long(0) for _ in range(4)]
-    st = lib().orc_fmm_rank_iteration(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+    st = lib_exp().orc_fmm_rank_iteration(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
                                       C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), C.c_int(prefix), _p(g),
                                       C.c_int(max_rounds), *[C.byref(o) for o in out])
     if st:

@@ -69,7 +69,7 @@ def main():
     os.environ.pop("ORC_FIM_EXPERIMENT", None)
     ref = po.gbuild(*args, tables=tb, nthreads=8)
     os.environ["ORC_FIM_EXPERIMENT"] = "1"
-    alt = po.gbuild(*args, tables=tb, nthreads=8)
+    alt = po.gbuild(*args, tables=tb, nthreads=8, experiments=True)
     os.environ.pop("ORC_FIM_EXPERIMENT", None)
     ka = set(zip(ref["row"].tolist(), ref["col"].tolist())); kb = set(zip(alt["row"].tolist(), alt["col"].tolist()))
     common = ka & kb

@@ -20,7 +20,8 @@ def test_fixed_point_is_close_to_but_not_the_heap_march(oracle, test1, test1_tab
 
 
 def test_default_path_ignores_the_experiment_switch(oracle, test1, test1_tables, monkeypatch):
-    """ORC_FIM_EXPERIMENT only acts inside gbuild when set; unset, the oracle is the reference's algorithm."""
+    """The library the tests check against and bench.py times (liboracle.so) has no experiment code in it at all:
+    ORC_FIM_EXPERIMENT=1 changes nothing there; it only acts in liboracle_experiments.so."""
     p = test1["para"]
     import copy
     sv = copy.copy(test1["sv"])
@@ -29,9 +30,12 @@ def test_default_path_ignores_the_experiment_switch(oracle, test1, test1_tables,
     args = (0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv, test1["gc"], test1["gs"])
     monkeypatch.delenv("ORC_FIM_EXPERIMENT", raising=False)
     a = oracle.gbuild(*args, tables=test1_tables)
-    monkeypatch.setenv("ORC_FIM_EXPERIMENT", "0")
+    monkeypatch.setenv("ORC_FIM_EXPERIMENT", "1")
     b = oracle.gbuild(*args, tables=test1_tables)
     assert np.array_equal(a["dsurf"], b["dsurf"]) and np.array_equal(a["obsTaa"], b["obsTaa"])
+    c = oracle.gbuild(*args, tables=test1_tables, experiments=True)
+    assert not np.array_equal(a["dsurf"], c["dsurf"])             # the switch is live only in the experiments build
+    assert np.abs(a["dsurf"] - c["dsurf"]).max() < 1e-5 * a["dsurf"].max()
 
 
 def test_values_are_a_local_function_of_the_acceptance_order(oracle, test1, test1_tables):

@@ -400,3 +400,87 @@ def test_every_eikonal_kernel_variant_is_bit_identical(gpu, oracle, test1, test1
     o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv,
                       test1["gc"], test1["gs"], tables=test1_tables)
     assert np.array_equal(a["dsurf"], o["dsurf"]) and np.array_equal(a["obsTaa"], o["obsTaa"])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 2 = the grid bench.py measures: S200 (202 x 202 x 9 model, 996 x 996 propagation grid).
+# 11-12 heap levels, real spill traffic at hcap 512, interleaved slab offsets ~1e6: paths T1 never reaches.
+@pytest.fixture(scope="module")
+def s200():
+    from dazimsurftomo_b200 import synthetic
+    w = synthetic.s200(src_per_period=2)            # 8 periods x 2 sources = 16 solves, 512 rays
+    return w, synthetic.proxy_tables(w)
+
+
+_S200_ORACLE = {}
+
+
+def _s200_oracle_fields(oracle, w, tb, k, srcs):
+    key = (k, tuple(srcs))
+    if key not in _S200_ORACLE:
+        pv = np.ascontiguousarray(tb["pvRc"][:, k])
+        _S200_ORACLE[key] = [oracle.fmm_source(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, pv, x, z) for x, z in srcs]
+    return _S200_ORACLE[key]
+
+
+@pytest.mark.parametrize("env", [dict(DAZIM_DUO="0", DAZIM_HCAP="512"), dict(DAZIM_DUO="0", DAZIM_HCAP="4096"),
+                                 dict(DAZIM_DUO="1", DAZIM_HCAP="512"), dict(DAZIM_DUO="1", DAZIM_HCAP="4096"), dict()])
+def test_s200_eikonal_fields_bit_exact(gpu, oracle, s200, monkeypatch, env):
+    """Coarse and refined travel-time fields + status flags on the benchmarked grid, every K3 mode (half-warp
+    throughput kernel / two-warp latency kernel), shared heap of 512 (spilling) and 4096 entries, and the library's
+    own choice: bit for bit against the oracle."""
+    w, tb = s200
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    k = 5
+    srcs = [(float(w.sv.scxf[s, k]), float(w.sv.sczf[s, k])) for s in range(2)]
+    # + a source near the model corner: clipped source box on the big grid
+    g0x = np.float32((90.0 - w.goxd) * np.pi / 180); g0z = np.float32(w.gozd * np.pi / 180); dv = np.float32(w.dvxd * np.pi / 180)
+    srcs.append((float(g0x + dv * 0.6), float(g0z + dv * 198.3)))
+    pv = np.ascontiguousarray(tb["pvRc"][:, k])
+    r = gpu.fmm_solve(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, pv, [s[0] for s in srcs], [s[1] for s in srcs])
+    assert r["ttn"].shape[:2] == (996, 996)
+    for i, o in enumerate(_s200_oracle_fields(oracle, w, tb, k, srcs)):
+        assert np.array_equal(r["veln"], o["veln"])
+        nzr, nxr = o["geom"][0], o["geom"][1]
+        assert tuple(r["geom"][:6, i]) == tuple(o["geom"][:6])
+        assert np.array_equal(r["ttn"][:, :, i], o["ttn"]), (i, int((r["ttn"][:, :, i] != o["ttn"]).sum()))
+        assert np.all(r["nsts"][:, :, i] == 0)
+        assert np.array_equal(r["nstsr"][:nzr, :nxr, i] == 0, o["nstsr"][:nzr, :nxr] == 0)      # alive sets
+        alive = o["nstsr"][:nzr, :nxr] >= 0
+        assert np.array_equal(r["ttnr"][:nzr, :nxr, i][alive], o["ttnr"][:nzr, :nxr][alive])
+        assert np.array_equal(r["nstsr"][:nzr, :nxr, i], o["nstsr"][:nzr, :nxr])                # heap slots too
+
+
+@pytest.mark.parametrize("env", [dict(DAZIM_DUO="0"), dict(DAZIM_DUO="1"), dict(DAZIM_REPLAY="0")])
+def test_s200_joint_system_bit_exact(gpu, oracle, s200, monkeypatch, env):
+    """dsurf + joint COO (rows, columns, values) of 16 solves / 512 rays on the S200 grid against the oracle."""
+    w, tb = s200
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    args = (w.vs, w.depz, w.tRc, w.sublayers, w.goxd, w.gozd, w.dvxd, w.dvzd, w.sv)
+    mx = int(w.sv.dall) * 60000
+    key = "joint"
+    if key not in _S200_ORACLE:
+        _S200_ORACLE[key] = oracle.gbuild(2, *args, tables=tb, maxnar=mx, nthreads=8)
+    o = _S200_ORACLE[key]
+    r = gpu.CalSurfGAnisoJoint(*args, tables=tb, maxnar=mx)
+    _cmp_coo(r, o)
+    assert r["times"]["n_accept"] == o["n_accept"] and r["times"]["n_steps"] == o["n_steps"]
+
+
+def test_footprint_pool_grows_inside_plan_run(gpu, oracle, test1, test1_tables, monkeypatch):
+    """a plan reused across outer iterations must survive rays that need more footprint room than the
+    straight-line estimate gave it.  A pool 50x too small: plan.run() re-allocates and re-runs by itself."""
+    p = test1["para"]
+    pv, svs, svp, srho, _ = oracle.depthkernel(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
+    tb = dict(test1_tables, sen_vs=svs, sen_vp=svp, sen_rho=srho)
+    args = (test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"])
+    full = gpu.CalSurfGAnisoJoint(*args, tables=tb)
+    monkeypatch.setenv("DAZIM_POOL_SCALE", "0.02")
+    plan = gpu.Plan(2, *args, tb)
+    plan.run()
+    out = plan.fetch()
+    plan.close()
+    assert np.array_equal(out["dsurf"], full["dsurf"]) and np.array_equal(out["val"], full["rw"])
+    assert np.array_equal(out["col"], full["col"])

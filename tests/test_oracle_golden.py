@@ -79,13 +79,22 @@ def test_forward_subset_vs_golden(oracle, test1, test1_tables):
 
 @pytest.mark.skipif(not os.path.isdir(REF_EX), reason="reference examples only exist in the build container")
 def test_forward_full_vs_golden(oracle, test1, test1_tables):
-    """All 261 360 rays of example/test1_syn_foward/output/surfphase_forward_RV3th.dat.
+    """All 261 360 rays of example/test1_syn_foward/output/surfphase_forward_RV3th.dat, every period.
 
-    Periods 1-4 (5-8 s, 29 040 rays) must agree to the print precision.  Beyond that the shipped
-    file is not reproducible from the shipped sources + inputs (DESIGN.md "Golden-file findings"):
-    (i) the reference's eikonal scheme is chaotic at the float32-ulp level (isolated rays jump by
-    ~0.1 s when the phase-velocity map moves by 1 ulp), (ii) from ~13 s on the file drifts smoothly
-    away from the phase velocities printed in the reference's own period_Azm_tomo.real."""
+    What is reproducible from the shipped sources + inputs, and is asserted here (DESIGN.md s2.1,
+    numbers in profiles/r2_golden_drift.json written by scripts/golden_drift.py):
+      * periods 1-4 (5-8 s, 29 040 rays): every ray to the f9.5 print quantum;
+      * periods 5-8 (9-12 s): the bulk of the rays still to print precision (median), the rest are the
+        eikonal scheme's ulp-chaos outliers (1 float32 ulp of the phase-velocity map moves 0.8 % of
+        the rays by up to 5.3e-3, measured) -- i.e. the file's phase-velocity maps start to differ
+        from the shipped inputs' in the last bits;
+      * periods 9-36: the file drifts smoothly and monotonically away (median |rel| doubling per
+        second of period, 0.90 % at 40 s): it was produced from phase-velocity maps / anisotropy
+        kernels that differ from what the shipped MODVs/Gc/Gs.true give -- and from the reference's
+        OWN period_Azm_tomo.real, which the oracle matches at all 36 periods -- in a way that is
+        invisible below 9 s, i.e. below ~60 km depth.  The per-period distance is pinned against the
+        committed table so that any change of the oracle (or of the finding) fails loudly."""
+    import json
     p = test1["para"]
     sv = fm.read_surfdata(os.path.join(REF_EX, p.datafile), p.kmaxRc)
     r = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, sv,
@@ -96,9 +105,21 @@ def test_forward_full_vs_golden(oracle, test1, test1_tables):
     d = np.abs(c - g)
     n = 7260
     assert d[:4 * n].max() < 1.5e-5, (d[:4 * n].max(), int((d[:4 * n] > 1.5e-5).sum()))
-    for k in (4, 5):      # 9 s, 10 s: only the chaotic outliers differ
-        assert np.median(d[k * n:(k + 1) * n]) < 6e-6
-        assert (d[k * n:(k + 1) * n] > 1.5e-5).mean() < 0.03
+    from scripts_golden import per_period_table
+    dist = fm.forward_velocities(sv, np.ones(sv.dall, np.float32)).astype(np.float64)
+    tab = per_period_table(dist / g, r["dsurf"].astype(np.float64), r["obsTaa"].astype(np.float64), n)
+    with open(os.path.join(os.path.dirname(__file__), "..", "profiles", "r2_golden_drift.json")) as f:
+        ref = json.load(f)["table"]
+    med = np.array([t["median_abs_rel"] for t in tab])
+    for k in range(4):                                   # 5-8 s: exact
+        assert tab[k]["share_beyond_print"] == 0.0 and abs(tab[k]["lsq_scale_Tiso"] - 1) < 1e-7
+    for k in range(4, 8):                                # 9-12 s: bulk exact, outliers = ulp chaos
+        assert med[k] < 4.5e-6 and tab[k]["max_abs_rel"] < 6e-3
+    assert np.all(np.diff(med[4:]) > 0)                  # smooth, monotone drift from 9 s on
+    assert 0.0085 < med[35] < 0.0095 and 1.0075 < tab[35]["lsq_scale_Tiso"] < 1.0082
+    for t, q in zip(tab, ref):                           # the finding itself is pinned
+        assert abs(t["mean_ratio"] - q["mean_ratio"]) < 2e-6, (t, q)
+        assert abs(t["lsq_scale_Tiso"] - q["lsq_scale_Tiso"]) < 1e-5, (t, q)
 
 
 def test_threads_do_not_change_results(oracle, test1, test1_tables):
