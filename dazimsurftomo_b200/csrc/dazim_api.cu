@@ -5,6 +5,7 @@
 // scalar code (grid constants, per-source box bounds, sin() of grid rows).
 #include "../../include/dazim_b200.h"
 #include "dazim_dev.h"
+#include "dazim_tps.h"
 #include "dazim_inv.h"
 #include <algorithm>
 #include <cmath>
@@ -22,6 +23,8 @@ cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
 cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas);
 cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st);
+cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int* nctas);
+cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, cudaStream_t st);
 cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, int nnz_tiled, float* ttn, int* nsts,
                                  cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
@@ -192,6 +195,10 @@ struct dazim_plan {
   int nctas = 0;
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
   int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
+  int tps = 0;   // thread-per-solve kernel (k_fmm_tps, dazim_tps.h): the default
+  int tps_idcap = 0, tps_node_bits = 0;
+  DBuf<unsigned short> d_pos_tab, d_free_stk;   // per solve (tps)
+  DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
   DBuf<int> d_fp_off, d_fp_cnt, d_fp_cell; DBuf<float> d_fp_fdm, d_fp_fdmc, d_fp_fdms;
@@ -276,6 +283,45 @@ extern "C" const char* dazim_strerror(int code) {
   return "unknown";
 }
 
+// kernel configuration of the round-1 eikonal kernels (two-warp latency kernel when every solve is resident, else the
+// half-warp throughput kernel with the shared heap halved while that buys more solves in flight)
+static int legacy_fmm_config(dazim_plan* P, long long nsrc, int hneed, int hmin, int* nctas_out) {
+  dazim_handle* h = P->h;
+  const GridC& g = P->g;
+  int nctas = 1;
+  P->hcap = hneed;
+  P->spc = 1;
+  P->duo = 1;
+  CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+  while (nctas < nsrc && P->hcap > 2048) {     // every solve resident with a (rarely spilling) smaller heap?
+    P->hcap /= 2;
+    CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+  }
+  if (nctas < nsrc) {
+    P->duo = 0;
+    P->hcap = hneed;
+    P->spc = 2;
+    CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
+    while (P->hcap > hmin && (long long)nctas * 2 < nsrc) {
+      P->hcap /= 2;
+      CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
+    }
+  }
+  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC") || getenv("DAZIM_DUO") || getenv("DAZIM_NCTAS")) {
+    if (const char* e = getenv("DAZIM_DUO")) P->duo = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
+    if (P->duo) P->spc = 1;
+    if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, (atoi(e) + 1) & ~1);
+    if (P->duo) CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+    else CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
+    if (const char* e = getenv("DAZIM_NCTAS")) nctas = std::max(1, std::min(nctas, atoi(e)));
+  }
+  if (nctas < 1) return DAZIM_EBADARG;
+  P->hspill = std::max(0, 8 * (g.nnx + g.nnz) + 1024 - P->hcap) + 16;
+  *nctas_out = nctas;
+  return DAZIM_OK;
+}
+
 // ---------------------------------------------------------------------------
 static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const dazim_tables* tb,
                       const float* Gc, const float* Gs, long long sb, long long se, int emit_all,
@@ -333,50 +379,59 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   int hneed = std::min(4096, std::max(256, pow2ceil(3 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
   int hmin = std::min(hneed, 512);
   if (const char* e = getenv("DAZIM_HCAP_MIN")) hmin = std::max(64, std::min(hneed, atoi(e)));
-  P->hcap = hneed;
-  P->spc = 1;
-  P->duo = 1;
+  const size_t ncf = coarse_field_size(g.nnx, g.nnz);     // E_c / hpos_c in the interleaved layout
+  P->hspill = 0;
   int nctas = 1;
-  CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
-  while (nctas < nsrc && P->hcap > 2048) {     // every solve resident with a (rarely spilling) smaller heap?
-    P->hcap /= 2;
-    CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
-  }
-  if (nctas < nsrc) {
-    P->duo = 0;
-    P->hcap = hneed;
-    P->spc = 2;
-    CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
-    while (P->hcap > hmin && (long long)nctas * 2 < nsrc) {
-      P->hcap /= 2;
-      CK(fmm_max_ctas(P->hcap, 2, h->nsm, &nctas));
+  // ---- kernel choice.  Default: thread per solve (dazim_tps.h).  DAZIM_TPS=0, or any of the legacy kernels' knobs
+  //      (DAZIM_DUO / DAZIM_SPC), selects the half-warp / two-warp kernels of round 1 (kept: bit-identical, and the
+  //      fall-back when a grid does not fit the packed heap entry of the new kernel). ----
+  P->tps = 1;
+  if (getenv("DAZIM_DUO") || getenv("DAZIM_SPC")) P->tps = 0;
+  if (const char* e = getenv("DAZIM_TPS")) P->tps = atoi(e) ? 1 : 0;
+  const int hspill_full = 8 * (g.nnx + g.nnz) + 1024 + 16;     // generous bound on the narrow band (measured 2.7 x edge)
+  if (P->tps) {
+    int nb = 1;
+    while ((1ull << nb) < std::max(ncf, (size_t)REF_N)) ++nb;
+    P->tps_node_bits = nb;
+    const long long idmax = std::min<long long>(65535, 1ll << std::min(30, 32 - nb));
+    if (nb > 28 || idmax < 2ll * (g.nnx + g.nnz)) P->tps = 0;    // entry word cannot hold node + id: legacy kernels
+    else {
+      const long long nres = std::max<long long>(1, nsrc);
+      const int ctas_needed = (int)((nres + 31) / 32);
+      // one warp of 32 solves per CTA; 1 CTA per SM while that holds every solve (bigger shared heap), else 2
+      int per_sm = ctas_needed <= h->nsm ? 1 : 2;
+      if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(e)));
+      P->hcap = std::min(hneed, (int)(((227 * 1024) / per_sm - 1024) / 256));
+      if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(896, atoi(e)));
+      CK(fmm_tps_max_ctas(P->hcap, h->nsm, &nctas));
+      if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
+      nctas = std::min(nctas, ctas_needed);
+      P->hspill = std::max(16, std::min(65535 - P->hcap, hspill_full));
+      P->tps_idcap = (int)std::min<long long>(idmax, (long long)P->hcap + P->hspill);
     }
   }
-  if (getenv("DAZIM_HCAP") || getenv("DAZIM_SPC") || getenv("DAZIM_DUO") || getenv("DAZIM_NCTAS")) {
-    if (const char* e = getenv("DAZIM_DUO")) P->duo = atoi(e) ? 1 : 0;
-    if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
-    if (P->duo) P->spc = 1;
-    if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, (atoi(e) + 1) & ~1);
-    if (P->duo) CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
-    else CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
-    if (const char* e = getenv("DAZIM_NCTAS")) nctas = std::max(1, std::min(nctas, atoi(e)));
+  if (!P->tps) {
+    int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nctas);
+    if (st_l) { plan_free(P); return st_l; }
   }
-  if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
-  const long long npairs_all = (nsrc + P->spc - 1) / P->spc;
-  P->hspill = std::max(0, 8 * (g.nnx + g.nnz) + 1024 - P->hcap) + 16;
+  const long long npairs_all = P->tps ? (nsrc + 31) / 32 : (nsrc + P->spc - 1) / P->spc;
   size_t free_b = 0;
   CK(available_bytes(h->dev, &free_b));
   double budget = 0.60 * (double)free_b;
   if (const char* e = getenv("DAZIM_WS_GB")) budget = std::min(budget, atof(e) * 1e9);
-  const size_t ncf = coarse_field_size(g.nnx, g.nnz);     // E_c / hpos_c in the interleaved layout
-  const double per_src = (double)ncf * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
-  const double per_slot = (double)ncf * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
+  double per_src = (double)ncf * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
+  double per_slot = (double)ncf * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
+  if (P->tps) {   // everything is per solve: no slot workspaces, no hpos fields
+    per_src += (double)REF_N * 4 + (double)P->hspill * 8 + (double)P->tps_idcap * 4 + (emit_all ? (double)REF_N * 4 : 0.0);
+    per_slot = 0;
+  }
   nctas = (int)std::min<long long>(nctas, std::max<long long>(npairs_all, 1));
   long long maxB = (long long)((budget - 2.0 * nctas * per_slot) / per_src);   // 2 slots per CTA are always laid out
   if (maxB < 2) maxB = 2;
   if (const char* e = getenv("DAZIM_BATCH")) maxB = std::max(1, atoi(e));
   maxB = std::min<long long>(maxB, std::max<long long>(nsrc, 1));
-  nctas = (int)std::min<long long>(nctas, (maxB + P->spc - 1) / P->spc);
+  if (P->tps) nctas = (int)std::min<long long>(nctas, (maxB + 31) / 32);
+  else nctas = (int)std::min<long long>(nctas, (maxB + P->spc - 1) / P->spc);
   P->nctas = nctas;
   P->maxB = (int)maxB;
   // batches + per-batch ray lists (long rays first so that a warp holds rays of similar length)
@@ -478,10 +533,18 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     const size_t B = (size_t)P->maxB, nslot = 2 * (size_t)P->nctas;
     CK(P->d_E_r.alloc(B * REF_N));
     CK(P->d_E_c.alloc(B * coarse_field_size(g.nnx, g.nnz)));
-    CK(P->d_hpos_c.alloc(nslot * coarse_field_size(g.nnx, g.nnz)));
-    CK(P->d_hpos_r.alloc(nslot * REF_N));
-    CK(P->d_slow_r.alloc(nslot * REF_N));
-    CK(P->d_hspill.alloc(nslot * P->hspill));
+    if (P->tps) {
+      CK(P->d_slow_r.alloc(B * REF_N));
+      CK(P->d_hspill.alloc(B * P->hspill));
+      CK(P->d_pos_tab.alloc(B * P->tps_idcap));
+      CK(P->d_free_stk.alloc(B * P->tps_idcap));
+      if (emit_all) CK(P->d_hpos_r_out.alloc(B * REF_N));
+    } else {
+      CK(P->d_hpos_c.alloc(nslot * coarse_field_size(g.nnx, g.nnz)));
+      CK(P->d_hpos_r.alloc(nslot * REF_N));
+      CK(P->d_slow_r.alloc(nslot * REF_N));
+      CK(P->d_hspill.alloc(nslot * P->hspill));
+    }
     CK(P->d_slot_of.alloc(B));
     CK(P->d_map.alloc(nthr * ncell));
     CK(cudaMemsetAsync(P->d_map.p, 0, nthr * ncell * sizeof(unsigned short), st));
@@ -568,7 +631,17 @@ static int plan_run_once(dazim_plan* P) {
       // far = 0xFFFFFFFF everywhere on the coarse grids of this batch; the refined boxes reset themselves
       CK(cudaMemsetAsync(P->d_E_c.p, 0xFF, (size_t)F.nsrc * coarse_field_size(g.nnx, g.nnz) * sizeof(unsigned), st));
       CK(cudaMemsetAsync(P->d_icnt.p + 2, 0, sizeof(int), st));
-      if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
+      if (P->tps) {
+        TpsArgs A;
+        A.g = g; A.src = F.src; A.nsrc = F.nsrc; A.velv = F.velv; A.slow_c = F.slow_c; A.risti_c = F.risti_c;
+        A.risti_r = F.risti_r; A.E_c = F.E_c; A.E_r = F.E_r; A.slow_r = P->d_slow_r.p; A.hspill = P->d_hspill.p;
+        A.hspill_n = P->hspill; A.hcap = P->hcap; A.pos_tab = P->d_pos_tab.p; A.free_stk = P->d_free_stk.p;
+        A.idcap = P->tps_idcap; A.node_bits = P->tps_node_bits; A.hpos_r_out = P->d_hpos_r_out.p;
+        A.flags = F.flags; A.n_accept = F.n_accept;
+        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + 31) / 32), st));
+        T.n_launch++;      // + k_tps_init
+      }
+      else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
       else CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + P->spc - 1) / P->spc), st));
       T.n_launch++; T.n_fmm_launch++;
     }
@@ -665,6 +738,26 @@ static int plan_run(dazim_plan* P) {
   int st = DAZIM_OK;
   for (int attempt = 0; attempt < 4; ++attempt) {
     st = plan_run_once(P);
+    if (st == DAZIM_EHEAP && P->tps) {
+      // the narrow band outgrew the ids a packed heap entry can hold: re-run on the round-1 kernels
+      CK(cudaSetDevice(P->h->dev));
+      g_alloc_stream = P->h->st;
+      const GridC& g = P->g;
+      const int hneed = std::min(4096, std::max(256, pow2ceil(3 * std::max(std::max(g.nnx, g.nnz), REF_LD))));
+      int nctas = 1;
+      P->tps = 0;
+      int st_l = legacy_fmm_config(P, (long long)P->maxB, hneed, std::min(hneed, 512), &nctas);
+      if (st_l) return st_l;
+      nctas = (int)std::min<long long>(nctas, ((long long)P->maxB + P->spc - 1) / P->spc);
+      P->nctas = nctas;
+      const size_t nslot = 2 * (size_t)nctas;
+      P->d_pos_tab.release(); P->d_free_stk.release();
+      CK(P->d_hpos_c.alloc(nslot * coarse_field_size(g.nnx, g.nnz)));
+      CK(P->d_hpos_r.alloc(nslot * REF_N));
+      CK(P->d_slow_r.alloc(nslot * REF_N));
+      CK(P->d_hspill.alloc(nslot * P->hspill));
+      continue;
+    }
     if (st != ST_POOL_OVERFLOW) return st;
     if (attempt == 3) break;
     CK(cudaSetDevice(P->h->dev));
@@ -1176,7 +1269,7 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
   // decode K3's (E, hpos) encoding into the reference's (ttn, nsts) pair; hpos lives in the slot that solved s
   {
     std::vector<int> slot_of(n);
-    if (e == cudaSuccess) e = cudaMemcpy(slot_of.data(), P->d_slot_of.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && !P->tps) e = cudaMemcpy(slot_of.data(), P->d_slot_of.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
     DBuf<float> d_t; DBuf<int> d_s;
     if (e == cudaSuccess) e = d_t.alloc(std::max(nc, (size_t)REF_N));
     if (e == cudaSuccess) e = d_s.alloc(std::max(nc, (size_t)REF_N));
@@ -1189,8 +1282,10 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
       if (nsts && e == cudaSuccess) e = cudaMemcpy(nsts + (size_t)i * nc, d_s.p, nc * 4, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) break;
       const bool own_slot = ((size_t)P->spc * (size_t)P->nctas >= (size_t)n);   // one solve per slot: refined heap slots are intact
-      e = launch_decode_status(P->d_E_r.p + (size_t)i * REF_N,
-                               own_slot ? P->d_hpos_r.p + (size_t)slot_of[i] * REF_N : nullptr, REF_N, 0, d_t.p, d_s.p, h->st);
+      const int* hp = nullptr;
+      if (P->tps) hp = P->d_hpos_r_out.p ? P->d_hpos_r_out.p + (size_t)i * REF_N : nullptr;
+      else if (own_slot) hp = P->d_hpos_r.p + (size_t)slot_of[i] * REF_N;
+      e = launch_decode_status(P->d_E_r.p + (size_t)i * REF_N, hp, REF_N, 0, d_t.p, d_s.p, h->st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
       if (ttnr && e == cudaSuccess) e = cudaMemcpy(ttnr + (size_t)i * REF_N, d_t.p, (size_t)REF_N * 4, cudaMemcpyDeviceToHost);
       if (nstsr && e == cudaSuccess) e = cudaMemcpy(nstsr + (size_t)i * REF_N, d_s.p, (size_t)REF_N * 4, cudaMemcpyDeviceToHost);
@@ -1205,6 +1300,78 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
     }
   plan_free(P);
   return e == cudaSuccess ? DAZIM_OK : DAZIM_ECUDA + (int)e;
+}
+
+// TEST SEAM, host only: the thread-per-solve eikonal code of dazim_tps.h (the very functions k_fmm_tps runs, they are
+// __host__ __device__) executed on the CPU for ONE source, so that the logic can be compared with the oracle on a
+// machine without a GPU (tests/test_tps_host_twin.py).  No product entry point calls this; it needs no device.
+extern "C" int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                                         float scx, float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr,
+                                         int* nstsr, int* geom, long long* n_accept) {
+  if (!pv || nx < 5 || ny < 5 || hcap < 8) return DAZIM_EBADARG;
+  const GridC g = make_grid(nx, ny, goxd, gozd, dvxd, dvzd);
+  SrcRec sr;
+  std::memset(&sr, 0, sizeof(sr));
+  int st = make_src(g, scx, scz, sr);
+  if (st) return st;
+  float ub[41 * 4], cb[6 * 4];
+  for (int j = 1; j <= 41; ++j) { float u = 40.0f; u = (float)(j - 1) / u; bspl_basis(u, &ub[(j - 1) * 4]); }
+  for (int i = 1; i <= 6; ++i) { float u = 5.0f; u = (float)(i - 1) / u; bspl_basis(u, &cb[(i - 1) * 4]); }
+  const size_t nxy = (size_t)nx * ny, nc = (size_t)g.nnx * g.nnz, ncf = coarse_field_size(g.nnx, g.nnz);
+  std::vector<float> velv(nxy), slow_c(nc), ric(g.nnx), rir(REF_LD, 0.0f), slow_r(REF_N, 0.0f);
+  for (size_t i = 0; i < nxy; ++i) velv[i] = (float)pv[i];
+  for (size_t i = 0; i < nc; ++i) slow_c[i] = 1.0f / dice_coarse_node(g, velv.data(), cb, (int)i);
+  for (int ix = 1; ix <= g.nnx; ++ix) ric[ix - 1] = g.earth * sin_r(g.gox + (float)(ix - 1) * g.dnx);
+  for (int ix = 1; ix <= sr.nnxr; ++ix) rir[ix - 1] = g.earth * sin_r(sr.goxr + (float)(ix - 1) * sr.dnxr);
+  std::vector<unsigned> E_c(ncf, E_FAR), E_r(REF_N, E_FAR);
+  for (int e = 0; e < sr.nnxr * sr.nnzr; ++e) {
+    const int idm1 = e % sr.nnzr + 1, idm2 = e / sr.nnzr + 1;
+    slow_r[(size_t)(idm2 - 1) * REF_LD + (idm1 - 1)] = 1.0f / refined_vel_t(g, sr, velv.data(), ub, idm1, idm2);
+  }
+  int nb = 1;
+  while ((1ull << nb) < std::max(ncf, (size_t)REF_N)) ++nb;
+  const long long idmax = std::min<long long>(65535, 1ll << std::min(30, 32 - nb));
+  std::vector<int2> sm((size_t)hcap), gl((size_t)std::max(1, hspill_n));
+  const int idcap = (int)std::min<long long>(idmax, (long long)hcap + hspill_n);
+  std::vector<unsigned short> pos((size_t)idcap), fstk((size_t)idcap);
+  std::vector<int> hpos_r(REF_N, 0);
+  TpsState S;
+  S.sm = sm.data(); S.stride = 1; S.gl = gl.data(); S.hcap = hcap; S.htot = hcap + hspill_n;
+  S.pos = pos.data(); S.fstk = fstk.data(); S.idcap = idcap; S.node_bits = nb; S.node_mask = (1u << nb) - 1u; S.overflow = 0;
+  unsigned long long nacc = 0;
+  tps_source_init(S, g, sr, velv.data(), ub, E_r.data());
+  {
+    const TpsGrid G = tps_grid_refined(g, sr, slow_r.data(), rir.data(), E_r.data());
+    while (tps_step<1>(S, G, nacc)) {}
+  }
+  if (!S.overflow) {
+    tps_refined_finish(S, E_r.data(), hpos_r.data());
+    tps_handoff(S, g, sr, E_r.data(), E_c.data());
+    const TpsGrid G = tps_grid_coarse(g, slow_c.data(), ric.data(), E_c.data());
+    while (tps_step<2>(S, G, nacc)) {}
+  }
+  if (S.overflow) return DAZIM_EHEAP;
+  auto decode = [](unsigned e, int hp, float& t, int& stt) {
+    if (e == E_FAR) { stt = -1; t = 0.0f; }
+    else if ((int)e >= 0) { stt = 0; t = tps_as_float((int)e); }
+    else { stt = hp; t = tps_as_float((int)(e & ~E_SIGN)); }
+  };
+  for (int ix = 0; ix < g.nnx; ++ix)
+    for (int iz = 0; iz < g.nnz; ++iz) {
+      float t; int stt;
+      decode(E_c[cidx(ix, iz, g.nnz)], 1, t, stt);
+      if (ttn) ttn[(size_t)ix * g.nnz + iz] = t;
+      if (nsts) nsts[(size_t)ix * g.nnz + iz] = stt;
+    }
+  for (int i = 0; i < REF_N; ++i) {
+    float t; int stt;
+    decode(E_r[i], hpos_r[i], t, stt);
+    if (ttnr) ttnr[i] = t;
+    if (nstsr) nstsr[i] = stt;
+  }
+  if (geom) { geom[0] = sr.nnzr; geom[1] = sr.nnxr; geom[2] = sr.vnl; geom[3] = sr.vnr; geom[4] = sr.vnt; geom[5] = sr.vnb; geom[6] = g.nnz; geom[7] = g.nnx; }
+  if (n_accept) *n_accept = (long long)nacc;
+  return DAZIM_OK;
 }
 
 extern "C" int dazim_raytrace(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,

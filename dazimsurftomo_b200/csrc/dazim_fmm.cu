@@ -25,8 +25,10 @@
 //    patched in registers while the pop / earlier sift-ups move entries, so no
 //    global read-after-write sits on the critical path.
 #include "dazim_dev.h"
+#include "dazim_tps.h"
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 
 namespace dz {
 
@@ -48,23 +50,7 @@ __global__ void k_dice_coarse(GridC g, const float* __restrict__ velv, float* __
   const int per = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.nnx * g.nnz) return;
-  const int stz = idx % g.nnz + 1, stx = idx / g.nnz + 1;
-  // cell (i,j) and local index (l,m): the last cell also owns its far edge
-  int i = (stz - 1) / g.gdz + 1, l = (stz - 1) % g.gdz + 1;
-  if (i > g.nvz - 1) { i = g.nvz - 1; l = g.gdz + 1; }
-  int j = (stx - 1) / g.gdx + 1, m = (stx - 1) % g.gdx + 1;
-  if (j > g.nvx - 1) { j = g.nvx - 1; m = g.gdx + 1; }
-  const float* vv = velv + (size_t)per * (g.nvz + 2) * (g.nvx + 2);
-  const int ldv = g.nvx + 2;
-  float sumi = 0.0f;
-#pragma unroll
-  for (int i1 = 1; i1 <= 4; ++i1) {
-    float sumj = 0.0f;
-#pragma unroll
-    for (int j1 = 1; j1 <= 4; ++j1)
-      sumj = sumj + c_cbasis[(m - 1) * 4 + (j1 - 1)] * vv[(i - 2 + i1) * ldv + (j - 2 + j1)];
-    sumi = sumi + c_cbasis[(l - 1) * 4 + (i1 - 1)] * sumj;
-  }
+  const float sumi = dice_coarse_node(g, velv + (size_t)per * (g.nvz + 2) * (g.nvx + 2), c_cbasis, idx);
   veln[(size_t)per * g.nnx * g.nnz + idx] = sumi;
   slow[(size_t)per * g.nnx * g.nnz + idx] = 1.0f / sumi;
 }
@@ -72,9 +58,8 @@ __global__ void k_dice_coarse(GridC g, const float* __restrict__ velv, float* __
 // ---------------------------------------------------------------------------
 // K3
 
-#define E_FAR 0xFFFFFFFFu     // never touched (nsts = -1)
-#define E_OUT 0xFFFFFFFEu     // outside the grid (register-only sentinel)
-#define E_SIGN 0x80000000u    // close: trial value with the sign bit set (nsts > 0)
+// E_FAR / E_OUT / E_SIGN, quadrant(), e_status(), nidx(), ndecode(): dazim_tps.h (shared with the thread-per-solve kernel).
+// In THIS file's kernels a close node keeps its trial value under the sign bit (nsts > 0 is hpos).
 
 // Heap entries are (key bits, node offset) pairs.  Positions 1..hcap-1 live in shared memory,
 // positions >= hcap in a per-slot global array ("spill").  hpos[node] is the reference's nsts
@@ -182,82 +167,6 @@ __device__ __forceinline__ void pop_root(Heap& h, int* __restrict__ hpos, const 
     }
   }
   hput(h, hpos, tpp, last);
-}
-
-// One quadrant of fouds2 (CalSurfG.f90:634-723): returns trial time, valid flag through ok.
-// sj/sk: status of the first neighbours (0 alive, -2 = outside grid); sj2/sk2: second neighbours.
-// The reference selects one of nine stencils (first/second order in x and z, or one-sided) by
-// nested IFs.  The 16 lanes of an accept step fall into different cases, so the nest is evaluated
-// here WITHOUT branches: every case's operands are chosen with selects and one common expression
-// tree is evaluated.  Each case keeps the reference's operation order (x2 and the commutations
-// used are exact in IEEE arithmetic), so the result is bit-identical to the branchy form:
-//   A swj&swk  : u=2Rdx v=2Rsdz em=4tj-tj2-4tk+tk2  a=v2+u2   b=(2em)u2   c=u2(em2-s2v2) tref=4tj-tj2 /3
-//   B swj&k1   : u=Rsdz v=2Rdx  em=3tk-4tj+tj2      a=v2+9u2  b=(6em)u2   c=u2(em2-s2v2) tref=tk
-//   C swj only : u=2Rdx                             a=1 b=0   c=-(u2 s2)                tref=4tj-tj2 /3
-//   D j1&swk   : u=Rdx  v=2Rsdz em=3tj-4tk+tk2      a=v2+9u2  b=(6em)u2   c=u2(em2-v2s2) tref=tj
-//   E j1&k1    : u=Rdx  v=Rsdz  em=tk-tj            a=u2+v2   b=(-2u2)em  c=u2(em2-v2s2) tref=tj
-//   F j1 only  :                                    a=1 b=0   c=-(s2 R2)dx2             tref=tj
-//   G swk only : u=2Rsdz                            a=1 b=0   c=-(u2 s2)                tref=4tk-tk2 /3
-//   H k1 only  :                                    a=1 b=0   c=-(s2 Rs2)dz2            tref=tk
-__device__ __forceinline__ float quadrant(int sj, int sj2, float tj, float tj2, int sk, int sk2, float tk,
-                                          float tk2, float slown, float ri, float risti, float dnx,
-                                          float dnz, bool& ok) {
-  const bool j1 = (sj == 0), k1 = (sk == 0);
-  const bool swj = j1 && (sj2 == 0) && (tj > tj2);
-  const bool swk = k1 && (sk2 == 0) && (tk > tk2);
-  const bool cA = swj && swk, cB = swj && !swk && k1, cC = swj && !k1;
-  const bool cD = !swj && j1 && swk, cE = !swj && j1 && !swk && k1, cF = !swj && j1 && !k1;
-  const bool cG = !j1 && swk, cH = !j1 && !swk && k1;
-  ok = (cA || cB || cC || cD || cE || cF || cG || cH) && sj != -2 && sk != -2;
-  const float ux1 = ri * dnx, ux2 = 2.0f * ri * dnx;          // 2.0f*ri*dnx == 2*(ri*dnx) exactly
-  const float vz1 = risti * dnz, vz2 = 2.0f * risti * dnz;
-  const float s2 = slown * slown;
-  const float u = (cA || cC) ? ux2 : (cB ? vz1 : (cG ? vz2 : ux1));
-  const float v = (cA || cD) ? vz2 : (cB ? ux2 : vz1);
-  const float fj = 4.0f * tj - tj2, fk = 4.0f * tk - tk2;      // second-order one-sided values
-  float emA = fj - 4.0f * tk;
-  emA = emA + tk2;
-  const float emB = 3.0f * tk - 4.0f * tj + tj2;
-  const float emD = 3.0f * tj - 4.0f * tk + tk2;
-  const float emE = tk - tj;
-  const float em = cA ? emA : (cB ? emB : (cD ? emD : emE));
-  const float uu = u * u, vv = v * v;
-  const bool two = cA || cB || cD || cE;                       // both directions contribute
-  float a = 1.0f;
-  if (cA || cE) a = vv + uu;
-  if (cB || cD) a = vv + 9.0f * uu;
-  float b = 0.0f;
-  if (cA) b = 2.0f * em * uu;
-  if (cB || cD) b = 6.0f * em * uu;
-  if (cE) b = -2.0f * uu * em;
-  float c = uu * (em * em - s2 * vv);                          // A, B, D, E
-  if (cC || cG) c = -uu * s2;
-  if (cF) c = -s2 * (ri * ri) * (dnx * dnx);
-  if (cH) c = -s2 * (risti * risti) * (dnz * dnz);
-  (void)two;
-  const float tref = (cA || cC) ? fj : (cG ? fk : ((cB || cH) ? tk : tj));
-  const float tdiv = (cA || cC || cG) ? 3.0f : 1.0f;
-  float rd1 = b * b - 4.0f * a * c;
-  if (rd1 < 0.0f) rd1 = 0.0f;
-  const float tdsh = (-b + sqrtf(rd1)) / (2.0f * a);
-  return (tref + tdsh) / tdiv;
-}
-
-__device__ __forceinline__ int e_status(unsigned e) { return e == E_OUT ? -2 : ((int)e >= 0 ? 0 : 1); }
-
-// Node offset of (ix, iz) in a per-solve field: the refined box (URG == 1) is plain column-major with
-// leading dimension ld; the coarse grid (URG == 2, ld == nnz) uses the interleaved layout of dazim_dev.h.
-template <int URG>
-__device__ __forceinline__ int nidx(int ix, int iz, int ld) { return URG == 2 ? cidx(ix, iz, ld) : ix * ld + iz; }
-// inverse: float quotient, exact after one correction (offsets < 2^30, ld <= 32767)
-template <int URG>
-__device__ __forceinline__ void ndecode(int o, int ld, float inv_ld, int& ix, int& iz) {
-  const int b = (URG == 2) ? (o >> 3) : o;
-  int q = (int)((float)b * inv_ld);
-  int r = b - q * ld;
-  if (r < 0) { q -= 1; r += ld; } else if (r >= ld) { q += 1; r -= ld; }
-  ix = (URG == 2) ? (q * 8 + (o & 7)) : q;
-  iz = r;
 }
 
 // Software prefetch of the words an accept step of node pn will gather (hint only).
@@ -1143,6 +1052,106 @@ cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st) {
   if (e != cudaSuccess) return e;
   if (wide) k_fmm_duo<16><<<nctas, 64, smem, st>>>(A);
   else k_fmm_duo<10><<<nctas, 64, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K3, thread per solve (dazim_tps.h): the default eikonal kernel.
+// k_tps_init: refined slowness nodes (bsplrefine) + status reset, one thread per refined node.
+__global__ void k_tps_init(TpsArgs A) {
+  const GridC& g = A.g;
+  for (int s = blockIdx.y; s < A.nsrc; s += gridDim.y) {
+    const SrcRec sr = A.src[s];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= sr.nnxr * sr.nnzr) continue;
+    const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
+    const int idm1 = e % sr.nnzr + 1, idm2 = e / sr.nnzr + 1;
+    const size_t o = (size_t)s * REF_N + (size_t)(idm2 - 1) * REF_LD + (idm1 - 1);
+    A.slow_r[o] = 1.0f / refined_vel_t(g, sr, vv, c_ubasis, idm1, idm2);
+    A.E_r[o] = E_FAR;
+  }
+}
+
+__global__ void __launch_bounds__(32, 2) k_fmm_tps(TpsArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const GridC& g = A.g;
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;          // slow_c (plain column-major)
+  const size_t ncf = coarse_field_size(g.nnx, g.nnz);    // E_c (interleaved layout)
+  TpsState S;
+  S.sm = reinterpret_cast<int2*>(smem_raw) + lane;
+  S.stride = 32;
+  S.hcap = A.hcap;
+  S.htot = A.hcap + A.hspill_n;
+  S.idcap = A.idcap;
+  S.node_bits = A.node_bits;
+  S.node_mask = (1u << A.node_bits) - 1u;
+  S.overflow = 0;
+  tps_reset(S);
+  unsigned long long nacc = 0;
+  for (int s0 = blockIdx.x * 32; s0 < A.nsrc; s0 += gridDim.x * 32) {
+    const int s = s0 + lane;
+    const bool act = (s < A.nsrc) && !S.overflow;
+    const int sc = min(s, A.nsrc - 1);                   // inactive lane: valid addresses, no side effects
+    const SrcRec sr = A.src[sc];
+    unsigned* E_r = A.E_r + (size_t)sc * REF_N;
+    unsigned* E_c = A.E_c + (size_t)sc * ncf;
+    const float* slow_r = A.slow_r + (size_t)sc * REF_N;
+    const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
+    const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
+    S.gl = A.hspill + (size_t)sc * A.hspill_n;
+    S.pos = A.pos_tab + (size_t)sc * A.idcap;
+    S.fstk = A.free_stk + (size_t)sc * A.idcap;
+    if (act) tps_source_init(S, g, sr, vv, c_ubasis, E_r);
+    __syncwarp();
+    {
+      const TpsGrid G = tps_grid_refined(g, sr, slow_r, A.risti_r + (size_t)sc * REF_LD, E_r);
+      bool run = act;
+      for (;;) {
+        if (run) run = tps_step<1>(S, G, nacc);
+        if (!__any_sync(0xffffffffu, run)) break;
+      }
+    }
+    if (act && !S.overflow) {
+      tps_refined_finish(S, E_r, A.hpos_r_out ? A.hpos_r_out + (size_t)sc * REF_N : nullptr);
+      tps_handoff(S, g, sr, E_r, E_c);
+    }
+    __syncwarp();
+    {
+      const TpsGrid G = tps_grid_coarse(g, slow_c, A.risti_c, E_c);
+      bool run = act && !S.overflow;
+      for (;;) {
+        if (run) run = tps_step<2>(S, G, nacc);
+        if (!__any_sync(0xffffffffu, run)) break;
+      }
+    }
+  }
+  if (S.overflow) atomicOr(A.flags, 16);
+  if (nacc) atomicAdd(A.n_accept, nacc);
+}
+
+// resident warps (= CTAs of 32 solves) per SM for a given shared heap capacity
+cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int* nctas) {
+  const size_t smem = (size_t)hcap * 32 * 8;
+  cudaError_t e = cudaFuncSetAttribute(k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fmm_tps, 32, smem);
+  if (e != cudaSuccess) return e;
+  *nctas = per_sm * nsm;
+  return cudaSuccess;
+}
+
+cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, cudaStream_t st) {
+  if (A.nsrc <= 0) return cudaSuccess;
+  dim3 gi((REF_N + 255) / 256, (unsigned)std::min(A.nsrc, 65535));
+  k_tps_init<<<gi, 256, 0, st>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t smem = (size_t)A.hcap * 32 * 8;
+  e = cudaFuncSetAttribute(k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_fmm_tps<<<nctas, 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 

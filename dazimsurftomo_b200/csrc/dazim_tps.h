@@ -1,0 +1,533 @@
+// K3 "thread per solve" (TPS): the reference's narrow-band fast-marching solve (module traveltime,
+// CalSurfG.f90:234-893) with ONE THREAD PER (period, source) SOLVE, 32 solves per warp.
+//
+// Why: the accept chain of one solve is strictly serial (the result depends on the binary heap's pop
+// order, ties included), so the chip's parallelism has to come from the (period x source) axis.  The half-warp and
+// two-warp kernels of dazim_fmm.cu spend ~600 warp instructions per accept, almost all of them scalar heap code
+// executed redundantly by 16-32 lanes, and can keep at most 1 480 - 5 920 solves resident.  Here every lane runs the
+// scalar code of its OWN solve: ~1 500 thread instructions per accept = ~47 warp instructions per accept, 9 472 solves
+// resident on 148 SMs (2 warps per SM), the 16 quadrant quadratics of an accept step are independent instructions
+// of one thread (ILP instead of lanes), and no shuffle, vote-free inner loops, no barrier and no shared state exist
+// between solves.
+//
+// Data layout (per solve):
+//   heap      (key bits, id << node_bits | node) pairs; positions 1..hcap-1 in shared memory, INTERLEAVED across the
+//             32 lanes of the warp (entry p of lane l at sm[p * 32 + l]: every lane always hits its own two banks),
+//             positions >= hcap in a per-solve global array.
+//   E         one 32-bit word per node: alive = +t, far = 0xFFFFFFFF, close = 0x80000000 | id.  A close node's
+//             trial time lives only in the heap (fouds2 never reads it, CalSurfG.f90:592-629).
+//   pos_tab   u16 [id] -> heap position.  The reference's nsts back pointer (heap position of a close node) is
+//             E -> id -> pos_tab: the ~13 entry moves of an accept step write a 5 KB per-solve table that stays in
+//             the L2 instead of 13 scattered sectors of a 4 MB field (that scatter was 2/3 of the DRAM traffic of
+//             the round-1 kernels), and the 4 MB hpos field per resident solve is gone.
+//   free_stk  u16 stack of released ids (an accept step releases one id and takes 0-3).
+//
+// The code below is __host__ __device__: dazim_fmm.cu instantiates it in the kernel k_fmm_tps AND in a host twin
+// (dazim_debug_fmm_host_twin, test seam only) so that the exact logic is checked against the oracle on machines
+// without a GPU.  No product entry point calls the host twin.
+#pragma once
+#include "dazim_dev.h"
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TPS_HD __host__ __device__ __forceinline__
+#else
+#define TPS_HD inline
+#endif
+
+namespace dz {
+
+#define E_FAR 0xFFFFFFFFu     // never touched (nsts = -1)
+#define E_OUT 0xFFFFFFFEu     // outside the grid (register-only sentinel)
+#define E_SIGN 0x80000000u    // close (nsts > 0)
+
+TPS_HD int e_status(unsigned e) { return e == E_OUT ? -2 : ((int)e >= 0 ? 0 : 1); }
+
+// One quadrant of fouds2 (CalSurfG.f90:634-723): returns trial time, valid flag through ok.
+// sj/sk: status of the first neighbours (0 alive, -2 = outside grid); sj2/sk2: second neighbours.
+// The reference selects one of nine stencils (first/second order in x and z, or one-sided) by
+// nested IFs.  The nest is evaluated here WITHOUT branches: every case's operands are chosen with selects and one
+// common expression tree is evaluated.  Each case keeps the reference's operation order (x2 and the commutations
+// used are exact in IEEE arithmetic), so the result is bit-identical to the branchy form:
+//   A swj&swk  : u=2Rdx v=2Rsdz em=4tj-tj2-4tk+tk2  a=v2+u2   b=(2em)u2   c=u2(em2-s2v2) tref=4tj-tj2 /3
+//   B swj&k1   : u=Rsdz v=2Rdx  em=3tk-4tj+tj2      a=v2+9u2  b=(6em)u2   c=u2(em2-s2v2) tref=tk
+//   C swj only : u=2Rdx                             a=1 b=0   c=-(u2 s2)                tref=4tj-tj2 /3
+//   D j1&swk   : u=Rdx  v=2Rsdz em=3tj-4tk+tk2      a=v2+9u2  b=(6em)u2   c=u2(em2-v2s2) tref=tj
+//   E j1&k1    : u=Rdx  v=Rsdz  em=tk-tj            a=u2+v2   b=(-2u2)em  c=u2(em2-v2s2) tref=tj
+//   F j1 only  :                                    a=1 b=0   c=-(s2 R2)dx2             tref=tj
+//   G swk only : u=2Rsdz                            a=1 b=0   c=-(u2 s2)                tref=4tk-tk2 /3
+//   H k1 only  :                                    a=1 b=0   c=-(s2 Rs2)dz2            tref=tk
+TPS_HD float quadrant(int sj, int sj2, float tj, float tj2, int sk, int sk2, float tk, float tk2, float slown, float ri,
+                      float risti, float dnx, float dnz, bool& ok) {
+  const bool j1 = (sj == 0), k1 = (sk == 0);
+  const bool swj = j1 && (sj2 == 0) && (tj > tj2);
+  const bool swk = k1 && (sk2 == 0) && (tk > tk2);
+  const bool cA = swj && swk, cB = swj && !swk && k1, cC = swj && !k1;
+  const bool cD = !swj && j1 && swk, cE = !swj && j1 && !swk && k1, cF = !swj && j1 && !k1;
+  const bool cG = !j1 && swk, cH = !j1 && !swk && k1;
+  ok = (cA || cB || cC || cD || cE || cF || cG || cH) && sj != -2 && sk != -2;
+  const float ux1 = ri * dnx, ux2 = 2.0f * ri * dnx;          // 2.0f*ri*dnx == 2*(ri*dnx) exactly
+  const float vz1 = risti * dnz, vz2 = 2.0f * risti * dnz;
+  const float s2 = slown * slown;
+  const float u = (cA || cC) ? ux2 : (cB ? vz1 : (cG ? vz2 : ux1));
+  const float v = (cA || cD) ? vz2 : (cB ? ux2 : vz1);
+  const float fj = 4.0f * tj - tj2, fk = 4.0f * tk - tk2;      // second-order one-sided values
+  float emA = fj - 4.0f * tk;
+  emA = emA + tk2;
+  const float emB = 3.0f * tk - 4.0f * tj + tj2;
+  const float emD = 3.0f * tj - 4.0f * tk + tk2;
+  const float emE = tk - tj;
+  const float em = cA ? emA : (cB ? emB : (cD ? emD : emE));
+  const float uu = u * u, vv = v * v;
+  float a = 1.0f;
+  if (cA || cE) a = vv + uu;
+  if (cB || cD) a = vv + 9.0f * uu;
+  float b = 0.0f;
+  if (cA) b = 2.0f * em * uu;
+  if (cB || cD) b = 6.0f * em * uu;
+  if (cE) b = -2.0f * uu * em;
+  float c = uu * (em * em - s2 * vv);                          // A, B, D, E
+  if (cC || cG) c = -uu * s2;
+  if (cF) c = -s2 * (ri * ri) * (dnx * dnx);
+  if (cH) c = -s2 * (risti * risti) * (dnz * dnz);
+  const float tref = (cA || cC) ? fj : (cG ? fk : ((cB || cH) ? tk : tj));
+  const float tdiv = (cA || cC || cG) ? 3.0f : 1.0f;
+  float rd1 = b * b - 4.0f * a * c;
+  if (rd1 < 0.0f) rd1 = 0.0f;
+  const float tdsh = (-b + sqrtf(rd1)) / (2.0f * a);
+  return (tref + tdsh) / tdiv;
+}
+
+// Node offset of (ix, iz) in a per-solve field: the refined box (URG == 1) is plain column-major with
+// leading dimension ld; the coarse grid (URG == 2, ld == nnz) uses the interleaved layout of dazim_dev.h.
+template <int URG>
+TPS_HD int nidx(int ix, int iz, int ld) { return URG == 2 ? cidx(ix, iz, ld) : ix * ld + iz; }
+// inverse: float quotient, exact after one correction (offsets < 2^30, ld <= 32767)
+template <int URG>
+TPS_HD void ndecode(int o, int ld, float inv_ld, int& ix, int& iz) {
+  const int b = (URG == 2) ? (o >> 3) : o;
+  int q = (int)((float)b * inv_ld);
+  int r = b - q * ld;
+  if (r < 0) { q -= 1; r += ld; } else if (r >= ld) { q += 1; r -= ld; }
+  ix = (URG == 2) ? (q * 8 + (o & 7)) : q;
+  iz = r;
+}
+
+// coarse dicing of one propagation node (gridder, CalSurfG.f90:1450-1488): idx = (stx-1)*nnz + (stz-1);
+// vv = control values of the period, velv(i,j) at i*(nvx+2)+j; cb = coarse basis table [6][4]
+TPS_HD float dice_coarse_node(const GridC& g, const float* vv, const float* cb, int idx) {
+  const int stz = idx % g.nnz + 1, stx = idx / g.nnz + 1;
+  // cell (i,j) and local index (l,m): the last cell also owns its far edge
+  int i = (stz - 1) / g.gdz + 1, l = (stz - 1) % g.gdz + 1;
+  if (i > g.nvz - 1) { i = g.nvz - 1; l = g.gdz + 1; }
+  int j = (stx - 1) / g.gdx + 1, m = (stx - 1) % g.gdx + 1;
+  if (j > g.nvx - 1) { j = g.nvx - 1; m = g.gdx + 1; }
+  const int ldv = g.nvx + 2;
+  float sumi = 0.0f;
+  for (int i1 = 1; i1 <= 4; ++i1) {
+    float sumj = 0.0f;
+    for (int j1 = 1; j1 <= 4; ++j1)
+      sumj = sumj + cb[(m - 1) * 4 + (j1 - 1)] * vv[(i - 2 + i1) * ldv + (j - 2 + j1)];
+    sumi = sumi + cb[(l - 1) * 4 + (i1 - 1)] * sumj;
+  }
+  return sumi;
+}
+
+// refined velocity node (bsplrefine, CalSurfG.f90:1559-1590); idm1/idm2 1-based refined indices;
+// ub = refined B-spline basis table [41][4] (constant memory on the device)
+TPS_HD float refined_vel_t(const GridC& g, const SrcRec& sr, const float* vv, const float* ub, int idm1, int idm2) {
+  const int ldv = g.nvx + 2;
+  const int nrxr = g.gdx * g.sgdl, nrzr = g.gdz * g.sgdl;
+  const int origx = (sr.vnl - 1) * g.sgdl + 1, origz = (sr.vnt - 1) * g.sgdl + 1;
+  const int st1 = idm1 + origz - 1, st2 = idm2 + origx - 1;
+  int i = (st1 - 1) / nrzr + 1, k = (st1 - 1) % nrzr + 1;
+  if (i > g.nvz - 1) { i = g.nvz - 1; k = nrzr + 1; }
+  int j = (st2 - 1) / nrxr + 1, l = (st2 - 1) % nrxr + 1;
+  if (j > g.nvx - 1) { j = g.nvx - 1; l = nrxr + 1; }
+  float sum[4];
+  for (int i1 = 1; i1 <= 4; ++i1) {
+    float sacc = 0.0f;
+    for (int j1 = 1; j1 <= 4; ++j1)
+      sacc = sacc + ub[(l - 1) * 4 + (j1 - 1)] * vv[(i - 2 + i1) * ldv + (j - 2 + j1)];
+    sum[i1 - 1] = ub[(k - 1) * 4 + (i1 - 1)] * sacc;
+  }
+  return sum[0] + sum[1] + sum[2] + sum[3];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct TpsArgs {
+  GridC g;
+  const SrcRec* src;          // [nsrc]
+  int nsrc;
+  const float* velv;          // [nper][(nvz+2)(nvx+2)]
+  const float* slow_c;        // [nper][nnx*nnz]  1/veln (fouds2's slown), plain column-major
+  const float* risti_c;       // [nnx]   earth*sin(gox+(ix-1)*dnx), host computed
+  const float* risti_r;       // [nsrc][REF_LD]
+  unsigned* E_c;              // [nsrc][coarse_field_size]  (preset to E_FAR by the host)
+  unsigned* E_r;              // [nsrc][REF_N]              (preset + slow_r by k_tps_init)
+  float* slow_r;              // [nsrc][REF_N]   refined slowness
+  int2* hspill;               // [nsrc][hspill_n] heap entries beyond the shared capacity
+  int hspill_n;
+  int hcap;                   // heap positions 1..hcap-1 live in shared memory
+  unsigned short* pos_tab;    // [nsrc][idcap]
+  unsigned short* free_stk;   // [nsrc][idcap]
+  int idcap;                  // ids per solve (<= 65535, <= 2^(32-node_bits))
+  int node_bits;              // bits of the node offset inside a heap entry's second word
+  int* hpos_r_out;            // optional test seam [nsrc][REF_N]: heap slots of the close nodes after the refined march
+  int* flags;                 // bit4 (16): heap / id overflow
+  unsigned long long* n_accept;
+};
+
+struct TpsState {
+  int2* sm;                   // this solve's shared heap part; position p at sm[p * stride]
+  int stride;
+  int2* gl;                   // spill part: position p at gl[p - hcap]
+  int hcap, htot;             // htot = hcap + hspill_n
+  int ntr;
+  unsigned short* pos;
+  unsigned short* fstk;
+  int nfree, next_id, spare, idcap;
+  int node_bits;
+  unsigned node_mask;
+  int overflow;
+  int stopped_at_root;        // refined march left through the exit test: the root is alive and stays in the heap
+};
+
+#define TKEY(e) tps_as_float((e).x)
+TPS_HD float tps_as_float(int b) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(b);
+#else
+  union { int i; float f; } u; u.i = b; return u.f;
+#endif
+}
+TPS_HD int tps_as_int(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  union { int i; float f; } u; u.f = f; return u.i;
+#endif
+}
+TPS_HD float tps_inf() { return tps_as_float(0x7f800000); }
+
+TPS_HD int tps_node(const TpsState& S, int2 e) { return (int)((unsigned)e.y & S.node_mask); }
+TPS_HD int tps_id(const TpsState& S, int2 e) { return (int)((unsigned)e.y >> S.node_bits); }
+TPS_HD int tps_pack(const TpsState& S, int id, int node) { return (int)(((unsigned)id << S.node_bits) | (unsigned)node); }
+
+TPS_HD int2 tps_hget(const TpsState& S, int p) { return p < S.hcap ? S.sm[(size_t)p * S.stride] : S.gl[p - S.hcap]; }
+TPS_HD void tps_hput(TpsState& S, int p, int2 e) {
+  if (p < S.hcap) S.sm[(size_t)p * S.stride] = e; else S.gl[p - S.hcap] = e;
+  S.pos[tps_id(S, e)] = (unsigned short)p;
+}
+
+TPS_HD void tps_release_id(TpsState& S, int id) {
+  if (S.spare < 0) { S.spare = id; return; }
+  S.fstk[S.nfree++] = (unsigned short)id;
+}
+TPS_HD int tps_alloc_id(TpsState& S) {
+  if (S.spare >= 0) { const int id = S.spare; S.spare = -1; return id; }
+  if (S.nfree > 0) return (int)S.fstk[--S.nfree];
+  if (S.next_id >= S.idcap) { S.overflow = 1; return 0; }
+  return S.next_id++;
+}
+TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.nfree = 0; S.next_id = 0; S.spare = -1; S.stopped_at_root = 0; }
+
+// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).  q = index of the neighbour being applied;
+// later close neighbours that sit on the path move down with their parent slot: their positions (read before) are
+// patched in registers.
+TPS_HD void tps_sift_up(TpsState& S, int tpc, float k, int packed, int q, const int (&qid)[4], const int (&qst)[4],
+                        int (&spos)[4]) {
+  int tpp = tpc >> 1;
+  while (tpp > 0) {
+    const int2 par = tps_hget(S, tpp);
+    if (!(k < TKEY(par))) break;
+    tps_hput(S, tpc, par);
+    const int pid = tps_id(S, par);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 4; ++r)
+      if (r > q && qst[r] == 1 && qid[r] == pid) spos[r] = tpc;
+    tpc = tpp;
+    tpp = tpc >> 1;
+  }
+  tps_hput(S, tpc, make_int2(tps_as_int(k), packed));
+}
+// plain version (source-cell initialisation, coarse heap build)
+TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int packed) {
+  int tpp = tpc >> 1;
+  while (tpp > 0) {
+    const int2 par = tps_hget(S, tpp);
+    if (!(k < TKEY(par))) break;
+    tps_hput(S, tpc, par);
+    tpc = tpp;
+    tpp = tpc >> 1;
+  }
+  tps_hput(S, tpc, make_int2(tps_as_int(k), packed));
+}
+
+// downtree (CalSurfG.f90:786-855).  `last` = heap[ntr] (fetched early by the caller).
+TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
+  if (S.ntr == 1) { S.ntr = 0; return; }
+  const float k = TKEY(last);
+  S.ntr -= 1;
+  const int ntr = S.ntr;
+  int tpp = 1, tpc = 2;
+  // shared levels: both children exist and live in shared memory
+  const int lim = ntr < S.hcap - 1 ? ntr : S.hcap - 1;
+  bool placed = false;
+  while (tpc < lim) {
+    const int2 c0 = S.sm[(size_t)tpc * S.stride], c1 = S.sm[(size_t)(tpc + 1) * S.stride];
+    const bool right = TKEY(c0) > TKEY(c1);
+    const int2 c = right ? c1 : c0;
+    tpc += right ? 1 : 0;
+    if (!(TKEY(c) < k)) { placed = true; break; }
+    S.sm[(size_t)tpp * S.stride] = c;
+    S.pos[tps_id(S, c)] = (unsigned short)tpp;
+    tpp = tpc;
+    tpc = 2 * tpp;
+  }
+  // remaining levels (single child, or children in the spill part)
+  while (!placed && tpc <= ntr) {
+    int2 c = tps_hget(S, tpc);
+    if (tpc < ntr) {
+      const int2 c1 = tps_hget(S, tpc + 1);
+      if (TKEY(c) > TKEY(c1)) { c = c1; tpc += 1; }
+    }
+    if (!(TKEY(c) < k)) break;
+    tps_hput(S, tpp, c);
+    tpp = tpc;
+    tpc = 2 * tpp;
+  }
+  tps_hput(S, tpp, last);
+}
+
+// Grid view of one march
+struct TpsGrid {
+  int nnx, nnz, ld;
+  float dnx, dnz, earth;
+  const float* slow;          // [ix * ld + iz] plain
+  const float* risti_tab;     // [ix]
+  unsigned* E;
+  bool ex_l, ex_r, ex_t, ex_b;
+};
+
+// One accept step of travel's DO WHILE (CalSurfG.f90:356-456).  Returns false when the march is over.
+template <int URG>
+TPS_HD bool tps_step(TpsState& S, const TpsGrid& G, unsigned long long& nacc) {
+  if (S.ntr <= 0 || S.overflow) return false;
+  const int2 root = tps_hget(S, 1);
+  const int pn = tps_node(S, root);
+  const int2 last = tps_hget(S, S.ntr);
+  const int ld = G.ld;
+  const float inv_ld = 1.0f / (float)ld;
+  int ix, iz;
+  ndecode<URG>(pn, ld, inv_ld, ix, iz);
+  unsigned* E = G.E;
+  const unsigned tself = (unsigned)root.x & ~E_SIGN;
+  E[pn] = tself;                                   // the popped node becomes alive with its trial value (= its heap key)
+  if (URG == 1) {
+    if ((ix == 0 && G.ex_l) || (ix == G.nnx - 1 && G.ex_r) || (iz == 0 && G.ex_t) || (iz == G.nnz - 1 && G.ex_b)) {
+      S.stopped_at_root = 1;
+      return false;
+    }
+  }
+  ++nacc;
+  // ---- gather the 24 nodes of the radius-3 diamond the four neighbours' stencils need (static indices only) ----
+  unsigned ev[7][7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 7; ++a) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 7; ++b) {
+      const int dx = a - 3, dz = b - 3;
+      const int ad = (dx < 0 ? -dx : dx) + (dz < 0 ? -dz : dz);
+      unsigned v = E_OUT;
+      if (ad >= 1 && ad <= 3) {
+        const int x = ix + dx, z = iz + dz;
+        if (x >= 0 && x < G.nnx && z >= 0 && z < G.nnz) v = E[nidx<URG>(x, z, ld)];
+      } else if (ad == 0) {
+        v = tself;
+      }
+      ev[a][b] = v;
+    }
+  }
+  float slown[4], risti[4];
+  bool cin[4];
+  int co[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    const int cx = ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0)), cz = iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0));
+    cin[q] = (cx >= 0 && cx < G.nnx && cz >= 0 && cz < G.nnz);
+    co[q] = nidx<URG>(cx, cz, ld);
+    slown[q] = 0.0f; risti[q] = 0.0f;
+    if (cin[q]) { slown[q] = G.slow[cx * ld + cz]; risti[q] = G.risti_tab[cx]; }
+  }
+  // the id of the popped node is free from here on (the root entry is overwritten by the pop)
+  const int root_id = tps_id(S, root);
+  // ---- pop the root while the loads are in flight ----
+  tps_pop_root(S, last);
+  tps_release_id(S, root_id);
+  // ---- the four neighbours: status + trial time (16 quadrant solves) ----
+  int qst[4], qid[4], spos[4];
+  float qt[4];
+  int nins = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    const int ndx = (q == 0) ? -1 : (q == 1 ? 1 : 0), ndz = (q == 2) ? -1 : (q == 3 ? 1 : 0);
+    const unsigned cE = ev[3 + ndx][3 + ndz];
+    qst[q] = !cin[q] ? -2 : (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
+    qid[q] = (int)(cE & ~E_SIGN);
+    qt[q] = tps_inf();
+    spos[q] = 0;
+    if (qst[q] == -1 || qst[q] == 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int js = 0; js < 2; ++js) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int ks = 0; ks < 2; ++ks) {
+          const int jx = js == 0 ? -1 : 1, kz = ks == 0 ? -1 : 1;
+          // a neighbour outside the grid has E_OUT everywhere (the reference never evaluates it)
+          const unsigned ej1 = ev[3 + ndx + jx][3 + ndz], ej2 = ev[3 + ndx + 2 * jx][3 + ndz];
+          const unsigned ek1 = ev[3 + ndx][3 + ndz + kz], ek2 = ev[3 + ndx][3 + ndz + 2 * kz];
+          bool ok = false;
+          float trav = quadrant(e_status(ej1), e_status(ej2), tps_as_float((int)ej1), tps_as_float((int)ej2), e_status(ek1),
+                                e_status(ek2), tps_as_float((int)ek1), tps_as_float((int)ek2), slown[q], G.earth, risti[q],
+                                G.dnx, G.dnz, ok);
+          if (!ok) trav = tps_inf();
+          qt[q] = fminf(qt[q], trav);
+        }
+      }
+      if (qst[q] == -1) ++nins;
+    }
+  }
+  if (S.ntr + nins >= S.htot) { S.overflow = 1; S.ntr = 0; return false; }
+  // heap positions of the close neighbours (as of after the pop)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q)
+    if (qst[q] == 1) spos[q] = (int)S.pos[qid[q]];
+  // ---- apply in the reference order: x-1, x+1, z-1, z+1 ----
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    if (qst[q] == -1) {
+      const int id = tps_alloc_id(S);
+      E[co[q]] = E_SIGN | (unsigned)id;
+      S.ntr += 1;
+      tps_sift_up(S, S.ntr, qt[q], tps_pack(S, id, co[q]), q, qid, qst, spos);
+    } else if (qst[q] == 1) {
+      tps_sift_up(S, spos[q], qt[q], tps_pack(S, qid[q], co[q]), q, qid, qst, spos);
+    }
+  }
+  return true;
+}
+
+// ---- source cell initialisation (travel, CalSurfG.f90:324-345) on the refined grid ----
+TPS_HD void tps_source_init(TpsState& S, const GridC& g, const SrcRec& sr, const float* vv, const float* ub, unsigned* E_r) {
+  tps_reset(S);
+  const int isx = sr.isx_r, isz = sr.isz_r;
+  float vss[2][2];
+  for (int i = 1; i <= 2; ++i)
+    for (int j = 1; j <= 2; ++j) vss[i - 1][j - 1] = refined_vel_t(g, sr, vv, ub, isz - 1 + j, isx - 1 + i);
+  const float dsx = sr.dsx_r, dsz = sr.dsz_r;
+  float vsrc = 0.0f;
+  for (int i = 1; i <= 2; ++i)
+    for (int j = 1; j <= 2; ++j) {
+      const float produ = (1.0f - fabsf(((float)(i - 1) * sr.dnxr - dsx) / sr.dnxr)) *
+                          (1.0f - fabsf(((float)(j - 1) * sr.dnzr - dsz) / sr.dnzr));
+      vsrc = vsrc + vss[i - 1][j - 1] * produ;
+    }
+  for (int i = 1; i <= 2; ++i)
+    for (int j = 1; j <= 2; ++j) {
+      const float ax = dsx - (float)(i - 1) * sr.dnxr;
+      const float az = dsz - (float)(j - 1) * sr.dnzr;
+      const float ds = sqrtf(ax * ax + az * az);
+      const float t0 = 2.0f * ds / (vss[i - 1][j - 1] + vsrc);
+      const int o = (isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1);
+      const int id = tps_alloc_id(S);
+      E_r[o] = E_SIGN | (unsigned)id;
+      S.ntr += 1;
+      tps_sift_up_plain(S, S.ntr, t0, tps_pack(S, id, o));
+    }
+}
+
+// ---- after the refined march: the close nodes get their trial value back (the hand-off and the ray tracer read
+//      E_r as "alive = +t, close = t | sign, far"), optionally their heap slots (test seam = the reference's nstsr) ----
+TPS_HD void tps_refined_finish(TpsState& S, unsigned* E_r, int* hpos_out) {
+  for (int p = 1; p <= S.ntr; ++p) {
+    if (p == 1 && S.stopped_at_root) { if (hpos_out) hpos_out[tps_node(S, tps_hget(S, 1))] = 1; continue; }
+    const int2 e = tps_hget(S, p);
+    const int n = tps_node(S, e);
+    E_r[n] = (unsigned)e.x | E_SIGN;
+    if (hpos_out) hpos_out[n] = p;
+  }
+}
+
+// ---- hand-off to the coarse grid (FwdTraveltimeCPS.f90:576-632) + heap build (travel urg=2, CalSurfG.f90:311-317).
+//      E_c was preset to FAR. ----
+TPS_HD void tps_handoff(TpsState& S, const GridC& g, const SrcRec& sr, const unsigned* E_r, unsigned* E_c) {
+  const int nkx = (sr.nnxr - 1) / g.sgdl + 1, nkz = (sr.nnzr - 1) / g.sgdl + 1;
+  for (int kx = 0; kx < nkx; ++kx)
+    for (int kz = 0; kz < nkz; ++kz)
+      E_c[cidx(sr.vnl + kx - 1, sr.vnt + kz - 1, g.nnz)] = E_r[(kx * g.sgdl) * REF_LD + (kz * g.sgdl)];
+  // alive nodes with a far neighbour become close (:615-632).  Restricted to the injected box: everything outside it
+  // is far.  The test runs on the ORIGINAL alive set: a node marked close here keeps its time under the sign bit, and
+  // "far" is an exact bit pattern, so marking in place cannot change a later test.
+  for (int k = sr.vnl; k <= sr.vnr; ++k)
+    for (int l = sr.vnt; l <= sr.vnb; ++l) {
+      const int o = cidx(k - 1, l - 1, g.nnz);
+      if ((int)E_c[o] >= 0) {
+        bool mk = false;
+        if (l - 1 >= 1 && E_c[cidx(k - 1, l - 2, g.nnz)] == E_FAR) mk = true;
+        if (l + 1 <= g.nnz && E_c[cidx(k - 1, l, g.nnz)] == E_FAR) mk = true;
+        if (k - 1 >= 1 && E_c[cidx(k - 2, l - 1, g.nnz)] == E_FAR) mk = true;
+        if (k + 1 <= g.nnx && E_c[cidx(k, l - 1, g.nnz)] == E_FAR) mk = true;
+        if (mk) E_c[o] |= E_SIGN;
+      }
+    }
+  // heap build in scan order i=1..nnx, j=1..nnz; the node's word switches from "t | sign" to "id | sign"
+  tps_reset(S);
+  for (int k = sr.vnl; k <= sr.vnr && !S.overflow; ++k)
+    for (int l = sr.vnt; l <= sr.vnb; ++l) {
+      const int o = cidx(k - 1, l - 1, g.nnz);
+      const unsigned ev = E_c[o];
+      if ((int)ev < 0 && ev != E_FAR) {
+        if (S.ntr + 1 >= S.htot) { S.overflow = 1; break; }
+        const int id = tps_alloc_id(S);
+        E_c[o] = E_SIGN | (unsigned)id;
+        S.ntr += 1;
+        tps_sift_up_plain(S, S.ntr, tps_as_float((int)(ev & ~E_SIGN)), tps_pack(S, id, o));
+      }
+    }
+}
+
+TPS_HD TpsGrid tps_grid_refined(const GridC& g, const SrcRec& sr, const float* slow_r, const float* risti_r, unsigned* E_r) {
+  TpsGrid G;
+  G.nnx = sr.nnxr; G.nnz = sr.nnzr; G.ld = REF_LD; G.dnx = sr.dnxr; G.dnz = sr.dnzr; G.earth = g.earth;
+  G.slow = slow_r; G.risti_tab = risti_r; G.E = E_r;
+  // exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz)
+  G.ex_l = sr.vnl != 1; G.ex_r = sr.vnr != sr.nnxr; G.ex_t = sr.vnt != 1; G.ex_b = sr.vnb != sr.nnzr;
+  return G;
+}
+TPS_HD TpsGrid tps_grid_coarse(const GridC& g, const float* slow_c, const float* risti_c, unsigned* E_c) {
+  TpsGrid G;
+  G.nnx = g.nnx; G.nnz = g.nnz; G.ld = g.nnz; G.dnx = g.dnx; G.dnz = g.dnz; G.earth = g.earth;
+  G.slow = slow_c; G.risti_tab = risti_c; G.E = E_c;
+  G.ex_l = G.ex_r = G.ex_t = G.ex_b = false;
+  return G;
+}
+
+}  // namespace dz

@@ -134,6 +134,14 @@ int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, dazim_tables
 int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
                     const double* pv, int n, const float* scx, const float* scz, float* veln,
                     float* ttn, int* nsts, float* ttnr, int* nstsr, int* geom);
+
+/* Host-only test seam: the eikonal code of the thread-per-solve kernel (csrc/dazim_tps.h, __host__ __device__) run on
+ * the CPU for ONE source, with a shared heap part of hcap entries and hspill_n spilled entries.  Same outputs as
+ * dazim_fmm_solve for n = 1.  Lets the CPU-only test suite compare the kernel's logic with the oracle; never called by
+ * a product entry point and needs no device. */
+int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                              float scx, float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr,
+                              int* nstsr, int* geom, long long* n_accept);
 /* Rays: n (source, receiver) pairs on one map; outputs travel time tt(n) and dense
  * Frechet maps fdm/fdmc/fdms (nvz+2, nvx+2, n) column-major (zero where untouched). */
 int dazim_raytrace(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
