@@ -329,7 +329,7 @@ def fmm_host_twin(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, hcap=448, hspill
     Only tests call this: it is how the kernel's logic is checked against the oracle without a GPU."""
     nnx = (nx - 3) * 5 + 1; nnz = (ny - 3) * 5 + 1
     if hspill is None:
-        hspill = 8 * (nnx + nnz) + 1024 + 16
+        hspill = (8 * (nnx + nnz) + 1024 + 16) & ~1
     pv = np.ascontiguousarray(pv, np.float64)
     ttn = np.zeros((nnz, nnx), np.float32, order="F"); nsts = np.zeros((nnz, nnx), np.int32, order="F")
     ttnr = np.zeros((129, 129), np.float32, order="F"); nstsr = np.zeros((129, 129), np.int32, order="F")

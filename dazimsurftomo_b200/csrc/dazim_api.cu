@@ -23,8 +23,8 @@ cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
 cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas);
 cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st);
-cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int* nctas);
-cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, cudaStream_t st);
+cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int* nctas);
+cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, cudaStream_t st);
 cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, int nnz_tiled, float* ttn, int* nsts,
                                  cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
@@ -195,7 +195,8 @@ struct dazim_plan {
   int nctas = 0;
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
   int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
-  int tps = 0;   // thread-per-solve kernel (k_fmm_tps, dazim_tps.h): the default
+  int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
+  int coh = 1;   // 1: five-warp cohort kernel; 0: the one-thread-per-solve kernel
   int tps_idcap = 0, tps_node_bits = 0;
   DBuf<unsigned short> d_pos_tab, d_free_stk;   // per solve (tps)
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
@@ -401,12 +402,14 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
       // one warp of 32 solves per CTA; 1 CTA per SM while that holds every solve (bigger shared heap), else 2
       int per_sm = ctas_needed <= h->nsm ? 1 : 2;
       if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(e)));
-      P->hcap = std::min(hneed, (int)(((227 * 1024) / per_sm - 1024) / 256));
-      if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(896, atoi(e)));
-      CK(fmm_tps_max_ctas(P->hcap, h->nsm, &nctas));
+      if (const char* e = getenv("DAZIM_COH")) P->coh = atoi(e) ? 1 : 0;
+      P->hcap = std::min(hneed, (int)(((227 * 1024) / per_sm - 1024 - 2752) / 256));
+      if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
+      P->hcap &= ~1;                                  // even: a sibling pair never straddles shared / spilled
+      CK(fmm_tps_max_ctas(P->hcap, h->nsm, P->coh, &nctas));
       if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
       nctas = std::min(nctas, ctas_needed);
-      P->hspill = std::max(16, std::min(65535 - P->hcap, hspill_full));
+      P->hspill = (std::max(16, std::min(65535 - P->hcap, hspill_full)) + 1) & ~1;
       P->tps_idcap = (int)std::min<long long>(idmax, (long long)P->hcap + P->hspill);
     }
   }
@@ -638,7 +641,8 @@ static int plan_run_once(dazim_plan* P) {
         A.hspill_n = P->hspill; A.hcap = P->hcap; A.pos_tab = P->d_pos_tab.p; A.free_stk = P->d_free_stk.p;
         A.idcap = P->tps_idcap; A.node_bits = P->tps_node_bits; A.hpos_r_out = P->d_hpos_r_out.p;
         A.flags = F.flags; A.n_accept = F.n_accept;
-        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + 31) / 32), st));
+        A.prof = getenv("DAZIM_COH_PROF") ? atoi(getenv("DAZIM_COH_PROF")) : 0;
+        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + 31) / 32), P->coh, st));
         T.n_launch++;      // + k_tps_init
       }
       else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
@@ -1308,7 +1312,7 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
 extern "C" int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
                                          float scx, float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr,
                                          int* nstsr, int* geom, long long* n_accept) {
-  if (!pv || nx < 5 || ny < 5 || hcap < 8) return DAZIM_EBADARG;
+  if (!pv || nx < 5 || ny < 5 || hcap < 8 || (hcap & 1) || (hspill_n & 1) || hspill_n < 4) return DAZIM_EBADARG;
   const GridC g = make_grid(nx, ny, goxd, gozd, dvxd, dvzd);
   SrcRec sr;
   std::memset(&sr, 0, sizeof(sr));
@@ -1336,7 +1340,7 @@ extern "C" int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd,
   std::vector<unsigned short> pos((size_t)idcap), fstk((size_t)idcap);
   std::vector<int> hpos_r(REF_N, 0);
   TpsState S;
-  S.sm = sm.data(); S.stride = 1; S.gl = gl.data(); S.hcap = hcap; S.htot = hcap + hspill_n;
+  S.sm = sm.data(); S.stride = 1; S.gl = gl.data(); S.hcap = hcap; S.htot = hcap + hspill_n - 2;
   S.pos = pos.data(); S.fstk = fstk.data(); S.idcap = idcap; S.node_bits = nb; S.node_mask = (1u << nb) - 1u; S.overflow = 0;
   unsigned long long nacc = 0;
   tps_source_init(S, g, sr, velv.data(), ub, E_r.data());

@@ -1082,7 +1082,7 @@ __global__ void __launch_bounds__(32, 2) k_fmm_tps(TpsArgs A) {
   S.sm = reinterpret_cast<int2*>(smem_raw) + lane;
   S.stride = 32;
   S.hcap = A.hcap;
-  S.htot = A.hcap + A.hspill_n;
+  S.htot = A.hcap + A.hspill_n - 2;     // two slots of slack: tps_pop_root reads sibling pairs as one int4
   S.idcap = A.idcap;
   S.node_bits = A.node_bits;
   S.node_mask = (1u << A.node_bits) - 1u;
@@ -1130,28 +1130,161 @@ __global__ void __launch_bounds__(32, 2) k_fmm_tps(TpsArgs A) {
   if (nacc) atomicAdd(A.n_accept, nacc);
 }
 
+// ---------------------------------------------------------------------------
+// K3, cohort kernel: one CTA of FIVE warps per 32 solves.  Warp 0 ("heap warp") runs, one lane per solve, the scalar
+// heap code of dazim_tps.h (tps_pre, tps_pop, tps_apply); warps 1-4 ("stencil warps") each own ONE of the four
+// neighbours of the node being accepted, again one lane per solve: the gather of that neighbour's stencil and its four
+// quadrant quadratics (tps_neighbour) run while the heap warp sifts the root down.  No shuffle and no shared state
+// between solves; the two roles hand over through 2.7 KB of shared memory and two producer/consumer named barriers
+// per accept round.  Arithmetic and heap discipline are exactly those of the one-thread kernel (and of its host twin).
+#define COH_X 1      // heap warp arrives after posting the nodes being accepted, stencil warps wait
+#define COH_Y 2      // stencil warps arrive after posting the four neighbour records, heap warp waits
+#define COH_THREADS 160
+__device__ __forceinline__ void coh_sync(int id) { asm volatile("bar.sync %0, 160;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void coh_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, 160;" ::"r"(id) : "memory");
+}
+// exchange area (ints): [0,32) node or -1, [32,64) ix, [64,96) iz, [96,128) tself, [128] any lane still running,
+// [160 + ((q*4 + k)*32 + lane)] neighbour q, field k (0 status, 1 id, 2 trial time, 3 offset)
+#define COH_XCH_INTS (160 + 16 * 32)
+
+template <int URG>
+__device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch, const int lane, const bool act,
+                               unsigned long long& nacc, const bool prof) {
+  bool run = act;
+  long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, t0 = 0, t1 = 0;
+  unsigned long long rounds = 0;
+  for (;;) {
+    if (prof) t0 = clock64();
+    TpsPre P;
+    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.root_id = 0; P.last = make_int2(0, 0);
+    if (run) run = tps_pre<URG>(S, G, nacc, P);
+    xch[lane] = run ? P.pn : -1;
+    xch[32 + lane] = P.ix;
+    xch[64 + lane] = P.iz;
+    xch[96 + lane] = (int)P.tself;
+    const bool any = __any_sync(0xffffffffu, run);
+    if (lane == 0) xch[128] = any ? 1 : 0;
+    coh_arrive(COH_X);
+    if (!any) break;
+    if (prof) { t1 = clock64(); c_pre += t1 - t0; t0 = t1; }
+    if (run) tps_pop(S, P);                          // sift the root down while the stencil warps work
+    if (prof) { __syncwarp(); t1 = clock64(); c_pop += t1 - t0; t0 = t1; }
+    coh_sync(COH_Y);
+    if (prof) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
+    if (run) {
+      TpsNb N[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        N[q].qst = xch[160 + ((q * 4 + 0) * 32 + lane)];
+        N[q].qid = xch[160 + ((q * 4 + 1) * 32 + lane)];
+        N[q].qt = __int_as_float(xch[160 + ((q * 4 + 2) * 32 + lane)]);
+        N[q].co = xch[160 + ((q * 4 + 3) * 32 + lane)];
+      }
+      run = tps_apply<URG>(S, G, N);
+    }
+    if (prof) { __syncwarp(); t1 = clock64(); c_apply += t1 - t0; ++rounds; }
+  }
+  if (prof && lane == 0 && rounds)
+    printf("[coh prof] urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f apply %.0f (heap size at end %d)\n",
+           URG, rounds, (double)c_pre / rounds, (double)c_pop / rounds, (double)c_wait / rounds, (double)c_apply / rounds, S.ntr);
+}
+
+template <int URG>
+__device__ void coh_march_stencil(const TpsGrid& G, volatile int* xch, const int lane, const int q) {
+  for (;;) {
+    coh_sync(COH_X);
+    if (!xch[128]) break;
+    const int pn = xch[lane];
+    if (pn >= 0) {
+      const TpsNb R = tps_neighbour<URG>(G, xch[32 + lane], xch[64 + lane], (unsigned)xch[96 + lane], q);
+      xch[160 + ((q * 4 + 0) * 32 + lane)] = R.qst;
+      xch[160 + ((q * 4 + 1) * 32 + lane)] = R.qid;
+      xch[160 + ((q * 4 + 2) * 32 + lane)] = __float_as_int(R.qt);
+      xch[160 + ((q * 4 + 3) * 32 + lane)] = R.co;
+    }
+    coh_arrive(COH_Y);
+  }
+}
+
+__global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const GridC& g = A.g;
+  const size_t ncoarse = (size_t)g.nnx * g.nnz;          // slow_c (plain column-major)
+  const size_t ncf = coarse_field_size(g.nnx, g.nnz);    // E_c (interleaved layout)
+  volatile int* xch = reinterpret_cast<volatile int*>(smem_raw + (size_t)A.hcap * 32 * 8);
+  TpsState S;
+  S.sm = reinterpret_cast<int2*>(smem_raw) + lane;
+  S.stride = 32;
+  S.hcap = A.hcap;
+  S.htot = A.hcap + A.hspill_n - 2;     // two slots of slack: tps_pop_root reads sibling pairs as one int4
+  S.idcap = A.idcap;
+  S.node_bits = A.node_bits;
+  S.node_mask = (1u << A.node_bits) - 1u;
+  S.overflow = 0;
+  tps_reset(S);
+  unsigned long long nacc = 0;
+  for (int s0 = blockIdx.x * 32; s0 < A.nsrc; s0 += gridDim.x * 32) {
+    const int s = s0 + lane;
+    const int sc = min(s, A.nsrc - 1);                   // inactive lane: valid addresses, no side effects
+    const SrcRec sr = A.src[sc];
+    unsigned* E_r = A.E_r + (size_t)sc * REF_N;
+    unsigned* E_c = A.E_c + (size_t)sc * ncf;
+    const float* slow_r = A.slow_r + (size_t)sc * REF_N;
+    const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
+    const TpsGrid Gr = tps_grid_refined(g, sr, slow_r, A.risti_r + (size_t)sc * REF_LD, E_r);
+    const TpsGrid Gc = tps_grid_coarse(g, slow_c, A.risti_c, E_c);
+    if (warp == 0) {
+      const bool act = (s < A.nsrc) && !S.overflow;
+      const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
+      S.gl = A.hspill + (size_t)sc * A.hspill_n;
+      S.pos = A.pos_tab + (size_t)sc * A.idcap;
+      S.fstk = A.free_stk + (size_t)sc * A.idcap;
+      if (act) tps_source_init(S, g, sr, vv, c_ubasis, E_r);
+      coh_march_heap<1>(S, Gr, xch, lane, act, nacc, A.prof && blockIdx.x == 0);
+      if (act && !S.overflow) {
+        tps_refined_finish(S, E_r, A.hpos_r_out ? A.hpos_r_out + (size_t)sc * REF_N : nullptr);
+        tps_handoff(S, g, sr, E_r, E_c);
+      }
+      __syncwarp();
+      coh_march_heap<2>(S, Gc, xch, lane, act && !S.overflow, nacc, A.prof && blockIdx.x == 0);
+    } else {
+      coh_march_stencil<1>(Gr, xch, lane, warp - 1);
+      coh_march_stencil<2>(Gc, xch, lane, warp - 1);
+    }
+  }
+  if (warp == 0) {
+    if (S.overflow) atomicOr(A.flags, 16);
+    if (nacc) atomicAdd(A.n_accept, nacc);
+  }
+}
+
 // resident warps (= CTAs of 32 solves) per SM for a given shared heap capacity
-cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int* nctas) {
-  const size_t smem = (size_t)hcap * 32 * 8;
-  cudaError_t e = cudaFuncSetAttribute(k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int* nctas) {
+  const size_t smem = (size_t)hcap * 32 * 8 + (coh ? COH_XCH_INTS * 4 : 0);
+  const void* fn = coh ? (const void*)k_fmm_coh : (const void*)k_fmm_tps;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fmm_tps, 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, coh ? COH_THREADS : 32, smem);
   if (e != cudaSuccess) return e;
   *nctas = per_sm * nsm;
   return cudaSuccess;
 }
 
-cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, cudaStream_t st) {
+cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, cudaStream_t st) {
   if (A.nsrc <= 0) return cudaSuccess;
   dim3 gi((REF_N + 255) / 256, (unsigned)std::min(A.nsrc, 65535));
   k_tps_init<<<gi, 256, 0, st>>>(A);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const size_t smem = (size_t)A.hcap * 32 * 8;
-  e = cudaFuncSetAttribute(k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)A.hcap * 32 * 8 + (coh ? COH_XCH_INTS * 4 : 0);
+  e = cudaFuncSetAttribute(coh ? (const void*)k_fmm_coh : (const void*)k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_fmm_tps<<<nctas, 32, smem, st>>>(A);
+  if (coh) k_fmm_coh<<<nctas, COH_THREADS, smem, st>>>(A);
+  else k_fmm_tps<<<nctas, 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 

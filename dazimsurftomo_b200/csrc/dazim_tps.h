@@ -176,6 +176,7 @@ struct TpsArgs {
   int* hpos_r_out;            // optional test seam [nsrc][REF_N]: heap slots of the close nodes after the refined march
   int* flags;                 // bit4 (16): heap / id overflow
   unsigned long long* n_accept;
+  int prof;                   // DAZIM_COH_PROF=1: lane 0 of CTA 0 prints its cycle split per accept (cohort kernel)
 };
 
 struct TpsState {
@@ -186,7 +187,7 @@ struct TpsState {
   int ntr;
   unsigned short* pos;
   unsigned short* fstk;
-  int nfree, next_id, spare, idcap;
+  int nfree, next_id, spare, spare2, idcap;
   int node_bits;
   unsigned node_mask;
   int overflow;
@@ -220,17 +221,19 @@ TPS_HD void tps_hput(TpsState& S, int p, int2 e) {
   S.pos[tps_id(S, e)] = (unsigned short)p;
 }
 
+// ids: two spares in registers (an accept step releases one id and takes 0-3, so the global stack is touched rarely)
 TPS_HD void tps_release_id(TpsState& S, int id) {
   if (S.spare < 0) { S.spare = id; return; }
+  if (S.spare2 < 0) { S.spare2 = id; return; }
   S.fstk[S.nfree++] = (unsigned short)id;
 }
 TPS_HD int tps_alloc_id(TpsState& S) {
-  if (S.spare >= 0) { const int id = S.spare; S.spare = -1; return id; }
+  if (S.spare >= 0) { const int id = S.spare; S.spare = S.spare2; S.spare2 = -1; return id; }
   if (S.nfree > 0) return (int)S.fstk[--S.nfree];
   if (S.next_id >= S.idcap) { S.overflow = 1; return 0; }
   return S.next_id++;
 }
-TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.nfree = 0; S.next_id = 0; S.spare = -1; S.stopped_at_root = 0; }
+TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.nfree = 0; S.next_id = 0; S.spare = -1; S.spare2 = -1; S.stopped_at_root = 0; }
 
 // addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).  q = index of the neighbour being applied;
 // later close neighbours that sit on the path move down with their parent slot: their positions (read before) are
@@ -267,6 +270,11 @@ TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int packed) {
 }
 
 // downtree (CalSurfG.f90:786-855).  `last` = heap[ntr] (fetched early by the caller).
+// Shared levels one by one (two loads from the lane's own banks).  Spilled levels: the 14 entries of the next THREE
+// levels under the hole are contiguous per level (2p..2p+1, 4p..4p+3, 8p..8p+7) and are fetched with seven 16-byte
+// loads in ONE round trip, then the path is resolved from registers with selects -- a dependent global load per level
+// was the largest single term of the accept chain.  hcap and the spill stride are even, so a sibling pair never
+// straddles the shared / spilled boundary and every pair is one aligned int4.
 TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
   if (S.ntr == 1) { S.ntr = 0; return; }
   const float k = TKEY(last);
@@ -287,17 +295,55 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
     tpp = tpc;
     tpc = 2 * tpp;
   }
-  // remaining levels (single child, or children in the spill part)
+  if (!placed && tpc <= ntr && tpc < S.hcap) {
+    // tpc == ntr: a single child, in shared memory
+    const int2 c = S.sm[(size_t)tpc * S.stride];
+    if (TKEY(c) < k) { tps_hput(S, tpp, c); tpp = tpc; }
+    placed = true;
+  }
+  // spilled levels, three at a time
   while (!placed && tpc <= ntr) {
-    int2 c = tps_hget(S, tpc);
-    if (tpc < ntr) {
-      const int2 c1 = tps_hget(S, tpc + 1);
-      if (TKEY(c) > TKEY(c1)) { c = c1; tpc += 1; }
+    const int4* g4 = reinterpret_cast<const int4*>(S.gl);
+    const int b1 = (2 * tpp - S.hcap) >> 1, b2 = (4 * tpp - S.hcap) >> 1, b3 = (8 * tpp - S.hcap) >> 1;   // int4 indices
+    const int4 z = make_int4(0x7f800000, 0, 0x7f800000, 0);
+    int4 l1 = z, l2a = z, l2b = z, l3a = z, l3b = z, l3c = z, l3d = z;
+    l1 = g4[b1];                                   // 2p <= ntr here; the slot after ntr exists (spill slack)
+    if (4 * tpp <= ntr) l2a = g4[b2];
+    if (4 * tpp + 2 <= ntr) l2b = g4[b2 + 1];
+    if (8 * tpp <= ntr) l3a = g4[b3];
+    if (8 * tpp + 2 <= ntr) l3b = g4[b3 + 1];
+    if (8 * tpp + 4 <= ntr) l3c = g4[b3 + 2];
+    if (8 * tpp + 6 <= ntr) l3d = g4[b3 + 3];
+    // level 1
+    {
+      const int2 c0 = make_int2(l1.x, l1.y), c1 = make_int2(l1.z, l1.w);
+      const bool right = (tpc < ntr) && (TKEY(c0) > TKEY(c1));
+      const int2 c = right ? c1 : c0;
+      tpc += right ? 1 : 0;
+      if (!(TKEY(c) < k)) break;
+      tps_hput(S, tpp, c);
+      tpp = tpc; tpc = 2 * tpp;
+      if (tpc > ntr) break;
+      // level 2
+      const int4 m = right ? l2b : l2a;
+      const int2 d0 = make_int2(m.x, m.y), d1 = make_int2(m.z, m.w);
+      const bool right2 = (tpc < ntr) && (TKEY(d0) > TKEY(d1));
+      const int2 d = right2 ? d1 : d0;
+      tpc += right2 ? 1 : 0;
+      if (!(TKEY(d) < k)) break;
+      tps_hput(S, tpp, d);
+      tpp = tpc; tpc = 2 * tpp;
+      if (tpc > ntr) break;
+      // level 3
+      const int4 n = right ? (right2 ? l3d : l3c) : (right2 ? l3b : l3a);
+      const int2 f0 = make_int2(n.x, n.y), f1 = make_int2(n.z, n.w);
+      const bool right3 = (tpc < ntr) && (TKEY(f0) > TKEY(f1));
+      const int2 f = right3 ? f1 : f0;
+      tpc += right3 ? 1 : 0;
+      if (!(TKEY(f) < k)) break;
+      tps_hput(S, tpp, f);
+      tpp = tpc; tpc = 2 * tpp;
     }
-    if (!(TKEY(c) < k)) break;
-    tps_hput(S, tpp, c);
-    tpp = tpc;
-    tpc = 2 * tpp;
   }
   tps_hput(S, tpp, last);
 }
@@ -312,127 +358,182 @@ struct TpsGrid {
   bool ex_l, ex_r, ex_t, ex_b;
 };
 
-// One accept step of travel's DO WHILE (CalSurfG.f90:356-456).  Returns false when the march is over.
+// One accept step of travel's DO WHILE (CalSurfG.f90:356-456) in three pieces, so that the same code serves the
+// one-thread-per-solve kernel (pre + 4 x neighbour + post in one thread), the cohort kernel (pre/post on the heap
+// warp, one neighbour per stencil warp) and the host twin.
+struct TpsPre { int pn, ix, iz, root_id; unsigned tself; int2 last; };
+struct TpsNb { int qst, qid, co; float qt; };     // neighbour status (-2 outside, -1 far, 0 alive, 1 close), id, offset, trial
+
+// (1) the node on top of the heap becomes alive.  Returns false when the march is over (heap empty, overflow, or the
+//     refined march reached the edge of the source box: CalSurfG.f90:362-382).
 template <int URG>
-TPS_HD bool tps_step(TpsState& S, const TpsGrid& G, unsigned long long& nacc) {
+TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, TpsPre& P) {
   if (S.ntr <= 0 || S.overflow) return false;
   const int2 root = tps_hget(S, 1);
-  const int pn = tps_node(S, root);
-  const int2 last = tps_hget(S, S.ntr);
-  const int ld = G.ld;
-  const float inv_ld = 1.0f / (float)ld;
-  int ix, iz;
-  ndecode<URG>(pn, ld, inv_ld, ix, iz);
-  unsigned* E = G.E;
-  const unsigned tself = (unsigned)root.x & ~E_SIGN;
-  E[pn] = tself;                                   // the popped node becomes alive with its trial value (= its heap key)
+  P.pn = tps_node(S, root);
+  P.root_id = tps_id(S, root);
+  P.last = tps_hget(S, S.ntr);
+  ndecode<URG>(P.pn, G.ld, 1.0f / (float)G.ld, P.ix, P.iz);
+  P.tself = (unsigned)root.x & ~E_SIGN;
+  G.E[P.pn] = P.tself;                             // the popped node becomes alive with its trial value (= its heap key)
   if (URG == 1) {
-    if ((ix == 0 && G.ex_l) || (ix == G.nnx - 1 && G.ex_r) || (iz == 0 && G.ex_t) || (iz == G.nnz - 1 && G.ex_b)) {
+    if ((P.ix == 0 && G.ex_l) || (P.ix == G.nnx - 1 && G.ex_r) || (P.iz == 0 && G.ex_t) || (P.iz == G.nnz - 1 && G.ex_b)) {
       S.stopped_at_root = 1;
       return false;
     }
   }
   ++nacc;
-  // ---- gather the 24 nodes of the radius-3 diamond the four neighbours' stencils need (static indices only) ----
-  unsigned ev[7][7];
+  return true;
+}
+
+// (2) neighbour q of the accepted node (ix, iz): its status and, if it is far or close, its trial time = the minimum
+//     of fouds2's four quadrant solves over the nodes that are alive now.  Reads E only.
+template <int URG>
+TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const unsigned tself, const int q) {
+  const int ndx = (q == 0) ? -1 : (q == 1 ? 1 : 0), ndz = (q == 2) ? -1 : (q == 3 ? 1 : 0);
+  const int cx = ix + ndx, cz = iz + ndz, ld = G.ld;
+  TpsNb R;
+  R.co = nidx<URG>(cx, cz, ld);
+  R.qid = 0;
+  R.qt = tps_inf();
+  if (!(cx >= 0 && cx < G.nnx && cz >= 0 && cz < G.nnz)) { R.qst = -2; return R; }
+  const unsigned* E = G.E;
+  const unsigned cE = E[R.co];
+  R.qst = (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
+  R.qid = (int)(cE & ~E_SIGN);
+  if (R.qst == 0) return R;
+  // first / second stencil nodes in the four directions x-1, x+1, z-1, z+1; the first node back towards the accepted
+  // node is that node itself (alive with tself)
+  unsigned e1[4], e2[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int a = 0; a < 7; ++a) {
+  for (int d = 0; d < 4; ++d) {
+    const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+    const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+    e1[d] = E_OUT; e2[d] = E_OUT;
+    if (ddx == -ndx && ddz == -ndz) e1[d] = tself;
+    else if (s1x >= 0 && s1x < G.nnx && s1z >= 0 && s1z < G.nnz) e1[d] = E[nidx<URG>(s1x, s1z, ld)];
+    if (s2x >= 0 && s2x < G.nnx && s2z >= 0 && s2z < G.nnz) e2[d] = E[nidx<URG>(s2x, s2z, ld)];
+  }
+  const float slown = G.slow[cx * ld + cz], risti = G.risti_tab[cx];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int b = 0; b < 7; ++b) {
-      const int dx = a - 3, dz = b - 3;
-      const int ad = (dx < 0 ? -dx : dx) + (dz < 0 ? -dz : dz);
-      unsigned v = E_OUT;
-      if (ad >= 1 && ad <= 3) {
-        const int x = ix + dx, z = iz + dz;
-        if (x >= 0 && x < G.nnx && z >= 0 && z < G.nnz) v = E[nidx<URG>(x, z, ld)];
-      } else if (ad == 0) {
-        v = tself;
-      }
-      ev[a][b] = v;
+  for (int js = 0; js < 2; ++js) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int ks = 0; ks < 2; ++ks) {
+      bool ok = false;
+      float trav = quadrant(e_status(e1[js]), e_status(e2[js]), tps_as_float((int)e1[js]), tps_as_float((int)e2[js]),
+                            e_status(e1[2 + ks]), e_status(e2[2 + ks]), tps_as_float((int)e1[2 + ks]),
+                            tps_as_float((int)e2[2 + ks]), slown, G.earth, risti, G.dnx, G.dnz, ok);
+      if (!ok) trav = tps_inf();
+      R.qt = fminf(R.qt, trav);
     }
   }
-  float slown[4], risti[4];
-  bool cin[4];
-  int co[4];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int q = 0; q < 4; ++q) {
-    const int cx = ix + ((q == 0) ? -1 : (q == 1 ? 1 : 0)), cz = iz + ((q == 2) ? -1 : (q == 3 ? 1 : 0));
-    cin[q] = (cx >= 0 && cx < G.nnx && cz >= 0 && cz < G.nnz);
-    co[q] = nidx<URG>(cx, cz, ld);
-    slown[q] = 0.0f; risti[q] = 0.0f;
-    if (cin[q]) { slown[q] = G.slow[cx * ld + cz]; risti[q] = G.risti_tab[cx]; }
-  }
-  // the id of the popped node is free from here on (the root entry is overwritten by the pop)
-  const int root_id = tps_id(S, root);
-  // ---- pop the root while the loads are in flight ----
-  tps_pop_root(S, last);
-  tps_release_id(S, root_id);
-  // ---- the four neighbours: status + trial time (16 quadrant solves) ----
-  int qst[4], qid[4], spos[4];
-  float qt[4];
+  return R;
+}
+
+// (3) pop the root ...
+TPS_HD void tps_pop(TpsState& S, const TpsPre& P) {
+  tps_pop_root(S, P.last);
+  tps_release_id(S, P.root_id);      // the id of the popped node is free from here on
+}
+// (4) ... then insert / update the four neighbours in the reference order x-1, x+1, z-1, z+1 (addtree / updtree,
+//     CalSurfG.f90:738-774, :864-890).  Written so that the 32 lanes of a heap warp share ONE instruction stream
+//     whatever mix of far / close / alive neighbours their solves have: start positions, ids and entry words are
+//     selected first, the four parents are fetched together (one round trip), and the common case "the new key is
+//     not smaller than its parent" is a single store.  Only a key that really moves up enters the generic loop.
+template <int URG>
+TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
+  int qst[4], qid[4], spos[4], ppos[4], pk[4];
+  int2 pent[4];
   int nins = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    const int ndx = (q == 0) ? -1 : (q == 1 ? 1 : 0), ndz = (q == 2) ? -1 : (q == 3 ? 1 : 0);
-    const unsigned cE = ev[3 + ndx][3 + ndz];
-    qst[q] = !cin[q] ? -2 : (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
-    qid[q] = (int)(cE & ~E_SIGN);
-    qt[q] = tps_inf();
-    spos[q] = 0;
-    if (qst[q] == -1 || qst[q] == 1) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int js = 0; js < 2; ++js) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int ks = 0; ks < 2; ++ks) {
-          const int jx = js == 0 ? -1 : 1, kz = ks == 0 ? -1 : 1;
-          // a neighbour outside the grid has E_OUT everywhere (the reference never evaluates it)
-          const unsigned ej1 = ev[3 + ndx + jx][3 + ndz], ej2 = ev[3 + ndx + 2 * jx][3 + ndz];
-          const unsigned ek1 = ev[3 + ndx][3 + ndz + kz], ek2 = ev[3 + ndx][3 + ndz + 2 * kz];
-          bool ok = false;
-          float trav = quadrant(e_status(ej1), e_status(ej2), tps_as_float((int)ej1), tps_as_float((int)ej2), e_status(ek1),
-                                e_status(ek2), tps_as_float((int)ek1), tps_as_float((int)ek2), slown[q], G.earth, risti[q],
-                                G.dnx, G.dnz, ok);
-          if (!ok) trav = tps_inf();
-          qt[q] = fminf(qt[q], trav);
-        }
-      }
-      if (qst[q] == -1) ++nins;
-    }
+    qst[q] = N[q].qst; qid[q] = N[q].qid; spos[q] = 0;
+    if (qst[q] == -1) ++nins;
   }
   if (S.ntr + nins >= S.htot) { S.overflow = 1; S.ntr = 0; return false; }
-  // heap positions of the close neighbours (as of after the pop)
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int q = 0; q < 4; ++q)
-    if (qst[q] == 1) spos[q] = (int)S.pos[qid[q]];
-  // ---- apply in the reference order: x-1, x+1, z-1, z+1 ----
+  // start positions: close = back pointer (as of after the pop), far = next free heap slots in order
+  int nt = S.ntr;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    if (qst[q] == -1) {
-      const int id = tps_alloc_id(S);
-      E[co[q]] = E_SIGN | (unsigned)id;
-      S.ntr += 1;
-      tps_sift_up(S, S.ntr, qt[q], tps_pack(S, id, co[q]), q, qid, qst, spos);
-    } else if (qst[q] == 1) {
-      tps_sift_up(S, spos[q], qt[q], tps_pack(S, qid[q], co[q]), q, qid, qst, spos);
+    if (qst[q] == 1) spos[q] = (int)S.pos[qid[q]];
+    else if (qst[q] == -1) {
+      spos[q] = ++nt;
+      qid[q] = tps_alloc_id(S);
+      G.E[N[q].co] = E_SIGN | (unsigned)qid[q];
     }
+    pk[q] = tps_pack(S, qid[q], N[q].co);
+  }
+  // the four parents in one round trip
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    ppos[q] = spos[q] >> 1;
+    pent[q] = make_int2(0, 0);
+    if ((qst[q] == 1 || qst[q] == -1) && ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]);
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    if (qst[q] != 1 && qst[q] != -1) continue;
+    if (qst[q] == -1) S.ntr += 1;
+    const float k = N[q].qt;
+    int tpc = spos[q];
+    if ((tpc >> 1) != ppos[q]) { ppos[q] = tpc >> 1; if (ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]); }   // moved by an earlier sift-up
+    if (ppos[q] > 0 && k < TKEY(pent[q])) {
+      // the key moves up: generic loop (addtree / updtree sift-up), patching what later neighbours hold in registers
+      int tpp = ppos[q];
+      int2 par = pent[q];
+      for (;;) {
+        tps_hput(S, tpc, par);
+        const int pid = tps_id(S, par);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 4; ++r) {
+          if (r > q && qst[r] == 1 && qid[r] == pid) spos[r] = tpc;      // a later close neighbour moved down
+          if (r > q && ppos[r] == tpc) pent[r] = par;                    // a later parent slot changed content
+        }
+        tpc = tpp;
+        tpp = tpc >> 1;
+        if (tpp == 0) break;
+        par = tps_hget(S, tpp);
+        if (!(k < TKEY(par))) break;
+      }
+    }
+    const int2 e = make_int2(tps_as_int(k), pk[q]);
+    tps_hput(S, tpc, e);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 4; ++r)
+      if (r > q && ppos[r] == tpc) pent[r] = e;
   }
   return true;
+}
+
+template <int URG>
+TPS_HD bool tps_step(TpsState& S, const TpsGrid& G, unsigned long long& nacc) {
+  TpsPre P;
+  if (!tps_pre<URG>(S, G, nacc, P)) return false;
+  TpsNb N[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) N[q] = tps_neighbour<URG>(G, P.ix, P.iz, P.tself, q);
+  tps_pop(S, P);
+  return tps_apply<URG>(S, G, N);
 }
 
 // ---- source cell initialisation (travel, CalSurfG.f90:324-345) on the refined grid ----

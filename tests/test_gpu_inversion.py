@@ -115,6 +115,9 @@ def test_plan_iterate_matches_oracle(gpu, oracle, test1, iso):
     assert s["lsmr"]["istop"] == oinfo["istop"] and abs(s["lsmr"]["itn"] - oinfo["itn"]) <= max(1, 0.03 * oinfo["itn"])
     scale = np.abs(odv).max()
     assert scale > 1e-3
+    from conftest import note
+    note("iteration tail iso=%s: LSMR itn gpu %d / oracle %d, max|dv - dv_oracle| = %.2e x max|dv|" % (
+        iso, s["lsmr"]["itn"], oinfo["itn"], np.abs(r["dv"] - odv).max() / scale))
     assert np.abs(r["dv"] - odv).max() <= 5e-3 * scale, np.abs(r["dv"] - odv).max() / scale
     assert np.abs(r["vsf"] - ovsf).max() <= 5e-3 * scale + 1e-6
     assert np.array_equal(r["vsf"][:, :, -1], vs[:, :, -1]) and np.array_equal(r["vsf"][0], vs[0])

