@@ -239,8 +239,8 @@ def surfdisp96(thk, vp, vs, rho, periods, handle: Optional[Handle] = None):
     return cg
 
 
-def _gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc, gs, tables, maxnar, handle):
-    h = handle or default_handle()
+def _gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc, gs, tables, maxnar, handle, devices=None):
+    h = None if devices is not None else (handle or default_handle())
     pr = _Prob(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv)
     nx, ny, nz = pr.shape
     k = len(pr.tRc)
@@ -258,10 +258,20 @@ def _gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc, gs, t
         rw = _pinned.get("rw", maxnar, np.float32); iw = _pinned.get("iw", maxnar, np.int32)
         col = _pinned.get("col", maxnar, np.int32)
         coo.rw, coo.iw_row, coo.col, coo.maxnar = _p(rw), _p(iw), _p(col), maxnar
-    _chk(load().dazim_gbuild(h._h, C.c_int(mode), C.byref(pr.c), C.byref(tb.c), C.c_int(0 if tables is None else 1),
-                             _p(gc), _p(gs), _p(dsurf), _p(taa), _p(tRcV), C.byref(coo) if mode != 0 else None))
+    if devices is not None:
+        # single process, several GPUs behind ONE C-ABI call (what a Fortran / C host gets): dazim_gbuild_multi
+        dv = np.ascontiguousarray(devices, np.int32)
+        tm = Times()
+        _chk(load().dazim_gbuild_multi(C.c_int(len(dv)), _p(dv), C.c_int(mode), C.byref(pr.c), C.byref(tb.c),
+                                       C.c_int(0 if tables is None else 1), _p(gc), _p(gs), _p(dsurf), _p(taa), _p(tRcV),
+                                       C.byref(coo) if mode != 0 else None, C.byref(tm)))
+        times = tm.as_dict()
+    else:
+        _chk(load().dazim_gbuild(h._h, C.c_int(mode), C.byref(pr.c), C.byref(tb.c), C.c_int(0 if tables is None else 1),
+                                 _p(gc), _p(gs), _p(dsurf), _p(taa), _p(tRcV), C.byref(coo) if mode != 0 else None))
+        times = h.times
     out = dict(dsurf=dsurf, obsTaa=taa, tRcV=tRcV, pvRc=tb.pvRc, sen_vs=tb.sen[0], sen_vp=tb.sen[1], sen_rho=tb.sen[2],
-               Lsen_Gsc=tb.L, times=h.times)
+               Lsen_Gsc=tb.L, times=times)
     if mode != 0:
         n = coo.nar
         out.update(rw=rw[:n], row=iw[:n], col=col[:n], nar=n)
@@ -269,21 +279,22 @@ def _gbuild(mode, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, gc, gs, t
 
 
 def FwdObsTraveltimeCPS(vels, Gctrue, Gstrue, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables=None,
-                        handle: Optional[Handle] = None):
-    """FwdTraveltimeCPS.f90:208: returns dict(dsurf=T_iso, obsTaa=T_aa, tRcV, Lsen_Gsc, pvRc)."""
-    return _gbuild(0, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, Gctrue, Gstrue, tables, None, handle)
+                        handle: Optional[Handle] = None, devices=None):
+    """FwdTraveltimeCPS.f90:208: returns dict(dsurf=T_iso, obsTaa=T_aa, tRcV, Lsen_Gsc, pvRc).
+    devices=[0, 1, ...]: one call, several GPUs (dazim_gbuild_multi)."""
+    return _gbuild(0, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, Gctrue, Gstrue, tables, None, handle, devices)
 
 
 def CalSurfG(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables=None, maxnar=None,
-             handle: Optional[Handle] = None):
+             handle: Optional[Handle] = None, devices=None):
     """CalSurfG.f90:909: returns dict(dsurf, rw, row (1-based, = iw(2:nar+1)), col (1-based), nar)."""
-    return _gbuild(1, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle)
+    return _gbuild(1, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle, devices)
 
 
 def CalSurfGAnisoJoint(vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv: Survey, tables=None, maxnar=None,
-                       handle: Optional[Handle] = None):
+                       handle: Optional[Handle] = None, devices=None):
     """CalSurfGAniso_Joint.f90:209: COO over [dVs | Gc | Gs] (3*nparpi columns)."""
-    return _gbuild(2, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle)
+    return _gbuild(2, vels, depz, tRc, minthk, goxd, gozd, dvxd, dvzd, sv, None, None, tables, maxnar, handle, devices)
 
 
 class LsmrInfo(C.Structure):

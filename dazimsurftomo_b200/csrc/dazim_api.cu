@@ -197,8 +197,6 @@ struct dazim_plan {
   int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
   int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
   int coh = 1;   // 1: five-warp cohort kernel; 0: the one-thread-per-solve kernel
-  int tps_idcap = 0, tps_node_bits = 0;
-  DBuf<unsigned short> d_pos_tab, d_free_stk;   // per solve (tps)
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
@@ -391,27 +389,19 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   if (const char* e = getenv("DAZIM_TPS")) P->tps = atoi(e) ? 1 : 0;
   const int hspill_full = 8 * (g.nnx + g.nnz) + 1024 + 16;     // generous bound on the narrow band (measured 2.7 x edge)
   if (P->tps) {
-    int nb = 1;
-    while ((1ull << nb) < std::max(ncf, (size_t)REF_N)) ++nb;
-    P->tps_node_bits = nb;
-    const long long idmax = std::min<long long>(65535, 1ll << std::min(30, 32 - nb));
-    if (nb > 28 || idmax < 2ll * (g.nnx + g.nnz)) P->tps = 0;    // entry word cannot hold node + id: legacy kernels
-    else {
-      const long long nres = std::max<long long>(1, nsrc);
-      const int ctas_needed = (int)((nres + 31) / 32);
-      // one warp of 32 solves per CTA; 1 CTA per SM while that holds every solve (bigger shared heap), else 2
-      int per_sm = ctas_needed <= h->nsm ? 1 : 2;
-      if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(e)));
-      if (const char* e = getenv("DAZIM_COH")) P->coh = atoi(e) ? 1 : 0;
-      P->hcap = std::min(hneed, (int)(((227 * 1024) / per_sm - 1024 - 2752) / 256));
-      if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
-      P->hcap &= ~1;                                  // even: a sibling pair never straddles shared / spilled
-      CK(fmm_tps_max_ctas(P->hcap, h->nsm, P->coh, &nctas));
-      if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
-      nctas = std::min(nctas, ctas_needed);
-      P->hspill = (std::max(16, std::min(65535 - P->hcap, hspill_full)) + 1) & ~1;
-      P->tps_idcap = (int)std::min<long long>(idmax, (long long)P->hcap + P->hspill);
-    }
+    const long long nres = std::max<long long>(1, nsrc);
+    const int ctas_needed = (int)((nres + 31) / 32);
+    // one heap warp of 32 solves per CTA; 1 CTA per SM while that holds every solve (bigger shared heap), else 2
+    int per_sm = ctas_needed <= h->nsm ? 1 : 2;
+    if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("DAZIM_COH")) P->coh = atoi(e) ? 1 : 0;
+    P->hcap = std::min(hneed, (int)(((227 * 1024) / per_sm - 1024 - 2752) / 256));
+    if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
+    P->hcap &= ~1;                                  // even: a sibling pair never straddles shared / spilled
+    CK(fmm_tps_max_ctas(P->hcap, h->nsm, P->coh, &nctas));
+    if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
+    nctas = std::min(nctas, ctas_needed);
+    P->hspill = (std::max(16, hspill_full) + 1) & ~1;
   }
   if (!P->tps) {
     int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nctas);
@@ -425,7 +415,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   double per_src = (double)ncf * 4 + (double)REF_N * 4 + REF_LD * 4 + 64;
   double per_slot = (double)ncf * 4 + (double)REF_N * 8 + (double)P->hspill * 8;
   if (P->tps) {   // everything is per solve: no slot workspaces, no hpos fields
-    per_src += (double)REF_N * 4 + (double)P->hspill * 8 + (double)P->tps_idcap * 4 + (emit_all ? (double)REF_N * 4 : 0.0);
+    per_src += (double)REF_N * 4 + (double)P->hspill * 8 + (emit_all ? (double)REF_N * 4 : 0.0);
     per_slot = 0;
   }
   nctas = (int)std::min<long long>(nctas, std::max<long long>(npairs_all, 1));
@@ -539,8 +529,6 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     if (P->tps) {
       CK(P->d_slow_r.alloc(B * REF_N));
       CK(P->d_hspill.alloc(B * P->hspill));
-      CK(P->d_pos_tab.alloc(B * P->tps_idcap));
-      CK(P->d_free_stk.alloc(B * P->tps_idcap));
       if (emit_all) CK(P->d_hpos_r_out.alloc(B * REF_N));
     } else {
       CK(P->d_hpos_c.alloc(nslot * coarse_field_size(g.nnx, g.nnz)));
@@ -638,11 +626,12 @@ static int plan_run_once(dazim_plan* P) {
         TpsArgs A;
         A.g = g; A.src = F.src; A.nsrc = F.nsrc; A.velv = F.velv; A.slow_c = F.slow_c; A.risti_c = F.risti_c;
         A.risti_r = F.risti_r; A.E_c = F.E_c; A.E_r = F.E_r; A.slow_r = P->d_slow_r.p; A.hspill = P->d_hspill.p;
-        A.hspill_n = P->hspill; A.hcap = P->hcap; A.pos_tab = P->d_pos_tab.p; A.free_stk = P->d_free_stk.p;
-        A.idcap = P->tps_idcap; A.node_bits = P->tps_node_bits; A.hpos_r_out = P->d_hpos_r_out.p;
+        A.hspill_n = P->hspill; A.hcap = P->hcap; A.hpos_r_out = P->d_hpos_r_out.p;
         A.flags = F.flags; A.n_accept = F.n_accept;
         A.prof = getenv("DAZIM_COH_PROF") ? atoi(getenv("DAZIM_COH_PROF")) : 0;
-        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + 31) / 32), P->coh, st));
+        A.lanes = 32;
+        if (const char* e = getenv("DAZIM_COH_LANES")) A.lanes = P->coh ? std::max(1, std::min(32, atoi(e))) : 32;
+        CK(launch_fmm_tps(A, A.lanes == 32 ? std::min(P->nctas, (F.nsrc + 31) / 32) : (F.nsrc + A.lanes - 1) / A.lanes, P->coh, st));
         T.n_launch++;      // + k_tps_init
       }
       else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
@@ -743,7 +732,7 @@ static int plan_run(dazim_plan* P) {
   for (int attempt = 0; attempt < 4; ++attempt) {
     st = plan_run_once(P);
     if (st == DAZIM_EHEAP && P->tps) {
-      // the narrow band outgrew the ids a packed heap entry can hold: re-run on the round-1 kernels
+      // the narrow band outgrew the spill workspace of the cohort kernel: re-run on the round-1 kernels
       CK(cudaSetDevice(P->h->dev));
       g_alloc_stream = P->h->st;
       const GridC& g = P->g;
@@ -755,7 +744,6 @@ static int plan_run(dazim_plan* P) {
       nctas = (int)std::min<long long>(nctas, ((long long)P->maxB + P->spc - 1) / P->spc);
       P->nctas = nctas;
       const size_t nslot = 2 * (size_t)nctas;
-      P->d_pos_tab.release(); P->d_free_stk.release();
       CK(P->d_hpos_c.alloc(nslot * coarse_field_size(g.nnx, g.nnz)));
       CK(P->d_hpos_r.alloc(nslot * REF_N));
       CK(P->d_slow_r.alloc(nslot * REF_N));
@@ -906,6 +894,190 @@ extern "C" int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, d
           tRcV[(size_t)(jj - 1) * (nx - 2) + (ii - 1) + (size_t)(tt - 1) * (nx - 2) * (ny - 2)] =
               tb.pvRc[(size_t)jj * nx + ii + (size_t)(tt - 1) * nxy];
   }
+  return DAZIM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU behind the C ABI (what a Fortran / C host that links libdazim_b200.so gets: Main_Jt.f90:403-406 calls ONE
+// subroutine).  Single process, one host thread + one stream per device:
+//   stage A  depth kernels on strips of grid rows (nodes are independent), tables merged on the host;
+//   stage B  contiguous (period, source) ranges balanced by ray count, one plan per device, no collective;
+//   exchange the caller owns dsurf / rw / iw / col on the host (the reference's driver does), so every device copies
+//            its row block straight to its offset of the caller's arrays: the "all-gather" is the D2H copy that the
+//            single-GPU call does anyway, now over ndev PCIe links at once.
+// Results are bit-identical to the single-device call for any ndev (row blocks are disjoint, no floating-point
+// reduction crosses devices).
+#include <map>
+#include <mutex>
+#include <thread>
+static std::mutex g_multi_mu;
+static std::map<int, dazim_handle*> g_multi_handles;
+
+static int multi_handle(int dev, dazim_handle** out) {
+  std::lock_guard<std::mutex> lk(g_multi_mu);
+  auto it = g_multi_handles.find(dev);
+  if (it != g_multi_handles.end()) { *out = it->second; return DAZIM_OK; }
+  dazim_handle* h = nullptr;
+  int st = dazim_create(&h, dev);
+  if (st) return st;
+  g_multi_handles[dev] = h;
+  *out = h;
+  return DAZIM_OK;
+}
+
+__global__ void k_add_row_offset(int* rowid, long long n, int off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rowid[i] += off;
+}
+
+extern "C" int dazim_gbuild_multi(int ndev, const int* devices, int mode, const dazim_problem* p, dazim_tables* tables,
+                                  int tables_precomputed, const float* Gc, const float* Gs, float* dsurf, float* obsTaa,
+                                  double* tRcV, dazim_coo* coo, dazim_times* times_max) {
+  if (ndev < 1 || !devices || !p || !tables) return DAZIM_EBADARG;
+  if (mode < 0 || mode > 2) return DAZIM_EBADARG;
+  std::vector<dazim_handle*> H(ndev, nullptr);
+  for (int r = 0; r < ndev; ++r) {
+    for (int q = 0; q < r; ++q) if (devices[q] == devices[r]) return DAZIM_EBADARG;
+    int st = multi_handle(devices[r], &H[r]);
+    if (st) return st;
+  }
+  const int nx = p->nx, ny = p->ny, nz = p->nz, kmax = p->kmaxRc;
+  const size_t nxy = (size_t)nx * ny;
+  std::vector<double> own_pv, own_s[3];
+  std::vector<float> own_l;
+  dazim_tables tb = *tables;
+  if (!tb.pvRc) { own_pv.resize(nxy * kmax); tb.pvRc = own_pv.data(); }
+  std::vector<int> status(ndev, DAZIM_OK);
+  std::vector<float> kms(ndev, 0.0f);
+  // ---- stage A: strips of grid rows ----
+  if (!tables_precomputed) {
+    if ((mode == 0 || mode == 2) && !tb.Lsen_Gsc) { own_l.resize(nxy * kmax * (nz - 1)); tb.Lsen_Gsc = own_l.data(); }
+    if (mode == 1 || mode == 2) {
+      double** ps[3] = {&tb.sen_vs, &tb.sen_vp, &tb.sen_rho};
+      for (int i = 0; i < 3; ++i)
+        if (!*ps[i]) { own_s[i].resize(nxy * kmax * nz); *ps[i] = own_s[i].data(); }
+    }
+    auto stageA = [&](int r) {
+      const int j0 = (int)((long long)ny * r / ndev), j1 = (int)((long long)ny * (r + 1) / ndev), nj = j1 - j0;
+      if (nj <= 0) return;
+      if (cudaSetDevice(H[r]->dev) != cudaSuccess) { status[r] = DAZIM_ECUDA; return; }
+      const size_t ns = (size_t)nx * nj;
+      std::vector<float> vel(ns * nz);
+      for (int k = 0; k < nz; ++k)
+        std::memcpy(&vel[(size_t)k * ns], p->vels + (size_t)k * nxy + (size_t)j0 * nx, ns * sizeof(float));
+      std::vector<double> pv(ns * kmax);
+      long long nl = 0;
+      auto scatter2 = [&](const double* src, double* dst, int nlast) {     // (ns, kmax[, nlast]) -> (nxy, kmax[, nlast])
+        for (int c = 0; c < kmax * nlast; ++c)
+          std::memcpy(dst + (size_t)c * nxy + (size_t)j0 * nx, src + (size_t)c * ns, ns * sizeof(double));
+      };
+      if (mode == 0 || mode == 2) {
+        std::vector<float> L(ns * kmax * (nz - 1));
+        float ms = 0;
+        int st = th_depthkernel_ti(H[r]->st, nx, nj, nz, vel.data(), pv.data(), kmax, p->tRc, p->depz, p->minthk, L.data(), &ms, &nl);
+        if (st) { status[r] = st; return; }
+        kms[r] += ms;
+        for (int c = 0; c < kmax * (nz - 1); ++c)
+          std::memcpy(tb.Lsen_Gsc + (size_t)c * nxy + (size_t)j0 * nx, &L[(size_t)c * ns], ns * sizeof(float));
+      }
+      if (mode == 1 || mode == 2) {
+        std::vector<double> a(ns * kmax * nz), b(ns * kmax * nz), c3(ns * kmax * nz);
+        float ms = 0;
+        int st = th_depthkernel(H[r]->st, nx, nj, nz, vel.data(), pv.data(), a.data(), b.data(), c3.data(), kmax, p->tRc,
+                                p->depz, p->minthk, &ms, &nl);
+        if (st) { status[r] = st; return; }
+        kms[r] += ms;
+        scatter2(a.data(), tb.sen_vs, nz); scatter2(b.data(), tb.sen_vp, nz); scatter2(c3.data(), tb.sen_rho, nz);
+      }
+      scatter2(pv.data(), tb.pvRc, 1);
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r) th.emplace_back(stageA, r);
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ndev; ++r) if (status[r]) return status[r];
+  }
+  // ---- stage B: contiguous unit ranges balanced by rays ----
+  std::vector<long long> rays;      // per unit in loop order
+  for (int knumi = 1; knumi <= p->kmax; ++knumi)
+    for (int srcnum = 1; srcnum <= p->nsrcsurf1[knumi - 1]; ++srcnum)
+      rays.push_back(p->nrc1[(size_t)(srcnum - 1) + (size_t)(knumi - 1) * p->nsrc]);
+  const long long nunit = (long long)rays.size();
+  long long total = 0;
+  for (auto v : rays) total += v;
+  std::vector<long long> bound(ndev + 1, nunit);
+  bound[0] = 0;
+  {
+    long long acc = 0, u = 0;
+    for (int r = 1; r < ndev; ++r) {
+      const long long target = total * r / ndev;
+      while (u < nunit && acc + rays[u] / 2 < target) { acc += rays[u]; ++u; }
+      bound[r] = u;
+    }
+  }
+  std::vector<dazim_plan*> P(ndev, nullptr);
+  auto stageB = [&](int r) {
+    if (bound[r + 1] <= bound[r]) return;
+    int st = plan_build(H[r], mode, p, &tb, Gc, Gs, bound[r], bound[r + 1], 0, &P[r]);
+    if (!st) st = plan_run(P[r]);
+    status[r] = st;
+  };
+  {
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r) th.emplace_back(stageB, r);
+    for (auto& t : th) t.join();
+  }
+  int st = DAZIM_OK;
+  for (int r = 0; r < ndev; ++r) if (status[r] && !st) st = status[r];
+  std::vector<long long> off(ndev + 1, 0);
+  for (int r = 0; r < ndev; ++r) off[r + 1] = off[r] + (P[r] ? P[r]->nnz : 0);
+  if (!st && coo && mode != 0) {
+    coo->nar = off[ndev];
+    if (off[ndev] > coo->maxnar) st = DAZIM_ENNZ_OVERFLOW;
+  }
+  if (!st) {
+    auto fetch = [&](int r) {
+      if (!P[r]) return;
+      dazim_plan* Q = P[r];
+      int s2 = dazim_plan_fetch(Q, dsurf ? dsurf + Q->row0 : nullptr, (obsTaa && mode == 0) ? obsTaa + Q->row0 : nullptr, nullptr,
+                                (coo && mode != 0) ? coo->col + off[r] : nullptr, (coo && mode != 0) ? coo->rw + off[r] : nullptr);
+      if (!s2 && coo && mode != 0 && coo->iw_row && Q->nnz) {
+        cudaStream_t cs = Q->h->st;
+        if (Q->row0) k_add_row_offset<<<(unsigned)((Q->nnz + 255) / 256), 256, 0, cs>>>(Q->d_rowid.p, Q->nnz, (int)Q->row0);
+        cudaError_t e = cudaMemcpyAsync(coo->iw_row + off[r], Q->d_rowid.p, (size_t)Q->nnz * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+        if (e != cudaSuccess) s2 = DAZIM_ECUDA + (int)e;
+        Q->h->times.d2h_bytes += Q->nnz * 4;
+      }
+      status[r] = s2;
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r) th.emplace_back(fetch, r);
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ndev; ++r) if (status[r] && !st) st = status[r];
+  }
+  if (times_max) {
+    std::memset(times_max, 0, sizeof(*times_max));
+    for (int r = 0; r < ndev; ++r) {
+      const dazim_times& T = H[r]->times;
+      times_max->kernels_ms = std::max(times_max->kernels_ms, kms[r]);
+      times_max->dice_ms = std::max(times_max->dice_ms, T.dice_ms);
+      times_max->fmm_ms = std::max(times_max->fmm_ms, T.fmm_ms);
+      times_max->trace_ms = std::max(times_max->trace_ms, T.trace_ms);
+      times_max->assemble_ms = std::max(times_max->assemble_ms, T.assemble_ms);
+      times_max->total_ms = std::max(times_max->total_ms, T.total_ms);
+      if (P[r]) { times_max->n_accept += T.n_accept; times_max->n_steps += T.n_steps; times_max->n_launch += T.n_launch;
+                  times_max->n_fmm_launch += T.n_fmm_launch; times_max->n_trace_launch += T.n_trace_launch;
+                  times_max->h2d_bytes += T.h2d_bytes; times_max->d2h_bytes += T.d2h_bytes; times_max->rbint |= T.rbint; }
+    }
+  }
+  for (int r = 0; r < ndev; ++r) if (P[r]) plan_free(P[r]);
+  if (st) return st;
+  if (tRcV)
+    for (int tt = 1; tt <= kmax; ++tt)
+      for (int jj = 1; jj <= ny - 2; ++jj)
+        for (int ii = 1; ii <= nx - 2; ++ii)
+          tRcV[(size_t)(jj - 1) * (nx - 2) + (ii - 1) + (size_t)(tt - 1) * (nx - 2) * (ny - 2)] =
+              tb.pvRc[(size_t)jj * nx + ii + (size_t)(tt - 1) * nxy];
   return DAZIM_OK;
 }
 
@@ -1332,16 +1504,11 @@ extern "C" int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd,
     const int idm1 = e % sr.nnzr + 1, idm2 = e / sr.nnzr + 1;
     slow_r[(size_t)(idm2 - 1) * REF_LD + (idm1 - 1)] = 1.0f / refined_vel_t(g, sr, velv.data(), ub, idm1, idm2);
   }
-  int nb = 1;
-  while ((1ull << nb) < std::max(ncf, (size_t)REF_N)) ++nb;
-  const long long idmax = std::min<long long>(65535, 1ll << std::min(30, 32 - nb));
   std::vector<int2> sm((size_t)hcap), gl((size_t)std::max(1, hspill_n));
-  const int idcap = (int)std::min<long long>(idmax, (long long)hcap + hspill_n);
-  std::vector<unsigned short> pos((size_t)idcap), fstk((size_t)idcap);
   std::vector<int> hpos_r(REF_N, 0);
   TpsState S;
   S.sm = sm.data(); S.stride = 1; S.gl = gl.data(); S.hcap = hcap; S.htot = hcap + hspill_n - 2;
-  S.pos = pos.data(); S.fstk = fstk.data(); S.idcap = idcap; S.node_bits = nb; S.node_mask = (1u << nb) - 1u; S.overflow = 0;
+  S.E = nullptr; S.overflow = 0; S.prof = nullptr; S.pt0 = 0;
   unsigned long long nacc = 0;
   tps_source_init(S, g, sr, velv.data(), ub, E_r.data());
   {

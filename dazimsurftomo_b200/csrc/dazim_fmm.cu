@@ -1083,10 +1083,9 @@ __global__ void __launch_bounds__(32, 2) k_fmm_tps(TpsArgs A) {
   S.stride = 32;
   S.hcap = A.hcap;
   S.htot = A.hcap + A.hspill_n - 2;     // two slots of slack: tps_pop_root reads sibling pairs as one int4
-  S.idcap = A.idcap;
-  S.node_bits = A.node_bits;
-  S.node_mask = (1u << A.node_bits) - 1u;
+  S.E = nullptr;
   S.overflow = 0;
+  S.prof = nullptr; S.pt0 = 0;
   tps_reset(S);
   unsigned long long nacc = 0;
   for (int s0 = blockIdx.x * 32; s0 < A.nsrc; s0 += gridDim.x * 32) {
@@ -1100,8 +1099,6 @@ __global__ void __launch_bounds__(32, 2) k_fmm_tps(TpsArgs A) {
     const float* slow_c = A.slow_c + (size_t)sr.period * ncoarse;
     const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
     S.gl = A.hspill + (size_t)sc * A.hspill_n;
-    S.pos = A.pos_tab + (size_t)sc * A.idcap;
-    S.fstk = A.free_stk + (size_t)sc * A.idcap;
     if (act) tps_source_init(S, g, sr, vv, c_ubasis, E_r);
     __syncwarp();
     {
@@ -1158,7 +1155,7 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
   for (;;) {
     if (prof) t0 = clock64();
     TpsPre P;
-    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.root_id = 0; P.last = make_int2(0, 0);
+    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.last = make_int2(0, 0);
     if (run) run = tps_pre<URG>(S, G, nacc, P);
     xch[lane] = run ? P.pn : -1;
     xch[32 + lane] = P.ix;
@@ -1186,9 +1183,18 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
     }
     if (prof) { __syncwarp(); t1 = clock64(); c_apply += t1 - t0; ++rounds; }
   }
-  if (prof && lane == 0 && rounds)
+  if (prof && lane == 0 && rounds) {
     printf("[coh prof] urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f apply %.0f (heap size at end %d)\n",
            URG, rounds, (double)c_pre / rounds, (double)c_pop / rounds, (double)c_wait / rounds, (double)c_apply / rounds, S.ntr);
+    if (S.prof) {
+      printf("[coh prof] urg %d lane 0 split: pop{last %.0f shared %.0f spilled+place %.0f} apply{setup %.0f backptr+parents-issue %.0f",
+             URG, (double)S.prof[0] / rounds, (double)S.prof[1] / rounds, (double)S.prof[2] / rounds, (double)S.prof[3] / rounds,
+             (double)S.prof[4] / rounds);
+      printf(" q-boundary %.0f parent-wait %.0f move %.0f place %.0f}\n", (double)S.prof[5] / rounds, (double)S.prof[6] / rounds,
+             (double)S.prof[7] / rounds, (double)S.prof[8] / rounds);
+      for (int i = 0; i < 16; ++i) S.prof[i] = 0;
+    }
+  }
 }
 
 template <int URG>
@@ -1220,14 +1226,18 @@ __global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
   S.stride = 32;
   S.hcap = A.hcap;
   S.htot = A.hcap + A.hspill_n - 2;     // two slots of slack: tps_pop_root reads sibling pairs as one int4
-  S.idcap = A.idcap;
-  S.node_bits = A.node_bits;
-  S.node_mask = (1u << A.node_bits) - 1u;
+  S.E = nullptr;
   S.overflow = 0;
+  __shared__ long long s_prof[16];
+  if (tid < 16) s_prof[tid] = 0;
+  __syncthreads();
+  S.prof = (A.prof && blockIdx.x == 0 && warp == 0) ? s_prof : nullptr;   // every lane of the heap warp adds: divide by 32
+  S.pt0 = 0;
   tps_reset(S);
   unsigned long long nacc = 0;
-  for (int s0 = blockIdx.x * 32; s0 < A.nsrc; s0 += gridDim.x * 32) {
-    const int s = s0 + lane;
+  const int L = A.lanes;
+  for (int s0 = blockIdx.x * L; s0 < A.nsrc; s0 += gridDim.x * L) {
+    const int s = (lane < L) ? s0 + lane : A.nsrc;
     const int sc = min(s, A.nsrc - 1);                   // inactive lane: valid addresses, no side effects
     const SrcRec sr = A.src[sc];
     unsigned* E_r = A.E_r + (size_t)sc * REF_N;
@@ -1240,8 +1250,6 @@ __global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
       const bool act = (s < A.nsrc) && !S.overflow;
       const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
       S.gl = A.hspill + (size_t)sc * A.hspill_n;
-      S.pos = A.pos_tab + (size_t)sc * A.idcap;
-      S.fstk = A.free_stk + (size_t)sc * A.idcap;
       if (act) tps_source_init(S, g, sr, vv, c_ubasis, E_r);
       coh_march_heap<1>(S, Gr, xch, lane, act, nacc, A.prof && blockIdx.x == 0);
       if (act && !S.overflow) {

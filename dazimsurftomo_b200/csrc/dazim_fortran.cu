@@ -28,6 +28,37 @@ static dazim_handle* handle() {
   return g_handle;
 }
 
+// DAZIM_DEVICES="0,1,2,3" or "all": the three orchestrators spread ONE call over several GPUs (dazim_gbuild_multi);
+// unset or a single device: dazim_gbuild on DAZIM_DEVICE (default 0).
+#include <cuda_runtime.h>
+#include <vector>
+static std::vector<int> device_list() {
+  std::vector<int> out;
+  const char* e = getenv("DAZIM_DEVICES");
+  if (!e || !*e) return out;
+  if (!strcmp(e, "all")) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess)
+      for (int i = 0; i < n; ++i) out.push_back(i);
+    return out;
+  }
+  for (const char* q = e; *q;) {
+    char* end = nullptr;
+    const long v = strtol(q, &end, 10);
+    if (end == q) break;
+    out.push_back((int)v);
+    q = (*end == ',') ? end + 1 : end;
+  }
+  return out;
+}
+static int gbuild_any(int mode, const dazim_problem* p, dazim_tables* tb, const float* Gc, const float* Gs, float* dsurf,
+                      float* obsTaa, double* tRcV, dazim_coo* coo) {
+  const std::vector<int> dev = device_list();
+  if (dev.size() > 1)
+    return dazim_gbuild_multi((int)dev.size(), dev.data(), mode, p, tb, 0, Gc, Gs, dsurf, obsTaa, tRcV, coo, nullptr);
+  return dazim_gbuild(handle(), mode, p, tb, 0, Gc, Gs, dsurf, obsTaa, tRcV, coo);
+}
+
 // writepath (FwdTraveltimeCPS.f90:673-686, rpathsAzim.f90:617-625) dumps every ray's nodes to
 // raypath_refmdl_<T>s.dat; all shipped examples run with it off.  It is a diagnostic, not an input of the
 // inversion: say so loudly instead of silently ignoring the request.
@@ -100,7 +131,7 @@ extern "C" void fwdobstraveltimecps_(int* nx, int* ny, int* nz, int* nparpi, flo
   std::memset(&tb, 0, sizeof(tb));
   tb.Lsen_Gsc = Lsen_Gsc;
   printf("  DepthkernelTI begin!\n");
-  stop_on(dazim_gbuild(handle(), 0, &p, &tb, 0, Gctrue, Gstrue, dsurf, obsTaa, tRcV, nullptr), "FwdObsTraveltimeCPS");
+  stop_on(gbuild_any(0, &p, &tb, Gctrue, Gstrue, dsurf, obsTaa, tRcV, nullptr), "FwdObsTraveltimeCPS");
   printf("  DepthkernelTI time cost= %13.1f s\n", dazim_last_times(handle())->kernels_ms * 1e-3);
 }
 
@@ -118,7 +149,7 @@ extern "C" void calsurfg_(int* nx, int* ny, int* nz, int* nparpi, float* vels, i
   c.rw = rw; c.iw_row = iw + 1; c.col = col; c.nar = 0;
   // the caller sized rw/col by spfra (Main_Jt.f90:325); the bound is not passed down, so trust it like the reference
   c.maxnar = (long long)1 << 62;
-  stop_on(dazim_gbuild(handle(), 1, &p, &tb, 0, nullptr, nullptr, dsurf, nullptr, nullptr, &c), "CalSurfG");
+  stop_on(gbuild_any(1, &p, &tb, nullptr, nullptr, dsurf, nullptr, nullptr, &c), "CalSurfG");
   if (c.nar > 2147483647ll) stop_on(DAZIM_ENNZ_OVERFLOW, "CalSurfG: nar exceeds the reference's default INTEGER");
   *nar = (int)c.nar;
   if (GVs) densify(c, *dall, *nparpi, GVs, nullptr, nullptr);
@@ -141,7 +172,7 @@ extern "C" void calsurfganisojoint_(int* nx, int* ny, int* nz, int* nparpi, floa
   dazim_coo c;
   c.rw = rw; c.iw_row = iw + 1; c.col = col; c.nar = 0;
   c.maxnar = (long long)1 << 62;
-  stop_on(dazim_gbuild(handle(), 2, &p, &tb, 0, nullptr, nullptr, dsurf, nullptr, tRcV, &c), "CalSurfGAnisoJoint");
+  stop_on(gbuild_any(2, &p, &tb, nullptr, nullptr, dsurf, nullptr, tRcV, &c), "CalSurfGAnisoJoint");
   if (c.nar > 2147483647ll) stop_on(DAZIM_ENNZ_OVERFLOW, "CalSurfGAnisoJoint: nar exceeds the reference's default INTEGER");
   *nar = (int)c.nar;
   if (GVs || GGc || GGs) densify(c, *dall, *nparpi, GVs, GGc, GGs);

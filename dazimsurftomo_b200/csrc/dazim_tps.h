@@ -11,16 +11,16 @@
 // between solves.
 //
 // Data layout (per solve):
-//   heap      (key bits, id << node_bits | node) pairs; positions 1..hcap-1 in shared memory, INTERLEAVED across the
-//             32 lanes of the warp (entry p of lane l at sm[p * 32 + l]: every lane always hits its own two banks),
+//   heap      (key bits, node offset) pairs; positions 1..hcap-1 in shared memory, INTERLEAVED across the lanes of
+//             the heap warp (entry p of lane l at sm[p * 32 + l]: every lane always hits its own two banks),
 //             positions >= hcap in a per-solve global array.
-//   E         one 32-bit word per node: alive = +t, far = 0xFFFFFFFF, close = 0x80000000 | id.  A close node's
-//             trial time lives only in the heap (fouds2 never reads it, CalSurfG.f90:592-629).
-//   pos_tab   u16 [id] -> heap position.  The reference's nsts back pointer (heap position of a close node) is
-//             E -> id -> pos_tab: the ~13 entry moves of an accept step write a 5 KB per-solve table that stays in
-//             the L2 instead of 13 scattered sectors of a 4 MB field (that scatter was 2/3 of the DRAM traffic of
-//             the round-1 kernels), and the 4 MB hpos field per resident solve is gone.
-//   free_stk  u16 stack of released ids (an accept step releases one id and takes 0-3).
+//   E         one 32-bit word per node: alive = +t, far = 0xFFFFFFFF, close = 0x80000000 | heap position.  A close
+//             node's trial time lives only in the heap (fouds2 never reads it, CalSurfG.f90:592-629), so the word is
+//             free to hold the reference's nsts back pointer: the gather that tells a stencil warp "this neighbour
+//             is close" hands the heap warp its position in the same word, and the separate 4 MB hpos field per
+//             resident solve of the round-1 kernels is gone.  (A first version kept positions in a per-solve
+//             id -> position table; measured on the B200 its id allocator and the extra dependent load cost the heap
+//             warp ~3 000 cycles per accept: profiles/r2_k3_cohort_cycle_split.txt.)
 //
 // The code below is __host__ __device__: dazim_fmm.cu instantiates it in the kernel k_fmm_tps AND in a host twin
 // (dazim_debug_fmm_host_twin, test seam only) so that the exact logic is checked against the oracle on machines
@@ -169,13 +169,10 @@ struct TpsArgs {
   int2* hspill;               // [nsrc][hspill_n] heap entries beyond the shared capacity
   int hspill_n;
   int hcap;                   // heap positions 1..hcap-1 live in shared memory
-  unsigned short* pos_tab;    // [nsrc][idcap]
-  unsigned short* free_stk;   // [nsrc][idcap]
-  int idcap;                  // ids per solve (<= 65535, <= 2^(32-node_bits))
-  int node_bits;              // bits of the node offset inside a heap entry's second word
   int* hpos_r_out;            // optional test seam [nsrc][REF_N]: heap slots of the close nodes after the refined march
   int* flags;                 // bit4 (16): heap / id overflow
   unsigned long long* n_accept;
+  int lanes;                  // solves per heap warp (32; fewer = experiment knob DAZIM_COH_LANES)
   int prof;                   // DAZIM_COH_PROF=1: lane 0 of CTA 0 prints its cycle split per accept (cohort kernel)
 };
 
@@ -183,16 +180,22 @@ struct TpsState {
   int2* sm;                   // this solve's shared heap part; position p at sm[p * stride]
   int stride;
   int2* gl;                   // spill part: position p at gl[p - hcap]
-  int hcap, htot;             // htot = hcap + hspill_n
+  int hcap, htot;             // htot = hcap + hspill_n - 2
   int ntr;
-  unsigned short* pos;
-  unsigned short* fstk;
-  int nfree, next_id, spare, spare2, idcap;
-  int node_bits;
-  unsigned node_mask;
+  unsigned* E;                // status / time / back-pointer words of the grid being marched
   int overflow;
   int stopped_at_root;        // refined march left through the exit test: the root is alive and stays in the heap
+  long long* prof;            // cycle accumulators of the profiled lane (DAZIM_COH_PROF), else nullptr
+  long long pt0;
 };
+
+#if defined(__CUDA_ARCH__)
+#define TPS_TICK0(S) do { if ((S).prof) (S).pt0 = clock64(); } while (0)
+#define TPS_TICK(S, i) do { if ((S).prof) { const long long t_ = clock64(); (S).prof[i] += t_ - (S).pt0; (S).pt0 = t_; } } while (0)
+#else
+#define TPS_TICK0(S) do { } while (0)
+#define TPS_TICK(S, i) do { } while (0)
+#endif
 
 #define TKEY(e) tps_as_float((e).x)
 TPS_HD float tps_as_float(int b) {
@@ -211,53 +214,17 @@ TPS_HD int tps_as_int(float f) {
 }
 TPS_HD float tps_inf() { return tps_as_float(0x7f800000); }
 
-TPS_HD int tps_node(const TpsState& S, int2 e) { return (int)((unsigned)e.y & S.node_mask); }
-TPS_HD int tps_id(const TpsState& S, int2 e) { return (int)((unsigned)e.y >> S.node_bits); }
-TPS_HD int tps_pack(const TpsState& S, int id, int node) { return (int)(((unsigned)id << S.node_bits) | (unsigned)node); }
-
 TPS_HD int2 tps_hget(const TpsState& S, int p) { return p < S.hcap ? S.sm[(size_t)p * S.stride] : S.gl[p - S.hcap]; }
+// every placement of an entry updates the node's back pointer (the reference's nsts(node) = heap position)
 TPS_HD void tps_hput(TpsState& S, int p, int2 e) {
   if (p < S.hcap) S.sm[(size_t)p * S.stride] = e; else S.gl[p - S.hcap] = e;
-  S.pos[tps_id(S, e)] = (unsigned short)p;
+  S.E[e.y] = E_SIGN | (unsigned)p;
 }
+TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.stopped_at_root = 0; }
 
-// ids: two spares in registers (an accept step releases one id and takes 0-3, so the global stack is touched rarely)
-TPS_HD void tps_release_id(TpsState& S, int id) {
-  if (S.spare < 0) { S.spare = id; return; }
-  if (S.spare2 < 0) { S.spare2 = id; return; }
-  S.fstk[S.nfree++] = (unsigned short)id;
-}
-TPS_HD int tps_alloc_id(TpsState& S) {
-  if (S.spare >= 0) { const int id = S.spare; S.spare = S.spare2; S.spare2 = -1; return id; }
-  if (S.nfree > 0) return (int)S.fstk[--S.nfree];
-  if (S.next_id >= S.idcap) { S.overflow = 1; return 0; }
-  return S.next_id++;
-}
-TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.nfree = 0; S.next_id = 0; S.spare = -1; S.spare2 = -1; S.stopped_at_root = 0; }
-
-// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).  q = index of the neighbour being applied;
-// later close neighbours that sit on the path move down with their parent slot: their positions (read before) are
-// patched in registers.
-TPS_HD void tps_sift_up(TpsState& S, int tpc, float k, int packed, int q, const int (&qid)[4], const int (&qst)[4],
-                        int (&spos)[4]) {
-  int tpp = tpc >> 1;
-  while (tpp > 0) {
-    const int2 par = tps_hget(S, tpp);
-    if (!(k < TKEY(par))) break;
-    tps_hput(S, tpc, par);
-    const int pid = tps_id(S, par);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int r = 0; r < 4; ++r)
-      if (r > q && qst[r] == 1 && qid[r] == pid) spos[r] = tpc;
-    tpc = tpp;
-    tpp = tpc >> 1;
-  }
-  tps_hput(S, tpc, make_int2(tps_as_int(k), packed));
-}
+// addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).
 // plain version (source-cell initialisation, coarse heap build)
-TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int packed) {
+TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int node) {
   int tpp = tpc >> 1;
   while (tpp > 0) {
     const int2 par = tps_hget(S, tpp);
@@ -266,7 +233,7 @@ TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int packed) {
     tpc = tpp;
     tpp = tpc >> 1;
   }
-  tps_hput(S, tpc, make_int2(tps_as_int(k), packed));
+  tps_hput(S, tpc, make_int2(tps_as_int(k), node));
 }
 
 // downtree (CalSurfG.f90:786-855).  `last` = heap[ntr] (fetched early by the caller).
@@ -277,10 +244,12 @@ TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int packed) {
 // straddles the shared / spilled boundary and every pair is one aligned int4.
 TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
   if (S.ntr == 1) { S.ntr = 0; return; }
+  TPS_TICK0(S);
   const float k = TKEY(last);
   S.ntr -= 1;
   const int ntr = S.ntr;
   int tpp = 1, tpc = 2;
+  TPS_TICK(S, 0);      // 0: wait for `last`
   // shared levels: both children exist and live in shared memory
   const int lim = ntr < S.hcap - 1 ? ntr : S.hcap - 1;
   bool placed = false;
@@ -291,7 +260,7 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
     tpc += right ? 1 : 0;
     if (!(TKEY(c) < k)) { placed = true; break; }
     S.sm[(size_t)tpp * S.stride] = c;
-    S.pos[tps_id(S, c)] = (unsigned short)tpp;
+    S.E[c.y] = E_SIGN | (unsigned)tpp;
     tpp = tpc;
     tpc = 2 * tpp;
   }
@@ -301,6 +270,7 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
     if (TKEY(c) < k) { tps_hput(S, tpp, c); tpp = tpc; }
     placed = true;
   }
+  TPS_TICK(S, 1);      // 1: shared levels
   // spilled levels, three at a time
   while (!placed && tpc <= ntr) {
     const int4* g4 = reinterpret_cast<const int4*>(S.gl);
@@ -346,6 +316,7 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
     }
   }
   tps_hput(S, tpp, last);
+  TPS_TICK(S, 2);      // 2: spilled levels + placement
 }
 
 // Grid view of one march
@@ -361,8 +332,8 @@ struct TpsGrid {
 // One accept step of travel's DO WHILE (CalSurfG.f90:356-456) in three pieces, so that the same code serves the
 // one-thread-per-solve kernel (pre + 4 x neighbour + post in one thread), the cohort kernel (pre/post on the heap
 // warp, one neighbour per stencil warp) and the host twin.
-struct TpsPre { int pn, ix, iz, root_id; unsigned tself; int2 last; };
-struct TpsNb { int qst, qid, co; float qt; };     // neighbour status (-2 outside, -1 far, 0 alive, 1 close), id, offset, trial
+struct TpsPre { int pn, ix, iz; unsigned tself; int2 last; };
+struct TpsNb { int qst, qid, co; float qt; };     // neighbour status (-2 outside, -1 far, 0 alive, 1 close), heap position read, offset, trial
 
 // (1) the node on top of the heap becomes alive.  Returns false when the march is over (heap empty, overflow, or the
 //     refined march reached the edge of the source box: CalSurfG.f90:362-382).
@@ -370,8 +341,7 @@ template <int URG>
 TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, TpsPre& P) {
   if (S.ntr <= 0 || S.overflow) return false;
   const int2 root = tps_hget(S, 1);
-  P.pn = tps_node(S, root);
-  P.root_id = tps_id(S, root);
+  P.pn = root.y;
   P.last = tps_hget(S, S.ntr);
   ndecode<URG>(P.pn, G.ld, 1.0f / (float)G.ld, P.ix, P.iz);
   P.tself = (unsigned)root.x & ~E_SIGN;
@@ -437,51 +407,52 @@ TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const u
 }
 
 // (3) pop the root ...
-TPS_HD void tps_pop(TpsState& S, const TpsPre& P) {
-  tps_pop_root(S, P.last);
-  tps_release_id(S, P.root_id);      // the id of the popped node is free from here on
-}
+TPS_HD void tps_pop(TpsState& S, const TpsPre& P) { tps_pop_root(S, P.last); }
 // (4) ... then insert / update the four neighbours in the reference order x-1, x+1, z-1, z+1 (addtree / updtree,
-//     CalSurfG.f90:738-774, :864-890).  Written so that the 32 lanes of a heap warp share ONE instruction stream
-//     whatever mix of far / close / alive neighbours their solves have: start positions, ids and entry words are
-//     selected first, the four parents are fetched together (one round trip), and the common case "the new key is
-//     not smaller than its parent" is a single store.  Only a key that really moves up enters the generic loop.
+//     CalSurfG.f90:738-774, :864-890).  A close neighbour's position was read by the stencil warp BEFORE the pop, so
+//     it is verified against the heap ("does that slot hold the neighbour?") together with the fetch of its parent:
+//     one round trip for the four neighbours; only a position the pop really moved is re-read from E.  The common
+//     case "the new key is not smaller than its parent" is a single store.
 template <int URG>
 TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
-  int qst[4], qid[4], spos[4], ppos[4], pk[4];
-  int2 pent[4];
+  int qst[4], spos[4], ppos[4];
+  int2 pent[4], sent[4];
   int nins = 0;
+  TPS_TICK0(S);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    qst[q] = N[q].qst; qid[q] = N[q].qid; spos[q] = 0;
+    qst[q] = N[q].qst;
     if (qst[q] == -1) ++nins;
   }
   if (S.ntr + nins >= S.htot) { S.overflow = 1; S.ntr = 0; return false; }
-  // start positions: close = back pointer (as of after the pop), far = next free heap slots in order
+  // start positions: close = back pointer as read before the pop, far = next free heap slots in order
   int nt = S.ntr;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    if (qst[q] == 1) spos[q] = (int)S.pos[qid[q]];
-    else if (qst[q] == -1) {
-      spos[q] = ++nt;
-      qid[q] = tps_alloc_id(S);
-      G.E[N[q].co] = E_SIGN | (unsigned)qid[q];
-    }
-    pk[q] = tps_pack(S, qid[q], N[q].co);
+    spos[q] = 0;
+    if (qst[q] == 1) spos[q] = N[q].qid;
+    else if (qst[q] == -1) spos[q] = ++nt;
+    ppos[q] = spos[q] >> 1;
+    sent[q] = make_int2(0, -1);
+    pent[q] = make_int2(0, 0);
+    if (qst[q] == 1 && spos[q] >= 1 && spos[q] <= S.ntr) sent[q] = tps_hget(S, spos[q]);
+    if ((qst[q] == 1 || qst[q] == -1) && ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]);
   }
-  // the four parents in one round trip
+  TPS_TICK(S, 3);      // 3: statuses, issue of the slot + parent loads
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    ppos[q] = spos[q] >> 1;
-    pent[q] = make_int2(0, 0);
-    if ((qst[q] == 1 || qst[q] == -1) && ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]);
+    if (qst[q] == 1 && sent[q].y != N[q].co) {       // moved by the pop: take the fresh back pointer
+      spos[q] = (int)(S.E[N[q].co] & ~E_SIGN);
+      ppos[q] = -1;                                   // parent is fetched below
+    }
   }
+  TPS_TICK(S, 4);      // 4: wait for the loads + verification
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -490,20 +461,20 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
     if (qst[q] == -1) S.ntr += 1;
     const float k = N[q].qt;
     int tpc = spos[q];
-    if ((tpc >> 1) != ppos[q]) { ppos[q] = tpc >> 1; if (ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]); }   // moved by an earlier sift-up
+    if ((tpc >> 1) != ppos[q]) { ppos[q] = tpc >> 1; if (ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]); }   // moved earlier in this step
+    TPS_TICK(S, 6);    // 6: set-up of neighbour q
     if (ppos[q] > 0 && k < TKEY(pent[q])) {
       // the key moves up: generic loop (addtree / updtree sift-up), patching what later neighbours hold in registers
       int tpp = ppos[q];
       int2 par = pent[q];
       for (;;) {
         tps_hput(S, tpc, par);
-        const int pid = tps_id(S, par);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int r = 0; r < 4; ++r) {
-          if (r > q && qst[r] == 1 && qid[r] == pid) spos[r] = tpc;      // a later close neighbour moved down
-          if (r > q && ppos[r] == tpc) pent[r] = par;                    // a later parent slot changed content
+          if (r > q && qst[r] == 1 && N[r].co == par.y) spos[r] = tpc;    // a later close neighbour moved down
+          if (r > q && ppos[r] == tpc) pent[r] = par;                     // a later parent slot changed content
         }
         tpc = tpp;
         tpp = tpc >> 1;
@@ -512,13 +483,15 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
         if (!(k < TKEY(par))) break;
       }
     }
-    const int2 e = make_int2(tps_as_int(k), pk[q]);
+    TPS_TICK(S, 7);    // 7: move loop
+    const int2 e = make_int2(tps_as_int(k), N[q].co);
     tps_hput(S, tpc, e);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int r = 0; r < 4; ++r)
       if (r > q && ppos[r] == tpc) pent[r] = e;
+    TPS_TICK(S, 8);    // 8: placement + patches
   }
   return true;
 }
@@ -539,6 +512,7 @@ TPS_HD bool tps_step(TpsState& S, const TpsGrid& G, unsigned long long& nacc) {
 // ---- source cell initialisation (travel, CalSurfG.f90:324-345) on the refined grid ----
 TPS_HD void tps_source_init(TpsState& S, const GridC& g, const SrcRec& sr, const float* vv, const float* ub, unsigned* E_r) {
   tps_reset(S);
+  S.E = E_r;
   const int isx = sr.isx_r, isz = sr.isz_r;
   float vss[2][2];
   for (int i = 1; i <= 2; ++i)
@@ -558,10 +532,8 @@ TPS_HD void tps_source_init(TpsState& S, const GridC& g, const SrcRec& sr, const
       const float ds = sqrtf(ax * ax + az * az);
       const float t0 = 2.0f * ds / (vss[i - 1][j - 1] + vsrc);
       const int o = (isx - 1 + i - 1) * REF_LD + (isz - 1 + j - 1);
-      const int id = tps_alloc_id(S);
-      E_r[o] = E_SIGN | (unsigned)id;
       S.ntr += 1;
-      tps_sift_up_plain(S, S.ntr, t0, tps_pack(S, id, o));
+      tps_sift_up_plain(S, S.ntr, t0, o);
     }
 }
 
@@ -569,9 +541,9 @@ TPS_HD void tps_source_init(TpsState& S, const GridC& g, const SrcRec& sr, const
 //      E_r as "alive = +t, close = t | sign, far"), optionally their heap slots (test seam = the reference's nstsr) ----
 TPS_HD void tps_refined_finish(TpsState& S, unsigned* E_r, int* hpos_out) {
   for (int p = 1; p <= S.ntr; ++p) {
-    if (p == 1 && S.stopped_at_root) { if (hpos_out) hpos_out[tps_node(S, tps_hget(S, 1))] = 1; continue; }
+    if (p == 1 && S.stopped_at_root) { if (hpos_out) hpos_out[tps_hget(S, 1).y] = 1; continue; }
     const int2 e = tps_hget(S, p);
-    const int n = tps_node(S, e);
+    const int n = e.y;
     E_r[n] = (unsigned)e.x | E_SIGN;
     if (hpos_out) hpos_out[n] = p;
   }
@@ -599,18 +571,17 @@ TPS_HD void tps_handoff(TpsState& S, const GridC& g, const SrcRec& sr, const uns
         if (mk) E_c[o] |= E_SIGN;
       }
     }
-  // heap build in scan order i=1..nnx, j=1..nnz; the node's word switches from "t | sign" to "id | sign"
+  // heap build in scan order i=1..nnx, j=1..nnz; the node's word switches from "t | sign" to "position | sign"
   tps_reset(S);
+  S.E = E_c;
   for (int k = sr.vnl; k <= sr.vnr && !S.overflow; ++k)
     for (int l = sr.vnt; l <= sr.vnb; ++l) {
       const int o = cidx(k - 1, l - 1, g.nnz);
       const unsigned ev = E_c[o];
       if ((int)ev < 0 && ev != E_FAR) {
         if (S.ntr + 1 >= S.htot) { S.overflow = 1; break; }
-        const int id = tps_alloc_id(S);
-        E_c[o] = E_SIGN | (unsigned)id;
         S.ntr += 1;
-        tps_sift_up_plain(S, S.ntr, tps_as_float((int)(ev & ~E_SIGN)), tps_pack(S, id, o));
+        tps_sift_up_plain(S, S.ntr, tps_as_float((int)(ev & ~E_SIGN)), o);
       }
     }
 }

@@ -127,6 +127,17 @@ int dazim_gbuild(dazim_handle* h, int mode, const dazim_problem* p, dazim_tables
                  int tables_precomputed, const float* Gctrue, const float* Gstrue, float* dsurf,
                  float* obsTaa, double* tRcV, dazim_coo* coo);
 
+/* Multi-GPU variant of dazim_gbuild for a host that makes ONE subroutine call per outer iteration (the reference's
+ * drivers: Main_Jt.f90:398-406, MainForward.f90:372-375).  Single process; the ndev devices listed in devices[] each
+ * get one host thread, one stream, a strip of grid rows for the depth kernels and a contiguous (period, source) range
+ * balanced by ray count; every device copies its row block straight into the caller's arrays at its offset (rows,
+ * columns and values come out in the reference's order, bit-identical to the single-device call for any ndev).
+ * times_max (may be NULL) receives the per-stage maximum over the devices and the summed counters.  The gfortran
+ * drop-in symbols use it when the environment variable DAZIM_DEVICES lists more than one device ("0,1,2,3" or "all"). */
+int dazim_gbuild_multi(int ndev, const int* devices, int mode, const dazim_problem* p, dazim_tables* tables,
+                       int tables_precomputed, const float* Gctrue, const float* Gstrue, float* dsurf, float* obsTaa,
+                       double* tRcV, dazim_coo* coo, dazim_times* times_max);
+
 /* --- test seams ------------------------------------------------------------ */
 /* Eikonal solves for n sources on one phase-velocity map pv (nx*ny doubles).
  * Outputs per source: ttn/nsts coarse (nnz,nnx), ttnr/nstsr (129,129), geom[8]

@@ -28,6 +28,34 @@ def _fortran_tables(test1):
     return p, sv, keep
 
 
+def call_calsurfganisojoint(test1):
+    """calsurfganisojoint_ exactly as gfortran-compiled Main_Jt.f90:403-406 calls it; returns the caller-owned arrays."""
+    from dazimsurftomo_b200 import api
+    lib = api.load()
+    p, sv, k = _fortran_tables(test1)
+    nx, ny, nz = p.nx, p.ny, p.nz
+    nparpi = (nx - 2) * (ny - 2) * (nz - 1)
+    dall = int(sv.dall)
+    maxnar = dall * 3 * 400
+    iw = np.zeros(2 * maxnar + 1, np.int32); rw = np.zeros(maxnar, np.float32); col = np.zeros(maxnar, np.int32)
+    dsurf = np.zeros(dall, np.float32)
+    GVs = np.zeros((dall, nparpi), np.float32, order="F"); GGc = np.zeros_like(GVs); GGs = np.zeros_like(GVs)
+    L = np.zeros((nx * ny, p.kmaxRc, nz - 1), np.float32, order="F")
+    tRcV = np.zeros(((nx - 2) * (ny - 2), p.kmaxRc), np.float64, order="F")
+    nar = C.c_int(0)
+    lib.calsurfganisojoint_(_ref(nx, C.c_int), _ref(ny, C.c_int), _ref(nz, C.c_int), _ref(nparpi, C.c_int), _ptr(k["vs"]),
+                            _ptr(iw), _ptr(rw), _ptr(col), _ptr(dsurf), _ptr(GVs), _ptr(GGc), _ptr(GGs), _ptr(L),
+                            _ref(dall, C.c_int), _ref(10, C.c_int), _ptr(tRcV), _ref(p.goxd, C.c_float),
+                            _ref(p.gozd, C.c_float), _ref(p.dvxd, C.c_float), _ref(p.dvzd, C.c_float),
+                            _ref(p.kmaxRc, C.c_int), _ptr(k["tRc"]), _ptr(k["periods"]), _ptr(k["depz"]),
+                            _ref(p.sublayers, C.c_float), _ptr(k["scxf"]), _ptr(k["sczf"]), _ptr(k["rcxf"]), _ptr(k["rczf"]),
+                            _ptr(k["nrc1"]), _ptr(k["nsrc1"]), _ref(sv.kmax, C.c_int), _ref(sv.nsrc, C.c_int),
+                            _ref(sv.nrcf, C.c_int), C.byref(nar), _ref(0, C.c_int))
+    n = nar.value
+    return dict(nar=np.array([n]), rw=rw[:n].copy(), col=col[:n].copy(), row=iw[1:n + 1].copy(), dsurf=dsurf, L=L, tRcV=tRcV,
+                GVs=GVs, GGc=GGc, GGs=GGs)
+
+
 def test_fwdobstraveltimecps_symbol(gpu, test1):
     lib = gpu.load()
     p, sv, k = _fortran_tables(test1)
