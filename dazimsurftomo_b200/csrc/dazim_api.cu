@@ -196,7 +196,7 @@ struct dazim_plan {
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
   int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
   int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
-  int coh = 1;   // 1: five-warp cohort kernel; 0: the one-thread-per-solve kernel
+  int coh = 16;  // solves per heap warp of the cohort kernel (8 / 16 / 32); 0: the one-thread-per-solve kernel
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
@@ -389,15 +389,20 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   if (const char* e = getenv("DAZIM_TPS")) P->tps = atoi(e) ? 1 : 0;
   const int hspill_full = 8 * (g.nnx + g.nnz) + 1024 + 16;     // generous bound on the narrow band (measured 2.7 x edge)
   if (P->tps) {
+    if (const char* e = getenv("DAZIM_COH")) P->coh = atoi(e) ? P->coh : 0;
+    if (const char* e = getenv("DAZIM_COH_LANES")) { const int v = atoi(e); if (P->coh) P->coh = (v <= 8) ? 8 : (v <= 16 ? 16 : 32); }
+    const int L = P->coh ? P->coh : 32;                  // solves per CTA
     const long long nres = std::max<long long>(1, nsrc);
-    const int ctas_needed = (int)((nres + 31) / 32);
-    // one heap warp of 32 solves per CTA; 1 CTA per SM while that holds every solve (bigger shared heap), else 2
-    int per_sm = ctas_needed <= h->nsm ? 1 : 2;
-    if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(e)));
-    if (const char* e = getenv("DAZIM_COH")) P->coh = atoi(e) ? 1 : 0;
-    P->hcap = std::min(hneed, (int)(((227 * 1024) / per_sm - 1024 - 2752) / 256));
+    const int ctas_needed = (int)((nres + L - 1) / L);
+    // shared heap part: as large as possible while every solve is resident (else as many resident as the SM holds)
+    const int sm_budget = 227 * 1024;
+    int per_sm = std::max(1, (ctas_needed + h->nsm - 1) / h->nsm);
+    per_sm = std::min(per_sm, 64 / L > 0 ? 64 / L : 1);       // at most 64 solves per SM
+    if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(16, atoi(e)));
+    const int xch_bytes = P->coh ? (4 * L + 32 + 16 * L) * 4 + 128 : 0;
+    P->hcap = std::min(hneed, (int)((sm_budget / per_sm - 1024 - xch_bytes) / (8 * L)));
     if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
-    P->hcap &= ~1;                                  // even: a sibling pair never straddles shared / spilled
+    P->hcap = std::max(8, P->hcap & ~1);            // even: a sibling pair never straddles shared / spilled
     CK(fmm_tps_max_ctas(P->hcap, h->nsm, P->coh, &nctas));
     if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
     nctas = std::min(nctas, ctas_needed);
@@ -407,7 +412,8 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nctas);
     if (st_l) { plan_free(P); return st_l; }
   }
-  const long long npairs_all = P->tps ? (nsrc + 31) / 32 : (nsrc + P->spc - 1) / P->spc;
+  const int tpsL = P->coh ? P->coh : 32;
+  const long long npairs_all = P->tps ? (nsrc + tpsL - 1) / tpsL : (nsrc + P->spc - 1) / P->spc;
   size_t free_b = 0;
   CK(available_bytes(h->dev, &free_b));
   double budget = 0.60 * (double)free_b;
@@ -423,7 +429,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   if (maxB < 2) maxB = 2;
   if (const char* e = getenv("DAZIM_BATCH")) maxB = std::max(1, atoi(e));
   maxB = std::min<long long>(maxB, std::max<long long>(nsrc, 1));
-  if (P->tps) nctas = (int)std::min<long long>(nctas, (maxB + 31) / 32);
+  if (P->tps) nctas = (int)std::min<long long>(nctas, (maxB + tpsL - 1) / tpsL);
   else nctas = (int)std::min<long long>(nctas, (maxB + P->spc - 1) / P->spc);
   P->nctas = nctas;
   P->maxB = (int)maxB;
@@ -629,9 +635,8 @@ static int plan_run_once(dazim_plan* P) {
         A.hspill_n = P->hspill; A.hcap = P->hcap; A.hpos_r_out = P->d_hpos_r_out.p;
         A.flags = F.flags; A.n_accept = F.n_accept;
         A.prof = getenv("DAZIM_COH_PROF") ? atoi(getenv("DAZIM_COH_PROF")) : 0;
-        A.lanes = 32;
-        if (const char* e = getenv("DAZIM_COH_LANES")) A.lanes = P->coh ? std::max(1, std::min(32, atoi(e))) : 32;
-        CK(launch_fmm_tps(A, A.lanes == 32 ? std::min(P->nctas, (F.nsrc + 31) / 32) : (F.nsrc + A.lanes - 1) / A.lanes, P->coh, st));
+        const int Lc = P->coh ? P->coh : 32;
+        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + Lc - 1) / Lc), P->coh, st));
         T.n_launch++;      // + k_tps_init
       }
       else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));

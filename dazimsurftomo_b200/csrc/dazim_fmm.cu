@@ -1128,27 +1128,33 @@ __global__ void __launch_bounds__(32, 2) k_fmm_tps(TpsArgs A) {
 }
 
 // ---------------------------------------------------------------------------
-// K3, cohort kernel: one CTA of FIVE warps per 32 solves.  Warp 0 ("heap warp") runs, one lane per solve, the scalar
-// heap code of dazim_tps.h (tps_pre, tps_pop, tps_apply); warps 1-4 ("stencil warps") each own ONE of the four
-// neighbours of the node being accepted, again one lane per solve: the gather of that neighbour's stencil and its four
-// quadrant quadratics (tps_neighbour) run while the heap warp sifts the root down.  No shuffle and no shared state
-// between solves; the two roles hand over through 2.7 KB of shared memory and two producer/consumer named barriers
-// per accept round.  Arithmetic and heap discipline are exactly those of the one-thread kernel (and of its host twin).
-#define COH_X 1      // heap warp arrives after posting the nodes being accepted, stencil warps wait
-#define COH_Y 2      // stencil warps arrive after posting the four neighbour records, heap warp waits
-#define COH_THREADS 160
-__device__ __forceinline__ void coh_sync(int id) { asm volatile("bar.sync %0, 160;" ::"r"(id) : "memory"); }
+// K3, cohort kernel: one CTA per LANES solves (LANES = 8, 16 or 32).  Warp 0 ("heap warp") runs, one lane per solve,
+// the scalar heap code of dazim_tps.h (tps_pre, tps_pop, tps_apply); the 4 x LANES threads of the "stencil warps" each
+// own ONE of the four neighbours of the node one solve is accepting: the gather of that neighbour's stencil and its
+// four quadrant quadratics (tps_neighbour) run while the heap warp sifts the root down.  No shuffle and no shared
+// state between solves; the two roles hand over through a few KB of shared memory and two producer/consumer named
+// barriers per accept round.  Arithmetic and heap discipline are exactly those of the one-thread kernel (and of its
+// host twin).  Fewer lanes per heap warp = less SIMT divergence in the heap code (every lane's solve takes its own
+// path through pop / insert / update: measured 37 % of the round at 32 lanes) at the price of more warps.
+#define COH_X 1      // heap warp arrives after posting the nodes being accepted, stencil threads wait
+#define COH_Y 2      // stencil threads arrive after posting the neighbour records, heap warp waits
+template <int NT>
+__device__ __forceinline__ void coh_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+template <int NT>
 __device__ __forceinline__ void coh_arrive(int id) {
   __threadfence_block();
-  asm volatile("bar.arrive %0, 160;" ::"r"(id) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory");
 }
-// exchange area (ints): [0,32) node or -1, [32,64) ix, [64,96) iz, [96,128) tself, [128] any lane still running,
-// [160 + ((q*4 + k)*32 + lane)] neighbour q, field k (0 status, 1 id, 2 trial time, 3 offset)
-#define COH_XCH_INTS (160 + 16 * 32)
+// exchange area (ints): [0,L) node or -1, [L,2L) ix, [2L,3L) iz, [3L,4L) tself, [4L] any lane still running,
+// [4L + 32 + ((q*4 + k)*L + lane)] neighbour q, field k (0 status, 1 heap position read, 2 trial time, 3 offset)
+__host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 32 + 16 * L; }
+__host__ __device__ constexpr int coh_threads(int L) { return 32 + 4 * L; }
 
-template <int URG>
+template <int URG, int LANES>
 __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch, const int lane, const bool act,
                                unsigned long long& nacc, const bool prof) {
+  constexpr int NT = coh_threads(LANES);
+  constexpr int RES = 4 * LANES + 32;
   bool run = act;
   long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, t0 = 0, t1 = 0;
   unsigned long long rounds = 0;
@@ -1157,73 +1163,81 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
     TpsPre P;
     P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.last = make_int2(0, 0);
     if (run) run = tps_pre<URG>(S, G, nacc, P);
-    xch[lane] = run ? P.pn : -1;
-    xch[32 + lane] = P.ix;
-    xch[64 + lane] = P.iz;
-    xch[96 + lane] = (int)P.tself;
+    if (lane < LANES) {
+      xch[lane] = run ? P.pn : -1;
+      xch[LANES + lane] = P.ix;
+      xch[2 * LANES + lane] = P.iz;
+      xch[3 * LANES + lane] = (int)P.tself;
+    }
     const bool any = __any_sync(0xffffffffu, run);
-    if (lane == 0) xch[128] = any ? 1 : 0;
-    coh_arrive(COH_X);
+    if (lane == 0) xch[4 * LANES] = any ? 1 : 0;
+    coh_arrive<NT>(COH_X);
     if (!any) break;
     if (prof) { t1 = clock64(); c_pre += t1 - t0; t0 = t1; }
-    if (run) tps_pop(S, P);                          // sift the root down while the stencil warps work
+    if (run) tps_pop(S, P);                          // sift the root down while the stencil threads work
     if (prof) { __syncwarp(); t1 = clock64(); c_pop += t1 - t0; t0 = t1; }
-    coh_sync(COH_Y);
+    coh_sync<NT>(COH_Y);
     if (prof) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
     if (run) {
       TpsNb N[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        N[q].qst = xch[160 + ((q * 4 + 0) * 32 + lane)];
-        N[q].qid = xch[160 + ((q * 4 + 1) * 32 + lane)];
-        N[q].qt = __int_as_float(xch[160 + ((q * 4 + 2) * 32 + lane)]);
-        N[q].co = xch[160 + ((q * 4 + 3) * 32 + lane)];
+        N[q].qst = xch[RES + ((q * 4 + 0) * LANES + lane)];
+        N[q].qid = xch[RES + ((q * 4 + 1) * LANES + lane)];
+        N[q].qt = __int_as_float(xch[RES + ((q * 4 + 2) * LANES + lane)]);
+        N[q].co = xch[RES + ((q * 4 + 3) * LANES + lane)];
       }
       run = tps_apply<URG>(S, G, N);
     }
     if (prof) { __syncwarp(); t1 = clock64(); c_apply += t1 - t0; ++rounds; }
   }
   if (prof && lane == 0 && rounds) {
-    printf("[coh prof] urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f apply %.0f (heap size at end %d)\n",
-           URG, rounds, (double)c_pre / rounds, (double)c_pop / rounds, (double)c_wait / rounds, (double)c_apply / rounds, S.ntr);
+    printf("[coh prof] lanes %d urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f apply %.0f (heap size at end %d)\n",
+           LANES, URG, rounds, (double)c_pre / rounds, (double)c_pop / rounds, (double)c_wait / rounds, (double)c_apply / rounds, S.ntr);
     if (S.prof) {
-      printf("[coh prof] urg %d lane 0 split: pop{last %.0f shared %.0f spilled+place %.0f} apply{setup %.0f backptr+parents-issue %.0f",
+      printf("[coh prof] urg %d lane 0 split: pop{last %.0f shared %.0f spilled+place %.0f} apply{setup+issue %.0f wait+verify %.0f",
              URG, (double)S.prof[0] / rounds, (double)S.prof[1] / rounds, (double)S.prof[2] / rounds, (double)S.prof[3] / rounds,
              (double)S.prof[4] / rounds);
-      printf(" q-boundary %.0f parent-wait %.0f move %.0f place %.0f}\n", (double)S.prof[5] / rounds, (double)S.prof[6] / rounds,
-             (double)S.prof[7] / rounds, (double)S.prof[8] / rounds);
+      printf(" neighbour set-up %.0f move %.0f place %.0f}\n", (double)S.prof[6] / rounds, (double)S.prof[7] / rounds,
+             (double)S.prof[8] / rounds);
       for (int i = 0; i < 16; ++i) S.prof[i] = 0;
     }
   }
 }
 
-template <int URG>
-__device__ void coh_march_stencil(const TpsGrid& G, volatile int* xch, const int lane, const int q) {
+template <int URG, int LANES>
+__device__ void coh_march_stencil(const TpsGrid& G, volatile int* xch, const int l, const int q) {
+  constexpr int NT = coh_threads(LANES);
+  constexpr int RES = 4 * LANES + 32;
   for (;;) {
-    coh_sync(COH_X);
-    if (!xch[128]) break;
-    const int pn = xch[lane];
+    coh_sync<NT>(COH_X);
+    if (!xch[4 * LANES]) break;
+    const int pn = xch[l];
     if (pn >= 0) {
-      const TpsNb R = tps_neighbour<URG>(G, xch[32 + lane], xch[64 + lane], (unsigned)xch[96 + lane], q);
-      xch[160 + ((q * 4 + 0) * 32 + lane)] = R.qst;
-      xch[160 + ((q * 4 + 1) * 32 + lane)] = R.qid;
-      xch[160 + ((q * 4 + 2) * 32 + lane)] = __float_as_int(R.qt);
-      xch[160 + ((q * 4 + 3) * 32 + lane)] = R.co;
+      const TpsNb R = tps_neighbour<URG>(G, xch[LANES + l], xch[2 * LANES + l], (unsigned)xch[3 * LANES + l], q);
+      xch[RES + ((q * 4 + 0) * LANES + l)] = R.qst;
+      xch[RES + ((q * 4 + 1) * LANES + l)] = R.qid;
+      xch[RES + ((q * 4 + 2) * LANES + l)] = __float_as_int(R.qt);
+      xch[RES + ((q * 4 + 3) * LANES + l)] = R.co;
     }
-    coh_arrive(COH_Y);
+    coh_arrive<NT>(COH_Y);
   }
 }
 
-__global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
+template <int LANES>
+__global__ void __launch_bounds__(32 + 4 * LANES, LANES == 32 ? 2 : (LANES == 16 ? 4 : 7)) k_fmm_coh(TpsArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // solve served by this thread: heap warp lane l < LANES; stencil thread t = tid - 32: neighbour t / LANES of solve t % LANES
+  const int l = warp == 0 ? lane : (tid - 32) % LANES;
+  const int q = warp == 0 ? 0 : (tid - 32) / LANES;
   const GridC& g = A.g;
   const size_t ncoarse = (size_t)g.nnx * g.nnz;          // slow_c (plain column-major)
   const size_t ncf = coarse_field_size(g.nnx, g.nnz);    // E_c (interleaved layout)
-  volatile int* xch = reinterpret_cast<volatile int*>(smem_raw + (size_t)A.hcap * 32 * 8);
+  volatile int* xch = reinterpret_cast<volatile int*>(smem_raw + (size_t)A.hcap * LANES * 8);
   TpsState S;
-  S.sm = reinterpret_cast<int2*>(smem_raw) + lane;
-  S.stride = 32;
+  S.sm = reinterpret_cast<int2*>(smem_raw) + l;
+  S.stride = LANES;
   S.hcap = A.hcap;
   S.htot = A.hcap + A.hspill_n - 2;     // two slots of slack: tps_pop_root reads sibling pairs as one int4
   S.E = nullptr;
@@ -1231,13 +1245,12 @@ __global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
   __shared__ long long s_prof[16];
   if (tid < 16) s_prof[tid] = 0;
   __syncthreads();
-  S.prof = (A.prof && blockIdx.x == 0 && warp == 0) ? s_prof : nullptr;   // every lane of the heap warp adds: divide by 32
+  S.prof = (A.prof && blockIdx.x == 0 && warp == 0 && lane == 0) ? s_prof : nullptr;
   S.pt0 = 0;
   tps_reset(S);
   unsigned long long nacc = 0;
-  const int L = A.lanes;
-  for (int s0 = blockIdx.x * L; s0 < A.nsrc; s0 += gridDim.x * L) {
-    const int s = (lane < L) ? s0 + lane : A.nsrc;
+  for (int s0 = blockIdx.x * LANES; s0 < A.nsrc; s0 += gridDim.x * LANES) {
+    const int s = (warp != 0 || lane < LANES) ? s0 + l : A.nsrc;
     const int sc = min(s, A.nsrc - 1);                   // inactive lane: valid addresses, no side effects
     const SrcRec sr = A.src[sc];
     unsigned* E_r = A.E_r + (size_t)sc * REF_N;
@@ -1251,16 +1264,16 @@ __global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
       const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
       S.gl = A.hspill + (size_t)sc * A.hspill_n;
       if (act) tps_source_init(S, g, sr, vv, c_ubasis, E_r);
-      coh_march_heap<1>(S, Gr, xch, lane, act, nacc, A.prof && blockIdx.x == 0);
+      coh_march_heap<1, LANES>(S, Gr, xch, lane, act, nacc, A.prof && blockIdx.x == 0);
       if (act && !S.overflow) {
         tps_refined_finish(S, E_r, A.hpos_r_out ? A.hpos_r_out + (size_t)sc * REF_N : nullptr);
         tps_handoff(S, g, sr, E_r, E_c);
       }
       __syncwarp();
-      coh_march_heap<2>(S, Gc, xch, lane, act && !S.overflow, nacc, A.prof && blockIdx.x == 0);
+      coh_march_heap<2, LANES>(S, Gc, xch, lane, act && !S.overflow, nacc, A.prof && blockIdx.x == 0);
     } else {
-      coh_march_stencil<1>(Gr, xch, lane, warp - 1);
-      coh_march_stencil<2>(Gc, xch, lane, warp - 1);
+      coh_march_stencil<1, LANES>(Gr, xch, l, q);
+      coh_march_stencil<2, LANES>(Gc, xch, l, q);
     }
   }
   if (warp == 0) {
@@ -1269,14 +1282,20 @@ __global__ void __launch_bounds__(COH_THREADS, 2) k_fmm_coh(TpsArgs A) {
   }
 }
 
+static const void* coh_fn(int lanes) {
+  return lanes == 8 ? (const void*)k_fmm_coh<8> : (lanes == 16 ? (const void*)k_fmm_coh<16> : (const void*)k_fmm_coh<32>);
+}
+size_t fmm_coh_smem(int hcap, int lanes) { return (size_t)hcap * lanes * 8 + (size_t)coh_xch_ints(lanes) * 4; }
+
 // resident warps (= CTAs of 32 solves) per SM for a given shared heap capacity
+// resident CTAs for a given shared heap capacity; coh = lanes per heap warp (8 / 16 / 32) or 0 for the one-thread kernel
 cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int* nctas) {
-  const size_t smem = (size_t)hcap * 32 * 8 + (coh ? COH_XCH_INTS * 4 : 0);
-  const void* fn = coh ? (const void*)k_fmm_coh : (const void*)k_fmm_tps;
+  const size_t smem = coh ? fmm_coh_smem(hcap, coh) : (size_t)hcap * 32 * 8;
+  const void* fn = coh ? coh_fn(coh) : (const void*)k_fmm_tps;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, coh ? COH_THREADS : 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, coh ? coh_threads(coh) : 32, smem);
   if (e != cudaSuccess) return e;
   *nctas = per_sm * nsm;
   return cudaSuccess;
@@ -1288,10 +1307,12 @@ cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, cudaStream_t st
   k_tps_init<<<gi, 256, 0, st>>>(A);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const size_t smem = (size_t)A.hcap * 32 * 8 + (coh ? COH_XCH_INTS * 4 : 0);
-  e = cudaFuncSetAttribute(coh ? (const void*)k_fmm_coh : (const void*)k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = coh ? fmm_coh_smem(A.hcap, coh) : (size_t)A.hcap * 32 * 8;
+  e = cudaFuncSetAttribute(coh ? coh_fn(coh) : (const void*)k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (coh) k_fmm_coh<<<nctas, COH_THREADS, smem, st>>>(A);
+  if (coh == 8) k_fmm_coh<8><<<nctas, coh_threads(8), smem, st>>>(A);
+  else if (coh == 16) k_fmm_coh<16><<<nctas, coh_threads(16), smem, st>>>(A);
+  else if (coh == 32) k_fmm_coh<32><<<nctas, coh_threads(32), smem, st>>>(A);
   else k_fmm_tps<<<nctas, 32, smem, st>>>(A);
   return cudaGetLastError();
 }

@@ -6,8 +6,12 @@
 // HBM-bound (8 B per non-zero: value + index; the gathered vector lives in L2).  The COO triplets are
 // turned once into CSR (for A x) and CSC (for A^T y) with a stable radix sort, so both products are
 // race-free, deterministic row/column reductions (one warp per row or column) instead of atomics.
-// Vector norms are two-stage deterministic reductions accumulated in double; the scalar recurrences
-// of LSMR run on the host in float exactly as in the Fortran.
+// Vector norms are two-stage deterministic reductions accumulated in double.  The scalar recurrences of LSMR
+// (lsmrModule.f90:470-640) run ON THE DEVICE, in float and in the Fortran's operation order, inside the single-thread
+// tails of the norm reductions; every kernel of an iteration starts with "if (state->istop) return", so the host
+// enqueues iterations in batches (one CUDA graph of an iteration, replayed) and synchronises once per batch instead
+// of three times per iteration.  Iterations enqueued past the stopping one are no-ops: istop / itn / x are exactly
+// those of the synchronous loop.
 #include "../../include/dazim_b200.h"
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -15,6 +19,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace dzl {
@@ -149,11 +155,200 @@ __global__ void k_update(float* __restrict__ hbar, float* __restrict__ h, float*
   }
 }
 
-static float d2norm(float a, float b) {      // lsmrModule.f90:686-711
-  const float scale = std::fabs(a) + std::fabs(b);
+// ---- device-resident LSMR state (scalars of lsmrModule.f90:36-640) ----
+struct LsmrState {
+  float alpha, beta, rho, rhobar, cbar, sbar, zeta, zetabar, alphabar, betadd, betad, rhodold, tautildeold, thetatilde, d;
+  float normA2, maxrbar, minrbar, normb, normA, condA, normx, normr, normAr;
+  float c1, c2, c3;                      // coefficients of the hbar / x / h update
+  float damp, atol, btol, ctol;
+  int itn, istop, itnlim;
+  int beta_pos;                          // beta > 0 in this iteration (lsmrModule.f90:486)
+  int localVecs, localPointer, queueFull;
+};
+
+__device__ __host__ inline float d2norm(float a, float b) {      // lsmrModule.f90:686-711
+  const float scale = fabsf(a) + fabsf(b);
   if (scale == 0.0f) return 0.0f;
   const float ra = a / scale, rb = b / scale;
-  return scale * std::sqrt(ra * ra + rb * rb);
+  return scale * sqrtf(ra * ra + rb * rb);
+}
+
+// x = a * x with a taken from the state: mode 0: -alpha, 1: 1/beta (if beta > 0), 2: -beta (if beta > 0), 3: 1/alpha (if alpha > 0)
+__global__ void k_scal_state(float* __restrict__ x, int n, const LsmrState* __restrict__ S, int mode) {
+  if (S->istop) return;
+  float a;
+  if (mode == 0) a = -S->alpha;
+  else if (mode == 1) { if (!S->beta_pos) return; a = 1.0f / S->beta; }
+  else if (mode == 2) { if (!S->beta_pos) return; a = -S->beta; }
+  else { if (!S->beta_pos || !(S->alpha > 0.0f)) return; a = 1.0f / S->alpha; }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = a * x[i];
+}
+__global__ void __launch_bounds__(256) k_spmv_add_state(int nrow, const long long* __restrict__ ptr, const int* __restrict__ idx,
+                                                         const float* __restrict__ val, const float* __restrict__ x,
+                                                         float* __restrict__ y, const LsmrState* __restrict__ S, int need_beta) {
+  if (S->istop || (need_beta && !S->beta_pos)) return;
+  const int lane = threadIdx.x & 31;
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= nrow) return;
+  const long long b = ptr[w], e = ptr[w + 1];
+  float acc = 0.0f;
+  long long k = b + lane;
+  for (; k + 96 < e; k += 128) {
+    const float v0 = val[k], v1 = val[k + 32], v2 = val[k + 64], v3 = val[k + 96];
+    const int i0 = idx[k], i1 = idx[k + 32], i2 = idx[k + 64], i3 = idx[k + 96];
+    acc += v0 * x[i0];
+    acc += v1 * x[i1];
+    acc += v2 * x[i2];
+    acc += v3 * x[i3];
+  }
+  for (; k < e; k += 32) acc += val[k] * x[idx[k]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && e > b) y[w] = y[w] + acc;
+}
+__global__ void __launch_bounds__(256) k_dot_partial_state(const float* __restrict__ a, int n, double* __restrict__ partial,
+                                                            const LsmrState* __restrict__ S, int need_beta) {
+  if (S->istop || (need_beta && !S->beta_pos)) return;
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    acc += (double)a[i] * (double)a[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += sh[i];
+    partial[blockIdx.x] = s;
+  }
+}
+__device__ inline float final_norm(const double* partial, int nb) {
+  double s = 0.0;
+  for (int i = 0; i < nb; ++i) s += partial[i];
+  return (float)sqrt(s);
+}
+// beta = ||u|| (lsmrModule.f90:484) + the bookkeeping of the local reorthogonalisation queue (:489-497)
+__global__ void k_tail_beta(const double* __restrict__ partial, int nb, LsmrState* S) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || S->istop) return;
+  S->itn = S->itn + 1;
+  S->beta = final_norm(partial, nb);
+  S->beta_pos = S->beta > 0.0f ? 1 : 0;
+  if (S->beta_pos && S->localVecs > 0) {
+    if (S->localPointer < S->localVecs) S->localPointer = S->localPointer + 1;
+    else { S->localPointer = 1; S->queueFull = 1; }
+  }
+}
+__global__ void k_store_local(float* __restrict__ localV, const float* __restrict__ v, int n, const LsmrState* __restrict__ S) {
+  if (S->istop || !S->beta_pos || S->localVecs <= 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) localV[(size_t)(S->localPointer - 1) * n + i] = v[i];
+}
+// alpha = ||v|| (:505) and every scalar recurrence up to the coefficients of the vector update (:514-541) and the
+// norm estimates that do not need ||x|| (:548-590)
+__global__ void k_tail_alpha(const double* __restrict__ partial, int nb, LsmrState* S) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || S->istop) return;
+  if (S->beta_pos) S->alpha = final_norm(partial, nb);
+  const float alpha = S->alpha, beta = S->beta, damp = S->damp;
+  const float alphahat = d2norm(S->alphabar, damp);
+  const float chat = S->alphabar / alphahat, shat = damp / alphahat;
+  const float rhoold = S->rho;
+  const float rho = d2norm(alphahat, beta);
+  const float cc = alphahat / rho, s = beta / rho;
+  const float thetanew = s * alpha;
+  S->alphabar = cc * alpha;
+  const float rhobarold = S->rhobar, zetaold = S->zeta;
+  const float thetabar = S->sbar * rho, rhotemp = S->cbar * rho;
+  const float rhobar = d2norm(S->cbar * rho, thetanew);
+  const float cbar = S->cbar * rho / rhobar;
+  const float sbar = thetanew / rhobar;
+  const float zeta = cbar * S->zetabar;
+  const float zetabar = -sbar * S->zetabar;
+  S->c1 = thetabar * rho / (rhoold * rhobarold);
+  S->c2 = zeta / (rho * rhobar);
+  S->c3 = thetanew / rho;
+  const float betaacute = chat * S->betadd, betacheck = -shat * S->betadd;
+  const float betahat = cc * betaacute;
+  const float betadd = -s * betaacute;
+  const float thetatildeold = S->thetatilde;
+  const float rhotildeold = d2norm(S->rhodold, thetabar);
+  const float ctildeold = S->rhodold / rhotildeold, stildeold = thetabar / rhotildeold;
+  const float thetatilde = stildeold * rhobar;
+  const float rhodold = ctildeold * rhobar;
+  const float betad = -stildeold * S->betad + ctildeold * betahat;
+  const float tautildeold = (zetaold - thetatildeold * S->tautildeold) / rhotildeold;
+  const float taud = (zeta - thetatilde * tautildeold) / rhodold;
+  const float d = S->d + betacheck * betacheck;
+  S->normr = sqrtf(d + (betad - taud) * (betad - taud) + betadd * betadd);
+  float normA2 = S->normA2 + beta * beta;
+  S->normA = sqrtf(normA2);
+  normA2 = normA2 + alpha * alpha;
+  S->normA2 = normA2;
+  S->maxrbar = fmaxf(S->maxrbar, rhobarold);
+  if (S->itn > 1) S->minrbar = fminf(S->minrbar, rhobarold);
+  S->condA = fmaxf(S->maxrbar, rhotemp) / fminf(S->minrbar, rhotemp);
+  S->normAr = fabsf(zetabar);
+  S->rho = rho; S->rhobar = rhobar; S->cbar = cbar; S->sbar = sbar; S->zeta = zeta; S->zetabar = zetabar;
+  S->betadd = betadd; S->thetatilde = thetatilde; S->rhodold = rhodold; S->betad = betad; S->tautildeold = tautildeold;
+  S->d = d;
+}
+// hbar = h - c1*hbar ; x = x + c2*hbar ; h = v - c3*h   (lsmrModule.f90:539-541)
+__global__ void k_update_state(float* __restrict__ hbar, float* __restrict__ h, float* __restrict__ x,
+                               const float* __restrict__ v, int n, const LsmrState* __restrict__ S) {
+  if (S->istop) return;
+  const float c1 = S->c1, c2 = S->c2, c3 = S->c3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float hb = h[i] - c1 * hbar[i];
+    hbar[i] = hb;
+    x[i] = x[i] + c2 * hb;
+    h[i] = v[i] - c3 * h[i];
+  }
+}
+// normx = ||x|| (:592) and the stopping tests (:596-640)
+__global__ void k_tail_normx(const double* __restrict__ partial, int nb, LsmrState* S) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || S->istop) return;
+  S->normx = final_norm(partial, nb);
+  const float normA = S->normA, normx = S->normx, normb = S->normb;
+  const float test1 = S->normr / normb, test2 = S->normAr / (normA * S->normr), test3 = 1.0f / S->condA;
+  const float t1 = test1 / (1.0f + normA * normx / normb);
+  const float rtol = S->btol + S->atol * normA * normx / normb;
+  int istop = 0;
+  if (S->itn >= S->itnlim) istop = 7;
+  if (1.0f + test3 <= 1.0f) istop = 6;
+  if (1.0f + test2 <= 1.0f) istop = 5;
+  if (1.0f + t1 <= 1.0f) istop = 4;
+  if (test3 <= S->ctol) istop = 3;
+  if (test2 <= S->atol) istop = 2;
+  if (test1 <= rtol) istop = 1;
+  S->istop = istop;
+}
+__global__ void __launch_bounds__(1024) k_reorth_state(float* __restrict__ v, const float* __restrict__ localV, int n,
+                                                        const LsmrState* __restrict__ S) {
+  if (S->istop || !S->beta_pos || S->localVecs <= 0) return;
+  const int lim = S->queueFull ? S->localVecs : S->localPointer;
+  __shared__ double sh[32];
+  __shared__ float sh_d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < lim; ++q) {
+    const float* __restrict__ lq = localV + (size_t)q * n;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) acc += (double)v[i] * (double)lq[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double t = sh[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sh_d = (float)t;
+    }
+    __syncthreads();
+    const float d = sh_d;
+    for (int i = threadIdx.x; i < n; i += 1024) v[i] = v[i] - d * lq[i];
+  }
 }
 
 struct Ctx {
@@ -170,6 +365,24 @@ static int norm2(Ctx& c, const float* a, int n, float* out_host) {
   LCK(cudaMemcpyAsync(out_host, c.scal, sizeof(float), cudaMemcpyDeviceToHost, c.st));
   LCK(cudaStreamSynchronize(c.st));
   return 0;
+}
+
+// events / graphs that are released on every exit path
+struct Guard {
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  ~Guard() {
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+// 1-based indices of the caller must lie in [1, lim]: a wrong index would corrupt device memory silently
+__global__ void k_minmax(const int* __restrict__ a, long long n, int lim, int* __restrict__ bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (a[i] < 1 || a[i] > lim)) atomicOr(bad, 1);
 }
 
 // COO (1-based) -> compressed structure over `key` (row for CSR, col for CSC)
@@ -204,15 +417,16 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
                const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize, float* x,
                dazim_lsmr_info* info, bool coo_on_device) {
   if (m < 1 || n < 1 || nnz < 0 || nnz >= (1ll << 31) || !row || !col || !rw || !b || !x || !info) return DAZIM_EBADARG;
-  cudaEvent_t e0, e1, e2;
-  LCK(cudaEventCreate(&e0)); LCK(cudaEventCreate(&e1)); LCK(cudaEventCreate(&e2));
+  Guard G;
+  for (int i = 0; i < 3; ++i) LCK(cudaEventCreate(&G.ev[i]));
+  cudaEvent_t e0 = G.ev[0], e1 = G.ev[1], e2 = G.ev[2];
   // ---- upload + CSR / CSC ----
-  Buf<int> d_row, d_col, csr_idx, csc_idx;
+  Buf<int> d_row, d_col, csr_idx, csc_idx, d_bad;
   Buf<float> d_val, csr_val, csc_val;
   Buf<long long> csr_ptr, csc_ptr;
   if (!coo_on_device) { LCK(d_row.alloc(nnz, st)); LCK(d_col.alloc(nnz, st)); LCK(d_val.alloc(nnz, st)); }
   LCK(csr_idx.alloc(nnz, st)); LCK(csc_idx.alloc(nnz, st)); LCK(csr_val.alloc(nnz, st)); LCK(csc_val.alloc(nnz, st));
-  LCK(csr_ptr.alloc((size_t)m + 1, st)); LCK(csc_ptr.alloc((size_t)n + 1, st));
+  LCK(csr_ptr.alloc((size_t)m + 1, st)); LCK(csc_ptr.alloc((size_t)n + 1, st)); LCK(d_bad.alloc(1, st));
   LCK(cudaEventRecord(e0, st));
   if (nnz > 0 && !coo_on_device) {
     LCK(cudaMemcpyAsync(d_row.p, row, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -222,6 +436,17 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   const int* k_row = coo_on_device ? row : d_row.p;
   const int* k_col = coo_on_device ? col : d_col.p;
   const float* k_val = coo_on_device ? rw : d_val.p;
+  if (nnz > 0) {
+    // the indices come from the caller (dazim_lsmr, __lsmrmodule_MOD_lsmr): validate before they index device memory
+    int bad = 0;
+    LCK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+    const unsigned nbk = (unsigned)((nnz + 255) / 256);
+    k_minmax<<<nbk, 256, 0, st>>>(k_row, nnz, m, d_bad.p);
+    k_minmax<<<nbk, 256, 0, st>>>(k_col, nnz, n, d_bad.p);
+    LCK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LCK(cudaStreamSynchronize(st));
+    if (bad) return DAZIM_EBADARG;
+  }
   int rc = compress(st, nnz, m, k_row, k_col, k_val, csr_ptr.p, csr_idx.p, csr_val.p);
   if (rc) return rc;
   rc = compress(st, nnz, n, k_col, k_row, k_val, csc_ptr.p, csc_idx.p, csc_val.p);
@@ -230,8 +455,9 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   const int localVecs = std::max(0, std::min(localSize, std::min(m, n)));
   Buf<float> u, v, h, hbar, dx, localV, scal;
   Buf<double> partial;
+  Buf<LsmrState> dS;
   LCK(u.alloc(m, st)); LCK(v.alloc(n, st)); LCK(h.alloc(n, st)); LCK(hbar.alloc(n, st)); LCK(dx.alloc(n, st));
-  LCK(localV.alloc((size_t)localVecs * n, st)); LCK(scal.alloc(4, st)); LCK(partial.alloc(1024, st));
+  LCK(localV.alloc((size_t)localVecs * n, st)); LCK(scal.alloc(4, st)); LCK(partial.alloc(1024, st)); LCK(dS.alloc(1, st));
   Ctx c{st, partial.p, scal.p, 592};
   const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256);
   const unsigned gwm = (unsigned)(((long long)m * 32 + 255) / 256), gwn = (unsigned)(((long long)n * 32 + 255) / 256);
@@ -251,103 +477,78 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   if (alpha > 0.0f) k_scal<<<gn, 256, 0, st>>>(v.p, n, 1.0f / alpha);
   float normAr = alpha * beta;
   info->normAr = normAr; info->normr = beta;
-  int itn = 0, istop = 0;
-  float normA = 0, condA = 0, normx = 0, normr = beta;
+  LsmrState hs;
+  std::memset(&hs, 0, sizeof(hs));
+  hs.normr = beta;
   if (normAr != 0.0f) {
-    bool queueFull = false;
-    int localPointer = 0;
     const bool localOrtho = localVecs > 0;
-    if (localOrtho) {
-      localPointer = 1;
-      LCK(cudaMemcpyAsync(localV.p, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-    }
-    float zetabar = alpha * beta, alphabar = alpha, rho = 1, rhobar = 1, cbar = 1, sbar = 0;
+    if (localOrtho) LCK(cudaMemcpyAsync(localV.p, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
     LCK(cudaMemcpyAsync(h.p, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-    float betadd = beta, betad = 0, rhodold = 1, tautildeold = 0, thetatilde = 0, zeta = 0, d = 0;
-    float normA2 = alpha * alpha, maxrbar = 0.0f, minrbar = 1e+30f;
-    const float normb = beta;
-    const float ctol = conlim > 0.0f ? 1.0f / conlim : 0.0f;
-    for (;;) {
-      itn = itn + 1;
-      k_scal<<<gm, 256, 0, st>>>(u.p, m, -alpha);
-      k_spmv_add<<<gwm, 256, 0, st>>>(m, csr_ptr.p, csr_idx.p, csr_val.p, v.p, u.p);    // u = u + A v
-      if ((rc = norm2(c, u.p, m, &beta))) return rc;
-      if (beta > 0.0f) {
-        k_scal<<<gm, 256, 0, st>>>(u.p, m, 1.0f / beta);
-        if (localOrtho) {
-          if (localPointer < localVecs) localPointer = localPointer + 1;
-          else { localPointer = 1; queueFull = true; }
-          LCK(cudaMemcpyAsync(localV.p + (size_t)(localPointer - 1) * n, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-        }
-        k_scal<<<gn, 256, 0, st>>>(v.p, n, -beta);
-        k_spmv_add<<<gwn, 256, 0, st>>>(n, csc_ptr.p, csc_idx.p, csc_val.p, u.p, v.p);  // v = v + A^T u
-        if (localOrtho) {
-          const int lim = queueFull ? localVecs : localPointer;
-          k_reorth<<<1, 1024, 0, st>>>(v.p, localV.p, n, lim);
-        }
-        if ((rc = norm2(c, v.p, n, &alpha))) return rc;
-        if (alpha > 0.0f) k_scal<<<gn, 256, 0, st>>>(v.p, n, 1.0f / alpha);
-      }
-      const float alphahat = d2norm(alphabar, damp);
-      const float chat = alphabar / alphahat, shat = damp / alphahat;
-      const float rhoold = rho;
-      rho = d2norm(alphahat, beta);
-      const float cc = alphahat / rho, s = beta / rho;
-      const float thetanew = s * alpha;
-      alphabar = cc * alpha;
-      const float rhobarold = rhobar, zetaold = zeta;
-      const float thetabar = sbar * rho, rhotemp = cbar * rho;
-      rhobar = d2norm(cbar * rho, thetanew);
-      cbar = cbar * rho / rhobar;
-      sbar = thetanew / rhobar;
-      zeta = cbar * zetabar;
-      zetabar = -sbar * zetabar;
-      k_update<<<gn, 256, 0, st>>>(hbar.p, h.p, dx.p, v.p, n, thetabar * rho / (rhoold * rhobarold), zeta / (rho * rhobar),
-                                   thetanew / rho);
-      const float betaacute = chat * betadd, betacheck = -shat * betadd;
-      const float betahat = cc * betaacute;
-      betadd = -s * betaacute;
-      const float thetatildeold = thetatilde;
-      const float rhotildeold = d2norm(rhodold, thetabar);
-      const float ctildeold = rhodold / rhotildeold, stildeold = thetabar / rhotildeold;
-      thetatilde = stildeold * rhobar;
-      rhodold = ctildeold * rhobar;
-      betad = -stildeold * betad + ctildeold * betahat;
-      tautildeold = (zetaold - thetatildeold * tautildeold) / rhotildeold;
-      const float taud = (zeta - thetatilde * tautildeold) / rhodold;
-      d = d + betacheck * betacheck;
-      normr = std::sqrt(d + (betad - taud) * (betad - taud) + betadd * betadd);
-      normA2 = normA2 + beta * beta;
-      normA = std::sqrt(normA2);
-      normA2 = normA2 + alpha * alpha;
-      maxrbar = std::max(maxrbar, rhobarold);
-      if (itn > 1) minrbar = std::min(minrbar, rhobarold);
-      condA = std::max(maxrbar, rhotemp) / std::min(minrbar, rhotemp);
-      normAr = std::fabs(zetabar);
-      if ((rc = norm2(c, dx.p, n, &normx))) return rc;
-      const float test1 = normr / normb, test2 = normAr / (normA * normr), test3 = 1.0f / condA;
-      const float t1 = test1 / (1.0f + normA * normx / normb);
-      const float rtol = btol + atol * normA * normx / normb;
-      if (itn >= itnlim) istop = 7;
-      if (1.0f + test3 <= 1.0f) istop = 6;
-      if (1.0f + test2 <= 1.0f) istop = 5;
-      if (1.0f + t1 <= 1.0f) istop = 4;
-      if (test3 <= ctol) istop = 3;
-      if (test2 <= atol) istop = 2;
-      if (test1 <= rtol) istop = 1;
-      if (istop != 0) break;
+    // initial scalars (lsmrModule.f90:420-460)
+    hs.alpha = alpha; hs.beta = beta; hs.zetabar = alpha * beta; hs.alphabar = alpha; hs.rho = 1; hs.rhobar = 1; hs.cbar = 1;
+    hs.sbar = 0; hs.betadd = beta; hs.betad = 0; hs.rhodold = 1; hs.tautildeold = 0; hs.thetatilde = 0; hs.zeta = 0; hs.d = 0;
+    hs.normA2 = alpha * alpha; hs.maxrbar = 0.0f; hs.minrbar = 1e+30f; hs.normb = beta;
+    hs.damp = damp; hs.atol = atol; hs.btol = btol; hs.ctol = conlim > 0.0f ? 1.0f / conlim : 0.0f;
+    hs.itn = 0; hs.istop = 0; hs.itnlim = itnlim; hs.beta_pos = 1;
+    hs.localVecs = localVecs; hs.localPointer = localOrtho ? 1 : 0; hs.queueFull = 0;
+    LCK(cudaMemcpyAsync(dS.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+    LCK(cudaStreamSynchronize(st));
+    LsmrState* S = dS.p;
+    const int nbm = std::min(c.nb, std::max(1, (m + 255) / 256)), nbn = std::min(c.nb, std::max(1, (n + 255) / 256));
+    auto enqueue_iteration = [&]() {
+      k_scal_state<<<gm, 256, 0, st>>>(u.p, m, S, 0);                                                  // u = -alpha u
+      k_spmv_add_state<<<gwm, 256, 0, st>>>(m, csr_ptr.p, csr_idx.p, csr_val.p, v.p, u.p, S, 0);       // u = u + A v
+      k_dot_partial_state<<<nbm, 256, 0, st>>>(u.p, m, partial.p, S, 0);
+      k_tail_beta<<<1, 32, 0, st>>>(partial.p, nbm, S);                                                // beta, queue pointer
+      k_scal_state<<<gm, 256, 0, st>>>(u.p, m, S, 1);                                                  // u = u / beta
+      if (localOrtho) k_store_local<<<gn, 256, 0, st>>>(localV.p, v.p, n, S);
+      k_scal_state<<<gn, 256, 0, st>>>(v.p, n, S, 2);                                                  // v = -beta v
+      k_spmv_add_state<<<gwn, 256, 0, st>>>(n, csc_ptr.p, csc_idx.p, csc_val.p, u.p, v.p, S, 1);       // v = v + A^T u
+      if (localOrtho) k_reorth_state<<<1, 1024, 0, st>>>(v.p, localV.p, n, S);
+      k_dot_partial_state<<<nbn, 256, 0, st>>>(v.p, n, partial.p, S, 1);
+      k_tail_alpha<<<1, 32, 0, st>>>(partial.p, nbn, S);                                               // alpha + recurrences
+      k_scal_state<<<gn, 256, 0, st>>>(v.p, n, S, 3);                                                  // v = v / alpha
+      k_update_state<<<gn, 256, 0, st>>>(hbar.p, h.p, dx.p, v.p, n, S);
+      k_dot_partial_state<<<nbn, 256, 0, st>>>(dx.p, n, partial.p, S, 0);
+      k_tail_normx<<<1, 32, 0, st>>>(partial.p, nbn, S);                                               // ||x||, stopping tests
+    };
+    // one iteration captured as a CUDA graph, replayed `batch` times between host checks of the stop flag
+    bool use_graph = getenv("DAZIM_LSMR_NOGRAPH") == nullptr;
+    if (use_graph) {
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueue_iteration();
+        if (cudaStreamEndCapture(st, &G.graph) != cudaSuccess || !G.graph ||
+            cudaGraphInstantiate(&G.exec, G.graph, 0) != cudaSuccess) use_graph = false;
+      } else use_graph = false;
+      if (!use_graph) cudaGetLastError();
     }
-    if (damp > 0.0f && istop == 2) istop = 3;
+    int batch = 8;
+    if (const char* e = getenv("DAZIM_LSMR_BATCH")) batch = std::max(1, atoi(e));
+    int ist_itn[2] = {0, 0};
+    for (;;) {
+      for (int k = 0; k < batch; ++k) {
+        if (use_graph) LCK(cudaGraphLaunch(G.exec, st));
+        else enqueue_iteration();
+      }
+      LCK(cudaMemcpyAsync(&ist_itn[0], &S->istop, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LCK(cudaMemcpyAsync(&ist_itn[1], &S->itn, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LCK(cudaStreamSynchronize(st));
+      LCK(cudaGetLastError());
+      if (ist_itn[0] != 0) break;
+    }
+    LCK(cudaMemcpyAsync(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    LCK(cudaStreamSynchronize(st));
+    if (damp > 0.0f && hs.istop == 2) hs.istop = 3;
+    normAr = hs.normAr;
   }
   LCK(cudaEventRecord(e2, st));
   LCK(cudaMemcpyAsync(x, dx.p, sizeof(float) * n, cudaMemcpyDefault, st));    // so may x
   LCK(cudaStreamSynchronize(st));
   LCK(cudaGetLastError());
-  info->istop = istop; info->itn = itn; info->normA = normA; info->condA = condA; info->normr = normr;
-  info->normAr = normAr; info->normx = normx;
+  info->istop = hs.istop; info->itn = hs.itn; info->normA = hs.normA; info->condA = hs.condA; info->normr = hs.normr;
+  info->normAr = normAr; info->normx = hs.normx;
   cudaEventElapsedTime(&info->setup_ms, e0, e1);
   cudaEventElapsedTime(&info->solve_ms, e1, e2);
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   return DAZIM_OK;
 }
 

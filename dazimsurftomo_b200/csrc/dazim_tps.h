@@ -172,7 +172,6 @@ struct TpsArgs {
   int* hpos_r_out;            // optional test seam [nsrc][REF_N]: heap slots of the close nodes after the refined march
   int* flags;                 // bit4 (16): heap / id overflow
   unsigned long long* n_accept;
-  int lanes;                  // solves per heap warp (32; fewer = experiment knob DAZIM_COH_LANES)
   int prof;                   // DAZIM_COH_PROF=1: lane 0 of CTA 0 prints its cycle split per accept (cohort kernel)
 };
 
