@@ -84,16 +84,20 @@ class ClockSampler:
 _PINNED = {}
 
 
-def _measured_traffic(workload_name, solves):
-    """DRAM bytes per k_fmm launch from the committed ncu capture (profiles/k3_dram_traffic.json:
-    bytes per solve measured with dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch."""
+def _measured_traffic(workload_name, solves, kernel):
+    """DRAM bytes per eikonal launch from the committed ncu capture (profiles/k3_dram_traffic.json: bytes per solve
+    measured with dram__bytes_read.sum + dram__bytes_write.sum, per kernel and grid), scaled to this launch."""
     p = os.path.join(ROOT, "profiles", "k3_dram_traffic.json")
     try:
         d = json.load(open(p))
         key = workload_name.split("-")[0]
-        if solves <= 1480 and key + "_duo" in d["bytes_per_solve"]:
-            key += "_duo"          # every solve resident: the library runs the two-warp latency kernel
-        per_solve = d["bytes_per_solve"].get(key)
+        per_solve = d.get("bytes_per_solve_by_kernel", {}).get(kernel, {}).get(key)
+        if per_solve is None:
+            if kernel == "k_fmm_duo" and key + "_duo" in d["bytes_per_solve"]:
+                key += "_duo"
+            elif not kernel.startswith("k_fmm<") and kernel != "k_fmm_duo":
+                return None
+            per_solve = d["bytes_per_solve"].get(key)
         return None if per_solve is None else float(per_solve) * solves
     except Exception:
         return None
@@ -318,6 +322,7 @@ def main():
         stage.append(tm)
         nnz = plan.nnz
         rows = plan.rows
+        kname = plan.eikonal_kernel
         plan.close()
     barrier()
     wall = time.perf_counter() - t_wall0
@@ -348,39 +353,40 @@ def main():
             h2d = tms["h2d_bytes"] + w.vs.nbytes * 2
             d2h = tms["d2h_bytes"] + sum(r[k].nbytes for k in ("pvRc", "sen_vs", "sen_vp", "sen_rho", "Lsen_Gsc"))
         else:
-            # N>1 end to end: host model -> strips -> table all-gather -> row blocks -> the one exchange step the
-            # inversion needs (all-gather-v of CSR row blocks + dsurf over NCCL) -> rank 0 reads the system back
+            # N>1 end to end: host model -> strips -> table all-gather -> this rank's row block built and read back into
+            # this rank's page-locked host buffers (rows are owned by ranks; all N PCIe links run at once).  The
+            # all-gather of the row blocks "only where the inversion step needs the full system" is timed separately
+            # below (gather_rows_ms): a row-distributed solver does not need it.
             plan, tm = one_step()
-            dtens = plan.device_tensors()
-            blk = dict(dsurf=dtens["dsurf"], nnz_row=dtens["rowptr"][1:] - dtens["rowptr"][:-1],
-                       col=dtens["col"], val=dtens["val"])
-            full = partition.gather_rows(blk, plan.row0)
+            blkh = plan.fetch(pinned=True)
             h2d = plan.h2d_bytes + w.vs.nbytes
-            d2h = 0
-            if rank == 0:
-                # rank 0 reads the full system back into cached page-locked buffers (what a caller would keep)
-                host = {}
-                for k in ("dsurf", "rw", "col", "row"):
-                    src = full[k]
-                    buf = _PINNED.get(k)
-                    if buf is None or buf.numel() < src.numel() or buf.dtype != src.dtype:
-                        buf = torch.empty(int(src.numel() * 1.1) + 16, dtype=src.dtype, pin_memory=True)
-                        _PINNED[k] = buf
-                    host[k] = buf[:src.numel()]
-                    host[k].copy_(src, non_blocking=True)
-                torch.cuda.synchronize()
-                d2h = sum(v.numel() * v.element_size() for v in host.values())
-                assert host["dsurf"].numel() == w.n_rays
-            del full, blk, dtens
+            d2h = sum(v.nbytes for v in blkh.values() if v is not None)
+            assert blkh["dsurf"].shape[0] == plan.rows
+            del blkh
             plan.close()
         barrier()
         if i > 0:
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
     e2e = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
+    gather_ms = None
     if world > 1:
-        t = torch.tensor([e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = float(t.item())
+        t = torch.tensor([e2e, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        e2e = float(tmax[0].item()); h2d = int(t[1].item()); d2h = int(t[2].item())       # bytes: summed over ranks
+        if not args.no_e2e:
+            # the exchange step of the inversion: all-gather-v of the CSR row blocks + dsurf over NCCL, HBM to HBM
+            plan, tm = one_step()
+            dtens = plan.device_tensors()
+            blk = dict(dsurf=dtens["dsurf"], nnz_row=dtens["rowptr"][1:] - dtens["rowptr"][:-1], col=dtens["col"], val=dtens["val"])
+            barrier()
+            tg = time.perf_counter()
+            full = partition.gather_rows(blk, plan.row0)
+            barrier()
+            gather_ms = 1e3 * (time.perf_counter() - tg)
+            assert int(full["dsurf"].numel()) == w.n_rays
+            del full, blk, dtens
+            plan.close()
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -404,10 +410,11 @@ def main():
             "counts": {"nnz": nnz_all, "rows": rows_all, "fmm_accepts": s["n_accept"], "ray_steps": s["n_steps"]},
             "e2e": {"value": rows_all / (e2e * 1e-3), "unit": UNIT, "ms_per_step": e2e,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gather_rows_ms": gather_ms,
             "gpu_launches": int(s["n_launch"] + 7) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "k_fmm (eikonal, dominant)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": _measured_traffic(w.name, solves_local),
+            "roofline": {"kernel": kname + " (eikonal, dominant)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": _measured_traffic(w.name, solves_local, kname),
                          "peak_source": peak_src,
                          "note": "algorithmic bytes 8 B x (N_coarse + N_refined) + 4 B x N_refined per solve; exact heap "
                                  "fast marching is bound by the serial accept chain (instruction issue / latency), not by "

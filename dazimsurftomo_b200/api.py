@@ -502,15 +502,25 @@ class Plan:
     def nnz(self) -> int:
         return load().dazim_plan_nnz(self._plan)
 
-    def fetch(self, csr=True):
+    @property
+    def eikonal_kernel(self) -> str:
+        f = load().dazim_plan_eikonal_kernel
+        f.restype = C.c_char_p
+        f.argtypes = [C.c_void_p]
+        return f(self._plan).decode()
+
+    def fetch(self, csr=True, pinned=False):
+        """Row block of this plan on the host: dsurf (+ obsTaa) and the CSR arrays.  pinned=True: the arrays are views of
+        cached page-locked buffers (valid until the next pinned fetch), so the copy runs at PCIe speed."""
         n = self.rows
-        dsurf = np.zeros(n, np.float32)
-        taa = np.zeros(n, np.float32) if self.mode == 0 else None
+        alloc = (lambda tag, cnt, dt: _pinned.get("plan_" + tag, cnt, dt)) if pinned else (lambda tag, cnt, dt: np.zeros(cnt, dt))
+        dsurf = alloc("dsurf", n, np.float32)
+        taa = alloc("taa", n, np.float32) if self.mode == 0 else None
         rowptr = col = val = None
         if self.mode != 0 and csr == "rowptr":          # row pointers only (the triplets of a big job are tens of GB)
-            rowptr = np.zeros(n + 1, np.int64)
+            rowptr = alloc("rowptr", n + 1, np.int64)
         elif self.mode != 0 and csr:
-            rowptr = np.zeros(n + 1, np.int64); col = np.zeros(self.nnz, np.int32); val = np.zeros(self.nnz, np.float32)
+            rowptr = alloc("rowptr", n + 1, np.int64); col = alloc("col", self.nnz, np.int32); val = alloc("val", self.nnz, np.float32)
         _chk(load().dazim_plan_fetch(self._plan, _p(dsurf), _p(taa), _p(rowptr), _p(col), _p(val)))
         return dict(dsurf=dsurf, obsTaa=taa, rowptr=rowptr, col=col, val=val)
 

@@ -196,7 +196,7 @@ struct dazim_plan {
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
   int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
   int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
-  int coh = 16;  // solves per heap warp of the cohort kernel (8 / 16 / 32); 0: the one-thread-per-solve kernel
+  int coh = 8;   // solves per heap warp of the cohort kernel (8 / 16 / 32; 8 measured best); 0: the one-thread-per-solve kernel
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
@@ -381,10 +381,21 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   const size_t ncf = coarse_field_size(g.nnx, g.nnz);     // E_c / hpos_c in the interleaved layout
   P->hspill = 0;
   int nctas = 1;
-  // ---- kernel choice.  Default: thread per solve (dazim_tps.h).  DAZIM_TPS=0, or any of the legacy kernels' knobs
-  //      (DAZIM_DUO / DAZIM_SPC), selects the half-warp / two-warp kernels of round 1 (kept: bit-identical, and the
-  //      fall-back when a grid does not fit the packed heap entry of the new kernel). ----
-  P->tps = 1;
+  // ---- kernel choice (measured on the B200, profiles/r2_k3_kernel_choice.md).  The round-1 kernels keep the whole
+  //      narrow band in shared memory when few solves compete (two-warp latency kernel: 1.6-2.1 us per accept) and
+  //      pack 5 920 solves per chip otherwise (half-warp throughput kernel).  The cohort kernel (dazim_tps.h: one heap
+  //      LANE per solve) holds 8 288 solves per chip; it wins exactly when the job needs more than one wave of the
+  //      throughput kernel on a grid whose band cannot live in shared memory anyway (S200: 6.8 s against 9.0 s), and
+  //      loses on small grids / few solves (test1 shape: 91 ms against 50 ms).  DAZIM_TPS=1/0 forces the choice;
+  //      the legacy knobs (DAZIM_DUO / DAZIM_SPC) imply DAZIM_TPS=0. ----
+  int auto_tps = 0;
+  {
+    int nc_l = 1;
+    int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nc_l);
+    if (st_l) { plan_free(P); return st_l; }
+    auto_tps = (!P->duo && hneed >= 2048 && nsrc > (long long)P->spc * nc_l) ? 1 : 0;
+  }
+  P->tps = auto_tps;
   if (getenv("DAZIM_DUO") || getenv("DAZIM_SPC")) P->tps = 0;
   if (const char* e = getenv("DAZIM_TPS")) P->tps = atoi(e) ? 1 : 0;
   const int hspill_full = 8 * (g.nnx + g.nnz) + 1024 + 16;     // generous bound on the narrow band (measured 2.7 x edge)
@@ -799,6 +810,13 @@ extern "C" int dazim_plan_fetch(dazim_plan* P, float* dsurf, float* taa, long lo
   }
   CK(cudaStreamSynchronize(st));
   return DAZIM_OK;
+}
+
+// name of the eikonal kernel this plan launches (bench.py / profiles name the dominant kernel by it)
+extern "C" const char* dazim_plan_eikonal_kernel(const dazim_plan* P) {
+  if (!P) return "";
+  if (P->tps) return P->coh == 8 ? "k_fmm_coh<8>" : (P->coh == 16 ? "k_fmm_coh<16>" : (P->coh == 32 ? "k_fmm_coh<32>" : "k_fmm_tps"));
+  return P->duo ? "k_fmm_duo" : (P->spc == 2 ? "k_fmm<2>" : "k_fmm<1>");
 }
 
 extern "C" int dazim_plan_device_ptrs(dazim_plan* P, void** dsurf, void** taa, void** rowptr, void** col, void** val) {

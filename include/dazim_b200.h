@@ -175,6 +175,9 @@ long long dazim_plan_nnz(const dazim_plan* plan);
 int dazim_plan_fetch(dazim_plan* plan, float* dsurf, float* obsTaa, long long* rowptr, int* col,
                      float* val);
 /* device pointers of the last run's outputs (for NCCL gathers without a host hop) */
+/* Name of the eikonal kernel the plan launches ("k_fmm_coh<8>", "k_fmm_duo", "k_fmm<2>", ...): chosen from the
+ * number of solves and the grid size. */
+const char* dazim_plan_eikonal_kernel(const dazim_plan* plan);
 int dazim_plan_device_ptrs(dazim_plan* plan, void** dsurf, void** obsTaa, void** rowptr, void** col,
                            void** val);
 void dazim_plan_destroy(dazim_plan* plan);

@@ -112,20 +112,21 @@ def test_plan_iterate_matches_oracle(gpu, oracle, test1, iso):
     assert np.isclose(s["mean_weight"], float(np.cumsum(ow, dtype=F32)[-1] / F32(sv.dall)), rtol=1e-6)
     assert (s["nar1"], s["nar"], s["count3"]) == (g["nar"], len(rw_all), tk["count3"])
     # the solve: same stopping rule, the iterate to float32 round-off of 8-90 LSMR iterations
-    assert s["lsmr"]["istop"] == oinfo["istop"] and abs(s["lsmr"]["itn"] - oinfo["itn"]) <= max(1, 0.03 * oinfo["itn"])
+    assert s["lsmr"]["istop"] == oinfo["istop"] and abs(s["lsmr"]["itn"] - oinfo["itn"]) <= 1
     scale = np.abs(odv).max()
     assert scale > 1e-3
     from conftest import note
     note("iteration tail iso=%s: LSMR itn gpu %d / oracle %d, max|dv - dv_oracle| = %.2e x max|dv|" % (
         iso, s["lsmr"]["itn"], oinfo["itn"], np.abs(r["dv"] - odv).max() / scale))
-    assert np.abs(r["dv"] - odv).max() <= 5e-3 * scale, np.abs(r["dv"] - odv).max() / scale
-    assert np.abs(r["vsf"] - ovsf).max() <= 5e-3 * scale + 1e-6
+    # the iterate agrees with the oracle's to 2e-4 of its size (measured 1e-6 / 7e-6: parity_notes)
+    assert np.abs(r["dv"] - odv).max() <= 2e-4 * scale, np.abs(r["dv"] - odv).max() / scale
+    assert np.abs(r["vsf"] - ovsf).max() <= 2e-4 * scale + 1e-6
     assert np.array_equal(r["vsf"][:, :, -1], vs[:, :, -1]) and np.array_equal(r["vsf"][0], vs[0])
     if iso:
         dws = np.bincount(g["col"] - 1, weights=np.abs(orww).astype(np.float64), minlength=maxvp)
         assert np.allclose(r["dws"], dws, rtol=1e-5, atol=1e-6)
     else:
-        assert np.abs(r["gcf"] - ogc).max() <= 5e-3 * scale and np.abs(r["gsf"] - ogs).max() <= 5e-3 * scale
+        assert np.abs(r["gcf"] - ogc).max() <= 2e-4 * scale and np.abs(r["gsf"] - ogs).max() <= 2e-4 * scale
     for k in ("VsNorm2", "VswNorm2", "GcsNorm2", "GcswNorm2", "Mnorm2", "MwNorm2"):
         assert np.isclose(s["norms"][k], onm[k], rtol=2e-2, atol=1e-6), (k, s["norms"][k], onm[k])
     tscale = np.abs(cbst).max()
