@@ -93,9 +93,9 @@ def _measured_traffic(workload_name, solves, kernel):
         key = workload_name.split("-")[0]
         per_solve = d.get("bytes_per_solve_by_kernel", {}).get(kernel, {}).get(key)
         if per_solve is None:
-            if kernel == "k_fmm_duo" and key + "_duo" in d["bytes_per_solve"]:
+            if kernel.startswith("k_fmm_duo") and key + "_duo" in d["bytes_per_solve"]:
                 key += "_duo"
-            elif not kernel.startswith("k_fmm<") and kernel != "k_fmm_duo":
+            elif not kernel.startswith("k_fmm<") and not kernel.startswith("k_fmm_duo"):
                 return None
             per_solve = d["bytes_per_solve"].get(key)
         return None if per_solve is None else float(per_solve) * solves
@@ -242,8 +242,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="S200")
-    ap.add_argument("--cpu-sources", type=int, default=640,
-                    help="sources of period 1 in the CPU sample (640 ~ 8-10 s of wall time on 16 cores for S200)")
+    ap.add_argument("--cpu-sources", type=int, default=320,
+                    help="sources in one CPU slice, spread over all periods (320 ~ 8 s of wall time on 16 cores for S200)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()

@@ -21,8 +21,8 @@ cudaError_t upload_basis(const float* ub, const float* cb);
 cudaError_t launch_dice_coarse(const GridC& g, int nper, const float* velv, float* veln, float* slow, cudaStream_t st);
 cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
-cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas);
-cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st);
+cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int minb, int* nctas);
+cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, int minb, cudaStream_t st);
 cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int* nctas);
 cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, cudaStream_t st);
 cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, int nnz_tiled, float* ttn, int* nsts,
@@ -195,6 +195,7 @@ struct dazim_plan {
   int nctas = 0;
   DBuf<unsigned short> d_map; DBuf<int> d_skey; DBuf<float> d_sval;
   int duo = 0;   // latency mode: one two-warp CTA per solve (k_fmm_duo)
+  int duo_minb = 10;   // its register budget: 10 CTAs per SM (96 registers) or 16 (64 registers, 1.6 x the solves in flight)
   int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
   int coh = 8;   // solves per heap warp of the cohort kernel (8 / 16 / 32; 8 measured best); 0: the one-thread-per-solve kernel
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
@@ -288,13 +289,24 @@ static int legacy_fmm_config(dazim_plan* P, long long nsrc, int hneed, int hmin,
   dazim_handle* h = P->h;
   const GridC& g = P->g;
   int nctas = 1;
+  // Measured on S200 (profiles/r2_k3_kernel_choice.md): every solve resident in the two-warp kernel wins up to its
+  // capacity -- 1 480 solves with 96 registers, 2 368 with 64 (1 000 solves: 1.91 s / 2.01 s against 2.68 s for the
+  // half-warp kernel; 2 000 solves: 4.13 s in two waves of the 96-register build, 3.16 s in one wave of the 64-register
+  // build, 3.67 s half-warp) -- beyond that the half-warp throughput kernel.
   P->hcap = hneed;
   P->spc = 1;
   P->duo = 1;
-  CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+  P->duo_minb = 10;
+  if (const char* e = getenv("DAZIM_DUO_MINB")) P->duo_minb = atoi(e) >= 16 ? 16 : 10;
+  CK(fmm_duo_max_ctas(P->hcap, h->nsm, P->duo_minb, &nctas));
   while (nctas < nsrc && P->hcap > 2048) {     // every solve resident with a (rarely spilling) smaller heap?
     P->hcap /= 2;
-    CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+    CK(fmm_duo_max_ctas(P->hcap, h->nsm, P->duo_minb, &nctas));
+  }
+  if (nctas < nsrc && P->duo_minb == 10 && !getenv("DAZIM_DUO_MINB")) {
+    int n16 = 0;
+    CK(fmm_duo_max_ctas(P->hcap, h->nsm, 16, &n16));
+    if (n16 >= nsrc) { P->duo_minb = 16; nctas = n16; }
   }
   if (nctas < nsrc) {
     P->duo = 0;
@@ -311,7 +323,7 @@ static int legacy_fmm_config(dazim_plan* P, long long nsrc, int hneed, int hmin,
     if (const char* e = getenv("DAZIM_SPC")) P->spc = atoi(e) == 1 ? 1 : 2;
     if (P->duo) P->spc = 1;
     if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(64, (atoi(e) + 1) & ~1);
-    if (P->duo) CK(fmm_duo_max_ctas(P->hcap, h->nsm, &nctas));
+    if (P->duo) CK(fmm_duo_max_ctas(P->hcap, h->nsm, P->duo_minb, &nctas));
     else CK(fmm_max_ctas(P->hcap, P->spc, h->nsm, &nctas));
     if (const char* e = getenv("DAZIM_NCTAS")) nctas = std::max(1, std::min(nctas, atoi(e)));
   }
@@ -393,7 +405,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     int nc_l = 1;
     int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nc_l);
     if (st_l) { plan_free(P); return st_l; }
-    auto_tps = (!P->duo && hneed >= 2048 && nsrc > (long long)P->spc * nc_l) ? 1 : 0;
+    auto_tps = (!P->duo && hneed >= 2048 && 10 * nsrc > 9 * (long long)P->spc * nc_l) ? 1 : 0;
   }
   P->tps = auto_tps;
   if (getenv("DAZIM_DUO") || getenv("DAZIM_SPC")) P->tps = 0;
@@ -650,7 +662,7 @@ static int plan_run_once(dazim_plan* P) {
         CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + Lc - 1) / Lc), P->coh, st));
         T.n_launch++;      // + k_tps_init
       }
-      else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), st));
+      else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), P->duo_minb, st));
       else CK(launch_fmm(F, std::min(P->nctas, (F.nsrc + P->spc - 1) / P->spc), st));
       T.n_launch++; T.n_fmm_launch++;
     }
@@ -816,7 +828,7 @@ extern "C" int dazim_plan_fetch(dazim_plan* P, float* dsurf, float* taa, long lo
 extern "C" const char* dazim_plan_eikonal_kernel(const dazim_plan* P) {
   if (!P) return "";
   if (P->tps) return P->coh == 8 ? "k_fmm_coh<8>" : (P->coh == 16 ? "k_fmm_coh<16>" : (P->coh == 32 ? "k_fmm_coh<32>" : "k_fmm_tps"));
-  return P->duo ? "k_fmm_duo" : (P->spc == 2 ? "k_fmm<2>" : "k_fmm<1>");
+  return P->duo ? (P->duo_minb >= 16 ? "k_fmm_duo<16>" : "k_fmm_duo<10>") : (P->spc == 2 ? "k_fmm<2>" : "k_fmm<1>");
 }
 
 extern "C" int dazim_plan_device_ptrs(dazim_plan* P, void** dsurf, void** taa, void** rowptr, void** col, void** val) {

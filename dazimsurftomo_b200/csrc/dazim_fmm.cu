@@ -1026,15 +1026,10 @@ __global__ void __launch_bounds__(64, MINB) k_fmm_duo(FmmArgs A) {
   }
 }
 
-// MINB = 10: 96 registers (fastest single solve); MINB = 16: 64 registers, more solves per SM
-static int duo_minb() {
-  const char* e = getenv("DAZIM_DUO_MINB");
-  return (e && atoi(e) >= 16) ? 16 : 10;
-}
-
-cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas) {
+// MINB = 10: 96 registers (fastest single solve, 1 480 solves per chip); MINB = 16: 64 registers, 2 368 solves per chip
+cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int minb, int* nctas) {
   const size_t smem = (size_t)hcap * 8 + 128;
-  const void* fn = duo_minb() == 16 ? (const void*)k_fmm_duo<16> : (const void*)k_fmm_duo<10>;
+  const void* fn = minb >= 16 ? (const void*)k_fmm_duo<16> : (const void*)k_fmm_duo<10>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -1044,9 +1039,9 @@ cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int* nctas) {
   return cudaSuccess;
 }
 
-cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, cudaStream_t st) {
+cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, int minb, cudaStream_t st) {
   const size_t smem = (size_t)A.hcap * 8 + 128;
-  const bool wide = duo_minb() == 16;
+  const bool wide = minb >= 16;
   const void* fn = wide ? (const void*)k_fmm_duo<16> : (const void*)k_fmm_duo<10>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

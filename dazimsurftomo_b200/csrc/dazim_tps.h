@@ -409,18 +409,15 @@ TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const u
 TPS_HD void tps_pop(TpsState& S, const TpsPre& P) { tps_pop_root(S, P.last); }
 // (4) ... then insert / update the four neighbours in the reference order x-1, x+1, z-1, z+1 (addtree / updtree,
 //     CalSurfG.f90:738-774, :864-890).  A close neighbour's position was read by the stencil warp BEFORE the pop, so
-//     it is verified against the heap ("does that slot hold the neighbour?").  The slot and the first THREE ancestors
-//     of every neighbour's start position are fetched together: one round trip for the whole step in the common case.
-//     (With one lane per solve a heap warp pays for the slowest lane: a dependent global load inside the sift-up of
-//     ANY lane stalls all of them, and with 8-32 lanes some lane moves an entry in the spilled levels nearly every
-//     step -- measured 4 000 of 9 200 cycles.)  Entries written by an earlier neighbour of the same step are patched
-//     into what later neighbours hold in registers; a close neighbour that an earlier sift-up moved falls back to the
-//     plain loop.
+//     it is verified against the heap ("does that slot hold the neighbour?") together with the fetch of its parent:
+//     one round trip for the four neighbours; only a position the pop really moved is re-read from E.  The common
+//     case "the new key is not smaller than its parent" is a single store.  (Fetching three ancestor levels per
+//     neighbour up front was tried and measured slower: 11 600 against 9 200 cycles per round on S200 -- the extra
+//     loads and register patching cost more than the rare multi-level move saves; profiles/r2_k3_cohort_cycle_split.txt.)
 template <int URG>
 TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
-  int qst[4], spos[4], apos[4][3];
-  int2 sent[4], anc[4][3];
-  bool fresh[4];
+  int qst[4], spos[4], ppos[4];
+  int2 pent[4], sent[4];
   int nins = 0;
   TPS_TICK0(S);
 #if defined(__CUDA_ARCH__)
@@ -440,27 +437,20 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
     spos[q] = 0;
     if (qst[q] == 1) spos[q] = N[q].qid;
     else if (qst[q] == -1) spos[q] = ++nt;
-    const bool on = (qst[q] == 1 || qst[q] == -1);
+    ppos[q] = spos[q] >> 1;
     sent[q] = make_int2(0, -1);
+    pent[q] = make_int2(0, 0);
     if (qst[q] == 1 && spos[q] >= 1 && spos[q] <= S.ntr) sent[q] = tps_hget(S, spos[q]);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 3; ++j) {
-      apos[q][j] = on ? (spos[q] >> (j + 1)) : 0;
-      anc[q][j] = make_int2(0, 0);
-      if (apos[q][j] > 0) anc[q][j] = tps_hget(S, apos[q][j]);
-    }
-    fresh[q] = true;
+    if ((qst[q] == 1 || qst[q] == -1) && ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]);
   }
-  TPS_TICK(S, 3);      // 3: statuses, issue of the slot + ancestor loads
+  TPS_TICK(S, 3);      // 3: statuses, issue of the slot + parent loads
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    if (qst[q] == 1 && sent[q].y != N[q].co) {       // moved by the pop: take the fresh back pointer, plain loop below
+    if (qst[q] == 1 && sent[q].y != N[q].co) {       // moved by the pop: take the fresh back pointer
       spos[q] = (int)(S.E[N[q].co] & ~E_SIGN);
-      fresh[q] = false;
+      ppos[q] = -1;                                   // parent is fetched below
     }
   }
   TPS_TICK(S, 4);      // 4: wait for the loads + verification
@@ -472,79 +462,36 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
     if (qst[q] == -1) S.ntr += 1;
     const float k = N[q].qt;
     int tpc = spos[q];
-    int j = 0;
-    bool more = true;                     // the key may still have to move above position tpc
-    if (fresh[q]) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int jj = 0; jj < 3; ++jj) {
-        if (more && jj == j) {
-          if (apos[q][jj] > 0 && k < TKEY(anc[q][jj])) {
-            // parent moves down to tpc (addtree / updtree); keep later neighbours' registers coherent
-            const int2 par = anc[q][jj];
-            tps_hput(S, tpc, par);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int r = 0; r < 4; ++r) {
-              if (r > q) {
-                if (qst[r] == 1 && N[r].co == par.y) { spos[r] = tpc; fresh[r] = false; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int a = 0; a < 3; ++a)
-                  if (apos[r][a] == tpc) anc[r][a] = par;
-              }
-            }
-            tpc = apos[q][jj];
-            j = jj + 1;
-          } else {
-            more = false;
-          }
-        }
-      }
-    }
-    TPS_TICK(S, 6);    // 6: prefetched levels
-    if (more) {
-      // beyond the prefetched ancestors (or a neighbour whose registers are stale): plain sift-up
-      int tpp = tpc >> 1;
-      while (tpp > 0) {
-        const int2 par = tps_hget(S, tpp);
-        if (!(k < TKEY(par))) break;
+    if ((tpc >> 1) != ppos[q]) { ppos[q] = tpc >> 1; if (ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]); }   // moved earlier in this step
+    TPS_TICK(S, 6);    // 6: set-up of neighbour q
+    if (ppos[q] > 0 && k < TKEY(pent[q])) {
+      // the key moves up: generic loop (addtree / updtree sift-up), patching what later neighbours hold in registers
+      int tpp = ppos[q];
+      int2 par = pent[q];
+      for (;;) {
         tps_hput(S, tpc, par);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int r = 0; r < 4; ++r) {
-          if (r > q) {
-            if (qst[r] == 1 && N[r].co == par.y) { spos[r] = tpc; fresh[r] = false; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int a = 0; a < 3; ++a)
-              if (apos[r][a] == tpc) anc[r][a] = par;
-          }
+          if (r > q && qst[r] == 1 && N[r].co == par.y) spos[r] = tpc;    // a later close neighbour moved down
+          if (r > q && ppos[r] == tpc) pent[r] = par;                     // a later parent slot changed content
         }
         tpc = tpp;
         tpp = tpc >> 1;
+        if (tpp == 0) break;
+        par = tps_hget(S, tpp);
+        if (!(k < TKEY(par))) break;
       }
     }
-    TPS_TICK(S, 7);    // 7: plain loop
+    TPS_TICK(S, 7);    // 7: move loop
     const int2 e = make_int2(tps_as_int(k), N[q].co);
     tps_hput(S, tpc, e);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int r = 0; r < 4; ++r) {
-      if (r > q) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int a = 0; a < 3; ++a)
-          if (apos[r][a] == tpc) anc[r][a] = e;
-      }
-    }
+    for (int r = 0; r < 4; ++r)
+      if (r > q && ppos[r] == tpc) pent[r] = e;
     TPS_TICK(S, 8);    // 8: placement + patches
   }
   return true;
