@@ -229,14 +229,26 @@ def read_surfdata(path: str, kmax: int) -> Survey:
                 t = line[1:].split()
                 lat, lon, period, wavetp, veltp = float(t[0]), float(t[1]), int(t[2]), int(t[3]), int(t[4])
                 if wavetp == 2 and veltp == 0:
-                    knum = period
+                    new_knum = period
                 else:
                     raise ValueError("can only deal with Rayleigh wave phase velocity data")
+                if not 1 <= new_knum <= kmax:
+                    raise ValueError("period index %d of source block '%s' is outside 1..%d (kmaxRc of para.in)"
+                                     % (new_knum, line.strip(), kmax))
+                # The reference resets its source counter when the period index changes (Main_Jt.f90:283-286,
+                # MainForward.f90:248-251): a period that re-appears later in the file silently OVERWRITES its earlier
+                # sources while the ray counter keeps running.  That is a corrupt input, not a feature: refuse it.
+                if new_knum != knum and (src_lat[new_knum - 1]):
+                    raise ValueError("period index %d appears in two separate groups of the data file; the reference "
+                                     "would overwrite the first group (Main_Jt.f90:283-286): sort the file by period" % new_knum)
+                knum = new_knum
                 k = knum - 1
                 src_lat[k].append(lat); src_lon[k].append(lon)
                 src_per[k].append(period); src_wt[k].append(wavetp); src_vt[k].append(veltp)
                 rec[k].append([])
             else:
+                if knum == 0:
+                    raise ValueError("data line before the first '#' source line")
                 t = line.split()
                 rec[knum - 1][-1].append((float(t[0]), float(t[1])))
                 vels.append(float(t[2]))

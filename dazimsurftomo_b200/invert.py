@@ -17,6 +17,12 @@ per-row travel-time columns.  Files written (same names and formats as the refer
     DSurfTomo.inv  Gc_Gs_model.inv  MOD_Ref  period_phaseVMOD.dat  phaseV_FWD.dat  period_Azm_tomo.inv
     IterVel.out  Traveltime_statis_00th.dat  <para.in>_inv.log  lsmr.txt (one summary line per outer iteration)
 
+Deliberate deviations in ISOTROPIC mode (iso_mod = T), where the reference's own outputs are degenerate: CalSurfG has no
+tRcV argument, so Main_Jt.f90 writes zeros into period_phaseVMOD.dat / phaseV_FWD.dat and an all-zero
+period_Azm_tomo.inv (:784-787).  This driver writes the real phase velocities of the final model into the first two and
+does not write period_Azm_tomo.inv (there is no anisotropy to map).  Everything else, and every file in joint mode, has the
+reference's names, column layout and formats.
+
 There is no CPU fallback: everything numerical happens in libdazim_b200.so.
 """
 from __future__ import annotations
@@ -154,8 +160,12 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
                 torch.cuda.synchronize()
                 gpu_ms["gather"] = gpu_ms.get("gather", 0.0) + (time.perf_counter() - t0) * 1e3
                 nnz_all = system["nnz"]
-            maxnar = int(np.float32(p.spfra) * sv.dall * nx * ny * nz * 3)
-            if nnz_all > maxnar:                       # Main_Jt.f90:523
+            # maxnar = spfra*dall*nx*ny*nz*3 in default-real arithmetic (Main_Jt.f90:325); the reference tests nar AFTER
+            # the regularisation rows are appended (Main_Jt.f90:513-523)
+            maxnar = int(np.float32(np.float32(np.float32(np.float32(np.float32(p.spfra) * np.float32(sv.dall)) * np.float32(nx))
+                                               * np.float32(ny)) * np.float32(nz)) * np.float32(3))
+            nar_with_reg = nnz_all + (1 if iso_inv else 3) * partition.tikh_block_entries(nx, ny, nz)
+            if nar_with_reg > maxnar:
                 raise api.DazimError(3, "increase sparsity fraction(spfra)")
             tRcV = fm.interior_phase_velocity(tables["pvRc"], nx, ny)
             if it == 1:
