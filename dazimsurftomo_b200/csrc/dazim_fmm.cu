@@ -1167,7 +1167,12 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
     const bool any = __any_sync(0xffffffffu, run);
     if (lane == 0) xch[4 * LANES] = any ? 1 : 0;
     coh_arrive<NT>(COH_X);
-    if (!any) break;
+    if (!any) {
+      // end of this march: wait until every stencil thread has READ the stop flag before the exchange area is
+      // written again (the next march posts its first round right after the hand-off; found by racecheck)
+      coh_sync<NT>(COH_Y);
+      break;
+    }
     if (prof) { t1 = clock64(); c_pre += t1 - t0; t0 = t1; }
     if (run) tps_pop(S, P);                          // sift the root down while the stencil threads work
     if (prof) { __syncwarp(); t1 = clock64(); c_pop += t1 - t0; t0 = t1; }
@@ -1206,7 +1211,7 @@ __device__ void coh_march_stencil(const TpsGrid& G, volatile int* xch, const int
   constexpr int RES = 4 * LANES + 32;
   for (;;) {
     coh_sync<NT>(COH_X);
-    if (!xch[4 * LANES]) break;
+    if (!xch[4 * LANES]) { coh_arrive<NT>(COH_Y); break; }      // acknowledge the stop flag (see coh_march_heap)
     const int pn = xch[l];
     if (pn >= 0) {
       const TpsNb R = tps_neighbour<URG>(G, xch[LANES + l], xch[2 * LANES + l], (unsigned)xch[3 * LANES + l], q);
