@@ -5,7 +5,8 @@
 // The two products of an iteration, y += A x and x += A^T y, are the only O(nnz) work and are
 // HBM-bound (8 B per non-zero: value + index; the gathered vector lives in L2).  The COO triplets are
 // turned once into CSR (for A x) and CSC (for A^T y) with a stable radix sort, so both products are
-// race-free, deterministic row/column reductions (one warp per row or column) instead of atomics.
+// race-free, deterministic reductions instead of atomics: one warp per row for A x; for A^T y one warp per SEGMENT of a
+// column (<= 4 096 entries) and an in-order add of a column's partials (a column of G is long and there are few).
 // Vector norms are two-stage deterministic reductions accumulated in double.  The scalar recurrences of LSMR
 // (lsmrModule.f90:470-640) run ON THE DEVICE, in float and in the Fortran's operation order, inside the single-thread
 // tails of the norm reductions; every kernel of an iteration starts with "if (state->istop) return", so the host
@@ -84,6 +85,49 @@ __global__ void __launch_bounds__(256) k_spmv_add(int nrow, const long long* __r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0 && e > b) y[w] = y[w] + acc;
+}
+
+// Segmented product for the TRANSPOSED matrix (CSC): a column of G holds the entries of one model cell in every ray that
+// sees it -- 15 000 entries per column and only a few thousand columns at test3 size, so one warp per column leaves the
+// chip idle and runs a long dependent loop (measured 632 us against 149 us for the row product on the same 94 M
+// entries).  Columns are cut into segments of at most `seg` entries (every column boundary is a segment boundary),
+// one warp reduces one segment, and a second kernel adds the partials of a column in segment order: same work,
+// deterministic, 180 k warps instead of 2-6 k.  state == nullptr: unconditional (set-up product).
+struct LsmrState;
+__device__ inline bool lsmr_skip(const LsmrState* S, int need_beta);
+__global__ void __launch_bounds__(256) k_spmv_seg(int nseg, const long long* __restrict__ seg_off, const int* __restrict__ idx,
+                                                   const float* __restrict__ val, const float* __restrict__ x,
+                                                   float* __restrict__ partial, const LsmrState* __restrict__ S, int need_beta) {
+  if (S && lsmr_skip(S, need_beta)) return;
+  const int lane = threadIdx.x & 31;
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= nseg) return;
+  const long long b = seg_off[w], e = seg_off[w + 1];
+  float acc = 0.0f;
+  long long k = b + lane;
+  for (; k + 96 < e; k += 128) {
+    const float v0 = val[k], v1 = val[k + 32], v2 = val[k + 64], v3 = val[k + 96];
+    const int i0 = idx[k], i1 = idx[k + 32], i2 = idx[k + 64], i3 = idx[k + 96];
+    acc += v0 * x[i0];
+    acc += v1 * x[i1];
+    acc += v2 * x[i2];
+    acc += v3 * x[i3];
+  }
+  for (; k < e; k += 32) acc += val[k] * x[idx[k]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) partial[w] = acc;
+}
+__global__ void k_seg_reduce_add(int ncol, const int* __restrict__ colseg, const float* __restrict__ partial,
+                                 float* __restrict__ y, const LsmrState* __restrict__ S, int need_beta) {
+  if (S && lsmr_skip(S, need_beta)) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  const int b = colseg[c], e = colseg[c + 1];
+  if (e <= b) return;
+  float acc = partial[b];
+  for (int s = b + 1; s < e; ++s) acc += partial[s];
+  y[c] = y[c] + acc;
 }
 
 // stage 1 of a deterministic reduction: partial[b] = sum over the block's slice of a[i]*b[i] (double)
@@ -166,6 +210,8 @@ struct LsmrState {
   int localVecs, localPointer, queueFull;
 };
 
+__device__ inline bool lsmr_skip(const LsmrState* S, int need_beta) { return S->istop || (need_beta && !S->beta_pos); }
+
 __device__ __host__ inline float d2norm(float a, float b) {      // lsmrModule.f90:686-711
   const float scale = fabsf(a) + fabsf(b);
   if (scale == 0.0f) return 0.0f;
@@ -224,16 +270,23 @@ __global__ void __launch_bounds__(256) k_dot_partial_state(const float* __restri
     partial[blockIdx.x] = s;
   }
 }
+// sum of the block partials by ONE WARP in a fixed order (lane l adds partials l, l+32, ...; then a fixed shuffle tree):
+// deterministic, and 20 us shorter per norm than a single thread walking 592 doubles
 __device__ inline float final_norm(const double* partial, int nb) {
+  const int lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int i = 0; i < nb; ++i) s += partial[i];
+  for (int i = lane; i < nb; i += 32) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return (float)sqrt(s);
 }
 // beta = ||u|| (lsmrModule.f90:484) + the bookkeeping of the local reorthogonalisation queue (:489-497)
 __global__ void k_tail_beta(const double* __restrict__ partial, int nb, LsmrState* S) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || S->istop) return;
+  if (blockIdx.x != 0 || S->istop) return;
+  const float nrm = final_norm(partial, nb);
+  if (threadIdx.x != 0) return;
   S->itn = S->itn + 1;
-  S->beta = final_norm(partial, nb);
+  S->beta = nrm;
   S->beta_pos = S->beta > 0.0f ? 1 : 0;
   if (S->beta_pos && S->localVecs > 0) {
     if (S->localPointer < S->localVecs) S->localPointer = S->localPointer + 1;
@@ -248,8 +301,10 @@ __global__ void k_store_local(float* __restrict__ localV, const float* __restric
 // alpha = ||v|| (:505) and every scalar recurrence up to the coefficients of the vector update (:514-541) and the
 // norm estimates that do not need ||x|| (:548-590)
 __global__ void k_tail_alpha(const double* __restrict__ partial, int nb, LsmrState* S) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || S->istop) return;
-  if (S->beta_pos) S->alpha = final_norm(partial, nb);
+  if (blockIdx.x != 0 || S->istop) return;
+  const float nrm = S->beta_pos ? final_norm(partial, nb) : 0.0f;     // beta_pos is warp-uniform
+  if (threadIdx.x != 0) return;
+  if (S->beta_pos) S->alpha = nrm;
   const float alpha = S->alpha, beta = S->beta, damp = S->damp;
   const float alphahat = d2norm(S->alphabar, damp);
   const float chat = S->alphabar / alphahat, shat = damp / alphahat;
@@ -308,8 +363,10 @@ __global__ void k_update_state(float* __restrict__ hbar, float* __restrict__ h, 
 }
 // normx = ||x|| (:592) and the stopping tests (:596-640)
 __global__ void k_tail_normx(const double* __restrict__ partial, int nb, LsmrState* S) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || S->istop) return;
-  S->normx = final_norm(partial, nb);
+  if (blockIdx.x != 0 || S->istop) return;
+  const float nrm = final_norm(partial, nb);
+  if (threadIdx.x != 0) return;
+  S->normx = nrm;
   const float normA = S->normA, normx = S->normx, normb = S->normb;
   const float test1 = S->normr / normb, test2 = S->normAr / (normA * S->normr), test3 = 1.0f / S->condA;
   const float t1 = test1 / (1.0f + normA * normx / normb);
@@ -451,6 +508,35 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   if (rc) return rc;
   rc = compress(st, nnz, n, k_col, k_row, k_val, csc_ptr.p, csc_idx.p, csc_val.p);
   if (rc) return rc;
+  // ---- segments of the transposed product (k_spmv_seg): at most `seg` entries each, never across a column boundary ----
+  Buf<long long> seg_off;
+  Buf<int> colseg;
+  Buf<float> seg_partial;
+  int nseg = 0;
+  {
+    std::vector<long long> hptr((size_t)n + 1);
+    LCK(cudaMemcpyAsync(hptr.data(), csc_ptr.p, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    LCK(cudaStreamSynchronize(st));
+    long long seg = (nnz / 65536 + 127) / 128 * 128;           // ~64 k segments on a big system
+    seg = std::max<long long>(256, std::min<long long>(4096, seg));
+    if (const char* e = getenv("DAZIM_LSMR_SEG")) seg = std::max(32, atoi(e));
+    std::vector<long long> hoff;
+    std::vector<int> hcs((size_t)n + 1);
+    hoff.reserve((size_t)(nnz / seg) + n + 2);
+    for (int c = 0; c < n; ++c) {
+      hcs[c] = (int)hoff.size();
+      for (long long b = hptr[c]; b < hptr[c + 1]; b += seg) hoff.push_back(b);
+    }
+    hcs[n] = (int)hoff.size();
+    nseg = (int)hoff.size();
+    hoff.push_back(hptr[n]);
+    // a segment ends where the next one starts; the last segment of a column ends at the column's end = the next start
+    LCK(seg_off.alloc(hoff.size(), st)); LCK(colseg.alloc((size_t)n + 1, st)); LCK(seg_partial.alloc((size_t)std::max(nseg, 1), st));
+    LCK(cudaMemcpyAsync(seg_off.p, hoff.data(), sizeof(long long) * hoff.size(), cudaMemcpyHostToDevice, st));
+    LCK(cudaMemcpyAsync(colseg.p, hcs.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+    LCK(cudaStreamSynchronize(st));
+  }
+  const unsigned gws = (unsigned)(((long long)std::max(nseg, 1) * 32 + 255) / 256);
   // ---- vectors ----
   const int localVecs = std::max(0, std::min(localSize, std::min(m, n)));
   Buf<float> u, v, h, hbar, dx, localV, scal;
@@ -460,7 +546,7 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   LCK(localV.alloc((size_t)localVecs * n, st)); LCK(scal.alloc(4, st)); LCK(partial.alloc(1024, st)); LCK(dS.alloc(1, st));
   Ctx c{st, partial.p, scal.p, 592};
   const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256);
-  const unsigned gwm = (unsigned)(((long long)m * 32 + 255) / 256), gwn = (unsigned)(((long long)n * 32 + 255) / 256);
+  const unsigned gwm = (unsigned)(((long long)m * 32 + 255) / 256);
   LCK(cudaMemcpyAsync(u.p, b, sizeof(float) * m, cudaMemcpyDefault, st));     // b may live on the host or in HBM
   LCK(cudaMemsetAsync(v.p, 0, sizeof(float) * n, st));
   LCK(cudaMemsetAsync(dx.p, 0, sizeof(float) * n, st));
@@ -471,7 +557,8 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   if ((rc = norm2(c, u.p, m, &beta))) return rc;
   if (beta > 0.0f) {
     k_scal<<<gm, 256, 0, st>>>(u.p, m, 1.0f / beta);
-    k_spmv_add<<<gwn, 256, 0, st>>>(n, csc_ptr.p, csc_idx.p, csc_val.p, u.p, v.p);      // v = v + A^T u
+    k_spmv_seg<<<gws, 256, 0, st>>>(nseg, seg_off.p, csc_idx.p, csc_val.p, u.p, seg_partial.p, nullptr, 0);   // v = v + A^T u
+    k_seg_reduce_add<<<gn, 256, 0, st>>>(n, colseg.p, seg_partial.p, v.p, nullptr, 0);
     if ((rc = norm2(c, v.p, n, &alpha))) return rc;
   }
   if (alpha > 0.0f) k_scal<<<gn, 256, 0, st>>>(v.p, n, 1.0f / alpha);
@@ -503,7 +590,8 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
       k_scal_state<<<gm, 256, 0, st>>>(u.p, m, S, 1);                                                  // u = u / beta
       if (localOrtho) k_store_local<<<gn, 256, 0, st>>>(localV.p, v.p, n, S);
       k_scal_state<<<gn, 256, 0, st>>>(v.p, n, S, 2);                                                  // v = -beta v
-      k_spmv_add_state<<<gwn, 256, 0, st>>>(n, csc_ptr.p, csc_idx.p, csc_val.p, u.p, v.p, S, 1);       // v = v + A^T u
+      k_spmv_seg<<<gws, 256, 0, st>>>(nseg, seg_off.p, csc_idx.p, csc_val.p, u.p, seg_partial.p, S, 1);     // v = v + A^T u
+      k_seg_reduce_add<<<gn, 256, 0, st>>>(n, colseg.p, seg_partial.p, v.p, S, 1);
       if (localOrtho) k_reorth_state<<<1, 1024, 0, st>>>(v.p, localV.p, n, S);
       k_dot_partial_state<<<nbn, 256, 0, st>>>(v.p, n, partial.p, S, 1);
       k_tail_alpha<<<1, 32, 0, st>>>(partial.p, nbn, S);                                               // alpha + recurrences
