@@ -304,12 +304,14 @@ static int legacy_fmm_config(dazim_plan* P, long long nsrc, int hneed, int hmin,
     CK(fmm_duo_max_ctas(P->hcap, h->nsm, P->duo_minb, &nctas));
   }
   if (nctas < nsrc && P->duo_minb == 10 && !getenv("DAZIM_DUO_MINB")) {
+    // 64-register build with a shared heap small enough for 16 CTAs per SM (2 368 solves per chip): a second wave
+    // costs a whole solve chain however few solves it holds, so the tier only applies when every solve is resident
+    const int h16 = std::min(P->hcap, 1536);
     int n16 = 0;
-    CK(fmm_duo_max_ctas(P->hcap, h->nsm, 16, &n16));
-    // a short second wave still beats the half-warp kernel (2 000 solves on 1 924 slots: 3.16 s against 3.67 s)
-    if (10 * (long long)n16 >= 9 * nsrc) { P->duo_minb = 16; nctas = n16; }
+    CK(fmm_duo_max_ctas(h16, h->nsm, 16, &n16));
+    if (n16 >= nsrc) { P->duo_minb = 16; P->hcap = h16; nctas = n16; }
   }
-  if (nctas < nsrc && !(P->duo_minb == 16 && 10 * (long long)nctas >= 9 * nsrc)) {
+  if (nctas < nsrc) {
     P->duo = 0;
     P->hcap = hneed;
     P->spc = 2;

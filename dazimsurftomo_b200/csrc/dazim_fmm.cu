@@ -1140,16 +1140,19 @@ __device__ __forceinline__ void coh_arrive(int id) {
   __threadfence_block();
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory");
 }
-// exchange area (ints): [0,L) node or -1, [L,2L) ix, [2L,3L) iz, [3L,4L) tself, [4L] any lane still running,
-// [4L + 32 + ((q*4 + k)*L + lane)] neighbour q, field k (0 status, 1 heap position read, 2 trial time, 3 offset)
+// exchange area: head[lane] = int4 (node or -1, ix, iz, tself) posted by the heap warp; flag (one int, "any lane still
+// running"); res[q * L + lane] = int4 (status, heap position read, trial time, offset) posted by the stencil thread of
+// neighbour q.  One 16-byte shared access per record; the named barriers order the accesses (no volatile needed).
 __host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 32 + 16 * L; }
 __host__ __device__ constexpr int coh_threads(int L) { return 32 + 4 * L; }
 
 template <int URG, int LANES>
-__device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch, const int lane, const bool act,
+__device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const int lane, const bool act,
                                unsigned long long& nacc, const bool prof) {
   constexpr int NT = coh_threads(LANES);
-  constexpr int RES = 4 * LANES + 32;
+  int4* head = reinterpret_cast<int4*>(xch);
+  volatile int* flag = xch + 4 * LANES;
+  const int4* res = reinterpret_cast<const int4*>(xch + 4 * LANES + 32);
   bool run = act;
   long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, t0 = 0, t1 = 0;
   unsigned long long rounds = 0;
@@ -1158,14 +1161,9 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
     TpsPre P;
     P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.last = make_int2(0, 0);
     if (run) run = tps_pre<URG>(S, G, nacc, P);
-    if (lane < LANES) {
-      xch[lane] = run ? P.pn : -1;
-      xch[LANES + lane] = P.ix;
-      xch[2 * LANES + lane] = P.iz;
-      xch[3 * LANES + lane] = (int)P.tself;
-    }
+    if (lane < LANES) head[lane] = make_int4(run ? P.pn : -1, P.ix, P.iz, (int)P.tself);
     const bool any = __any_sync(0xffffffffu, run);
-    if (lane == 0) xch[4 * LANES] = any ? 1 : 0;
+    if (lane == 0) *flag = any ? 1 : 0;
     coh_arrive<NT>(COH_X);
     if (!any) {
       // end of this march: wait until every stencil thread has READ the stop flag before the exchange area is
@@ -1182,10 +1180,8 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
       TpsNb N[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        N[q].qst = xch[RES + ((q * 4 + 0) * LANES + lane)];
-        N[q].qid = xch[RES + ((q * 4 + 1) * LANES + lane)];
-        N[q].qt = __int_as_float(xch[RES + ((q * 4 + 2) * LANES + lane)]);
-        N[q].co = xch[RES + ((q * 4 + 3) * LANES + lane)];
+        const int4 r = res[q * LANES + lane];
+        N[q].qst = r.x; N[q].qid = r.y; N[q].qt = __int_as_float(r.z); N[q].co = r.w;
       }
       run = tps_apply<URG>(S, G, N);
     }
@@ -1206,19 +1202,18 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, volatile int* xch,
 }
 
 template <int URG, int LANES>
-__device__ void coh_march_stencil(const TpsGrid& G, volatile int* xch, const int l, const int q) {
+__device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const int q) {
   constexpr int NT = coh_threads(LANES);
-  constexpr int RES = 4 * LANES + 32;
+  const int4* head = reinterpret_cast<const int4*>(xch);
+  volatile int* flag = xch + 4 * LANES;
+  int4* res = reinterpret_cast<int4*>(xch + 4 * LANES + 32);
   for (;;) {
     coh_sync<NT>(COH_X);
-    if (!xch[4 * LANES]) { coh_arrive<NT>(COH_Y); break; }      // acknowledge the stop flag (see coh_march_heap)
-    const int pn = xch[l];
-    if (pn >= 0) {
-      const TpsNb R = tps_neighbour<URG>(G, xch[LANES + l], xch[2 * LANES + l], (unsigned)xch[3 * LANES + l], q);
-      xch[RES + ((q * 4 + 0) * LANES + l)] = R.qst;
-      xch[RES + ((q * 4 + 1) * LANES + l)] = R.qid;
-      xch[RES + ((q * 4 + 2) * LANES + l)] = __float_as_int(R.qt);
-      xch[RES + ((q * 4 + 3) * LANES + l)] = R.co;
+    if (!*flag) { coh_arrive<NT>(COH_Y); break; }      // acknowledge the stop flag (see coh_march_heap)
+    const int4 hd = head[l];
+    if (hd.x >= 0) {
+      const TpsNb R = tps_neighbour<URG>(G, hd.y, hd.z, (unsigned)hd.w, q);
+      res[q * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
     }
     coh_arrive<NT>(COH_Y);
   }
@@ -1234,7 +1229,7 @@ __global__ void __launch_bounds__(32 + 4 * LANES, LANES == 32 ? 2 : (LANES == 16
   const GridC& g = A.g;
   const size_t ncoarse = (size_t)g.nnx * g.nnz;          // slow_c (plain column-major)
   const size_t ncf = coarse_field_size(g.nnx, g.nnz);    // E_c (interleaved layout)
-  volatile int* xch = reinterpret_cast<volatile int*>(smem_raw + (size_t)A.hcap * LANES * 8);
+  int* xch = reinterpret_cast<int*>(smem_raw + (size_t)A.hcap * LANES * 8);    // 16-byte aligned: hcap even, LANES >= 8
   TpsState S;
   S.sm = reinterpret_cast<int2*>(smem_raw) + l;
   S.stride = LANES;

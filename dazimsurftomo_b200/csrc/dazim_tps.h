@@ -321,6 +321,7 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
 // Grid view of one march
 struct TpsGrid {
   int nnx, nnz, ld;
+  float inv_ld;               // 1 / ld (ndecode)
   float dnx, dnz, earth;
   const float* slow;          // [ix * ld + iz] plain
   const float* risti_tab;     // [ix]
@@ -342,7 +343,7 @@ TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, Tps
   const int2 root = tps_hget(S, 1);
   P.pn = root.y;
   P.last = tps_hget(S, S.ntr);
-  ndecode<URG>(P.pn, G.ld, 1.0f / (float)G.ld, P.ix, P.iz);
+  ndecode<URG>(P.pn, G.ld, G.inv_ld, P.ix, P.iz);
   P.tself = (unsigned)root.x & ~E_SIGN;
   G.E[P.pn] = P.tself;                             // the popped node becomes alive with its trial value (= its heap key)
   if (URG == 1) {
@@ -589,7 +590,7 @@ TPS_HD void tps_handoff(TpsState& S, const GridC& g, const SrcRec& sr, const uns
 
 TPS_HD TpsGrid tps_grid_refined(const GridC& g, const SrcRec& sr, const float* slow_r, const float* risti_r, unsigned* E_r) {
   TpsGrid G;
-  G.nnx = sr.nnxr; G.nnz = sr.nnzr; G.ld = REF_LD; G.dnx = sr.dnxr; G.dnz = sr.dnzr; G.earth = g.earth;
+  G.nnx = sr.nnxr; G.nnz = sr.nnzr; G.ld = REF_LD; G.inv_ld = 1.0f / (float)REF_LD; G.dnx = sr.dnxr; G.dnz = sr.dnzr; G.earth = g.earth;
   G.slow = slow_r; G.risti_tab = risti_r; G.E = E_r;
   // exit tests literal to CalSurfG.f90:366-377 (vnr/vnb vs *refined* nnx/nnz)
   G.ex_l = sr.vnl != 1; G.ex_r = sr.vnr != sr.nnxr; G.ex_t = sr.vnt != 1; G.ex_b = sr.vnb != sr.nnzr;
@@ -597,7 +598,7 @@ TPS_HD TpsGrid tps_grid_refined(const GridC& g, const SrcRec& sr, const float* s
 }
 TPS_HD TpsGrid tps_grid_coarse(const GridC& g, const float* slow_c, const float* risti_c, unsigned* E_c) {
   TpsGrid G;
-  G.nnx = g.nnx; G.nnz = g.nnz; G.ld = g.nnz; G.dnx = g.dnx; G.dnz = g.dnz; G.earth = g.earth;
+  G.nnx = g.nnx; G.nnz = g.nnz; G.ld = g.nnz; G.inv_ld = 1.0f / (float)g.nnz; G.dnx = g.dnx; G.dnz = g.dnz; G.earth = g.earth;
   G.slow = slow_c; G.risti_tab = risti_c; G.E = E_c;
   G.ex_l = G.ex_r = G.ex_t = G.ex_b = false;
   return G;
