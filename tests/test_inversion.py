@@ -260,6 +260,13 @@ def test_unsorted_data_file_is_refused(tmp_path):
     mixed = tmp_path / "mixed.dat"
     order = sorted(range(len(blocks)), key=lambda i: (i % 2, i))          # interleave the periods
     mixed.write_text("".join("".join(blocks[i]) for i in order))
-    bad = fm.read_surfdata(str(mixed), 36)
+    # the reader itself refuses it now (forward.py is covered too): a period that re-appears later would overwrite its
+    # first group in the reference (Main_Jt.f90:283-286)
+    with pytest.raises(ValueError, match="two separate groups"):
+        fm.read_surfdata(str(mixed), 36)
+    # and the driver's own check still catches a survey whose row order differs from its file order
+    import copy
+    bad = copy.copy(good)
+    bad.dist = good.dist[::-1].copy()
     with pytest.raises(ValueError, match="not sorted by period"):
         invert.loop_order_obst(bad)
