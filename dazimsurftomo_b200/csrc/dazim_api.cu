@@ -433,6 +433,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
     nctas = std::min(nctas, ctas_needed);
     P->hspill = (std::max(16, hspill_full) + 1) & ~1;
+    if (const char* e = getenv("DAZIM_TPS_HSPILL")) P->hspill = (std::max(4, atoi(e)) + 1) & ~1;   // test hook: force the overflow fall-back
   }
   if (!P->tps) {
     int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nctas);

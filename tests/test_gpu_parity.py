@@ -541,3 +541,18 @@ def test_footprint_pool_grows_inside_plan_run(gpu, oracle, test1, test1_tables, 
     plan.close()
     assert np.array_equal(out["dsurf"], full["dsurf"]) and np.array_equal(out["val"], full["rw"])
     assert np.array_equal(out["col"], full["col"])
+
+
+def test_cohort_kernel_falls_back_when_its_heap_workspace_overflows(gpu, oracle, test1, test1_tables, monkeypatch):
+    """The cohort kernel's spill workspace is a bound on the narrow band (8 x grid edge + 1 024); if a solve ever outgrows
+    it the plan re-runs on the round-1 kernels instead of failing (plan_run).  Forced here with a 16-entry shared heap and
+    a 32-entry spill area: same travel times as the oracle."""
+    p = test1["para"]
+    monkeypatch.setenv("DAZIM_TPS", "1")
+    monkeypatch.setenv("DAZIM_HCAP", "16")
+    monkeypatch.setenv("DAZIM_TPS_HSPILL", "32")
+    r = gpu.FwdObsTraveltimeCPS(test1["vs"], test1["gc"], test1["gs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd,
+                                p.dvxd, p.dvzd, test1["sv"], tables=test1_tables)
+    o = oracle.gbuild(0, test1["vs"], test1["depz"], p.tRc, p.sublayers, p.goxd, p.gozd, p.dvxd, p.dvzd, test1["sv"],
+                      test1["gc"], test1["gs"], tables=test1_tables)
+    assert np.array_equal(r["dsurf"], o["dsurf"]) and np.array_equal(r["obsTaa"], o["obsTaa"])
