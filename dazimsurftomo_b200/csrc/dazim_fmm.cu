@@ -1172,20 +1172,22 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
       break;
     }
     if (prof) { t1 = clock64(); c_pre += t1 - t0; t0 = t1; }
-    if (run) tps_pop(S, P);                          // sift the root down while the stencil threads work
-    if (prof) { __syncwarp(); t1 = clock64(); c_pop += t1 - t0; t0 = t1; }
+    tps_pop<true>(S, P, run);                        // sift the root down while the stencil threads work (all lanes enter:
+                                                     // the routine holds the warp's reconvergence points)
+    if (prof) { t1 = clock64(); c_pop += t1 - t0; t0 = t1; }
     coh_sync<NT>(COH_Y);
     if (prof) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
-    if (run) {
+    {
       TpsNb N[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int4 r = res[q * LANES + lane];
+        int4 r = make_int4(0, 0, 0, 0);
+        if (run) r = res[q * LANES + lane];
         N[q].qst = r.x; N[q].qid = r.y; N[q].qt = __int_as_float(r.z); N[q].co = r.w;
       }
-      run = tps_apply<URG>(S, G, N);
+      run = tps_apply<URG, true>(S, G, N, run);
     }
-    if (prof) { __syncwarp(); t1 = clock64(); c_apply += t1 - t0; ++rounds; }
+    if (prof) { t1 = clock64(); c_apply += t1 - t0; ++rounds; }
   }
   if (prof && lane == 0 && rounds) {
     printf("[coh prof] lanes %d urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f apply %.0f (heap size at end %d)\n",

@@ -188,6 +188,17 @@ struct TpsState {
   long long pt0;
 };
 
+// Reconvergence point for the lanes of a heap warp (cohort kernel).  The heap code is full of data-dependent branches and
+// early exits; without explicit convergence points the lanes of a warp, once diverged, tend to run the REST of the
+// routine one group after the other (measured: one lane's own path through tps_apply is 3 500 cycles, the warp needed
+// 9 200).  Every lane of the warp must reach these points: the routines below take a `run` flag instead of being
+// called conditionally.  No-op on the host and in the one-thread kernel (SYNC = false).
+#if defined(__CUDA_ARCH__)
+#define TPS_SYNCWARP(on) do { if (on) __syncwarp(); } while (0)
+#else
+#define TPS_SYNCWARP(on) do { } while (0)
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define TPS_TICK0(S) do { if ((S).prof) (S).pt0 = clock64(); } while (0)
 #define TPS_TICK(S, i) do { if ((S).prof) { const long long t_ = clock64(); (S).prof[i] += t_ - (S).pt0; (S).pt0 = t_; } } while (0)
@@ -241,18 +252,21 @@ TPS_HD void tps_sift_up_plain(TpsState& S, int tpc, float k, int node) {
 // loads in ONE round trip, then the path is resolved from registers with selects -- a dependent global load per level
 // was the largest single term of the accept chain.  hcap and the spill stride are even, so a sibling pair never
 // straddles the shared / spilled boundary and every pair is one aligned int4.
-TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
-  if (S.ntr == 1) { S.ntr = 0; return; }
+template <bool SYNC>
+TPS_HD void tps_pop_root(TpsState& S, const int2 last, const bool run) {
+  const bool single = (S.ntr == 1);
+  const bool go = run && !single;
+  if (run && single) S.ntr = 0;
   TPS_TICK0(S);
   const float k = TKEY(last);
-  S.ntr -= 1;
+  if (go) S.ntr -= 1;
   const int ntr = S.ntr;
   int tpp = 1, tpc = 2;
   TPS_TICK(S, 0);      // 0: wait for `last`
   // shared levels: both children exist and live in shared memory
   const int lim = ntr < S.hcap - 1 ? ntr : S.hcap - 1;
-  bool placed = false;
-  while (tpc < lim) {
+  bool placed = !go;
+  while (!placed && tpc < lim) {
     const int2 c0 = S.sm[(size_t)tpc * S.stride], c1 = S.sm[(size_t)(tpc + 1) * S.stride];
     const bool right = TKEY(c0) > TKEY(c1);
     const int2 c = right ? c1 : c0;
@@ -263,7 +277,8 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
     tpp = tpc;
     tpc = 2 * tpp;
   }
-  if (!placed && tpc <= ntr && tpc < S.hcap) {
+  TPS_SYNCWARP(SYNC);
+  if (go && !placed && tpc <= ntr && tpc < S.hcap) {
     // tpc == ntr: a single child, in shared memory
     const int2 c = S.sm[(size_t)tpc * S.stride];
     if (TKEY(c) < k) { tps_hput(S, tpp, c); tpp = tpc; }
@@ -271,7 +286,7 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
   }
   TPS_TICK(S, 1);      // 1: shared levels
   // spilled levels, three at a time
-  while (!placed && tpc <= ntr) {
+  while (go && !placed && tpc <= ntr) {
     const int4* g4 = reinterpret_cast<const int4*>(S.gl);
     const int b1 = (2 * tpp - S.hcap) >> 1, b2 = (4 * tpp - S.hcap) >> 1, b3 = (8 * tpp - S.hcap) >> 1;   // int4 indices
     const int4 z = make_int4(0x7f800000, 0, 0x7f800000, 0);
@@ -314,7 +329,8 @@ TPS_HD void tps_pop_root(TpsState& S, const int2 last) {
       tpp = tpc; tpc = 2 * tpp;
     }
   }
-  tps_hput(S, tpp, last);
+  if (go) tps_hput(S, tpp, last);
+  TPS_SYNCWARP(SYNC);
   TPS_TICK(S, 2);      // 2: spilled levels + placement
 }
 
@@ -407,7 +423,8 @@ TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const u
 }
 
 // (3) pop the root ...
-TPS_HD void tps_pop(TpsState& S, const TpsPre& P) { tps_pop_root(S, P.last); }
+template <bool SYNC>
+TPS_HD void tps_pop(TpsState& S, const TpsPre& P, const bool run) { tps_pop_root<SYNC>(S, P.last, run); }
 // (4) ... then insert / update the four neighbours in the reference order x-1, x+1, z-1, z+1 (addtree / updtree,
 //     CalSurfG.f90:738-774, :864-890).  A close neighbour's position was read by the stencil warp BEFORE the pop, so
 //     it is verified against the heap ("does that slot hold the neighbour?") together with the fetch of its parent:
@@ -415,8 +432,8 @@ TPS_HD void tps_pop(TpsState& S, const TpsPre& P) { tps_pop_root(S, P.last); }
 //     case "the new key is not smaller than its parent" is a single store.  (Fetching three ancestor levels per
 //     neighbour up front was tried and measured slower: 11 600 against 9 200 cycles per round on S200 -- the extra
 //     loads and register patching cost more than the rare multi-level move saves; profiles/r2_k3_cohort_cycle_split.txt.)
-template <int URG>
-TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
+template <int URG, bool SYNC>
+TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4], bool run) {
   int qst[4], spos[4], ppos[4];
   int2 pent[4], sent[4];
   int nins = 0;
@@ -425,10 +442,16 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    qst[q] = N[q].qst;
+    qst[q] = run ? N[q].qst : 0;                    // a lane that is not running sees four alive neighbours: nothing to do
     if (qst[q] == -1) ++nins;
   }
-  if (S.ntr + nins >= S.htot) { S.overflow = 1; S.ntr = 0; return false; }
+  if (run && S.ntr + nins >= S.htot) {
+    S.overflow = 1; S.ntr = 0; run = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) qst[q] = 0;
+  }
   // start positions: close = back pointer as read before the pop, far = next free heap slots in order
   int nt = S.ntr;
 #if defined(__CUDA_ARCH__)
@@ -444,6 +467,7 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
     if (qst[q] == 1 && spos[q] >= 1 && spos[q] <= S.ntr) sent[q] = tps_hget(S, spos[q]);
     if ((qst[q] == 1 || qst[q] == -1) && ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]);
   }
+  TPS_SYNCWARP(SYNC);
   TPS_TICK(S, 3);      // 3: statuses, issue of the slot + parent loads
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -454,48 +478,52 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4]) {
       ppos[q] = -1;                                   // parent is fetched below
     }
   }
+  TPS_SYNCWARP(SYNC);
   TPS_TICK(S, 4);      // 4: wait for the loads + verification
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) {
-    if (qst[q] != 1 && qst[q] != -1) continue;
-    if (qst[q] == -1) S.ntr += 1;
-    const float k = N[q].qt;
-    int tpc = spos[q];
-    if ((tpc >> 1) != ppos[q]) { ppos[q] = tpc >> 1; if (ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]); }   // moved earlier in this step
-    TPS_TICK(S, 6);    // 6: set-up of neighbour q
-    if (ppos[q] > 0 && k < TKEY(pent[q])) {
-      // the key moves up: generic loop (addtree / updtree sift-up), patching what later neighbours hold in registers
-      int tpp = ppos[q];
-      int2 par = pent[q];
-      for (;;) {
-        tps_hput(S, tpc, par);
+    if (qst[q] == 1 || qst[q] == -1) {
+      if (qst[q] == -1) S.ntr += 1;
+      const float k = N[q].qt;
+      int tpc = spos[q];
+      const int tpc0 = tpc;
+      if ((tpc >> 1) != ppos[q]) { ppos[q] = tpc >> 1; if (ppos[q] > 0) pent[q] = tps_hget(S, ppos[q]); }   // moved earlier in this step
+      if (ppos[q] > 0 && k < TKEY(pent[q])) {
+        // the key moves up: generic loop (addtree / updtree sift-up), patching what later neighbours hold in registers
+        int tpp = ppos[q];
+        int2 par = pent[q];
+        for (;;) {
+          tps_hput(S, tpc, par);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int r = 0; r < 4; ++r) {
-          if (r > q && qst[r] == 1 && N[r].co == par.y) spos[r] = tpc;    // a later close neighbour moved down
-          if (r > q && ppos[r] == tpc) pent[r] = par;                     // a later parent slot changed content
+          for (int r = 0; r < 4; ++r) {
+            if (r > q && qst[r] == 1 && N[r].co == par.y) spos[r] = tpc;    // a later close neighbour moved down
+            if (r > q && ppos[r] == tpc) pent[r] = par;                     // a later parent slot changed content
+          }
+          tpc = tpp;
+          tpp = tpc >> 1;
+          if (tpp == 0) break;
+          par = tps_hget(S, tpp);
+          if (!(k < TKEY(par))) break;
         }
-        tpc = tpp;
-        tpp = tpc >> 1;
-        if (tpp == 0) break;
-        par = tps_hget(S, tpp);
-        if (!(k < TKEY(par))) break;
       }
-    }
-    TPS_TICK(S, 7);    // 7: move loop
-    const int2 e = make_int2(tps_as_int(k), N[q].co);
-    tps_hput(S, tpc, e);
+      const int2 e = make_int2(tps_as_int(k), N[q].co);
+      // a close neighbour that stays where it is keeps its back pointer: only the key changes (no write to E)
+      if (qst[q] == 1 && tpc == tpc0) { if (tpc < S.hcap) S.sm[(size_t)tpc * S.stride] = e; else S.gl[tpc - S.hcap] = e; }
+      else tps_hput(S, tpc, e);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int r = 0; r < 4; ++r)
-      if (r > q && ppos[r] == tpc) pent[r] = e;
-    TPS_TICK(S, 8);    // 8: placement + patches
+      for (int r = 0; r < 4; ++r)
+        if (r > q && ppos[r] == tpc) pent[r] = e;
+    }
+    TPS_SYNCWARP(SYNC);
+    TPS_TICK(S, 6 + (q & 1));    // 6 / 7: neighbours
   }
-  return true;
+  return run;
 }
 
 template <int URG>
@@ -507,8 +535,8 @@ TPS_HD bool tps_step(TpsState& S, const TpsGrid& G, unsigned long long& nacc) {
 #pragma unroll
 #endif
   for (int q = 0; q < 4; ++q) N[q] = tps_neighbour<URG>(G, P.ix, P.iz, P.tself, q);
-  tps_pop(S, P);
-  return tps_apply<URG>(S, G, N);
+  tps_pop<false>(S, P, true);
+  return tps_apply<URG, false>(S, G, N, true);
 }
 
 // ---- source cell initialisation (travel, CalSurfG.f90:324-345) on the refined grid ----
