@@ -23,8 +23,8 @@ cudaError_t fmm_max_ctas(int hcap, int spc, int nsm, int* nctas);
 cudaError_t launch_fmm(const FmmArgs& A, int nctas, cudaStream_t st);
 cudaError_t fmm_duo_max_ctas(int hcap, int nsm, int minb, int* nctas);
 cudaError_t launch_fmm_duo(const FmmArgs& A, int nctas, int minb, cudaStream_t st);
-cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int* nctas);
-cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, cudaStream_t st);
+cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int qs, int* nctas);
+cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, int qs, cudaStream_t st);
 cudaError_t launch_decode_status(const unsigned* E, const int* hpos, size_t n, int nnz_tiled, float* ttn, int* nsts,
                                  cudaStream_t st);
 cudaError_t launch_trace(const TraceArgs& A, bool azim, int nblocks, cudaStream_t st);
@@ -198,6 +198,7 @@ struct dazim_plan {
   int duo_minb = 10;   // its register budget: 10 CTAs per SM (96 registers) or 16 (64 registers, 1.6 x the solves in flight)
   int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
   int coh = 8;   // solves per heap warp of the cohort kernel (8 / 16 / 32; 8 measured best); 0: the one-thread-per-solve kernel
+  int coh_qs = 2;   // stencil threads per neighbour (1 / 2 / 4)
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
@@ -417,6 +418,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   if (P->tps) {
     if (const char* e = getenv("DAZIM_COH")) P->coh = atoi(e) ? P->coh : 0;
     if (const char* e = getenv("DAZIM_COH_LANES")) { const int v = atoi(e); if (P->coh) P->coh = (v <= 8) ? 8 : (v <= 16 ? 16 : 32); }
+    if (const char* e = getenv("DAZIM_COH_QS")) P->coh_qs = std::max(1, atoi(e));
     const int L = P->coh ? P->coh : 32;                  // solves per CTA
     const long long nres = std::max<long long>(1, nsrc);
     const int ctas_needed = (int)((nres + L - 1) / L);
@@ -429,7 +431,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     P->hcap = std::min(hneed, (int)((sm_budget / per_sm - 1024 - xch_bytes) / (8 * L)));
     if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
     P->hcap = std::max(8, P->hcap & ~1);            // even: a sibling pair never straddles shared / spilled
-    CK(fmm_tps_max_ctas(P->hcap, h->nsm, P->coh, &nctas));
+    CK(fmm_tps_max_ctas(P->hcap, h->nsm, P->coh, P->coh_qs, &nctas));
     if (nctas < 1) { plan_free(P); return DAZIM_EBADARG; }
     nctas = std::min(nctas, ctas_needed);
     P->hspill = (std::max(16, hspill_full) + 1) & ~1;
@@ -663,7 +665,7 @@ static int plan_run_once(dazim_plan* P) {
         A.flags = F.flags; A.n_accept = F.n_accept;
         A.prof = getenv("DAZIM_COH_PROF") ? atoi(getenv("DAZIM_COH_PROF")) : 0;
         const int Lc = P->coh ? P->coh : 32;
-        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + Lc - 1) / Lc), P->coh, st));
+        CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + Lc - 1) / Lc), P->coh, P->coh_qs, st));
         T.n_launch++;      // + k_tps_init
       }
       else if (P->duo) CK(launch_fmm_duo(F, std::min(P->nctas, F.nsrc), P->duo_minb, st));

@@ -1144,17 +1144,17 @@ __device__ __forceinline__ void coh_arrive(int id) {
 // running"); res[q * L + lane] = int4 (status, heap position read, trial time, offset) posted by the stencil thread of
 // neighbour q.  One 16-byte shared access per record; the named barriers order the accesses (no volatile needed).
 __host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 32 + 16 * L; }
-__host__ __device__ constexpr int coh_threads(int L) { return 32 + 4 * L; }
+__host__ __device__ constexpr int coh_threads(int L, int QS) { return 32 + 4 * L * QS; }
 
-template <int URG, int LANES>
+template <int URG, int LANES, int QS>
 __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const int lane, const bool act,
                                unsigned long long& nacc, const bool prof) {
-  constexpr int NT = coh_threads(LANES);
+  constexpr int NT = coh_threads(LANES, QS);
   int4* head = reinterpret_cast<int4*>(xch);
   volatile int* flag = xch + 4 * LANES;
   const int4* res = reinterpret_cast<const int4*>(xch + 4 * LANES + 32);
   bool run = act;
-  long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, t0 = 0, t1 = 0;
+  long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, c_nread = 0, t0 = 0, t1 = 0;
   unsigned long long rounds = 0;
   for (;;) {
     if (prof) t0 = clock64();
@@ -1185,13 +1185,14 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
         if (run) r = res[q * LANES + lane];
         N[q].qst = r.x; N[q].qid = r.y; N[q].qt = __int_as_float(r.z); N[q].co = r.w;
       }
+      if (prof) { __syncwarp(); t1 = clock64(); c_nread += t1 - t0; t0 = t1; }
       run = tps_apply<URG, true>(S, G, N, run);
     }
-    if (prof) { t1 = clock64(); c_apply += t1 - t0; ++rounds; }
+    if (prof) { __syncwarp(); t1 = clock64(); c_apply += t1 - t0; ++rounds; }
   }
   if (prof && lane == 0 && rounds) {
-    printf("[coh prof] lanes %d urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f apply %.0f (heap size at end %d)\n",
-           LANES, URG, rounds, (double)c_pre / rounds, (double)c_pop / rounds, (double)c_wait / rounds, (double)c_apply / rounds, S.ntr);
+    printf("[coh prof] lanes %d urg %d: rounds %llu, cycles per round: pre %.0f pop %.0f waitY %.0f read-records %.0f apply %.0f (heap size at end %d)\n",
+           LANES, URG, rounds, (double)c_pre / rounds, (double)c_pop / rounds, (double)c_wait / rounds, (double)c_nread / rounds, (double)c_apply / rounds, S.ntr);
     if (S.prof) {
       printf("[coh prof] urg %d lane 0 split: pop{last %.0f shared %.0f spilled+place %.0f} apply{setup+issue %.0f wait+verify %.0f",
              URG, (double)S.prof[0] / rounds, (double)S.prof[1] / rounds, (double)S.prof[2] / rounds, (double)S.prof[3] / rounds,
@@ -1203,9 +1204,13 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
   }
 }
 
-template <int URG, int LANES>
-__device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const int q) {
-  constexpr int NT = coh_threads(LANES);
+// Stencil thread t serves solve l = t / (4 QS), neighbour q = (t / QS) % 4, part = t % QS of that neighbour's four
+// quadrant solves: the QS parts of one neighbour are adjacent lanes and reduce with shuffles.  (The four quadratics of a
+// neighbour in ONE thread take ~5 000 cycles with their IEEE divisions and square roots -- longer than the heap warp's pop,
+// so the heap warp used to wait for them; measured, profiles/r2_k3_cohort_cycle_split.txt.)
+template <int URG, int LANES, int QS>
+__device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const int q, const int part) {
+  constexpr int NT = coh_threads(LANES, QS);
   const int4* head = reinterpret_cast<const int4*>(xch);
   volatile int* flag = xch + 4 * LANES;
   int4* res = reinterpret_cast<int4*>(xch + 4 * LANES + 32);
@@ -1213,21 +1218,25 @@ __device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const
     coh_sync<NT>(COH_X);
     if (!*flag) { coh_arrive<NT>(COH_Y); break; }      // acknowledge the stop flag (see coh_march_heap)
     const int4 hd = head[l];
-    if (hd.x >= 0) {
-      const TpsNb R = tps_neighbour<URG>(G, hd.y, hd.z, (unsigned)hd.w, q);
-      res[q * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
-    }
+    TpsNb R;
+    R.qst = 0; R.qid = 0; R.co = 0; R.qt = tps_inf();
+    if (hd.x >= 0) R = tps_neighbour_part<URG, QS>(G, hd.y, hd.z, (unsigned)hd.w, q, part);
+    if (QS >= 2) R.qt = fminf(R.qt, __shfl_xor_sync(0xffffffffu, R.qt, 1));
+    if (QS >= 4) R.qt = fminf(R.qt, __shfl_xor_sync(0xffffffffu, R.qt, 2));
+    if (hd.x >= 0 && part == 0) res[q * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
     coh_arrive<NT>(COH_Y);
   }
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(32 + 4 * LANES, LANES == 32 ? 2 : (LANES == 16 ? 4 : 7)) k_fmm_coh(TpsArgs A) {
+template <int LANES, int QS>
+__global__ void __launch_bounds__(32 + 4 * LANES * QS, LANES == 32 ? 2 : (LANES == 16 ? 4 : 7)) k_fmm_coh(TpsArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // solve served by this thread: heap warp lane l < LANES; stencil thread t = tid - 32: neighbour t / LANES of solve t % LANES
-  const int l = warp == 0 ? lane : (tid - 32) % LANES;
-  const int q = warp == 0 ? 0 : (tid - 32) / LANES;
+  // solve served by this thread: heap warp lane l < LANES; stencil thread t = tid - 32: solve t / (4 QS), neighbour
+  // (t / QS) % 4, part t % QS
+  const int l = warp == 0 ? lane : (tid - 32) / (4 * QS);
+  const int q = warp == 0 ? 0 : ((tid - 32) / QS) % 4;
+  const int part = warp == 0 ? 0 : (tid - 32) % QS;
   const GridC& g = A.g;
   const size_t ncoarse = (size_t)g.nnx * g.nnz;          // slow_c (plain column-major)
   const size_t ncf = coarse_field_size(g.nnx, g.nnz);    // E_c (interleaved layout)
@@ -1261,16 +1270,16 @@ __global__ void __launch_bounds__(32 + 4 * LANES, LANES == 32 ? 2 : (LANES == 16
       const float* vv = A.velv + (size_t)sr.period * (g.nvz + 2) * (g.nvx + 2);
       S.gl = A.hspill + (size_t)sc * A.hspill_n;
       if (act) tps_source_init(S, g, sr, vv, c_ubasis, E_r);
-      coh_march_heap<1, LANES>(S, Gr, xch, lane, act, nacc, A.prof && blockIdx.x == 0);
+      coh_march_heap<1, LANES, QS>(S, Gr, xch, lane, act, nacc, A.prof && blockIdx.x == 0);
       if (act && !S.overflow) {
         tps_refined_finish(S, E_r, A.hpos_r_out ? A.hpos_r_out + (size_t)sc * REF_N : nullptr);
         tps_handoff(S, g, sr, E_r, E_c);
       }
       __syncwarp();
-      coh_march_heap<2, LANES>(S, Gc, xch, lane, act && !S.overflow, nacc, A.prof && blockIdx.x == 0);
+      coh_march_heap<2, LANES, QS>(S, Gc, xch, lane, act && !S.overflow, nacc, A.prof && blockIdx.x == 0);
     } else {
-      coh_march_stencil<1, LANES>(Gr, xch, l, q);
-      coh_march_stencil<2, LANES>(Gc, xch, l, q);
+      coh_march_stencil<1, LANES, QS>(Gr, xch, l, q, part);
+      coh_march_stencil<2, LANES, QS>(Gc, xch, l, q, part);
     }
   }
   if (warp == 0) {
@@ -1279,37 +1288,47 @@ __global__ void __launch_bounds__(32 + 4 * LANES, LANES == 32 ? 2 : (LANES == 16
   }
 }
 
-static const void* coh_fn(int lanes) {
-  return lanes == 8 ? (const void*)k_fmm_coh<8> : (lanes == 16 ? (const void*)k_fmm_coh<16> : (const void*)k_fmm_coh<32>);
+// (lanes, qs) variants built: 8 x {1, 2, 4}, 16 x {1, 2}, 32 x 1
+static const void* coh_fn(int lanes, int qs) {
+  if (lanes == 8) return qs == 4 ? (const void*)k_fmm_coh<8, 4> : (qs == 2 ? (const void*)k_fmm_coh<8, 2> : (const void*)k_fmm_coh<8, 1>);
+  if (lanes == 16) return qs >= 2 ? (const void*)k_fmm_coh<16, 2> : (const void*)k_fmm_coh<16, 1>;
+  return (const void*)k_fmm_coh<32, 1>;
 }
+int coh_norm_qs(int lanes, int qs) { return lanes == 8 ? (qs >= 4 ? 4 : (qs >= 2 ? 2 : 1)) : (lanes == 16 ? (qs >= 2 ? 2 : 1) : 1); }
 size_t fmm_coh_smem(int hcap, int lanes) { return (size_t)hcap * lanes * 8 + (size_t)coh_xch_ints(lanes) * 4; }
 
 // resident warps (= CTAs of 32 solves) per SM for a given shared heap capacity
-// resident CTAs for a given shared heap capacity; coh = lanes per heap warp (8 / 16 / 32) or 0 for the one-thread kernel
-cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int* nctas) {
+// resident CTAs for a given shared heap capacity; coh = lanes per heap warp (8 / 16 / 32) or 0 for the one-thread kernel;
+// qs = stencil threads per neighbour
+cudaError_t fmm_tps_max_ctas(int hcap, int nsm, int coh, int qs, int* nctas) {
   const size_t smem = coh ? fmm_coh_smem(hcap, coh) : (size_t)hcap * 32 * 8;
-  const void* fn = coh ? coh_fn(coh) : (const void*)k_fmm_tps;
+  qs = coh ? coh_norm_qs(coh, qs) : 1;
+  const void* fn = coh ? coh_fn(coh, qs) : (const void*)k_fmm_tps;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, coh ? coh_threads(coh) : 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, coh ? coh_threads(coh, qs) : 32, smem);
   if (e != cudaSuccess) return e;
   *nctas = per_sm * nsm;
   return cudaSuccess;
 }
 
-cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, cudaStream_t st) {
+cudaError_t launch_fmm_tps(const TpsArgs& A, int nctas, int coh, int qs, cudaStream_t st) {
   if (A.nsrc <= 0) return cudaSuccess;
   dim3 gi((REF_N + 255) / 256, (unsigned)std::min(A.nsrc, 65535));
   k_tps_init<<<gi, 256, 0, st>>>(A);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t smem = coh ? fmm_coh_smem(A.hcap, coh) : (size_t)A.hcap * 32 * 8;
-  e = cudaFuncSetAttribute(coh ? coh_fn(coh) : (const void*)k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  qs = coh ? coh_norm_qs(coh, qs) : 1;
+  e = cudaFuncSetAttribute(coh ? coh_fn(coh, qs) : (const void*)k_fmm_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (coh == 8) k_fmm_coh<8><<<nctas, coh_threads(8), smem, st>>>(A);
-  else if (coh == 16) k_fmm_coh<16><<<nctas, coh_threads(16), smem, st>>>(A);
-  else if (coh == 32) k_fmm_coh<32><<<nctas, coh_threads(32), smem, st>>>(A);
+  if (coh == 8 && qs == 4) k_fmm_coh<8, 4><<<nctas, coh_threads(8, 4), smem, st>>>(A);
+  else if (coh == 8 && qs == 2) k_fmm_coh<8, 2><<<nctas, coh_threads(8, 2), smem, st>>>(A);
+  else if (coh == 8) k_fmm_coh<8, 1><<<nctas, coh_threads(8, 1), smem, st>>>(A);
+  else if (coh == 16 && qs == 2) k_fmm_coh<16, 2><<<nctas, coh_threads(16, 2), smem, st>>>(A);
+  else if (coh == 16) k_fmm_coh<16, 1><<<nctas, coh_threads(16, 1), smem, st>>>(A);
+  else if (coh == 32) k_fmm_coh<32, 1><<<nctas, coh_threads(32, 1), smem, st>>>(A);
   else k_fmm_tps<<<nctas, 32, smem, st>>>(A);
   return cudaGetLastError();
 }

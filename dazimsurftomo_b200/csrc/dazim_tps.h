@@ -373,9 +373,12 @@ TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, Tps
 }
 
 // (2) neighbour q of the accepted node (ix, iz): its status and, if it is far or close, its trial time = the minimum
-//     of fouds2's four quadrant solves over the nodes that are alive now.  Reads E only.
-template <int URG>
-TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const unsigned tself, const int q) {
+//     of fouds2's four quadrant solves over the nodes that are alive now.  Reads E only.  The four quadrants can be
+//     split over QS = 1, 2 or 4 threads (part = 0..QS-1): thread `part` evaluates quadrants part, part + QS, ... and
+//     returns the minimum over ITS quadrants (the caller reduces over the parts; min is exact and order-free).
+//     quadrant index = js * 2 + ks (js: x-1 / x+1 side, ks: z-1 / z+1 side).
+template <int URG, int QS>
+TPS_HD TpsNb tps_neighbour_part(const TpsGrid& G, const int ix, const int iz, const unsigned tself, const int q, const int part) {
   const int ndx = (q == 0) ? -1 : (q == 1 ? 1 : 0), ndz = (q == 2) ? -1 : (q == 3 ? 1 : 0);
   const int cx = ix + ndx, cz = iz + ndz, ld = G.ld;
   TpsNb R;
@@ -389,37 +392,41 @@ TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const u
   R.qid = (int)(cE & ~E_SIGN);
   if (R.qst == 0) return R;
   // first / second stencil nodes in the four directions x-1, x+1, z-1, z+1; the first node back towards the accepted
-  // node is that node itself (alive with tself)
+  // node is that node itself (alive with tself).  A thread only loads the directions its quadrants use.
   unsigned e1[4], e2[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int d = 0; d < 4; ++d) {
-    const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
-    const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
     e1[d] = E_OUT; e2[d] = E_OUT;
-    if (ddx == -ndx && ddz == -ndz) e1[d] = tself;
-    else if (s1x >= 0 && s1x < G.nnx && s1z >= 0 && s1z < G.nnz) e1[d] = E[nidx<URG>(s1x, s1z, ld)];
-    if (s2x >= 0 && s2x < G.nnx && s2z >= 0 && s2z < G.nnz) e2[d] = E[nidx<URG>(s2x, s2z, ld)];
+    const bool need = (QS == 1) || (QS == 2 && (d >= 2 || d == part)) || (QS == 4 && (d == (part >> 1) || d == 2 + (part & 1)));
+    if (need) {
+      const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+      const int s1x = cx + ddx, s1z = cz + ddz, s2x = s1x + ddx, s2z = s1z + ddz;
+      if (ddx == -ndx && ddz == -ndz) e1[d] = tself;
+      else if (s1x >= 0 && s1x < G.nnx && s1z >= 0 && s1z < G.nnz) e1[d] = E[nidx<URG>(s1x, s1z, ld)];
+      if (s2x >= 0 && s2x < G.nnx && s2z >= 0 && s2z < G.nnz) e2[d] = E[nidx<URG>(s2x, s2z, ld)];
+    }
   }
   const float slown = G.slow[cx * ld + cz], risti = G.risti_tab[cx];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int js = 0; js < 2; ++js) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int ks = 0; ks < 2; ++ks) {
-      bool ok = false;
-      float trav = quadrant(e_status(e1[js]), e_status(e2[js]), tps_as_float((int)e1[js]), tps_as_float((int)e2[js]),
-                            e_status(e1[2 + ks]), e_status(e2[2 + ks]), tps_as_float((int)e1[2 + ks]),
-                            tps_as_float((int)e2[2 + ks]), slown, G.earth, risti, G.dnx, G.dnz, ok);
-      if (!ok) trav = tps_inf();
-      R.qt = fminf(R.qt, trav);
-    }
+  for (int i = 0; i < 4 / QS; ++i) {
+    const int qd = part + i * QS;
+    const int js = qd >> 1, ks = qd & 1;
+    bool ok = false;
+    float trav = quadrant(e_status(e1[js]), e_status(e2[js]), tps_as_float((int)e1[js]), tps_as_float((int)e2[js]),
+                          e_status(e1[2 + ks]), e_status(e2[2 + ks]), tps_as_float((int)e1[2 + ks]),
+                          tps_as_float((int)e2[2 + ks]), slown, G.earth, risti, G.dnx, G.dnz, ok);
+    if (!ok) trav = tps_inf();
+    R.qt = fminf(R.qt, trav);
   }
   return R;
+}
+template <int URG>
+TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const unsigned tself, const int q) {
+  return tps_neighbour_part<URG, 1>(G, ix, iz, tself, q, 0);
 }
 
 // (3) pop the root ...
