@@ -198,7 +198,7 @@ struct dazim_plan {
   int duo_minb = 10;   // its register budget: 10 CTAs per SM (96 registers) or 16 (64 registers, 1.6 x the solves in flight)
   int tps = 0;   // one heap lane per solve (dazim_tps.h): k_fmm_coh (cohort kernel, the default) or k_fmm_tps
   int coh = 8;   // solves per heap warp of the cohort kernel (8 / 16 / 32; 8 measured best); 0: the one-thread-per-solve kernel
-  int coh_qs = 2;   // stencil threads per neighbour (1 / 2 / 4)
+  int coh_qs = 1;   // stencil threads per neighbour (1 / 2 / 4; measured: the stencil side is DRAM-latency bound, more threads do not help)
   DBuf<int> d_hpos_r_out;                       // per solve, test seam only (tps)
   int hcap = 512, spc = 2, hspill = 0, cap = 0, trace_blocks = 0, maxB = 0;
   // footprint pool + outputs
@@ -427,7 +427,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     int per_sm = std::max(1, (ctas_needed + h->nsm - 1) / h->nsm);
     per_sm = std::min(per_sm, 64 / L > 0 ? 64 / L : 1);       // at most 64 solves per SM
     if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(16, atoi(e)));
-    const int xch_bytes = P->coh ? (4 * L + 32 + 16 * L) * 4 + 128 : 0;
+    const int xch_bytes = P->coh ? (4 * L + 64 + 16 * L) * 4 + 128 : 0;
     P->hcap = std::min(hneed, (int)((sm_budget / per_sm - 1024 - xch_bytes) / (8 * L)));
     if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
     P->hcap = std::max(8, P->hcap & ~1);            // even: a sibling pair never straddles shared / spilled

@@ -1143,7 +1143,7 @@ __device__ __forceinline__ void coh_arrive(int id) {
 // exchange area: head[lane] = int4 (node or -1, ix, iz, tself) posted by the heap warp; flag (one int, "any lane still
 // running"); res[q * L + lane] = int4 (status, heap position read, trial time, offset) posted by the stencil thread of
 // neighbour q.  One 16-byte shared access per record; the named barriers order the accesses (no volatile needed).
-__host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 32 + 16 * L; }
+__host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 64 + 16 * L; }   // head, flag + predicted nodes, records
 __host__ __device__ constexpr int coh_threads(int L, int QS) { return 32 + 4 * L * QS; }
 
 template <int URG, int LANES, int QS>
@@ -1152,16 +1152,17 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
   constexpr int NT = coh_threads(LANES, QS);
   int4* head = reinterpret_cast<int4*>(xch);
   volatile int* flag = xch + 4 * LANES;
-  const int4* res = reinterpret_cast<const int4*>(xch + 4 * LANES + 32);
+  int* pred = xch + 4 * LANES + 32;
+  const int4* res = reinterpret_cast<const int4*>(xch + 4 * LANES + 64);
   bool run = act;
   long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, c_nread = 0, t0 = 0, t1 = 0;
   unsigned long long rounds = 0;
   for (;;) {
     if (prof) t0 = clock64();
     TpsPre P;
-    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.last = make_int2(0, 0);
+    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.pred = -1; P.last = make_int2(0, 0);
     if (run) run = tps_pre<URG>(S, G, nacc, P);
-    if (lane < LANES) head[lane] = make_int4(run ? P.pn : -1, P.ix, P.iz, (int)P.tself);
+    if (lane < LANES) { head[lane] = make_int4(run ? P.pn : -1, P.ix, P.iz, (int)P.tself); pred[lane] = run ? P.pred : -1; }
     const bool any = __any_sync(0xffffffffu, run);
     if (lane == 0) *flag = any ? 1 : 0;
     coh_arrive<NT>(COH_X);
@@ -1213,7 +1214,9 @@ __device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const
   constexpr int NT = coh_threads(LANES, QS);
   const int4* head = reinterpret_cast<const int4*>(xch);
   volatile int* flag = xch + 4 * LANES;
-  int4* res = reinterpret_cast<int4*>(xch + 4 * LANES + 32);
+  const int* pred = xch + 4 * LANES + 32;
+  int4* res = reinterpret_cast<int4*>(xch + 4 * LANES + 64);
+  const float inv_ld = G.inv_ld;
   for (;;) {
     coh_sync<NT>(COH_X);
     if (!*flag) { coh_arrive<NT>(COH_Y); break; }      // acknowledge the stop flag (see coh_march_heap)
@@ -1224,7 +1227,14 @@ __device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const
     if (QS >= 2) R.qt = fminf(R.qt, __shfl_xor_sync(0xffffffffu, R.qt, 1));
     if (QS >= 4) R.qt = fminf(R.qt, __shfl_xor_sync(0xffffffffu, R.qt, 2));
     if (hd.x >= 0 && part == 0) res[q * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
+    const int pn2 = pred[l];
     coh_arrive<NT>(COH_Y);
+    // while the heap warp applies this node's updates: pull the stencil of the node that will be accepted next towards the L2
+    if (pn2 >= 0 && part == 0) {
+      int px, pz;
+      ndecode<URG>(pn2, G.ld, inv_ld, px, pz);
+      tps_neighbour_prefetch<URG>(G, px, pz, q);
+    }
   }
 }
 

@@ -348,7 +348,7 @@ struct TpsGrid {
 // One accept step of travel's DO WHILE (CalSurfG.f90:356-456) in three pieces, so that the same code serves the
 // one-thread-per-solve kernel (pre + 4 x neighbour + post in one thread), the cohort kernel (pre/post on the heap
 // warp, one neighbour per stencil warp) and the host twin.
-struct TpsPre { int pn, ix, iz; unsigned tself; int2 last; };
+struct TpsPre { int pn, ix, iz, pred; unsigned tself; int2 last; };   // pred: node that will be on top after this pop (hint)
 struct TpsNb { int qst, qid, co; float qt; };     // neighbour status (-2 outside, -1 far, 0 alive, 1 close), heap position read, offset, trial
 
 // (1) the node on top of the heap becomes alive.  Returns false when the march is over (heap empty, overflow, or the
@@ -362,6 +362,18 @@ TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, Tps
   ndecode<URG>(P.pn, G.ld, G.inv_ld, P.ix, P.iz);
   P.tself = (unsigned)root.x & ~E_SIGN;
   G.E[P.pn] = P.tself;                             // the popped node becomes alive with its trial value (= its heap key)
+  // which node will be the root after this pop?  (first level of downtree, decided now; unless one of the four updates
+  // puts a smaller key on top it is the next node to be accepted: the stencil threads prefetch its stencil lines)
+  P.pred = -1;
+  {
+    const int n1 = S.ntr - 1;
+    if (n1 == 1) P.pred = P.last.y;
+    else if (n1 >= 2) {
+      int2 c = tps_hget(S, 2);
+      if (n1 >= 3) { const int2 c3 = tps_hget(S, 3); if (TKEY(c) > TKEY(c3)) c = c3; }
+      P.pred = (TKEY(c) < TKEY(P.last)) ? c.y : P.last.y;
+    }
+  }
   if (URG == 1) {
     if ((P.ix == 0 && G.ex_l) || (P.ix == G.nnx - 1 && G.ex_r) || (P.iz == 0 && G.ex_t) || (P.iz == G.nnz - 1 && G.ex_b)) {
       S.stopped_at_root = 1;
@@ -387,12 +399,12 @@ TPS_HD TpsNb tps_neighbour_part(const TpsGrid& G, const int ix, const int iz, co
   R.qt = tps_inf();
   if (!(cx >= 0 && cx < G.nnx && cz >= 0 && cz < G.nnz)) { R.qst = -2; return R; }
   const unsigned* E = G.E;
+  // ALL loads of the neighbour are issued together -- its own word, the first / second stencil nodes in the four
+  // directions x-1, x+1, z-1, z+1, slowness, R sin(theta) -- before the status is looked at: with 8 000 fronts in flight
+  // every gather is a DRAM round trip, and "status first, stencil only if the neighbour is not alive" made it two in a
+  // row (measured: the heap warp waited 5 300 cycles per accept for its stencil threads).  The first node back towards
+  // the accepted node is that node itself (alive with tself).  A thread only loads the directions its quadrants use.
   const unsigned cE = E[R.co];
-  R.qst = (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
-  R.qid = (int)(cE & ~E_SIGN);
-  if (R.qst == 0) return R;
-  // first / second stencil nodes in the four directions x-1, x+1, z-1, z+1; the first node back towards the accepted
-  // node is that node itself (alive with tself).  A thread only loads the directions its quadrants use.
   unsigned e1[4], e2[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -409,11 +421,14 @@ TPS_HD TpsNb tps_neighbour_part(const TpsGrid& G, const int ix, const int iz, co
     }
   }
   const float slown = G.slow[cx * ld + cz], risti = G.risti_tab[cx];
+  R.qst = (cE == E_FAR ? -1 : ((int)cE >= 0 ? 0 : 1));
+  R.qid = (int)(cE & ~E_SIGN);
+  if (R.qst == 0) return R;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 0; i < 4 / QS; ++i) {
-    const int qd = part + i * QS;
+    const int qd = (QS == 2) ? part * 2 + i : part + i * QS;      // QS = 2: part = x side, i = z side
     const int js = qd >> 1, ks = qd & 1;
     bool ok = false;
     float trav = quadrant(e_status(e1[js]), e_status(e2[js]), tps_as_float((int)e1[js]), tps_as_float((int)e2[js]),
@@ -423,6 +438,26 @@ TPS_HD TpsNb tps_neighbour_part(const TpsGrid& G, const int ix, const int iz, co
     R.qt = fminf(R.qt, trav);
   }
   return R;
+}
+// hint only: pull the lines the gather of neighbour q of node (ix, iz) will touch towards the L2
+template <int URG>
+TPS_HD void tps_neighbour_prefetch(const TpsGrid& G, const int ix, const int iz, const int q) {
+#if defined(__CUDA_ARCH__)
+  const int ndx = (q == 0) ? -1 : (q == 1 ? 1 : 0), ndz = (q == 2) ? -1 : (q == 3 ? 1 : 0);
+  const int cx = ix + ndx, cz = iz + ndz, ld = G.ld;
+  if (!(cx >= 0 && cx < G.nnx && cz >= 0 && cz < G.nnz)) return;
+  const unsigned* E = G.E;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(E + nidx<URG>(cx, cz, ld)));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(G.slow + cx * ld + cz));
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const int ddx = (d == 0) ? -1 : (d == 1 ? 1 : 0), ddz = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+    const int s2x = cx + 2 * ddx, s2z = cz + 2 * ddz;      // the second stencil node; the first shares its sector or the centre's
+    if (s2x >= 0 && s2x < G.nnx && s2z >= 0 && s2z < G.nnz) asm volatile("prefetch.global.L2 [%0];" ::"l"(E + nidx<URG>(s2x, s2z, ld)));
+    const int s1x = cx + ddx, s1z = cz + ddz;
+    if (ddz != 0 && s1x >= 0 && s1x < G.nnx && s1z >= 0 && s1z < G.nnz) asm volatile("prefetch.global.L2 [%0];" ::"l"(E + nidx<URG>(s1x, s1z, ld)));
+  }
+#endif
 }
 template <int URG>
 TPS_HD TpsNb tps_neighbour(const TpsGrid& G, const int ix, const int iz, const unsigned tself, const int q) {
