@@ -427,7 +427,7 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     int per_sm = std::max(1, (ctas_needed + h->nsm - 1) / h->nsm);
     per_sm = std::min(per_sm, 64 / L > 0 ? 64 / L : 1);       // at most 64 solves per SM
     if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(16, atoi(e)));
-    const int xch_bytes = P->coh ? (4 * L + 64 + 16 * L) * 4 + 128 : 0;
+    const int xch_bytes = P->coh ? (4 * L + 32 + 4 * L + 32 * L) * 4 + 128 : 0;
     P->hcap = std::min(hneed, (int)((sm_budget / per_sm - 1024 - xch_bytes) / (8 * L)));
     if (const char* e = getenv("DAZIM_HCAP")) P->hcap = std::max(8, std::min(880, atoi(e)));
     P->hcap = std::max(8, P->hcap & ~1);            // even: a sibling pair never straddles shared / spilled
@@ -664,6 +664,7 @@ static int plan_run_once(dazim_plan* P) {
         A.hspill_n = P->hspill; A.hcap = P->hcap; A.hpos_r_out = P->d_hpos_r_out.p;
         A.flags = F.flags; A.n_accept = F.n_accept;
         A.prof = getenv("DAZIM_COH_PROF") ? atoi(getenv("DAZIM_COH_PROF")) : 0;
+        A.pf2 = getenv("DAZIM_COH_PF2") ? atoi(getenv("DAZIM_COH_PF2")) : 1;
         const int Lc = P->coh ? P->coh : 32;
         CK(launch_fmm_tps(A, std::min(P->nctas, (F.nsrc + Lc - 1) / Lc), P->coh, P->coh_qs, st));
         T.n_launch++;      // + k_tps_init

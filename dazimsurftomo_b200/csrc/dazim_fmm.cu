@@ -1143,7 +1143,7 @@ __device__ __forceinline__ void coh_arrive(int id) {
 // exchange area: head[lane] = int4 (node or -1, ix, iz, tself) posted by the heap warp; flag (one int, "any lane still
 // running"); res[q * L + lane] = int4 (status, heap position read, trial time, offset) posted by the stencil thread of
 // neighbour q.  One 16-byte shared access per record; the named barriers order the accesses (no volatile needed).
-__host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 64 + 16 * L; }   // head, flag + predicted nodes, records
+__host__ __device__ constexpr int coh_xch_ints(int L) { return 4 * L + 32 + 4 * L + 32 * L; }   // head, flag, predicted (node, key, node after), 2 x records
 __host__ __device__ constexpr int coh_threads(int L, int QS) { return 32 + 4 * L * QS; }
 
 template <int URG, int LANES, int QS>
@@ -1152,17 +1152,19 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
   constexpr int NT = coh_threads(LANES, QS);
   int4* head = reinterpret_cast<int4*>(xch);
   volatile int* flag = xch + 4 * LANES;
-  int* pred = xch + 4 * LANES + 32;
-  const int4* res = reinterpret_cast<const int4*>(xch + 4 * LANES + 64);
+  int4* pred = reinterpret_cast<int4*>(xch + 4 * LANES + 32);
+  const int4* res = reinterpret_cast<const int4*>(xch + 8 * LANES + 32);
   bool run = act;
+  int ins[4] = {-1, -1, -1, -1};      // nodes the previous round inserted (were far): see the note on records computed ahead
+  int cur = 0;                         // record buffer of this round
   long long c_pre = 0, c_pop = 0, c_wait = 0, c_apply = 0, c_nread = 0, t0 = 0, t1 = 0;
   unsigned long long rounds = 0;
   for (;;) {
     if (prof) t0 = clock64();
     TpsPre P;
-    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.pred = -1; P.last = make_int2(0, 0);
+    P.pn = -1; P.ix = 0; P.iz = 0; P.tself = 0; P.pred = -1; P.predk = 0; P.pred2 = -1; P.last = make_int2(0, 0);
     if (run) run = tps_pre<URG>(S, G, nacc, P);
-    if (lane < LANES) { head[lane] = make_int4(run ? P.pn : -1, P.ix, P.iz, (int)P.tself); pred[lane] = run ? P.pred : -1; }
+    if (lane < LANES) { head[lane] = make_int4(run ? P.pn : -1, P.ix, P.iz, (int)P.tself); pred[lane] = make_int4(run ? P.pred : -1, P.predk & 0x7fffffff, run ? P.pred2 : -1, 0); }
     const bool any = __any_sync(0xffffffffu, run);
     if (lane == 0) *flag = any ? 1 : 0;
     coh_arrive<NT>(COH_X);
@@ -1183,9 +1185,20 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         int4 r = make_int4(0, 0, 0, 0);
-        if (run) r = res[q * LANES + lane];
+        if (run) r = res[(cur * 4 + q) * LANES + lane];
         N[q].qst = r.x; N[q].qid = r.y; N[q].qt = __int_as_float(r.z); N[q].co = r.w;
       }
+      // Records may have been computed AHEAD (coh_march_stencil), while the previous round's updates were still being
+      // applied.  What can differ from a gather made now: (1) a neighbour that round inserted was still far when it was
+      // read -> it is close now: take its position from E (qid = 0 fails the slot check in tps_apply); (2) heap
+      // positions: verified in tps_apply anyway.  Alive values are final when written, so the trial times are exact.
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (N[q].qst == -1 && (N[q].co == ins[0] || N[q].co == ins[1] || N[q].co == ins[2] || N[q].co == ins[3])) { N[q].qst = 1; N[q].qid = 0; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ins[q] = (run && N[q].qst == -1) ? N[q].co : -1;
+      cur ^= 1;
       if (prof) { __syncwarp(); t1 = clock64(); c_nread += t1 - t0; t0 = t1; }
       run = tps_apply<URG, true>(S, G, N, run);
     }
@@ -1206,34 +1219,52 @@ __device__ void coh_march_heap(TpsState& S, const TpsGrid& G, int* xch, const in
 }
 
 // Stencil thread t serves solve l = t / (4 QS), neighbour q = (t / QS) % 4, part = t % QS of that neighbour's four
-// quadrant solves: the QS parts of one neighbour are adjacent lanes and reduce with shuffles.  (The four quadratics of a
-// neighbour in ONE thread take ~5 000 cycles with their IEEE divisions and square roots -- longer than the heap warp's pop,
-// so the heap warp used to wait for them; measured, profiles/r2_k3_cohort_cycle_split.txt.)
+// quadrant solves: the QS parts of one neighbour are adjacent lanes and reduce with shuffles.
+// WORKING AHEAD: the gather + quadratics of one neighbour take ~8 000 cycles (a DRAM round trip with 8 000 fronts in
+// flight, then four IEEE quadratics in a row) against ~3 000 for the heap warp's pop: done after the node is posted they
+// are the critical path.  So right after delivering the records of round r the stencil threads compute the records of
+// the node the heap warp PREDICTS for round r + 1 (the root after this pop, with its key), into the other record buffer,
+// while the heap warp applies round r.  In round r + 1 they compare the posted (node, key) with what they worked on:
+// equal -> the records are already there; different (an update of round r put another node, or a smaller key, on top:
+// 172 of 991 910 rounds on S200) -> computed now, as before.  What a record computed ahead can miss is patched by the
+// heap warp (coh_march_heap).  pf2: the stencil lines of the node expected AFTER the predicted one are pulled towards
+// the L2 one round earlier still (hint only).
 template <int URG, int LANES, int QS>
-__device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const int q, const int part) {
+__device__ void coh_march_stencil(const TpsGrid& G, int* xch, const int l, const int q, const int part, const bool pf2) {
   constexpr int NT = coh_threads(LANES, QS);
   const int4* head = reinterpret_cast<const int4*>(xch);
   volatile int* flag = xch + 4 * LANES;
-  const int* pred = xch + 4 * LANES + 32;
-  int4* res = reinterpret_cast<int4*>(xch + 4 * LANES + 64);
+  const int4* pred = reinterpret_cast<const int4*>(xch + 4 * LANES + 32);
+  int4* res = reinterpret_cast<int4*>(xch + 8 * LANES + 32);
   const float inv_ld = G.inv_ld;
+  int spec_node = -1, spec_key = 0, cur = 0;
+  const unsigned gm = QS == 1 ? 0u : (((1u << QS) - 1u) << ((threadIdx.x & 31) & ~(QS - 1)));   // the parts of my neighbour
   for (;;) {
     coh_sync<NT>(COH_X);
     if (!*flag) { coh_arrive<NT>(COH_Y); break; }      // acknowledge the stop flag (see coh_march_heap)
     const int4 hd = head[l];
-    TpsNb R;
-    R.qst = 0; R.qid = 0; R.co = 0; R.qt = tps_inf();
-    if (hd.x >= 0) R = tps_neighbour_part<URG, QS>(G, hd.y, hd.z, (unsigned)hd.w, q, part);
-    if (QS >= 2) R.qt = fminf(R.qt, __shfl_xor_sync(0xffffffffu, R.qt, 1));
-    if (QS >= 4) R.qt = fminf(R.qt, __shfl_xor_sync(0xffffffffu, R.qt, 2));
-    if (hd.x >= 0 && part == 0) res[q * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
-    const int pn2 = pred[l];
+    const int4 pd = pred[l];
+    if (hd.x >= 0 && !(hd.x == spec_node && hd.w == spec_key)) {
+      TpsNb R = tps_neighbour_part<URG, QS>(G, hd.y, hd.z, (unsigned)hd.w, q, part);
+      if (QS >= 2) R.qt = fminf(R.qt, __shfl_xor_sync(gm, R.qt, 1));
+      if (QS >= 4) R.qt = fminf(R.qt, __shfl_xor_sync(gm, R.qt, 2));
+      if (part == 0) res[(cur * 4 + q) * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
+    }
     coh_arrive<NT>(COH_Y);
-    // while the heap warp applies this node's updates: pull the stencil of the node that will be accepted next towards the L2
-    if (pn2 >= 0 && part == 0) {
+    cur ^= 1;
+    spec_node = pd.x; spec_key = pd.y;
+    if (pf2 && pd.z >= 0 && part == 0) {
       int px, pz;
-      ndecode<URG>(pn2, G.ld, inv_ld, px, pz);
+      ndecode<URG>(pd.z, G.ld, inv_ld, px, pz);
       tps_neighbour_prefetch<URG>(G, px, pz, q);
+    }
+    if (pd.x >= 0) {
+      int px, pz;
+      ndecode<URG>(pd.x, G.ld, inv_ld, px, pz);
+      TpsNb R = tps_neighbour_part<URG, QS>(G, px, pz, (unsigned)pd.y, q, part);
+      if (QS >= 2) R.qt = fminf(R.qt, __shfl_xor_sync(gm, R.qt, 1));
+      if (QS >= 4) R.qt = fminf(R.qt, __shfl_xor_sync(gm, R.qt, 2));
+      if (part == 0) res[(cur * 4 + q) * LANES + l] = make_int4(R.qst, R.qid, __float_as_int(R.qt), R.co);
     }
   }
 }
@@ -1288,8 +1319,8 @@ __global__ void __launch_bounds__(32 + 4 * LANES * QS, LANES == 32 ? 2 : (LANES 
       __syncwarp();
       coh_march_heap<2, LANES, QS>(S, Gc, xch, lane, act && !S.overflow, nacc, A.prof && blockIdx.x == 0);
     } else {
-      coh_march_stencil<1, LANES, QS>(Gr, xch, l, q, part);
-      coh_march_stencil<2, LANES, QS>(Gc, xch, l, q, part);
+      coh_march_stencil<1, LANES, QS>(Gr, xch, l, q, part, A.pf2 != 0);
+      coh_march_stencil<2, LANES, QS>(Gc, xch, l, q, part, A.pf2 != 0);
     }
   }
   if (warp == 0) {

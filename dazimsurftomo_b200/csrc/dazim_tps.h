@@ -172,6 +172,7 @@ struct TpsArgs {
   int* hpos_r_out;            // optional test seam [nsrc][REF_N]: heap slots of the close nodes after the refined march
   int* flags;                 // bit4 (16): heap / id overflow
   unsigned long long* n_accept;
+  int pf2;                    // cohort kernel: prefetch the stencil of the node after the predicted one (DAZIM_COH_PF2, default on)
   int prof;                   // DAZIM_COH_PROF=1: lane 0 of CTA 0 prints its cycle split per accept (cohort kernel)
 };
 
@@ -348,7 +349,7 @@ struct TpsGrid {
 // One accept step of travel's DO WHILE (CalSurfG.f90:356-456) in three pieces, so that the same code serves the
 // one-thread-per-solve kernel (pre + 4 x neighbour + post in one thread), the cohort kernel (pre/post on the heap
 // warp, one neighbour per stencil warp) and the host twin.
-struct TpsPre { int pn, ix, iz, pred; unsigned tself; int2 last; };   // pred: node that will be on top after this pop (hint)
+struct TpsPre { int pn, ix, iz, pred, predk, pred2; unsigned tself; int2 last; };   // pred / predk: node (and its key) that will be on top after this pop; pred2: a guess for the one after (hints)
 struct TpsNb { int qst, qid, co; float qt; };     // neighbour status (-2 outside, -1 far, 0 alive, 1 close), heap position read, offset, trial
 
 // (1) the node on top of the heap becomes alive.  Returns false when the march is over (heap empty, overflow, or the
@@ -365,13 +366,25 @@ TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, Tps
   // which node will be the root after this pop?  (first level of downtree, decided now; unless one of the four updates
   // puts a smaller key on top it is the next node to be accepted: the stencil threads prefetch its stencil lines)
   P.pred = -1;
+  P.predk = 0;
+  P.pred2 = -1;
   {
     const int n1 = S.ntr - 1;
-    if (n1 == 1) P.pred = P.last.y;
+    if (n1 == 1) { P.pred = P.last.y; P.predk = P.last.x; }
     else if (n1 >= 2) {
-      int2 c = tps_hget(S, 2);
-      if (n1 >= 3) { const int2 c3 = tps_hget(S, 3); if (TKEY(c) > TKEY(c3)) c = c3; }
-      P.pred = (TKEY(c) < TKEY(P.last)) ? c.y : P.last.y;
+      const int2 c2 = tps_hget(S, 2);
+      int2 c = c2, o = make_int2(0x7f800000, -1);
+      int pc = 2;
+      if (n1 >= 3) { const int2 c3 = tps_hget(S, 3); if (TKEY(c2) > TKEY(c3)) { c = c3; o = c2; pc = 3; } else o = c3; }
+      if (!(TKEY(c) < TKEY(P.last))) { o = c; c = P.last; pc = 0; }
+      P.pred = c.y; P.predk = c.x;
+      // the one after: the other child of the root or a child of the predicted node (prefetch hint only)
+      if (pc && 2 * pc + 1 <= n1) {
+        const int2 g0 = tps_hget(S, 2 * pc), g1 = tps_hget(S, 2 * pc + 1);
+        if (TKEY(g0) < TKEY(o)) o = g0;
+        if (TKEY(g1) < TKEY(o)) o = g1;
+      }
+      P.pred2 = o.y;
     }
   }
   if (URG == 1) {
