@@ -400,16 +400,17 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
   // ---- kernel choice (measured on the B200, profiles/r2_k3_kernel_choice.md).  The round-1 kernels keep the whole
   //      narrow band in shared memory when few solves compete (two-warp latency kernel: 1.6-2.1 us per accept) and
   //      pack 5 920 solves per chip otherwise (half-warp throughput kernel).  The cohort kernel (dazim_tps.h: one heap
-  //      LANE per solve) holds 8 288 solves per chip; it wins exactly when the job needs more than one wave of the
-  //      throughput kernel on a grid whose band cannot live in shared memory anyway (S200: 6.8 s against 9.0 s), and
-  //      loses on small grids / few solves (test1 shape: 91 ms against 50 ms).  DAZIM_TPS=1/0 forces the choice;
-  //      the legacy knobs (DAZIM_DUO / DAZIM_SPC) imply DAZIM_TPS=0. ----
+  //      LANE per solve, neighbour records computed one node ahead) holds 8 288 solves per chip; on a grid whose band
+  //      cannot live in shared memory anyway it beats the throughput kernel at every size measured (S200 grid: 3 000
+  //      solves 3.54 s against 3.99 s, 4 000: 3.89 / 4.72, 8 000: 5.18 / 8.97) and loses only to the two-warp kernel
+  //      while that one holds every solve resident (<= 2 368 solves) and on small grids (test1 shape: 91 ms against
+  //      50 ms).  DAZIM_TPS=1/0 forces the choice; the legacy knobs (DAZIM_DUO / DAZIM_SPC) imply DAZIM_TPS=0. ----
   int auto_tps = 0;
   {
     int nc_l = 1;
     int st_l = legacy_fmm_config(P, nsrc, hneed, hmin, &nc_l);
     if (st_l) { plan_free(P); return st_l; }
-    auto_tps = (!P->duo && hneed >= 2048 && 10 * nsrc > 9 * (long long)P->spc * nc_l) ? 1 : 0;
+    auto_tps = (!P->duo && hneed >= 2048) ? 1 : 0;
   }
   P->tps = auto_tps;
   if (getenv("DAZIM_DUO") || getenv("DAZIM_SPC")) P->tps = 0;
