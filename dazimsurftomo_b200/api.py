@@ -86,6 +86,8 @@ def load():
         lib.dazim_destroy.restype = None
         lib.dazim_host_free.argtypes = [C.c_void_p]
         lib.dazim_host_free.restype = None
+        lib.dazim_comm_destroy.argtypes = [C.c_void_p]
+        lib.dazim_comm_destroy.restype = None
         _lib = lib
     return _lib
 
@@ -317,6 +319,87 @@ def LSMR(m, n, row, col, rw, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, it
     return x, {k: getattr(info, k) for k, _ in info._fields_}
 
 
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """Communicator of the row-distributed solver (dazim_comm_create): one process per GPU.  `Comm.from_torch()` takes
+    rank / world size from an initialised torch.distributed group (any backend) and broadcasts rank 0's NCCL id over
+    it; `Comm(device, id_bytes, rank, nranks)` is the plain form for callers with their own launcher."""
+
+    def __init__(self, device: int, id_bytes: bytes, rank: int, nranks: int):
+        if len(id_bytes) != COMM_ID_BYTES:
+            raise ValueError("communicator id must have %d bytes" % COMM_ID_BYTES)
+        self._c = C.c_void_p()
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(id_bytes)
+        _chk(load().dazim_comm_create(C.c_int(device), buf, C.c_int(rank), C.c_int(nranks), C.byref(self._c)))
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * COMM_ID_BYTES)()
+        _chk(load().dazim_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def broadcast_id(cls) -> bytes:
+        """Rank 0's NCCL id on every rank of the initialised torch.distributed group (works over gloo and nccl)."""
+        import torch.distributed as dist
+        box = [cls.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    @classmethod
+    def from_torch(cls, device: int):
+        import torch.distributed as dist
+        return cls(device, cls.broadcast_id(), dist.get_rank(), dist.get_world_size())
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c:
+            load().dazim_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def split_rows(m: int, nranks: int):
+    """Contiguous row blocks of an m-row system for the row-distributed solve: [(first, count)] per rank (0-based)."""
+    base, extra = divmod(m, nranks)
+    out, first = [], 0
+    for r in range(nranks):
+        cnt = base + (1 if r < extra else 0)
+        out.append((first, cnt))
+        first += cnt
+    return out
+
+
+def row_block(row, col, rw, b, first: int, count: int):
+    """The triplets and right-hand side of rows first+1 .. first+count (1-based ids in `row`), re-numbered from 1:
+    what one rank passes to LSMR_rows."""
+    row = np.asarray(row); sel = (row > first) & (row <= first + count)
+    return (np.ascontiguousarray(row[sel] - first, np.int32), np.ascontiguousarray(np.asarray(col)[sel], np.int32),
+            np.ascontiguousarray(np.asarray(rw)[sel], np.float32), np.ascontiguousarray(np.asarray(b)[first:first + count], np.float32))
+
+
+def LSMR_rows(comm: Comm, m_local, m_total, n, row, col, rw, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, itnlim=500,
+              localSize=10, handle: Optional[Handle] = None):
+    """lsmrModule.f90:36 with the rows of A spread over the ranks of `comm` (dazim_lsmr_rows): this rank's m_local rows
+    (local 1-based ids) and b entries in, the replicated solution out.  Collective."""
+    h = handle or default_handle()
+    row = np.ascontiguousarray(row, np.int32); col = np.ascontiguousarray(col, np.int32)
+    rw = np.ascontiguousarray(rw, np.float32); b = np.ascontiguousarray(b, np.float32)
+    x = np.zeros(n, np.float32)
+    info = LsmrInfo()
+    _chk(load().dazim_lsmr_rows(h._h, comm._c, C.c_int(m_local), C.c_longlong(m_total), C.c_int(n), C.c_longlong(len(rw)),
+                                _p(row), _p(col), _p(rw), _p(b), C.c_float(damp), C.c_float(atol), C.c_float(btol),
+                                C.c_float(conlim), C.c_int(itnlim), C.c_int(localSize), _p(x), C.byref(info)))
+    return x, {k: getattr(info, k) for k, _ in info._fields_}
+
+
 def fmm_solve(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, handle: Optional[Handle] = None):
     """Test seam: eikonal fields of n sources on one phase-velocity map."""
     h = handle or default_handle()
@@ -538,6 +621,19 @@ class Plan:
         info = LsmrInfo()
         _chk(load().dazim_plan_lsmr(self._plan, _p(b), C.c_float(damp), C.c_float(atol), C.c_float(btol), C.c_float(conlim),
                                     C.c_int(itnlim), C.c_int(localSize), _p(x), C.byref(info)))
+        return x, {k: getattr(info, k) for k, _ in info._fields_}
+
+    def lsmr_rows(self, comm, m_total, b, damp=0.0, atol=1e-5, btol=1e-4, conlim=200.0, itnlim=500, localSize=10):
+        """Row-distributed LSMR over the G row blocks the ranks' plans built for their shares of the sources
+        (dazim_plan_lsmr_rows): no gather of G, one n-vector all-reduce per iteration.  b = this rank's rows."""
+        b = np.ascontiguousarray(b, np.float32)
+        nx, ny, nz = self._pr.shape
+        n = (3 if self.mode == 2 else 1) * (nx - 2) * (ny - 2) * (nz - 1)
+        x = np.zeros(n, np.float32)
+        info = LsmrInfo()
+        _chk(load().dazim_plan_lsmr_rows(self._plan, comm._c, C.c_longlong(m_total), _p(b), C.c_float(damp), C.c_float(atol),
+                                         C.c_float(btol), C.c_float(conlim), C.c_int(itnlim), C.c_int(localSize), _p(x),
+                                         C.byref(info)))
         return x, {k: getattr(info, k) for k, _ in info._fields_}
 
     def update_model(self, vels, tables: dict):

@@ -7,11 +7,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdazim_b200.so")
-SOURCES = ["dazim_fmm.cu", "dazim_trace.cu", "dazim_th.cu", "dazim_lsmr.cu", "dazim_invert.cu", "dazim_api.cu", "dazim_fortran.cu"]
+SOURCES = ["dazim_fmm.cu", "dazim_trace.cu", "dazim_th.cu", "dazim_lsmr.cu", "dazim_invert.cu", "dazim_api.cu", "dazim_fortran.cu", "dazim_comm.cu"]
 # --fmad=false: the reference is x86-64/SSE2 Fortran without FMA contraction; parity of the
 # float32 eikonal / ray arithmetic and of the float64 Thomson-Haskell chain depends on it.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
-              "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+              "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def needs_build() -> bool:

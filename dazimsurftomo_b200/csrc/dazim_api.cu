@@ -42,10 +42,11 @@ int th_depthkernel_ti(cudaStream_t st, int nx, int ny, int nz, const float* vel,
 int th_surfdisp96(cudaStream_t st, int nprof, int nlayer, const float* thk, const float* vp, const float* vs,
                   const float* rho, int kmax, const double* t, double* cg);
 }  // namespace dz
+#include "dazim_coll.h"
 namespace dzl {
 int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, const int* col, const float* rw,
                const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize, float* x,
-               dazim_lsmr_info* info, bool coo_on_device);
+               dazim_lsmr_info* info, bool coo_on_device, const Coll* coll = nullptr);
 }
 
 using namespace dz;
@@ -278,6 +279,7 @@ extern "C" const char* dazim_strerror(int code) {
     case DAZIM_EHEAP: return "narrow band exceeded heap workspace";
     case DAZIM_EFOOTPRINT: return "ray footprint exceeded workspace";
     case DAZIM_ENOROOT: return "improper initial value in disper - no zero found";
+    case DAZIM_ENCCL: return "NCCL not available or a collective failed";
     default: break;
   }
   if (code >= DAZIM_ECUDA) return cudaGetErrorString((cudaError_t)(code - DAZIM_ECUDA));
@@ -1141,6 +1143,29 @@ extern "C" int dazim_plan_lsmr(dazim_plan* P, const float* b, float damp, float 
   const long long ncol = (long long)nblk * P->g.nvx * P->g.nvz * (P->nz - 1);
   return dzl::lsmr_solve(h->st, (int)P->nrow, (int)ncol, P->nnz, P->d_rowid.p, P->d_col.p, P->d_val.p, b, damp, atol, btol,
                          conlim, itnlim, localSize, x, info, true);
+}
+
+extern "C" int dazim_lsmr_rows(dazim_handle* h, dazim_comm* comm, int m_local, long long m_total, int n, long long nnz,
+                               const int* iw_row, const int* col, const float* rw, const float* b, float damp, float atol,
+                               float btol, float conlim, int itnlim, int localSize, float* x, dazim_lsmr_info* info) {
+  if (!h || !comm || m_total < m_local) return DAZIM_EBADARG;
+  CK(cudaSetDevice(h->dev));
+  const dzl::Coll coll{comm, dzc::sum_f32, dzc::sum_f64, m_total};
+  return dzl::lsmr_solve(h->st, m_local, n, nnz, iw_row, col, rw, b, damp, atol, btol, conlim, itnlim, localSize, x, info,
+                         false, &coll);
+}
+
+extern "C" int dazim_plan_lsmr_rows(dazim_plan* P, dazim_comm* comm, long long m_total, const float* b, float damp,
+                                    float atol, float btol, float conlim, int itnlim, int localSize, float* x,
+                                    dazim_lsmr_info* info) {
+  if (!P || !comm || P->mode == 0 || P->nnz <= 0 || m_total < P->nrow) return DAZIM_EBADARG;
+  dazim_handle* h = P->h;
+  CK(cudaSetDevice(h->dev));
+  const int nblk = (P->mode == 2) ? 3 : 1;
+  const long long ncol = (long long)nblk * P->g.nvx * P->g.nvz * (P->nz - 1);
+  const dzl::Coll coll{comm, dzc::sum_f32, dzc::sum_f64, m_total};
+  return dzl::lsmr_solve(h->st, (int)P->nrow, (int)ncol, P->nnz, P->d_rowid.p, P->d_col.p, P->d_val.p, b, damp, atol, btol,
+                         conlim, itnlim, localSize, x, info, true, &coll);
 }
 
 // ---------------------------------------------------------------------------

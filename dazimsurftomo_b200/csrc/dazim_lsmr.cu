@@ -14,6 +14,7 @@
 // of three times per iteration.  Iterations enqueued past the stopping one are no-ops: istop / itn / x are exactly
 // those of the synchronous loop.
 #include "../../include/dazim_b200.h"
+#include "dazim_coll.h"
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -449,6 +450,23 @@ __global__ void k_reorth_axpy(float* __restrict__ v, const float* __restrict__ l
   if (i < n) v[i] = v[i] - d * lq[i];
 }
 
+// row-distributed solve: the block partials of a norm over the LOCAL rows fold into partial[0] (fixed order), the ranks'
+// sums are added by the all-reduce, and the tails then read ONE partial
+__global__ void k_fold_partial(double* __restrict__ partial, int nb) {
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int i = lane; i < nb; i += 32) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) partial[0] = s;
+}
+// v = v + t (the all-reduced A^T u of the row blocks)
+__global__ void k_add_state(float* __restrict__ v, const float* __restrict__ t, int n, const LsmrState* __restrict__ S, int need_beta) {
+  if (S && (S->istop || (need_beta && !S->beta_pos))) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = v[i] + t[i];
+}
+
 struct Ctx {
   cudaStream_t st;
   double* partial;
@@ -513,7 +531,7 @@ static int compress(cudaStream_t st, long long nnz, int nkey, const int* d_key, 
 // coo_on_device: row/col/rw already live in HBM (the G row block of a plan): no upload, G never leaves the GPU
 int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, const int* col, const float* rw,
                const float* b, float damp, float atol, float btol, float conlim, int itnlim, int localSize, float* x,
-               dazim_lsmr_info* info, bool coo_on_device) {
+               dazim_lsmr_info* info, bool coo_on_device, const Coll* coll) {
   if (m < 1 || n < 1 || nnz < 0 || nnz >= (1ll << 31) || !row || !col || !rw || !b || !x || !info) return DAZIM_EBADARG;
   Guard G;
   for (int i = 0; i < 3; ++i) LCK(cudaEventCreate(&G.ev[i]));
@@ -579,11 +597,13 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   }
   const unsigned gws = (unsigned)(((long long)std::max(nseg, 1) * 32 + 255) / 256);
   // ---- vectors ----
-  const int localVecs = std::max(0, std::min(localSize, std::min(m, n)));
-  Buf<float> u, v, h, hbar, dx, localV, scal;
+  const long long m_all = coll ? coll->m_total : (long long)m;      // the reference sizes the window by the whole system
+  const int localVecs = std::max(0, (int)std::min<long long>(localSize, std::min<long long>(m_all, n)));
+  Buf<float> u, v, h, hbar, dx, localV, scal, vt;
   Buf<double> partial;
   Buf<LsmrState> dS;
   LCK(u.alloc(m, st)); LCK(v.alloc(n, st)); LCK(h.alloc(n, st)); LCK(hbar.alloc(n, st)); LCK(dx.alloc(n, st));
+  if (coll) LCK(vt.alloc(n, st));
   LCK(localV.alloc((size_t)localVecs * n, st)); LCK(scal.alloc(4, st)); LCK(partial.alloc(1024, st)); LCK(dS.alloc(1, st));
   Ctx c{st, partial.p, scal.p, 592};
   const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256);
@@ -595,11 +615,23 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
   LCK(cudaEventRecord(e1, st));
   info->itn = 0; info->istop = 0; info->normA = 0; info->condA = 0; info->normx = 0;
   float alpha = 0.0f, beta = 0.0f;
-  if ((rc = norm2(c, u.p, m, &beta))) return rc;
+  if (!coll) {
+    if ((rc = norm2(c, u.p, m, &beta))) return rc;
+  } else {
+    // ||b|| over the row blocks of every rank
+    const int nb0 = std::min(c.nb, std::max(1, (m + 255) / 256));
+    k_dot_partial<<<nb0, 256, 0, st>>>(u.p, u.p, m, partial.p);
+    k_fold_partial<<<1, 32, 0, st>>>(partial.p, nb0);
+    if ((rc = coll->sum_f64(coll->ctx, partial.p, 1, st))) return rc;
+    k_dot_final<<<1, 32, 0, st>>>(partial.p, 1, 1, scal.p);
+    LCK(cudaMemcpyAsync(&beta, scal.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LCK(cudaStreamSynchronize(st));
+  }
   if (beta > 0.0f) {
     k_scal<<<gm, 256, 0, st>>>(u.p, m, 1.0f / beta);
     k_spmv_seg<<<gws, 256, 0, st>>>(nseg, seg_off.p, csc_idx.p, csc_val.p, u.p, seg_partial.p, nullptr, 0);   // v = v + A^T u
     k_seg_reduce_add<<<gn, 256, 0, st>>>(n, colseg.p, seg_partial.p, v.p, nullptr, 0);
+    if (coll && (rc = coll->sum_f32(coll->ctx, v.p, (size_t)n, st))) return rc;      // v was 0: the sum of the blocks' A^T u
     if ((rc = norm2(c, v.p, n, &alpha))) return rc;
   }
   if (alpha > 0.0f) k_scal<<<gn, 256, 0, st>>>(v.p, n, 1.0f / alpha);
@@ -623,16 +655,31 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
     LCK(cudaStreamSynchronize(st));
     LsmrState* S = dS.p;
     const int nbm = std::min(c.nb, std::max(1, (m + 255) / 256)), nbn = std::min(c.nb, std::max(1, (n + 255) / 256));
+    int coll_rc = 0;
     auto enqueue_iteration = [&]() {
       k_scal_state<<<gm, 256, 0, st>>>(u.p, m, S, 0);                                                  // u = -alpha u
       k_spmv_add_state<<<gwm, 256, 0, st>>>(m, csr_ptr.p, csr_idx.p, csr_val.p, v.p, u.p, S, 0);       // u = u + A v
       k_dot_partial_state<<<nbm, 256, 0, st>>>(u.p, m, partial.p, S, 0);
-      k_tail_beta<<<1, 32, 0, st>>>(partial.p, nbm, S);                                                // beta, queue pointer
+      if (coll) {                                                                                      // ||u||^2 over all row blocks
+        k_fold_partial<<<1, 32, 0, st>>>(partial.p, nbm);
+        coll_rc |= coll->sum_f64(coll->ctx, partial.p, 1, st);
+      }
+      k_tail_beta<<<1, 32, 0, st>>>(partial.p, coll ? 1 : nbm, S);                                     // beta, queue pointer
       k_scal_state<<<gm, 256, 0, st>>>(u.p, m, S, 1);                                                  // u = u / beta
       if (localOrtho) k_store_local<<<gn, 256, 0, st>>>(localV.p, v.p, n, S);
       k_scal_state<<<gn, 256, 0, st>>>(v.p, n, S, 2);                                                  // v = -beta v
-      k_spmv_seg<<<gws, 256, 0, st>>>(nseg, seg_off.p, csc_idx.p, csc_val.p, u.p, seg_partial.p, S, 1);     // v = v + A^T u
-      k_seg_reduce_add<<<gn, 256, 0, st>>>(n, colseg.p, seg_partial.p, v.p, S, 1);
+      if (!coll) {
+        k_spmv_seg<<<gws, 256, 0, st>>>(nseg, seg_off.p, csc_idx.p, csc_val.p, u.p, seg_partial.p, S, 1);   // v = v + A^T u
+        k_seg_reduce_add<<<gn, 256, 0, st>>>(n, colseg.p, seg_partial.p, v.p, S, 1);
+      } else {
+        // t = A_local^T u_local, summed over the ranks (the one n-vector exchange of the iteration), v = v + t.  The
+        // all-reduce is not guarded by the device state: after a stop it adds zeros that nobody reads.
+        cudaMemsetAsync(vt.p, 0, sizeof(float) * n, st);
+        k_spmv_seg<<<gws, 256, 0, st>>>(nseg, seg_off.p, csc_idx.p, csc_val.p, u.p, seg_partial.p, S, 1);
+        k_seg_reduce_add<<<gn, 256, 0, st>>>(n, colseg.p, seg_partial.p, vt.p, S, 1);
+        coll_rc |= coll->sum_f32(coll->ctx, vt.p, (size_t)n, st);
+        k_add_state<<<gn, 256, 0, st>>>(v.p, vt.p, n, S, 1);
+      }
       if (localOrtho && (n <= 32768 || localVecs > 64)) k_reorth_state<<<1, 1024, 0, st>>>(v.p, localV.p, n, S);
       else if (localOrtho)
         for (int q = 0; q < localVecs; ++q) {
@@ -669,6 +716,7 @@ int lsmr_solve(cudaStream_t st, int m, int n, long long nnz, const int* row, con
       LCK(cudaMemcpyAsync(&ist_itn[1], &S->itn, sizeof(int), cudaMemcpyDeviceToHost, st));
       LCK(cudaStreamSynchronize(st));
       LCK(cudaGetLastError());
+      if (coll_rc) return DAZIM_ENCCL;
       if (ist_itn[0] != 0) break;
     }
     LCK(cudaMemcpyAsync(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost, st));

@@ -33,6 +33,7 @@ enum {
   DAZIM_EHEAP = 6,             /* narrow band larger than the heap workspace */
   DAZIM_EFOOTPRINT = 7,        /* a ray touched more control points than the footprint workspace holds */
   DAZIM_ENOROOT = 9,           /* surfdisp96 found no root (reference prints a warning and zero-fills) */
+  DAZIM_ENCCL = 10,            /* NCCL not loadable / a collective failed (row-distributed solver) */
   DAZIM_ECUDA = 100            /* + cudaError_t */
 };
 
@@ -202,6 +203,33 @@ int dazim_lsmr(dazim_handle* h, int m, int n, long long nnz, const int* iw_row, 
  * x has nparpi (iso) or 3*nparpi (joint) entries) */
 int dazim_plan_lsmr(dazim_plan* plan, const float* b, float damp, float atol, float btol, float conlim, int itnlim,
                     int localSize, float* x, dazim_lsmr_info* info);
+
+/* --- row-distributed LSMR (SURVEY 8f-1 "keeping G resident and row-distributed", 8e: "if the solver is later
+ * distributed by rows the gather of G disappears and only an n-vector all-reduce per LSMR iteration remains") --------
+ * One process per GPU.  Every rank holds a block of ROWS of A (its rays' rows of G, any share of the regularisation
+ * rows) and the matching entries of b; x and every n-vector of lsmrModule.f90 are replicated.  Per iteration the ranks
+ * exchange one n-vector (A^T u: ncclAllReduce, float32 sum) and one scalar (||u||^2, float64); both sit in stream order
+ * between the solver's kernels and are captured into the per-iteration CUDA graph.  All ranks return the same x / info
+ * bit for bit; against the single-GPU solve the sums associate differently (tolerance, not bit, parity).
+ * The communicator: rank 0 calls dazim_comm_unique_id and hands the DAZIM_COMM_ID_BYTES to every rank by any means
+ * (torch.distributed broadcast, MPI_Bcast, a file); every rank then calls dazim_comm_create with its device. */
+#define DAZIM_COMM_ID_BYTES 128
+typedef struct dazim_comm dazim_comm;
+int dazim_comm_unique_id(unsigned char* id /* [DAZIM_COMM_ID_BYTES] */);
+int dazim_comm_create(int device, const unsigned char* id, int rank, int nranks, dazim_comm** out);
+void dazim_comm_destroy(dazim_comm* comm);
+int dazim_comm_rank(const dazim_comm* comm);
+int dazim_comm_size(const dazim_comm* comm);
+/* dazim_lsmr on a row block: m_local rows with LOCAL 1-based row ids in iw_row, b_local (m_local); m_total = rows of
+ * the whole system (sizes the reorthogonalisation window like the reference: min(localSize, m, n)).  Collective: every
+ * rank of the communicator must call it with the same n and controls. */
+int dazim_lsmr_rows(dazim_handle* h, dazim_comm* comm, int m_local, long long m_total, int n, long long nnz_local,
+                    const int* iw_row, const int* col, const float* rw, const float* b_local, float damp, float atol,
+                    float btol, float conlim, int itnlim, int localSize, float* x, dazim_lsmr_info* info);
+/* the same on the G row block a plan built for its share of the sources (resident in HBM, never gathered) */
+int dazim_plan_lsmr_rows(dazim_plan* plan, dazim_comm* comm, long long m_total, const float* b_local, float damp,
+                         float atol, float btol, float conlim, int itnlim, int localSize, float* x,
+                         dazim_lsmr_info* info);
 
 /* --- next stage: the rest of one outer iteration of Main_Jt.f90 ----------------------------
  * Everything the reference does between two G builds (Main_Jt.f90:416-727), on the device-resident G of a plan:
