@@ -636,6 +636,15 @@ class Plan:
                                          C.byref(info)))
         return x, {k: getattr(info, k) for k, _ in info._fields_}
 
+    def iterate_rows(self, comm, dall_total, obst, vsf, iso_inv, weightVs, weightGcs, damp, minvel, maxvel,
+                     controls: Optional[dict] = None, want_rows=False):
+        """The iteration tail with G left on the ranks that built it (dazim_plan_iterate_rows): this rank's plan covers
+        its share of the sources; obst and the per-row results have dall_total entries.  Collective; every rank gets the
+        same result."""
+        return _iterate(lambda *tail: load().dazim_plan_iterate_rows(self._plan, comm._c, C.c_longlong(dall_total), *tail),
+                        self._pr.shape, int(dall_total), obst, vsf, iso_inv, weightVs, weightGcs, damp, minvel, maxvel,
+                        controls, want_rows)
+
     def update_model(self, vels, tables: dict):
         """New model, same geometry (dazim_plan_update_model): re-uploads vels and the depth-kernel tables."""
         nx, ny, nz = self._pr.shape

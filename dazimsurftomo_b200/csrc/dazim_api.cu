@@ -1252,9 +1252,22 @@ struct IterSystem {
   float* vels;               // [nx*ny*nz] device workspace for the model update
 };
 
+// Row-distributed form (rd != nullptr): Y holds THIS rank's block of rows (global rows rd->row0 + 1 .. rd->row0 + Y.nrow of
+// rd->dall); obst and every per-row output have the length of the WHOLE system.  What is O(rows) -- synthetic times,
+// residuals, weights, their statistics -- is made complete on every rank by a sum over zero-padded arrays (x + 0 is
+// exact) and then computed redundantly by the same kernels in the same order as on one GPU, so everything but the LSMR
+// solution is bit-identical to the single-GPU tail; what is O(non-zeros) -- row scaling, DWS, products with G, the
+// solve -- stays with the rank that owns the rows.  The regularisation rows live on the last rank.
+struct RowsDist {
+  const dzl::Coll* coll;
+  long long row0, dall;
+  int rank, nranks;
+};
+#define CKC(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
 static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst, const dazim_iter_params* prm, float* vsf,
                         float* dv, float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
-                        float* fwdTaa, dazim_iter_stats* S) {
+                        float* fwdTaa, dazim_iter_stats* S, const RowsDist* rd = nullptr) {
   CK(cudaSetDevice(h->dev));
   g_alloc_stream = h->st;
   cudaStream_t st = h->st;
@@ -1263,8 +1276,12 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
   const int maxvp = (nx - 2) * (ny - 2) * (nz - 1);
   const int nblk = iso ? 1 : 3;
   const int n = nblk * maxvp;
-  if (Y.nrow > 0x7fffffffll - 3ll * maxvp) return DAZIM_EBADARG;
-  const int dall = (int)Y.nrow;
+  const long long dall_ll = rd ? rd->dall : Y.nrow;
+  if (dall_ll > 0x7fffffffll - 3ll * maxvp || (rd && (rd->row0 < 0 || rd->row0 + Y.nrow > rd->dall))) return DAZIM_EBADARG;
+  const int dall = (int)dall_ll;               // rows of the whole system
+  const int dl = (int)Y.nrow;                  // rows held here
+  const long long r0 = rd ? rd->row0 : 0;
+  const bool own_reg = !rd || rd->rank == rd->nranks - 1;
   std::memset(S, 0, sizeof(*S));
   struct Events {                               // destroyed on every return path
     cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1275,8 +1292,9 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
   DBuf<float> d_obst, d_cbst, d_tdata, d_dt, d_sig, d_w, d_stats, d_b, d_dv, d_gcf, d_gsf, d_tvs, d_taa, d_res, d_resw,
       d_lm, d_lmw, d_dws;
   DBuf<double> d_partial, d_dwsacc;
+  DBuf<float> d_dsyn;
   const long long reg_entries = (long long)nblk * dzi::tikh_block_entries(nx - 2, ny - 2, nz - 1);
-  if (Y.nnz + reg_entries > Y.cap) return DAZIM_ENNZ_OVERFLOW;   // the caller reserves this room (plan_run does)
+  if (own_reg && Y.nnz + reg_entries > Y.cap) return DAZIM_ENNZ_OVERFLOW;   // the caller reserves this room (plan_run does)
   CK(d_obst.alloc(dall)); CK(d_cbst.alloc(dall)); CK(d_tdata.alloc(dall)); CK(d_dt.alloc(dall)); CK(d_sig.alloc(dall));
   CK(d_w.alloc(dall)); CK(d_stats.alloc(64)); CK(d_b.alloc((size_t)dall + (size_t)nblk * maxvp)); CK(d_dv.alloc(n));
   CK(d_gcf.alloc(maxvp)); CK(d_gsf.alloc(maxvp)); CK(d_tvs.alloc(dall)); CK(d_taa.alloc(dall)); CK(d_res.alloc(dall));
@@ -1287,8 +1305,16 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
   CK(cudaMemsetAsync(d_stats.p, 0, sizeof(float) * 64, st));     // slots a mode does not use read back as zero
   CK(cudaMemcpyAsync(d_obst.p, obst, sizeof(float) * dall, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(e0, st));
+  const float* dsyn = Y.dsurf;
+  if (rd) {                                    // the synthetic times of every rank's rays
+    CK(d_dsyn.alloc(dall));
+    CK(cudaMemsetAsync(d_dsyn.p, 0, sizeof(float) * dall, st));
+    CK(cudaMemcpyAsync(d_dsyn.p + r0, Y.dsurf, sizeof(float) * dl, cudaMemcpyDeviceToDevice, st));
+    CKC(rd->coll->sum_f32(rd->coll->ctx, d_dsyn.p, (size_t)dall, st));
+    dsyn = d_dsyn.p;
+  }
   // ---- residual of the reference model, CalDdatSigma, weights (Main_Jt.f90:425-469) ----
-  CK(dzi::launch_resid(dall, d_obst.p, Y.dsurf, d_cbst.p, d_tdata.p, d_dt.p, st));
+  CK(dzi::launch_resid(dall, d_obst.p, dsyn, d_cbst.p, d_tdata.p, d_dt.p, st));
   {
     const float* arrs[2] = {d_cbst.p, d_dt.p};
     CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p, st));                       // [0..2] cbst, [3..5] deltaT
@@ -1300,21 +1326,36 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
     CK(dzi::launch_seq_stats(2, arrs, dall, d_stats.p + 6, st));                   // [6] sum w, [10] sum |cbst_w|
   }
   CK(cudaEventRecord(e2, st));
-  CK(dzi::launch_scale_rows(Y.nrow, Y.rowptr, d_w.p, Y.val, st));
+  CK(dzi::launch_scale_rows(Y.nrow, Y.rowptr, d_w.p + r0, Y.val, st));
   CK(cudaEventRecord(e3, st));
-  if (iso && dws) CK(dzi::launch_dws(Y.nnz, Y.col, Y.val, maxvp, d_dwsacc.p, d_dws.p, st));
+  if (iso && dws) {
+    CK(dzi::launch_dws(Y.nnz, Y.col, Y.val, maxvp, d_dwsacc.p, d_dws.p, st));
+    if (rd) {
+      CKC(rd->coll->sum_f64(rd->coll->ctx, d_dwsacc.p, (size_t)maxvp, st));
+      CK(dzi::launch_dws_finish(maxvp, d_dwsacc.p, d_dws.p, st));
+    }
+  }
   // ---- regularisation rows behind G (Main_Jt.f90:507-520) ----
   long long appended = 0, after_vs = -1;
   int count3 = 0;
-  {
-    int rc = tikh_append(st, iso ? 0 : 1, iso, nx, ny, nz, maxvp, dall, Y.nnz, prm->weightGcs, prm->weightVs, Y.val,
+  if (own_reg) {
+    int rc = tikh_append(st, iso ? 0 : 1, iso, nx, ny, nz, maxvp, dl, Y.nnz, prm->weightGcs, prm->weightVs, Y.val,
                          Y.col, Y.rowid, &appended, &count3, &after_vs);
     if (rc) return rc;
   }
-  const long long nar1 = Y.nnz, nar = Y.nnz + appended;
-  const int m = dall + count3;
-  CK(cudaMemcpyAsync(d_b.p, d_cbst.p, sizeof(float) * dall, cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemsetAsync(d_b.p + dall, 0, sizeof(float) * (size_t)count3, st));
+  const long long nar1 = Y.nnz, nar = Y.nnz + appended;     // of this rank's block
+  const int m = dl + count3;
+  long long nar1_all = nar1, nar_all = nar, count3_all = count3;
+  if (rd) {                                    // sizes of the whole system (integers below 2^53: exact in double)
+    double hc[3] = {(double)nar1, (double)nar, (double)count3};
+    CK(cudaMemcpyAsync(d_partial.p, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+    CKC(rd->coll->sum_f64(rd->coll->ctx, d_partial.p, 3, st));
+    CK(cudaMemcpyAsync(hc, d_partial.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nar1_all = (long long)hc[0]; nar_all = (long long)hc[1]; count3_all = (long long)hc[2];
+  }
+  CK(cudaMemcpyAsync(d_b.p, d_cbst.p + r0, sizeof(float) * dl, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(d_b.p + dl, 0, sizeof(float) * (size_t)count3, st));
   // ---- LSMR on [W G ; L] (Main_Jt.f90:527-564) ----
   float atol = prm->atol, btol = prm->btol, conlim = prm->conlim;
   int itnlim = prm->itnlim, localSize = prm->localSize;
@@ -1323,15 +1364,17 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
     else { atol = 1e-5f; btol = 1e-4f; conlim = 200.0f; itnlim = 500; localSize = 10; }
   }
   {
+    dzl::Coll cl;
+    if (rd) { cl = *rd->coll; cl.m_total = (long long)dall + count3_all; }
     int rc = dzl::lsmr_solve(st, m, n, nar, Y.rowid, Y.col, Y.val, d_b.p, prm->damp, atol, btol, conlim,
-                             itnlim, localSize, d_dv.p, &S->lsmr, true);
+                             itnlim, localSize, d_dv.p, &S->lsmr, true, rd ? &cl : nullptr);
     if (rc) return rc;
   }
   // ---- model update (Main_Jt.f90:582-620) ----
   CK(cudaMemcpyAsync(Y.vels, vsf, sizeof(float) * (size_t)nx * ny * nz, cudaMemcpyHostToDevice, st));
   CK(dzi::launch_model_update(nx, ny, nz, iso, d_dv.p, Y.vels, prm->minvel, prm->maxvel, d_gcf.p, d_gsf.p, st));
   // ---- ||Lm|| and the residual of the solution from the sparse rows (CalSigamNorm.f90) ----
-  const long long nre = nar - nar1, nre_vs = iso ? nre : after_vs - nar1;
+  const long long nre = nar - nar1, nre_vs = iso ? nre : (own_reg ? after_vs - nar1 : 0);
   CK(dzi::launch_lm_terms(nre, nre_vs, Y.val + nar1, Y.col + nar1, d_dv.p, prm->weightVs, prm->weightGcs, d_lm.p,
                           d_lmw.p, st));
   if (iso) {
@@ -1345,8 +1388,18 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
     CK(dzi::launch_norm2(d_lm.p, nre, d_partial.p, d_stats.p + 36, st));
     CK(dzi::launch_norm2(d_lmw.p, nre, d_partial.p, d_stats.p + 37, st));
   }
-  CK(dzi::launch_resid_rows(Y.nrow, Y.rowptr, Y.col, Y.val, d_dv.p, d_w.p, maxvp, nblk, d_tdata.p, d_tvs.p,
-                            d_taa.p, d_res.p, d_resw.p, st));
+  if (rd) {
+    // the model norms exist on the rank that owns the regularisation rows (zeros elsewhere): the sum hands them round
+    CKC(rd->coll->sum_f32(rd->coll->ctx, d_stats.p + 32, 6, st));
+    CK(cudaMemsetAsync(d_tvs.p, 0, sizeof(float) * dall, st)); CK(cudaMemsetAsync(d_taa.p, 0, sizeof(float) * dall, st));
+    CK(cudaMemsetAsync(d_res.p, 0, sizeof(float) * dall, st)); CK(cudaMemsetAsync(d_resw.p, 0, sizeof(float) * dall, st));
+  }
+  CK(dzi::launch_resid_rows(Y.nrow, Y.rowptr, Y.col, Y.val, d_dv.p, d_w.p + r0, maxvp, nblk, d_tdata.p + r0, d_tvs.p + r0,
+                            d_taa.p + r0, d_res.p + r0, d_resw.p + r0, st));
+  if (rd) {
+    CKC(rd->coll->sum_f32(rd->coll->ctx, d_tvs.p, (size_t)dall, st)); CKC(rd->coll->sum_f32(rd->coll->ctx, d_taa.p, (size_t)dall, st));
+    CKC(rd->coll->sum_f32(rd->coll->ctx, d_res.p, (size_t)dall, st)); CKC(rd->coll->sum_f32(rd->coll->ctx, d_resw.p, (size_t)dall, st));
+  }
   {
     const float* arrs[3] = {d_res.p, d_taa.p, d_tvs.p};
     CK(dzi::launch_seq_stats(3, arrs, dall, d_stats.p + 12, st));                  // [12..14] res, [16] |taa|, [19] |tvs|
@@ -1384,7 +1437,7 @@ static int iterate_core(dazim_handle* h, const IterSystem& Y, const float* obst,
   for (int q = 0; q < 6; ++q) S->norms[q] = hs[32 + q];
   S->res2Nm = hs[40];
   S->resW2Nm = hs[41];
-  S->nar1 = nar1; S->nar = nar; S->count3 = count3;
+  S->nar1 = nar1_all; S->nar = nar_all; S->count3 = (int)count3_all;
   cudaEventElapsedTime(&S->step_ms, e0, e1);
   cudaEventElapsedTime(&S->scale_ms, e2, e3);
   return DAZIM_OK;
@@ -1402,6 +1455,24 @@ extern "C" int dazim_plan_iterate(dazim_plan* P, const float* obst, const dazim_
   Y.rowptr = P->d_rowptr.p; Y.col = P->d_col.p; Y.val = P->d_val.p; Y.rowid = P->d_rowid.p; Y.dsurf = P->d_dsurf.p;
   Y.vels = P->d_vels.p;
   return iterate_core(P->h, Y, obst, prm, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa, S);
+}
+
+// The tail with the rows of G left where they were built: no gather of G, row-distributed LSMR.
+extern "C" int dazim_plan_iterate_rows(dazim_plan* P, dazim_comm* comm, long long dall_total, const float* obst,
+                                       const dazim_iter_params* prm, float* vsf, float* dv, float* gcf, float* gsf,
+                                       float* dws, float* sigmaT, float* resbst, float* fwdTvs, float* fwdTaa,
+                                       dazim_iter_stats* S) {
+  if (!P || !comm || !obst || !prm || !vsf || !dv || !S) return DAZIM_EBADARG;
+  if (P->mode != 1 && P->mode != 2) return DAZIM_EBADARG;
+  if ((P->mode == 1) != (prm->iso_inv != 0)) return DAZIM_EBADARG;
+  if (P->nrow < 1 || P->nnz < 1 || dall_total < P->row0 + P->nrow) return DAZIM_EBADARG;
+  IterSystem Y;
+  Y.nx = P->nx; Y.ny = P->ny; Y.nz = P->nz; Y.nrow = P->nrow; Y.nnz = P->nnz; Y.cap = P->val_cap;
+  Y.rowptr = P->d_rowptr.p; Y.col = P->d_col.p; Y.val = P->d_val.p; Y.rowid = P->d_rowid.p; Y.dsurf = P->d_dsurf.p;
+  Y.vels = P->d_vels.p;
+  const dzl::Coll coll{comm, dzc::sum_f32, dzc::sum_f64, 0};
+  const RowsDist rd{&coll, P->row0, dall_total, dazim_comm_rank(comm), dazim_comm_size(comm)};
+  return iterate_core(P->h, Y, obst, prm, vsf, dv, gcf, gsf, dws, sigmaT, resbst, fwdTvs, fwdTaa, S, &rd);
 }
 
 // The same tail on a system the caller holds in HBM -- the row blocks of several ranks after the NCCL all-gather

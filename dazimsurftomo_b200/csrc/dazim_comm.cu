@@ -77,6 +77,16 @@ extern "C" int dazim_comm_create(int device, const unsigned char* id, int rank, 
     delete c;
     return DAZIM_ENCCL;
   }
+  // first collective here, not inside the first solve: NCCL connects its channels lazily (hundreds of ms)
+  {
+    float* w = nullptr;
+    if (cudaMalloc(&w, sizeof(float)) == cudaSuccess) {
+      cudaMemset(w, 0, sizeof(float));
+      N->all_reduce(w, w, 1, ncclFloat32, ncclSum, c->comm, (cudaStream_t)0);
+      cudaStreamSynchronize((cudaStream_t)0);
+      cudaFree(w);
+    }
+  }
   *out = c;
   return DAZIM_OK;
 }

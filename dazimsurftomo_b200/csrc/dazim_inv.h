@@ -34,6 +34,7 @@ cudaError_t launch_seq_stats(int narr, const float* const* arrs, int n, float* o
 cudaError_t launch_sigma(int n, const float* deltaT, const float* obst, const float* st_dt, float* sigmaT,
                          float* datweight, float* cbst, cudaStream_t st);
 cudaError_t launch_scale_rows(long long nrow, const long long* rowptr, const float* w, float* val, cudaStream_t st);
+cudaError_t launch_dws_finish(int ncol, const double* acc, float* norm, cudaStream_t st);
 cudaError_t launch_dws(long long nnz, const int* col, const float* val, int ncol, double* acc, float* norm,
                        cudaStream_t st);
 cudaError_t launch_tikh(int nvx, int nvz, int nzm1, long long base, int row_base, int col_off, float weight, float* val,

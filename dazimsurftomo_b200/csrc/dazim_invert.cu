@@ -310,6 +310,11 @@ cudaError_t launch_dws(long long nnz, const int* col, const float* val, int ncol
   k_d2f<<<blocks(ncol, 256), 256, 0, st>>>(ncol, acc, norm);
   return cudaGetLastError();
 }
+// row-distributed tail: the per-column sums of the ranks' row blocks are added (double) before the conversion
+cudaError_t launch_dws_finish(int ncol, const double* acc, float* norm, cudaStream_t st) {
+  k_d2f<<<blocks(ncol, 256), 256, 0, st>>>(ncol, acc, norm);
+  return cudaGetLastError();
+}
 cudaError_t launch_tikh(int nvx, int nvz, int nzm1, long long base, int row_base, int col_off, float weight, float* val,
                         int* col, int* rowid, cudaStream_t st) {
   const int ncell = nvx * nvz * nzm1;

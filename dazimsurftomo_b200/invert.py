@@ -80,8 +80,13 @@ def tables_for(iso_inv: bool, vsf, depz, tRc, minthk, handle, rank=0, world=1, d
 
 
 def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | None = None, sv=None,
-        write_files: bool = True, log_stream=None) -> dict:
+        write_files: bool = True, log_stream=None, rows: bool | None = None) -> dict:
+    """rows (several ranks only; default: environment DAZIM_ROWS=1): leave every rank's rows of G where they were built
+    and run the tail row-distributed (Plan.iterate_rows: no all-gather of G, LSMR with one n-vector all-reduce per
+    iteration) instead of gathering the system on every rank."""
     t_start = time.time()
+    if rows is None:
+        rows = os.environ.get("DAZIM_ROWS", "0") not in ("", "0")
     base = os.path.dirname(os.path.abspath(para_path))
     outdir = outdir or base
     p = fm.read_para_inv(para_path)
@@ -123,6 +128,9 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
     say(" Number of all measurements%7d" % sv.dall)
 
     plan = None
+    comm = None
+    if world > 1 and rows:
+        comm = api.Comm.from_torch(device.index)
     history = []
     tRcV_first = tRcV = None
     tables = None
@@ -149,7 +157,14 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
             gpu_ms["gbuild"] += tm["total_ms"]
             system = None
             nnz_all = plan.nnz
-            if world > 1:
+            if world > 1 and comm is not None:
+                # rows stay where they are: only the non-zero count of the whole system is needed (spfra test below)
+                import torch
+                import torch.distributed as dist
+                cnt = torch.tensor([plan.nnz], dtype=torch.int64, device=device)
+                dist.all_reduce(cnt)
+                nnz_all = int(cnt.item())
+            elif world > 1:
                 # the exchange step: all-gather-v of the CSR row blocks and dsurf over NCCL, straight from HBM
                 import torch
                 t = plan.device_tensors()
@@ -174,6 +189,9 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
             if world == 1:
                 r = plan.iterate(obst, vsf, iso_inv, p.weightVs, p.weightGcs, p.damp, p.minvel, p.maxvel,
                                  want_rows=(it == 1 or last))
+            elif comm is not None:
+                r = plan.iterate_rows(comm, sv.dall, obst, vsf, iso_inv, p.weightVs, p.weightGcs, p.damp, p.minvel, p.maxvel,
+                                      want_rows=(it == 1 or last))
             else:
                 # every rank solves the gathered system (same data, same kernels: identical models, no broadcast needed)
                 r = api.iterate_device((nx, ny, nz), system, obst, vsf, iso_inv, p.weightVs, p.weightGcs, p.damp, p.minvel,
@@ -236,7 +254,18 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
                     for j in range(ny - 2):
                         iterf.write("".join("%10.3f" % dws[i, j, k] for i in range(nx - 2)) + "\n")
             if r.get("resbst") is not None:
-                dsyn = plan.fetch(csr=False)["dsurf"] if world == 1 else system["dsurf"].cpu().numpy()
+                if world == 1:
+                    dsyn = plan.fetch(csr=False)["dsurf"]
+                elif comm is not None:            # the synthetic times of every rank's rays (zero-padded sum)
+                    import torch
+                    import torch.distributed as dist
+                    loc = plan.fetch(csr=False)["dsurf"]
+                    full = torch.zeros(sv.dall, dtype=torch.float32, device=device)
+                    full[plan.row0:plan.row0 + len(loc)] = torch.from_numpy(np.ascontiguousarray(loc)).to(device)
+                    dist.all_reduce(full)
+                    dsyn = full.cpu().numpy()
+                else:
+                    dsyn = system["dsurf"].cpu().numpy()
                 rows_out = dict(dsyn=dsyn, Tdata=(obst - dsyn).astype(np.float32), fwdTvs=r["fwdTvs"], fwdTaa=r["fwdTaa"],
                                 resbst=r["resbst"], sigmaT=r["sigmaT"])
                 # Main_Jt.f90:701-717: written at iteration 1 and at the last one under the same name (id stays '00': its
@@ -274,7 +303,10 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
     say("   Program finishes successfully")
     say("   All time cost= %13.1fs   (GPU: depth kernels %.0f ms, G build %.0f ms, iteration tail %.0f ms of which LSMR %.0f ms%s)" %
         (time.time() - t_start, gpu_ms["kernels"], gpu_ms["gbuild"], gpu_ms["iterate"], gpu_ms["lsmr"],
-         "" if world == 1 else "; %d ranks, all-gather of the row blocks %.0f ms" % (world, gpu_ms.get("gather", 0.0))))
+         "" if world == 1 else ("; %d ranks, rows of G left in place, row-distributed LSMR" % world if comm is not None else
+                                "; %d ranks, all-gather of the row blocks %.0f ms" % (world, gpu_ms.get("gather", 0.0)))))
+    if comm is not None:
+        comm.close()
     for f in (logf, iterf, lsmrf):
         if f:
             f.close()
@@ -285,9 +317,11 @@ def run(para_path: str, outdir: str | None = None, handle=None, maxiter: int | N
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     if len(argv) < 1:
-        print("usage: python -m dazimsurftomo_b200.invert para.in [outdir]", file=sys.stderr)
+        print("usage: python -m dazimsurftomo_b200.invert para.in [outdir] [--rows]", file=sys.stderr)
         return 2
-    run(argv[0], argv[1] if len(argv) > 1 else None)
+    rows = True if "--rows" in argv else None
+    argv = [a for a in argv if a != "--rows"]
+    run(argv[0], argv[1] if len(argv) > 1 else None, rows=rows)
     return 0
 
 

@@ -275,6 +275,15 @@ int dazim_plan_iterate(dazim_plan* plan, const float* obst, const dazim_iter_par
                        float* gcf, float* gsf, float* dws, float* sigmaT, float* resbst, float* fwdTvs,
                        float* fwdTaa, dazim_iter_stats* stats);
 
+/* The same with the rows of G left on the ranks that built them (each rank's plan covers its share of the sources;
+ * no gather of G): obst and the per-row outputs have dall_total entries (the whole system, loop order), the
+ * regularisation rows live on the last rank, LSMR runs row-distributed (dazim_lsmr_rows).  Everything that is O(rows)
+ * is completed on every rank and computed in the single-GPU order, so statistics and weights are bit-identical to
+ * dazim_plan_iterate; the solution differs by the association of the LSMR sums (1e-7 relative).  Collective. */
+int dazim_plan_iterate_rows(dazim_plan* plan, dazim_comm* comm, long long dall_total, const float* obst,
+                            const dazim_iter_params* prm, float* vsf, float* dv, float* gcf, float* gsf, float* dws,
+                            float* sigmaT, float* resbst, float* fwdTvs, float* fwdTaa, dazim_iter_stats* stats);
+
 /* The same on a system the caller holds in HBM: the CSR row blocks of several ranks after the NCCL all-gather
  * (all rows; d_rowid = 1-based global row id of every entry).  d_* are DEVICE pointers on the handle's device and
  * must be complete before the call; d_val / d_col / d_rowid need cap >= nnz + (1 or 3) x dazim_tikh_block_entries and

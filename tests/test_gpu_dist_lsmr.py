@@ -78,3 +78,22 @@ def test_row_distributed_lsmr_two_gpus(gpu):
     from conftest import note
     note("row-distributed LSMR on 2 GPUs: " + json.dumps(d))
     assert d["ok"] and d["identical_on_all_ranks"] and d["rel_to_single"] < 2e-4 and d["itn_rows"] == d["itn_single"]
+
+
+@pytest.mark.gpu
+def test_rows_inversion_two_gpus(gpu, tmp_path):
+    """The inversion driver with the rows of G left on the ranks that built them (invert.run(rows=True),
+    dazim_plan_iterate_rows) against the gathered / replicated tail, test2 (iso) and test3 (joint) subset cases."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29800 + os.getpid() % 90
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_invert_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-4000:]
+    d = json.loads(lines[-1])
+    from conftest import note
+    note("row-distributed inversion tail on 2 GPUs: " + json.dumps(d))
+    assert d["ok"]
