@@ -686,7 +686,10 @@ class Plan:
 
     def close(self):
         if self._plan:
-            load().dazim_plan_destroy(self._plan)
+            # a plan frees its buffers on its handle's stream: if the handle is already gone (interpreter shutdown
+            # destroys objects in no particular order) the plan is abandoned rather than freed through a dead stream
+            if self.h is not None and self.h._h:
+                load().dazim_plan_destroy(self._plan)
             self._plan = C.c_void_p()
 
     def __del__(self):

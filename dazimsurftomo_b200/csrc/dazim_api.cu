@@ -426,7 +426,8 @@ static int plan_build(dazim_handle* h, int mode, const dazim_problem* p, const d
     const long long nres = std::max<long long>(1, nsrc);
     const int ctas_needed = (int)((nres + L - 1) / L);
     // shared heap part: as large as possible while every solve is resident (else as many resident as the SM holds)
-    const int sm_budget = 227 * 1024;
+    int sm_budget = 227 * 1024;
+    if (const char* e = getenv("DAZIM_SM_SLACK")) sm_budget -= std::max(0, std::min(65536, atoi(e)));   // shared memory left to co-resident kernels
     int per_sm = std::max(1, (ctas_needed + h->nsm - 1) / h->nsm);
     per_sm = std::min(per_sm, 64 / L > 0 ? 64 / L : 1);       // at most 64 solves per SM
     if (const char* e = getenv("DAZIM_TPS_PER_SM")) per_sm = std::max(1, std::min(16, atoi(e)));
