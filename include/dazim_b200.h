@@ -222,7 +222,9 @@ int dazim_comm_rank(const dazim_comm* comm);
 int dazim_comm_size(const dazim_comm* comm);
 /* dazim_lsmr on a row block: m_local rows with LOCAL 1-based row ids in iw_row, b_local (m_local); m_total = rows of
  * the whole system (sizes the reorthogonalisation window like the reference: min(localSize, m, n)).  Collective: every
- * rank of the communicator must call it with the same n and controls. */
+ * rank of the communicator must call it with the same n and controls, and every rank needs at least one row
+ * (m_local >= 1).  A rank that fails its argument checks returns early while the others wait in the first collective:
+ * validate on the host before the call, as with any collective. */
 int dazim_lsmr_rows(dazim_handle* h, dazim_comm* comm, int m_local, long long m_total, int n, long long nnz_local,
                     const int* iw_row, const int* col, const float* rw, const float* b_local, float damp, float atol,
                     float btol, float conlim, int itnlim, int localSize, float* x, dazim_lsmr_info* info);
