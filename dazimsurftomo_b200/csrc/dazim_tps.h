@@ -191,6 +191,8 @@ struct TpsState {
   int2* gl;                   // spill part: position p at gl[p - hcap]
   int hcap, htot;             // htot = hcap + hspill_n - 2
   int ntr;
+  int2 last_e;                // copy of heap[last_p], kept by tps_apply (valid while last_p == ntr): the next pop's `last`
+  int last_p;
   unsigned* E;                // status / time / back-pointer words of the grid being marched
   int overflow;
   int stopped_at_root;        // refined march left through the exit test: the root is alive and stays in the heap
@@ -240,7 +242,7 @@ TPS_HD void tps_hput(TpsState& S, int p, int2 e) {
   if (p < S.hcap) S.sm[(size_t)p * S.stride] = e; else S.gl[p - S.hcap] = e;
   S.E[e.y] = E_SIGN | (unsigned)p;
 }
-TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.stopped_at_root = 0; }
+TPS_HD void tps_reset(TpsState& S) { S.ntr = 0; S.stopped_at_root = 0; S.last_p = -1; S.last_e = make_int2(0, 0); }
 
 // addtree / updtree share the sift-up (CalSurfG.f90:760-774, :876-890).
 // plain version (source-cell initialisation, coarse heap build)
@@ -368,7 +370,7 @@ TPS_HD bool tps_pre(TpsState& S, const TpsGrid& G, unsigned long long& nacc, Tps
   if (S.ntr <= 0 || S.overflow) return false;
   const int2 root = tps_hget(S, 1);
   P.pn = root.y;
-  P.last = tps_hget(S, S.ntr);
+  P.last = (S.last_p == S.ntr) ? S.last_e : tps_hget(S, S.ntr);     // usually kept in registers by tps_apply (a spilled slot is a global load)
   ndecode<URG>(P.pn, G.ld, G.inv_ld, P.ix, P.iz);
   P.tself = (unsigned)root.x & ~E_SIGN;
   G.E[P.pn] = P.tself;                             // the popped node becomes alive with its trial value (= its heap key)
@@ -515,7 +517,13 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4], bool r
 #pragma unroll
 #endif
     for (int q = 0; q < 4; ++q) qst[q] = 0;
+    nins = 0;
   }
+  // The entry of the LAST heap slot as it will stand after this step is the next pop's `last`: with an insert that slot
+  // is written below (every write to it is seen here); without one it is read now, under the latency of the updates.
+  const int nfinal = S.ntr + nins;
+  int2 laste = make_int2(0, 0);
+  if (run && nins == 0 && S.ntr >= 1) laste = tps_hget(S, S.ntr);
   // start positions: close = back pointer as read before the pop, far = next free heap slots in order
   int nt = S.ntr;
 #if defined(__CUDA_ARCH__)
@@ -560,6 +568,7 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4], bool r
         int2 par = pent[q];
         for (;;) {
           tps_hput(S, tpc, par);
+          if (tpc == nfinal) laste = par;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -578,6 +587,7 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4], bool r
       // a close neighbour that stays where it is keeps its back pointer: only the key changes (no write to E)
       if (qst[q] == 1 && tpc == tpc0) { if (tpc < S.hcap) S.sm[(size_t)tpc * S.stride] = e; else S.gl[tpc - S.hcap] = e; }
       else tps_hput(S, tpc, e);
+      if (tpc == nfinal) laste = e;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -587,6 +597,8 @@ TPS_HD bool tps_apply(TpsState& S, const TpsGrid& G, const TpsNb (&N)[4], bool r
     TPS_SYNCWARP(SYNC);
     TPS_TICK(S, 6 + (q & 1));    // 6 / 7: neighbours
   }
+  S.last_e = laste;
+  S.last_p = (run && nfinal >= 1) ? nfinal : -1;
   return run;
 }
 
