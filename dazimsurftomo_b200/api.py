@@ -417,10 +417,13 @@ def fmm_solve(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, handle: Optional[Han
     return dict(veln=veln, ttn=ttn, nsts=nsts, ttnr=ttnr, nstsr=nstsr, geom=geom, times=h.times)
 
 
-def fmm_host_twin(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, hcap=448, hspill=None):
+def fmm_host_twin(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, hcap=448, hspill=None, ahead=None):
     """TEST SEAM (no device needed): the thread-per-solve eikonal code of csrc/dazim_tps.h -- the functions the CUDA kernel
     k_fmm_tps runs, compiled __host__ __device__ -- executed on the CPU for one source.  Same outputs as fmm_solve(n=1).
-    Only tests call this: it is how the kernel's logic is checked against the oracle without a GPU."""
+    Only tests call this: it is how the kernel's logic is checked against the oracle without a GPU.
+    ahead = 0 / 1: replay the cohort kernel's "records computed ahead" protocol (records of the predicted next node gathered
+    before / after the current updates are applied); the result then also holds `ahead_stats` = (rounds predicted, not
+    predicted, records patched)."""
     nnx = (nx - 3) * 5 + 1; nnz = (ny - 3) * 5 + 1
     if hspill is None:
         hspill = (8 * (nnx + nnz) + 1024 + 16) & ~1
@@ -429,10 +432,17 @@ def fmm_host_twin(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, hcap=448, hspill
     ttnr = np.zeros((129, 129), np.float32, order="F"); nstsr = np.zeros((129, 129), np.int32, order="F")
     geom = np.zeros(8, np.int32)
     nacc = C.c_longlong(0)
-    _chk(load().dazim_debug_fmm_host_twin(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
-                                          C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), C.c_int(hcap),
-                                          C.c_int(hspill), _p(ttn), _p(nsts), _p(ttnr), _p(nstsr), _p(geom), C.byref(nacc)))
-    return dict(ttn=ttn, nsts=nsts, ttnr=ttnr, nstsr=nstsr, geom=geom, n_accept=nacc.value)
+    if ahead is None:
+        _chk(load().dazim_debug_fmm_host_twin(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+                                              C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), C.c_int(hcap),
+                                              C.c_int(hspill), _p(ttn), _p(nsts), _p(ttnr), _p(nstsr), _p(geom), C.byref(nacc)))
+        return dict(ttn=ttn, nsts=nsts, ttnr=ttnr, nstsr=nstsr, geom=geom, n_accept=nacc.value)
+    stats = (C.c_longlong * 3)()
+    _chk(load().dazim_debug_fmm_host_twin_ahead(C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd),
+                                                C.c_float(dvzd), _p(pv), C.c_float(scx), C.c_float(scz), C.c_int(hcap),
+                                                C.c_int(hspill), C.c_int(int(ahead)), _p(ttn), _p(nsts), _p(ttnr), _p(nstsr),
+                                                _p(geom), C.byref(nacc), stats))
+    return dict(ttn=ttn, nsts=nsts, ttnr=ttnr, nstsr=nstsr, geom=geom, n_accept=nacc.value, ahead_stats=tuple(stats))
 
 
 def raytrace(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, rcx, rcz, azim=True, handle: Optional[Handle] = None):

@@ -1621,9 +1621,66 @@ extern "C" int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, floa
 // TEST SEAM, host only: the thread-per-solve eikonal code of dazim_tps.h (the very functions k_fmm_tps runs, they are
 // __host__ __device__) executed on the CPU for ONE source, so that the logic can be compared with the oracle on a
 // machine without a GPU (tests/test_tps_host_twin.py).  No product entry point calls this; it needs no device.
+// The cohort kernel's "records computed ahead" protocol (coh_march_heap / coh_march_stencil in dazim_fmm.cu) replayed
+// serially on the host: the four neighbour records of the PREDICTED next node are gathered either before (when = 0)
+// or after (when = 1) the current node's updates are applied -- the two ends of the window in which the stencil threads
+// read E on the device --, used in the next round if (node, key) were predicted right, and patched exactly as the heap
+// lane patches them (a neighbour the previous round inserted is "close, position unknown").  stats: rounds predicted,
+// not predicted, records patched.
+template <int URG>
+static void twin_march_ahead(TpsState& S, const TpsGrid& G, unsigned long long& nacc, const int when, long long* stats) {
+  TpsNb spec[4];
+  int spec_node = -1, spec_key = 0;
+  int ins[4] = {-1, -1, -1, -1};
+  for (;;) {
+    TpsPre P;
+    if (!tps_pre<URG>(S, G, nacc, P)) break;
+    TpsNb N[4];
+    const bool hit = (P.pn == spec_node && (int)P.tself == spec_key);
+    for (int q = 0; q < 4; ++q) N[q] = hit ? spec[q] : tps_neighbour<URG>(G, P.ix, P.iz, P.tself, q);
+    stats[hit ? 0 : 1] += 1;
+    for (int q = 0; q < 4; ++q)
+      if (N[q].qst == -1 && (N[q].co == ins[0] || N[q].co == ins[1] || N[q].co == ins[2] || N[q].co == ins[3])) {
+        N[q].qst = 1; N[q].qid = 0; stats[2] += 1;
+      }
+    for (int q = 0; q < 4; ++q) ins[q] = (N[q].qst == -1) ? N[q].co : -1;
+    tps_pop<false>(S, P, true);
+    auto gather = [&]() {
+      spec_node = P.pred; spec_key = P.predk & 0x7fffffff;
+      if (P.pred < 0) return;
+      int px, pz;
+      ndecode<URG>(P.pred, G.ld, G.inv_ld, px, pz);
+      for (int q = 0; q < 4; ++q) spec[q] = tps_neighbour<URG>(G, px, pz, (unsigned)spec_key, q);
+    };
+    if (when == 0) gather();
+    const bool go = tps_apply<URG, false>(S, G, N, true);
+    if (when != 0) gather();
+    if (!go) break;
+  }
+}
+
+static int fmm_host_twin_impl(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv, float scx,
+                              float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr, int* nstsr, int* geom,
+                              long long* n_accept, int ahead_when, long long* ahead_stats);
+
 extern "C" int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
                                          float scx, float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr,
                                          int* nstsr, int* geom, long long* n_accept) {
+  return fmm_host_twin_impl(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, hcap, hspill_n, ttn, nsts, ttnr, nstsr, geom,
+                            n_accept, -1, nullptr);
+}
+extern "C" int dazim_debug_fmm_host_twin_ahead(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                                               float scx, float scz, int hcap, int hspill_n, int when, float* ttn, int* nsts,
+                                               float* ttnr, int* nstsr, int* geom, long long* n_accept, long long* stats) {
+  if ((when != 0 && when != 1) || !stats) return DAZIM_EBADARG;
+  stats[0] = stats[1] = stats[2] = 0;
+  return fmm_host_twin_impl(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, hcap, hspill_n, ttn, nsts, ttnr, nstsr, geom,
+                            n_accept, when, stats);
+}
+
+static int fmm_host_twin_impl(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv, float scx,
+                              float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr, int* nstsr, int* geom,
+                              long long* n_accept, int ahead_when, long long* ahead_stats) {
   if (!pv || nx < 5 || ny < 5 || hcap < 8 || (hcap & 1) || (hspill_n & 1) || hspill_n < 4) return DAZIM_EBADARG;
   const GridC g = make_grid(nx, ny, goxd, gozd, dvxd, dvzd);
   SrcRec sr;
@@ -1653,13 +1710,15 @@ extern "C" int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd,
   tps_source_init(S, g, sr, velv.data(), ub, E_r.data());
   {
     const TpsGrid G = tps_grid_refined(g, sr, slow_r.data(), rir.data(), E_r.data());
-    while (tps_step<1>(S, G, nacc)) {}
+    if (ahead_when < 0) { while (tps_step<1>(S, G, nacc)) {} }
+    else twin_march_ahead<1>(S, G, nacc, ahead_when, ahead_stats);
   }
   if (!S.overflow) {
     tps_refined_finish(S, E_r.data(), hpos_r.data());
     tps_handoff(S, g, sr, E_r.data(), E_c.data());
     const TpsGrid G = tps_grid_coarse(g, slow_c.data(), ric.data(), E_c.data());
-    while (tps_step<2>(S, G, nacc)) {}
+    if (ahead_when < 0) { while (tps_step<2>(S, G, nacc)) {} }
+    else twin_march_ahead<2>(S, G, nacc, ahead_when, ahead_stats);
   }
   if (S.overflow) return DAZIM_EHEAP;
   auto decode = [](unsigned e, int hp, float& t, int& stt) {

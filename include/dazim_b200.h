@@ -154,6 +154,13 @@ int dazim_fmm_solve(dazim_handle* h, int nx, int ny, float goxd, float gozd, flo
 int dazim_debug_fmm_host_twin(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
                               float scx, float scz, int hcap, int hspill_n, float* ttn, int* nsts, float* ttnr,
                               int* nstsr, int* geom, long long* n_accept);
+/* The same with the cohort kernel's "neighbour records computed ahead" protocol replayed serially: the records of the
+ * predicted next node are gathered before (when = 0) or after (when = 1) the current updates are applied, used if the
+ * prediction holds and patched as the kernel's heap lane patches them.  stats[3] = rounds predicted, not predicted,
+ * records patched.  Host-only test seam. */
+int dazim_debug_fmm_host_twin_ahead(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, const double* pv,
+                                    float scx, float scz, int hcap, int hspill_n, int when, float* ttn, int* nsts,
+                                    float* ttnr, int* nstsr, int* geom, long long* n_accept, long long* stats);
 /* Rays: n (source, receiver) pairs on one map; outputs travel time tt(n) and dense
  * Frechet maps fdm/fdmc/fdms (nvz+2, nvx+2, n) column-major (zero where untouched). */
 int dazim_raytrace(dazim_handle* h, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
